@@ -1,0 +1,216 @@
+/*
+ * krige_b200.h — C ABI of libkrige_b200.so, the B200-native kriging execute() backend.
+ *
+ * This is the drop-in boundary for PyKrige's `execute(..., backend='cuda')`.
+ * It replaces, one level higher (coordinates in, not dense a/bd matrices), the
+ * reference's own native plug-in entry points:
+ *
+ *   _c_exec_loop(a_all, bd_all, mask, n, pars)                       src/pykrige/lib/cok.pyx:14-96
+ *   _c_exec_loop_moving_window(a_all, bd_all, mask, bd_idx, n_max, pars)
+ *                                                                    src/pykrige/lib/cok.pyx:98-193
+ * and the Python bodies they mirror:
+ *   OrdinaryKriging._get_kriging_matrix / _exec_vector               src/pykrige/ok.py:626-683
+ *   OrdinaryKriging._exec_loop_moving_window                         src/pykrige/ok.py:722-758
+ *   UniversalKriging._get_kriging_matrix / _exec_vector              src/pykrige/uk.py:861-1009
+ *   OrdinaryKriging3D / UniversalKriging3D equivalents               src/pykrige/ok3d.py:603-657, uk3d.py:688-811
+ *   core._adjust_for_anisotropy                                      src/pykrige/core.py:120-193
+ *   variogram_models.*                                               src/pykrige/variogram_models.py:25-81
+ *
+ * Conventions
+ *   - plain C types only; all array arguments are caller-owned.
+ *   - "host" pointers are ordinary host memory (pinned or pageable);
+ *     "dev" pointers are CUDA device memory on the handle's device.
+ *   - every function returns KB200_OK (0) or a negative KB200_E* code;
+ *     kb200_last_error() gives a human-readable message for the handle.
+ *   - a handle is bound to one CUDA device and one stream and is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device every entry point
+ *     that computes returns KB200_ECUDA.
+ */
+#ifndef KRIGE_B200_H
+#define KRIGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+#define KB200_OK            0
+#define KB200_EBADARG      -1   /* -> ValueError                                        */
+#define KB200_EUNSUPPORTED -2   /* -> NotImplementedError (cok.pyx / variogram_models.pyx:20-21 convention) */
+#define KB200_ESINGULAR    -3   /* -> numpy.linalg.LinAlgError (global) / ValueError('Singular matrix') (kNN, cok.pyx:176-179) */
+#define KB200_ECUDA        -4   /* -> RuntimeError (no device / CUDA runtime failure)   */
+#define KB200_ENOMEM       -5   /* -> MemoryError                                       */
+#define KB200_ESTATE       -6   /* -> RuntimeError (call order)                         */
+
+/* ---- variogram model ids (keyed on the reference's function __name__,
+ *      src/pykrige/lib/variogram_models.pyx:5-21; hole-effect added) ------- */
+#define KB200_VG_LINEAR       0  /* params [slope, nugget]            variogram_models.py:25 */
+#define KB200_VG_POWER        1  /* params [scale, exponent, nugget]  variogram_models.py:32 */
+#define KB200_VG_GAUSSIAN     2  /* params [psill, range, nugget]     variogram_models.py:40 */
+#define KB200_VG_EXPONENTIAL  3  /* params [psill, range, nugget]     variogram_models.py:48 */
+#define KB200_VG_SPHERICAL    4  /* params [psill, range, nugget]     variogram_models.py:56 */
+#define KB200_VG_HOLE_EFFECT  5  /* params [psill, range, nugget]     variogram_models.py:73 */
+
+/* ---- arithmetic of the big contraction ---------------------------------- */
+#define KB200_F64 0
+#define KB200_F32 1   /* factorisation stays fp64; W and the RHS tile are fp32 */
+
+#define KB200_MAX_DRIFT 15   /* drift columns (regional-linear + host supplied), excluding the unbiasedness column */
+
+typedef struct kb200_ctx* kb200_handle;
+
+/* Create a handle on CUDA device `device` (-1 = current device). */
+int  kb200_create(kb200_handle* out, int device);
+void kb200_destroy(kb200_handle h);
+const char* kb200_last_error(kb200_handle h);
+/* Library/ABI version (major*1000+minor). */
+int  kb200_version(void);
+
+/*
+ * Describe the kriging system (the data side) and factor it on the device.
+ * Replaces _get_kriging_matrix + scipy.linalg.inv of the reference
+ * (ok.py:626-648,663; uk.py:861-920,935).
+ *
+ *  dim            2 or 3
+ *  dtype          KB200_F64 / KB200_F32
+ *  n              number of data points
+ *  x,y,z          host, length n, ORIGINAL (un-adjusted) coordinates; z may be NULL when dim==2
+ *  values         host, length n (self.Z / self.VALUES)
+ *  center[dim]    anisotropy centre (XCENTER, YCENTER[, ZCENTER])                 ok.py:278-279
+ *  aniso[dim*dim] row-major matrix Mt = stretch @ rot of core._adjust_for_anisotropy  core.py:148-189
+ *                 (adjusted = Mt @ (p - center) + center); identity when isotropic
+ *  model          KB200_VG_*,  vparams: the reference's *stored* parameter list (psill form)
+ *  exact_values   ok.py:671-672 semantics;  eps: |d| <= eps counts as an exact hit (ok.py:177)
+ *  n_rl           0, or dim: regional-linear drift columns built on device from the adjusted coordinates
+ *                 (uk.py:877-883, uk3d.py:708-717)
+ *  n_hd           number of host-supplied drift columns (point_log, external_Z, specified, functional;
+ *                 uk.py:884-910) ; drift_data is host, column-major n x n_hd (column c at drift_data + c*n)
+ *  Work is asynchronous on the handle's stream; errors of the factorisation
+ *  (non positive-definite / singular) are reported here (the call synchronises once).
+ */
+int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
+                      const double* x, const double* y, const double* z,
+                      const double* values,
+                      const double* center, const double* aniso,
+                      int model, const double* vparams, int n_vparams,
+                      int exact_values, double eps,
+                      int n_rl, int n_hd, const double* drift_data);
+
+/*
+ * Krige explicit points (style='points', and 'masked' after compaction).
+ *   px,py,pz   host, length m, ORIGINAL coordinates (anisotropy is applied on device, ok.py:880-885)
+ *   drift_pts  host, column-major m x n_hd values of the host-supplied drift terms at the points (or NULL)
+ *   z_out, ss_out  host, length m  (zvalues, sigmasq of ok.py:680-681)
+ */
+int kb200_execute_points(kb200_handle h, int64_t m,
+                         const double* px, const double* py, const double* pz,
+                         const double* drift_pts,
+                         double* z_out, double* ss_out);
+
+/*
+ * Krige a rectangular grid (style='grid'): points are generated on the device
+ * in the reference's order — 2-D: meshgrid(x, y) flattened, x fastest (ok.py:864-866);
+ * 3-D: meshgrid(z, y, x, indexing='ij') flattened, x fastest (ok3d.py:863-866).
+ *   gx,gy,gz   host axis vectors of length nx, ny, nz (gz NULL and nz=1 for 2-D)
+ *   first,count  the slice [first, first+count) of the flattened grid to compute (multi-GPU sharding);
+ *                z_out/ss_out are host arrays of length `count`.
+ */
+int kb200_execute_grid(kb200_handle h,
+                       int64_t nx, int64_t ny, int64_t nz,
+                       const double* gx, const double* gy, const double* gz,
+                       const double* drift_pts,
+                       int64_t first, int64_t count,
+                       double* z_out, double* ss_out);
+
+/* Same as the two calls above but with DEVICE pointers for the point coordinates /
+ * axis vectors and for the outputs; nothing is copied to or from the host. */
+int kb200_execute_points_dev(kb200_handle h, int64_t m,
+                             const double* d_px, const double* d_py, const double* d_pz,
+                             const double* d_drift_pts,
+                             double* d_z_out, double* d_ss_out);
+int kb200_execute_grid_dev(kb200_handle h,
+                           int64_t nx, int64_t ny, int64_t nz,
+                           const double* d_gx, const double* d_gy, const double* d_gz,
+                           const double* d_drift_pts,
+                           int64_t first, int64_t count,
+                           double* d_z_out, double* d_ss_out);
+
+/*
+ * Moving-window kriging (n_closest_points=k): exact k nearest data points per
+ * prediction point (cKDTree.query(k, eps=0.0), ok.py:957-960), local (k+1)x(k+1)
+ * system assembled on the fly and solved per point (ok.py:722-758, cok.pyx:98-193).
+ * Ordinary kriging only (the reference has no moving window for UK, uk.py:1090-1098).
+ * Point sources as above: explicit points (grid = 0) or a grid slice (grid = 1).
+ */
+int kb200_execute_knn_points(kb200_handle h, int k, int64_t m,
+                             const double* px, const double* py, const double* pz,
+                             double* z_out, double* ss_out);
+int kb200_execute_knn_grid(kb200_handle h, int k,
+                           int64_t nx, int64_t ny, int64_t nz,
+                           const double* gx, const double* gy, const double* gz,
+                           int64_t first, int64_t count,
+                           double* z_out, double* ss_out);
+int kb200_execute_knn_grid_dev(kb200_handle h, int k,
+                               int64_t nx, int64_t ny, int64_t nz,
+                               const double* d_gx, const double* d_gy, const double* d_gz,
+                               int64_t first, int64_t count,
+                               double* d_z_out, double* d_ss_out);
+/* Set the data for the moving window only (no global factorisation). */
+int kb200_set_problem_knn(kb200_handle h, int dim, int64_t n,
+                          const double* x, const double* y, const double* z,
+                          const double* values,
+                          const double* center, const double* aniso,
+                          int model, const double* vparams, int n_vparams,
+                          int exact_values, double eps);
+
+/*
+ * Multi-GPU: the factor blob (packed inverse Cholesky factor + dual vectors +
+ * constants + adjusted data coordinates) lives in ONE contiguous device
+ * allocation so that rank 0 can factor and a single NCCL broadcast ships it.
+ *   kb200_blob_bytes    size of the blob for the current problem description
+ *   kb200_blob_ptr      device pointer of the blob owned by the handle
+ *   kb200_describe_problem  same arguments as kb200_set_problem but performs NO
+ *                       device work: it only records the description and allocates the blob,
+ *                       so that a non-root rank can receive the broadcast into kb200_blob_ptr()
+ *   kb200_blob_commit   mark the (received) blob as valid: the handle is ready to execute
+ */
+int64_t kb200_blob_bytes(kb200_handle h);
+void*   kb200_blob_ptr(kb200_handle h);
+int kb200_describe_problem(kb200_handle h, int dim, int dtype, int64_t n,
+                           const double* x, const double* y, const double* z,
+                           const double* values,
+                           const double* center, const double* aniso,
+                           int model, const double* vparams, int n_vparams,
+                           int exact_values, double eps,
+                           int n_rl, int n_hd, const double* drift_data);
+int kb200_blob_commit(kb200_handle h);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of the handle. */
+int kb200_set_stream(kb200_handle h, void* cuda_stream);
+
+/*
+ * Device-side timings (CUDA events on the handle's stream) of the last calls, in ms:
+ *  [0] assemble  [1] cholesky  [2] triangular inverse  [3] pack + dual vectors
+ *  [4] solve kernel (sum over chunks)  [5] finalize (sum)  [6] h2d  [7] d2h
+ *  [8] knn search  [9] knn local solve
+ *  [10] solve-kernel launches  [11] total kernel launches since the last kb200_reset_counters
+ * Returns the number of entries written (<= n).
+ */
+int  kb200_last_timings(kb200_handle h, double* ms, int n);
+void kb200_reset_counters(kb200_handle h);
+
+/* Debug/verification taps (used by tests only): copy device intermediates to host.
+ *  what = 0: shifted covariance matrix C (n_pad x n_pad, row-major, lower triangle valid)
+ *  what = 1: Cholesky factor L (same layout)
+ *  what = 2: W = inv(L) (same layout)
+ *  what = 3: dual block: Uz (n x (K+2), column-major), then Sinv ((K+1)^2), then phi (K+1), then c0
+ * `cap` is the capacity of `out` in doubles; returns the number of doubles written or a negative code. */
+int64_t kb200_debug_fetch(kb200_handle h, int what, double* out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRIGE_B200_H */

@@ -1,0 +1,210 @@
+"""CPU oracle for the kriging execute() hot path — TEST INFRASTRUCTURE ONLY.
+
+A plain numpy/scipy restatement of the reference's algorithm (GeoStat-Framework/PyKrige
+v1.7.3, commit 5e896fb), one function per reference step, each citing the file:line it follows.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product path (pykrige_b200) never does.
+
+Parity pinning: this oracle is checked in tests/test_oracle.py against
+  * the reference's own golden vectors (KT3D_H2O / KT3D answers of tests/test_core.py:490-507,
+    707-725, 1957-1989, stored in tests/golden/reference_goldens.npz), and
+  * outputs of the imported reference itself (backend='vectorized' / 'loop'), generated here by
+    tests/golden/make_golden.py and stored in tests/golden/*.npz.
+
+The arithmetic deliberately stays in the reference's form (gamma-form matrix with zero diagonal,
+explicit inverse, inverse x RHS) — NOT the covariance/Cholesky form the CUDA path uses — so that
+the comparison is between two independent formulations.
+"""
+import numpy as np
+import scipy.linalg
+from scipy.spatial import cKDTree
+from scipy.spatial.distance import cdist
+
+EPS = 1.0e-10  # ok.py:177
+
+
+# ---- variogram models: variogram_models.py:25-81 ------------------------------------
+def variogram(model, m, d):
+    d = np.asarray(d, dtype=np.float64)
+    if model == "linear":        # variogram_models.py:25-29
+        return float(m[0]) * d + float(m[1])
+    if model == "power":         # :32-37
+        return float(m[0]) * d ** float(m[1]) + float(m[2])
+    psill, rng, nugget = float(m[0]), float(m[1]), float(m[2])
+    if model == "gaussian":      # :40-45
+        return psill * (1.0 - np.exp(-(d**2.0) / (rng * 4.0 / 7.0) ** 2.0)) + nugget
+    if model == "exponential":   # :48-53
+        return psill * (1.0 - np.exp(-d / (rng / 3.0))) + nugget
+    if model == "spherical":     # :56-70
+        out = np.full(d.shape, psill + nugget)
+        s = d <= rng
+        out[s] = psill * ((3.0 * d[s]) / (2.0 * rng) - (d[s] ** 3.0) / (2.0 * rng**3.0)) + nugget
+        return out
+    if model == "hole-effect":   # :73-81
+        return psill * (1.0 - (1.0 - d / (rng / 3.0)) * np.exp(-d / (rng / 3.0))) + nugget
+    raise ValueError(model)
+
+
+def stored_parameters(model, plist):
+    """List input [FULL sill, range, nugget] -> stored [psill, range, nugget] (core.py:345-357)."""
+    if model in ("gaussian", "spherical", "exponential", "hole-effect"):
+        return [plist[0] - plist[2], plist[1], plist[2]]
+    return list(plist)
+
+
+# ---- anisotropy: core.py:120-193 -----------------------------------------------------
+def adjust_for_anisotropy(X, center, scaling, angle):
+    X = np.array(X, dtype=np.float64, copy=True)
+    center = np.asarray(center, dtype=np.float64)[None, :]
+    ang = np.asarray(angle, dtype=np.float64) * np.pi / 180.0
+    X -= center
+    nd = X.shape[1]
+    if nd == 2:
+        stretch = np.array([[1.0, 0.0], [0.0, scaling[0]]])
+        rot = np.array([[np.cos(-ang[0]), -np.sin(-ang[0])], [np.sin(-ang[0]), np.cos(-ang[0])]])
+    else:
+        stretch = np.diag([1.0, scaling[0], scaling[1]])
+        rx = np.array([[1, 0, 0], [0, np.cos(-ang[0]), -np.sin(-ang[0])], [0, np.sin(-ang[0]), np.cos(-ang[0])]])
+        ry = np.array([[np.cos(-ang[1]), 0, np.sin(-ang[1])], [0, 1, 0], [-np.sin(-ang[1]), 0, np.cos(-ang[1])]])
+        rz = np.array([[np.cos(-ang[2]), -np.sin(-ang[2]), 0], [np.sin(-ang[2]), np.cos(-ang[2]), 0], [0, 0, 1]])
+        rot = rz @ (ry @ rx)
+    return (stretch @ (rot @ X.T)).T + center
+
+
+# ---- kriging matrix: ok.py:626-648, uk.py:861-920, ok3d.py:603-622, uk3d.py:688-737 ----
+def kriging_matrix(P, model, m, drift_cols=()):
+    """P: [n, dim] adjusted data coordinates; drift_cols: list of length-n arrays (in the
+    reference's column order). Returns the (n+K+1)^2 matrix with the unbiasedness border."""
+    n = P.shape[0]
+    K = len(drift_cols)
+    a = np.zeros((n + K + 1, n + K + 1))
+    a[:n, :n] = -variogram(model, m, cdist(P, P, "euclidean"))
+    np.fill_diagonal(a, 0.0)                      # ok.py:644
+    for i, col in enumerate(drift_cols):          # uk.py:876-910
+        a[:n, n + i] = col
+        a[n + i, :n] = col
+    a[n + K, :n] = 1.0                            # ok.py:645-647 / uk.py:915-918
+    a[:n, n + K] = 1.0
+    a[n:, n:] = 0.0
+    return a
+
+
+# ---- global solve: ok.py:650-683, uk.py:922-1009 --------------------------------------
+def exec_vector(a, P, Q, values, model, m, exact_values=True, drift_pts=()):
+    """Q: [npt, dim] adjusted prediction points; drift_pts: list of length-npt arrays.
+    Returns (zvalues, sigmasq): inverse x RHS exactly as the reference's 'vectorized' backend."""
+    n = P.shape[0]
+    K = len(drift_pts)
+    npt = Q.shape[0]
+    a_inv = scipy.linalg.inv(a)                   # ok.py:663
+    bd = cdist(Q, P, "euclidean")                 # ok.py:989
+    b = np.zeros((npt, n + K + 1))
+    b[:, :n] = -variogram(model, m, bd)           # ok.py:670
+    if exact_values:
+        b[:, :n][np.absolute(bd) <= EPS] = 0.0    # ok.py:665-672
+    for i, col in enumerate(drift_pts):           # uk.py:949-979
+        b[:, n + i] = col
+    b[:, n + K] = 1.0                             # ok.py:673
+    x = a_inv @ b.T                               # ok.py:679
+    z = np.sum(x[:n, :].T * values, axis=1)       # ok.py:680
+    ss = np.sum(x.T * -b, axis=1)                 # ok.py:681
+    return z, ss
+
+
+# ---- moving window: ok.py:722-758, 957-960; cok.pyx:98-193 -----------------------------
+def exec_moving_window(P, Q, values, model, m, k, exact_values=True):
+    """Never builds the N x N matrix: the local (k+1)^2 system is assembled from the
+    neighbour coordinates, which is what gathering from the full matrix yields (cok.pyx:138-147)."""
+    tree = cKDTree(P)
+    bd_all, idx_all = tree.query(Q, k=k, eps=0.0)  # ok.py:957-960
+    npt = Q.shape[0]
+    z = np.zeros(npt)
+    ss = np.zeros(npt)
+    for i in range(npt):
+        sel = idx_all[i]
+        bd = bd_all[i]
+        a = kriging_matrix(P[sel], model, m)       # == a_all[sel+[n]][:, sel+[n]] (ok.py:738-739)
+        b = np.zeros(k + 1)
+        b[:k] = -variogram(model, m, bd)
+        if exact_values:
+            b[:k][np.absolute(bd) <= EPS] = 0.0    # ok.py:741-751
+        b[k] = 1.0
+        x = scipy.linalg.solve(a, b)               # ok.py:753
+        z[i] = x[:k].dot(values[sel])              # ok.py:755
+        ss[i] = -x.dot(b)                          # ok.py:756
+    return z, ss
+
+
+# ---- point set-up: ok.py:862-885, ok3d.py:860-898 ---------------------------------------
+def grid_points(axes):
+    """2-D: meshgrid(x, y) flattened (x fastest, ok.py:864-866); 3-D: meshgrid(z, y, x, 'ij')
+    flattened (ok3d.py:863-866). Returns [npt, dim] in (x, y[, z]) column order."""
+    if len(axes) == 2:
+        gx, gy = np.meshgrid(axes[0], axes[1])
+        return np.column_stack((gx.ravel(), gy.ravel()))
+    gz, gy, gx = np.meshgrid(axes[2], axes[1], axes[0], indexing="ij")
+    return np.column_stack((gx.ravel(), gy.ravel(), gz.ravel()))
+
+
+def krige(data_xyz, values, model, plist_stored, points, *, scaling=None, angle=None,
+          regional_linear=False, data_drift=(), point_drift=(), exact_values=True, n_closest_points=None):
+    """End-to-end oracle for one execute() call on explicit points (original coordinates).
+
+    data_xyz [n, dim], points [npt, dim]; centre = (max+min)/2 of the data (ok.py:278-279);
+    regional-linear drift uses the adjusted coordinates in x, y[, z] order (uk.py:877-883,
+    uk3d.py:708-717, 767-773). data_drift / point_drift: extra host drift columns.
+    """
+    data_xyz = np.asarray(data_xyz, dtype=np.float64)
+    points = np.asarray(points, dtype=np.float64)
+    dim = data_xyz.shape[1]
+    center = (data_xyz.max(axis=0) + data_xyz.min(axis=0)) / 2.0
+    if scaling is None:
+        scaling = [1.0] * (dim - 1)
+    if angle is None:
+        angle = [0.0] * (2 * dim - 3)
+    P = adjust_for_anisotropy(data_xyz, center, scaling, angle)
+    Q = adjust_for_anisotropy(points, center, scaling, angle)
+    if n_closest_points is not None:
+        return exec_moving_window(P, Q, np.asarray(values, float), model, plist_stored, n_closest_points, exact_values)
+    dcols, pcols = [], []
+    if regional_linear:
+        for c in range(dim):
+            dcols.append(P[:, c])
+            pcols.append(Q[:, c])
+    dcols += [np.asarray(c, float) for c in data_drift]
+    pcols += [np.asarray(c, float) for c in point_drift]
+    a = kriging_matrix(P, model, plist_stored, dcols)
+    return exec_vector(a, P, Q, np.asarray(values, float), model, plist_stored, exact_values, pcols)
+
+
+def krige_chunked(data_xyz, values, model, plist_stored, points, chunk=20000, **kw):
+    """Same as krige() for the global path but inverts once and streams the points in chunks, so
+    large M never materialises M x N. Used by bench.py's CPU baseline."""
+    data_xyz = np.asarray(data_xyz, dtype=np.float64)
+    points = np.asarray(points, dtype=np.float64)
+    dim = data_xyz.shape[1]
+    center = (data_xyz.max(axis=0) + data_xyz.min(axis=0)) / 2.0
+    scaling = kw.get("scaling") or [1.0] * (dim - 1)
+    angle = kw.get("angle") or [0.0] * (2 * dim - 3)
+    exact = kw.get("exact_values", True)
+    P = adjust_for_anisotropy(data_xyz, center, scaling, angle)
+    dcols = [P[:, c] for c in range(dim)] if kw.get("regional_linear") else []
+    a = kriging_matrix(P, model, plist_stored, dcols)
+    a_inv = scipy.linalg.inv(a)
+    n, K = P.shape[0], len(dcols)
+    vals = np.asarray(values, float)
+    z = np.empty(points.shape[0])
+    ss = np.empty(points.shape[0])
+    for s in range(0, points.shape[0], chunk):
+        Q = adjust_for_anisotropy(points[s:s + chunk], center, scaling, angle)
+        bd = cdist(Q, P, "euclidean")
+        b = np.ones((Q.shape[0], n + K + 1))
+        b[:, :n] = -variogram(model, plist_stored, bd)
+        if exact:
+            b[:, :n][np.absolute(bd) <= EPS] = 0.0
+        for c in range(K):
+            b[:, n + c] = Q[:, c]
+        x = a_inv @ b.T
+        z[s:s + chunk] = x[:n, :].T @ vals
+        ss[s:s + chunk] = -np.einsum("ij,ji->i", b, x)
+    return z, ss

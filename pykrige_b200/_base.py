@@ -1,0 +1,256 @@
+"""Shared host logic of the four kriging classes (not part of the reference's API surface).
+
+The reference repeats this logic in ok.py / uk.py / ok3d.py / uk3d.py; here it lives once:
+variogram model selection (ok.py:208-253), the ``backend='cuda'`` dispatch that replaces the
+``backend`` string switch of ``execute`` (ok.py:971-1010), point-list / grid / mask handling
+(ok.py:842-900, ok3d.py:833-898) and output shaping (ok.py:1012-1020).
+"""
+import warnings
+import numpy as np
+
+from . import variogram_models
+from . import core
+from . import _cabi
+
+
+class KrigeBase:
+    eps = 1.0e-10  # cutoff for comparison to zero (ok.py:177)
+    variogram_dict = {
+        "linear": variogram_models.linear_variogram_model,
+        "power": variogram_models.power_variogram_model,
+        "gaussian": variogram_models.gaussian_variogram_model,
+        "spherical": variogram_models.spherical_variogram_model,
+        "exponential": variogram_models.exponential_variogram_model,
+        "hole-effect": variogram_models.hole_effect_variogram_model,
+    }
+    _ndim = 2
+    _backend_name = "ordinary kriging"
+
+    # ---- variogram model selection (ok.py:208-253; GSTools models arrive as 'custom') ----
+    def _select_variogram(self, variogram_model, variogram_function, gstools_dim_ok):
+        self.variogram_model = variogram_model
+        self.model = None
+        overrides = {}
+        if hasattr(self.variogram_model, "pykrige_kwargs"):
+            self.model = self.variogram_model
+            gstools_dim_ok(self.model)
+            self.variogram_model = "custom"
+            variogram_function = self.model.pykrige_vario
+            overrides["variogram_parameters"] = []
+            overrides["gstools"] = self.model
+        if self.variogram_model not in self.variogram_dict.keys() and self.variogram_model != "custom":
+            raise ValueError("Specified variogram model '%s' is not supported." % variogram_model)
+        elif self.variogram_model == "custom":
+            if variogram_function is None or not callable(variogram_function):
+                raise ValueError("Must specify callable function for custom variogram model.")
+            self.variogram_function = variogram_function
+        else:
+            self.variogram_function = self.variogram_dict[self.variogram_model]
+        return overrides
+
+    def _print_variogram(self):
+        p = self.variogram_model_parameters
+        if self.variogram_model == "linear":
+            print("Using '%s' Variogram Model" % "linear")
+            print("Slope:", p[0])
+            print("Nugget:", p[1], "\n")
+        elif self.variogram_model == "power":
+            print("Using '%s' Variogram Model" % "power")
+            print("Scale:", p[0])
+            print("Exponent:", p[1])
+            print("Nugget:", p[2], "\n")
+        elif self.variogram_model == "custom":
+            print("Using Custom Variogram Model")
+        else:
+            print("Using '%s' Variogram Model" % self.variogram_model)
+            print("Partial Sill:", p[0])
+            print("Full Sill:", p[0] + p[2])
+            print("Range:", p[1])
+            print("Nugget:", p[2], "\n")
+
+    # ---- cross-validation statistics: lazy (the reference runs this O(N^4) loop in the
+    #      constructor of OK3D/UK/UK3D, ok3d.py:352, uk.py:380, uk3d.py:380) -----
+    def _stats_inputs(self):
+        raise NotImplementedError
+
+    def _compute_statistics(self):
+        X, y = self._stats_inputs()
+        self._delta, self._sigma, self._epsilon = core._find_statistics(
+            X, y, self.variogram_function, self.variogram_model_parameters, "euclidean",
+            getattr(self, "pseudo_inv", False),
+        )
+        self._Q1 = core.calcQ1(self._epsilon)
+        self._Q2 = core.calcQ2(self._epsilon)
+        self._cR = core.calc_cR(self._Q2, self._sigma)
+        self._stats_state = "done"
+
+    def _stat(self, name):
+        state = getattr(self, "_stats_state", "off")
+        if state == "off":
+            return None
+        if state == "lazy":
+            self._compute_statistics()
+        return getattr(self, "_" + name)
+
+    delta = property(lambda self: self._stat("delta"))
+    sigma = property(lambda self: self._stat("sigma"))
+    epsilon = property(lambda self: self._stat("epsilon"))
+    Q1 = property(lambda self: self._stat("Q1"))
+    Q2 = property(lambda self: self._stat("Q2"))
+    cR = property(lambda self: self._stat("cR"))
+
+    # ---- small public helpers kept from the reference API (ok.py:555-624) ---------------
+    def display_variogram_model(self):
+        """Displays variogram model with the actual binned data."""
+        import matplotlib.pyplot as plt
+
+        fig = plt.figure()
+        ax = fig.add_subplot(111)
+        ax.plot(self.lags, self.semivariance, "r*")
+        ax.plot(self.lags, self.variogram_function(self.variogram_model_parameters, self.lags), "k-")
+        plt.show()
+
+    def get_variogram_points(self):
+        """Returns both the lags and the variogram function evaluated at each of them."""
+        return self.lags, self.variogram_function(self.variogram_model_parameters, self.lags)
+
+    def switch_verbose(self):
+        self.verbose = not self.verbose
+
+    def switch_plotting(self):
+        self.enable_plotting = not self.enable_plotting
+
+    def get_epsilon_residuals(self):
+        return self.epsilon
+
+    def plot_epsilon_residuals(self):
+        import matplotlib.pyplot as plt
+
+        fig = plt.figure()
+        ax = fig.add_subplot(111)
+        ax.scatter(range(self.epsilon.size), self.epsilon, c="k", marker="*")
+        ax.axhline(y=0.0)
+        plt.show()
+
+    def get_statistics(self):
+        return self.Q1, self.Q2, self.cR
+
+    def print_statistics(self):
+        print("Q1 =", self.Q1)
+        print("Q2 =", self.Q2)
+        print("cR =", self.cR)
+
+    # ---- the backend='cuda' arm ---------------------------------------------------------
+    def _device_model(self):
+        """model id + stored parameters for the device; custom / GSTools callables have no device
+        twin -> NotImplementedError (the reference's 'C' backend convention, variogram_models.pyx:20-21)."""
+        name = getattr(self.variogram_function, "__name__", None)
+        mid = variogram_models.DEVICE_MODEL_IDS.get(name)
+        if mid is None or self.variogram_function is not self.variogram_dict.get(self.variogram_model):
+            raise NotImplementedError(
+                "backend='cuda' evaluates the built-in variogram models on the device; "
+                "'custom' / GSTools variogram callables are not supported (no CPU fallback)."
+            )
+        return mid, [float(v) for v in self.variogram_model_parameters]
+
+    def _data_arrays(self):
+        """(x, y, z|None, values, center, Mt) in ORIGINAL coordinates."""
+        raise NotImplementedError
+
+    def _drift_spec(self):
+        """(n_rl, [host drift data columns])"""
+        return 0, []
+
+    def _cuda_handle(self):
+        h = getattr(self, "_kb_handle", None)
+        if h is None:
+            h = _cabi.Handle()
+            self._kb_handle = h
+            self._kb_key = None
+        return h
+
+    def _problem_signature(self, dtype, knn):
+        x, y, z, v, center, Mt = self._data_arrays()
+        mid, vp = self._device_model()
+        n_rl, cols = self._drift_spec()
+        return (dtype, knn, mid, tuple(vp), bool(self.exact_values), tuple(np.ravel(Mt)), tuple(center),
+                n_rl, len(cols), x.size)
+
+    def _ensure_problem(self, dtype="float64", knn=False):
+        if getattr(self, "pseudo_inv", False):
+            raise NotImplementedError("pseudo_inv=True is not supported by backend='cuda' (SURVEY.md §8f next-4)")
+        if getattr(self, "coordinates_type", "euclidean") != "euclidean":
+            raise NotImplementedError("backend='cuda' supports euclidean coordinates only (SURVEY.md §8f next-3)")
+        dt = {"float64": _cabi.KB200_F64, "float32": _cabi.KB200_F32}.get(str(np.dtype(dtype)))
+        if dt is None:
+            raise ValueError("dtype must be float64 or float32")
+        h = self._cuda_handle()
+        key = self._problem_signature(dt, knn)
+        if self._kb_key == key:
+            return h
+        x, y, z, v, center, Mt = self._data_arrays()
+        mid, vp = self._device_model()
+        n_rl, cols = self._drift_spec()
+        self._kb_key = None
+        if knn:
+            h.set_problem_knn(self._ndim, x, y, z, v, center, Mt, mid, vp, self.exact_values, self.eps)
+        else:
+            h.set_problem(self._ndim, dt, x, y, z, v, center, Mt, mid, vp, self.exact_values, self.eps,
+                          n_rl=n_rl, drift_data=cols if cols else None)
+        self._kb_key = key
+        return h
+
+    def _run_cuda(self, style, axes, mask, n_closest_points=None, drift_at=None, dtype="float64"):
+        """axes: list of 1-D coordinate arrays [x, y(, z)] (grid axes or point lists, original coords).
+        mask: flattened bool mask (True = skip) or None.  drift_at: callable(pts list) -> [n_hd, m]
+        host-supplied drift values at the given points, or None.
+        Returns flat (z, ss) of length npt in the reference's flattened order."""
+        knn = n_closest_points is not None
+        h = self._ensure_problem(dtype, knn)
+        nd = self._ndim
+        if style == "points":
+            pts = [np.ascontiguousarray(a, dtype=np.float64) for a in axes]
+            dv = drift_at(pts, None) if drift_at is not None else None
+            if knn:
+                return h.execute_knn_points(n_closest_points, pts[0], pts[1], pts[2] if nd == 3 else None)
+            return h.execute_points(pts[0], pts[1], pts[2] if nd == 3 else None, dv)
+        # grid / masked
+        gx, gy = axes[0], axes[1]
+        gz = axes[2] if nd == 3 else None
+        nx, ny = gx.size, gy.size
+        nz = gz.size if nd == 3 else 1
+        npt = nx * ny * nz
+        need_points = (mask is not None) or (drift_at is not None)
+        if not need_points:
+            if knn:
+                return h.execute_knn_grid(n_closest_points, gx, gy, gz)
+            return h.execute_grid(gx, gy, gz)
+        idx = np.flatnonzero(~mask) if mask is not None else np.arange(npt)
+        ix = idx % nx
+        iy = (idx // nx) % ny
+        pts = [np.asarray(gx, dtype=np.float64)[ix], np.asarray(gy, dtype=np.float64)[iy]]
+        if nd == 3:
+            pts.append(np.asarray(gz, dtype=np.float64)[idx // (nx * ny)])
+        dv = drift_at(pts, idx) if drift_at is not None else None
+        if idx.size:
+            if knn:
+                zc, sc = h.execute_knn_points(n_closest_points, pts[0], pts[1], pts[2] if nd == 3 else None)
+            else:
+                zc, sc = h.execute_points(pts[0], pts[1], pts[2] if nd == 3 else None, dv)
+        else:
+            zc = sc = np.zeros(0)
+        if mask is None:
+            return zc, sc
+        z = np.zeros(npt)
+        ss = np.zeros(npt)
+        z[idx] = zc
+        ss[idx] = sc
+        return z, ss
+
+    @staticmethod
+    def _check_backend(backend, what):
+        if backend != "cuda":
+            raise ValueError(
+                "Specified backend {} is not supported for {}: this package implements backend='cuda' only "
+                "(the reference's 'vectorized'/'loop'/'C' CPU paths live in PyKrige).".format(backend, what)
+            )

@@ -1,0 +1,233 @@
+"""Host-side helpers of the B200 kriging backend (numpy/scipy, constructor-time only).
+
+Mirrors the behaviour of the reference's ``src/pykrige/core.py`` for the pieces the
+kriging classes need around ``execute()``; none of this is on the hot path:
+
+* anisotropy affine map                      core.py:120-193
+* variogram parameter normalisation          core.py:196-376  (list form = FULL sill -> psill)
+* experimental variogram + model fit         core.py:379-651
+* cross-validation statistics (lazy here)    core.py:654-851
+"""
+import numpy as np
+from scipy.optimize import least_squares
+from scipy.spatial.distance import pdist
+
+eps = 1.0e-10
+
+_BOUNDED = ("gaussian", "spherical", "exponential", "hole-effect")
+
+
+def anisotropy_matrix(ndim, scaling, angle):
+    """Return Mt = stretch @ rot (ndim x ndim) of the reference's anisotropy map.
+
+    2-D: rot = R(-angle), stretch = diag(1, s).  3-D: rot = Rz @ Ry @ Rx (each by the
+    negated angle), stretch = diag(1, s_y, s_z).  (core.py:148-189)
+    """
+    ang = -np.asarray(angle, dtype=float) * np.pi / 180.0
+    if ndim == 2:
+        c, s = np.cos(ang[0]), np.sin(ang[0])
+        rot = np.array([[c, -s], [s, c]])
+        stretch = np.diag([1.0, float(scaling[0])])
+    elif ndim == 3:
+        cx, sx = np.cos(ang[0]), np.sin(ang[0])
+        cy, sy = np.cos(ang[1]), np.sin(ang[1])
+        cz, sz = np.cos(ang[2]), np.sin(ang[2])
+        rx = np.array([[1.0, 0.0, 0.0], [0.0, cx, -sx], [0.0, sx, cx]])
+        ry = np.array([[cy, 0.0, sy], [0.0, 1.0, 0.0], [-sy, 0.0, cy]])
+        rz = np.array([[cz, -sz, 0.0], [sz, cz, 0.0], [0.0, 0.0, 1.0]])
+        rot = rz @ ry @ rx
+        stretch = np.diag([1.0, float(scaling[0]), float(scaling[1])])
+    elif ndim == 1:
+        raise NotImplementedError("1-D anisotropy is not implemented")
+    else:
+        raise ValueError("anisotropy adjustment supports 2-D and 3-D only")
+    return stretch @ rot
+
+
+def _adjust_for_anisotropy(X, center, scaling, angle):
+    """X_adj = (X - c) @ Mt.T + c   (core.py:120-193).  X is [n, ndim]; not modified."""
+    X = np.asarray(X, dtype=float)
+    c = np.asarray(center, dtype=float)[None, :]
+    Mt = anisotropy_matrix(X.shape[1], scaling, angle)
+    return (X - c) @ Mt.T + c
+
+
+def _make_variogram_parameter_list(variogram_model, variogram_model_parameters):
+    """User parameters (None | dict | list) -> stored list (core.py:196-376).
+
+    linear [slope, nugget]; power [scale, exponent, nugget]; bounded models
+    [psill, range, nugget] — a *list* gives the FULL sill first (core.py:345-357), a dict
+    may give either 'sill' or 'psill' (core.py:286-299).
+    """
+    p = variogram_model_parameters
+    if p is None:
+        return None
+    known = ("linear", "power") + _BOUNDED + ("custom",)
+    if variogram_model not in known:
+        raise ValueError(
+            "Specified variogram model must be one of the following: 'linear', 'power', "
+            "'gaussian', 'spherical', 'exponential', 'hole-effect', 'custom'."
+        )
+    if type(p) is dict:
+        if variogram_model == "custom":
+            raise TypeError("For user-specified custom variogram model, parameters must be specified in a list, not a dict.")
+        if variogram_model == "linear":
+            if "slope" not in p or "nugget" not in p:
+                raise KeyError("'linear' variogram model requires 'slope' and 'nugget' specified in variogram model parameter dictionary.")
+            return [p["slope"], p["nugget"]]
+        if variogram_model == "power":
+            if "scale" not in p or "exponent" not in p or "nugget" not in p:
+                raise KeyError("'power' variogram model requires 'scale', 'exponent', and 'nugget' specified in variogram model parameter dictionary.")
+            return [p["scale"], p["exponent"], p["nugget"]]
+        if "range" not in p or "nugget" not in p:
+            raise KeyError("'%s' variogram model requires 'range', 'nugget', and either 'sill' or 'psill' specified in variogram model parameter dictionary." % variogram_model)
+        if "sill" in p:
+            return [p["sill"] - p["nugget"], p["range"], p["nugget"]]
+        if "psill" in p:
+            return [p["psill"], p["range"], p["nugget"]]
+        raise KeyError("'%s' variogram model requires either 'sill' or 'psill' specified in variogram model parameter dictionary." % variogram_model)
+    if type(p) is list:
+        if variogram_model == "custom":
+            return p
+        want = 2 if variogram_model == "linear" else 3
+        if len(p) != want:
+            raise ValueError(
+                "Variogram model parameter list must have exactly %s entries when variogram model set to '%s'."
+                % ("two" if want == 2 else "three", variogram_model)
+            )
+        if variogram_model in _BOUNDED:
+            return [p[0] - p[2], p[1], p[2]]
+        return p
+    raise TypeError("Variogram model parameters must be provided in either a list or a dict when they are explicitly specified.")
+
+
+def _experimental_variogram(X, y, nlags):
+    """Equal-width binned semivariogram (core.py:432-505), euclidean coordinates."""
+    d = pdist(X, metric="euclidean")
+    g = 0.5 * pdist(y[:, None], metric="sqeuclidean")
+    dmax, dmin = np.amax(d), np.amin(d)
+    dd = (dmax - dmin) / nlags
+    edges = [dmin + k * dd for k in range(nlags)] + [dmax + 0.001]
+    lags, semi = [], []
+    for k in range(nlags):
+        sel = (d >= edges[k]) & (d < edges[k + 1])
+        if np.any(sel):
+            lags.append(d[sel].mean())
+            semi.append(g[sel].mean())
+    return np.array(lags), np.array(semi)
+
+
+def _variogram_residuals(params, x, y, variogram_function, weight):
+    """Residuals for the fit, with the reference's optional logistic lag weights (core.py:538-579)."""
+    if weight:
+        drange = np.amax(x) - np.amin(x)
+        k = 2.1972 / (0.1 * drange)
+        x0 = 0.7 * drange + np.amin(x)
+        w = 1.0 / (1.0 + np.exp(-k * (x0 - x)))
+        w /= np.sum(w)
+        return (variogram_function(params, x) - y) * w
+    return variogram_function(params, x) - y
+
+
+def _calculate_variogram_model(lags, semivariance, variogram_model, variogram_function, weight):
+    """soft-L1 least squares with the reference's start values and bounds (core.py:582-651)."""
+    smax, smin = np.amax(semivariance), np.amin(semivariance)
+    lmax, lmin = np.amax(lags), np.amin(lags)
+    if variogram_model == "linear":
+        x0 = [(smax - smin) / (lmax - lmin), smin]
+        bnds = ([0.0, 0.0], [np.inf, smax])
+    elif variogram_model == "power":
+        x0 = [(smax - smin) / (lmax - lmin), 1.1, smin]
+        bnds = ([0.0, 0.001, 0.0], [np.inf, 1.999, smax])
+    else:
+        x0 = [smax - smin, 0.25 * lmax, smin]
+        bnds = ([0.0, 0.0, 0.0], [10.0 * smax, lmax, smax])
+    res = least_squares(
+        _variogram_residuals, x0, bounds=bnds, loss="soft_l1",
+        args=(lags, semivariance, variogram_function, weight),
+    )
+    return res.x
+
+
+def _initialize_variogram_model(X, y, variogram_model, variogram_model_parameters,
+                                variogram_function, nlags, weight, coordinates_type):
+    """Returns (lags, semivariance, parameters) (core.py:379-535)."""
+    if coordinates_type != "euclidean":
+        if coordinates_type == "geographic":
+            raise NotImplementedError("coordinates_type='geographic' is not part of the B200 hot path (SURVEY.md §8f next-3)")
+        raise ValueError("Specified coordinate type '%s' is not supported." % coordinates_type)
+    if X.shape[0] > 1:
+        lags, semivariance = _experimental_variogram(X, y, nlags)
+    else:
+        lags, semivariance = np.zeros(0), np.zeros(0)
+    p = variogram_model_parameters
+    if p is not None:
+        if variogram_model == "linear" and len(p) != 2:
+            raise ValueError("Exactly two parameters required for linear variogram model.")
+        if variogram_model in ("power",) + _BOUNDED and len(p) != 3:
+            raise ValueError("Exactly three parameters required for %s variogram model" % variogram_model)
+    else:
+        if variogram_model == "custom":
+            raise ValueError("Variogram parameters must be specified when implementing custom variogram model.")
+        p = _calculate_variogram_model(lags, semivariance, variogram_model, variogram_function, weight)
+    return lags, semivariance, p
+
+
+def _krige(X, y, coords, variogram_function, variogram_model_parameters, coordinates_type="euclidean",
+           pseudo_inv=False):
+    """One ordinary-kriging estimate at ``coords`` from data (X, y) (core.py:654-756); host numpy,
+    used by the lazy cross-validation statistics only."""
+    from scipy.spatial.distance import cdist
+    import scipy.linalg
+
+    n = X.shape[0]
+    d = cdist(X, X)
+    a = np.zeros((n + 1, n + 1))
+    a[:n, :n] = -variogram_function(variogram_model_parameters, d)
+    np.fill_diagonal(a, 0.0)
+    a[n, :n] = 1.0
+    a[:n, n] = 1.0
+    bd = np.sqrt(np.sum((X - np.asarray(coords)[None, :]) ** 2, axis=1))
+    b = np.zeros(n + 1)
+    b[:n] = -variogram_function(variogram_model_parameters, bd)
+    b[np.nonzero(np.absolute(bd) <= 1e-10)[0]] = 0.0
+    b[n] = 1.0
+    res = scipy.linalg.lstsq(a, b)[0] if pseudo_inv else scipy.linalg.solve(a, b)
+    zinterp = float(np.sum(res[:n] * y))
+    sigmasq = float(np.sum(res * -b))
+    return zinterp, sigmasq
+
+
+def _find_statistics(X, y, variogram_function, variogram_model_parameters, coordinates_type="euclidean",
+                     pseudo_inv=False):
+    """Sequential cross-validation residuals (core.py:759-836): delta, sigma, epsilon."""
+    n = y.shape[0]
+    delta = np.zeros(n)
+    sigma = np.zeros(n)
+    for i in range(n):
+        if i == 0:
+            continue
+        k, ss = _krige(X[:i, :], y[:i], X[i, :], variogram_function, variogram_model_parameters,
+                       coordinates_type, pseudo_inv)
+        if np.absolute(ss) < eps:
+            continue
+        delta[i] = y[i] - k
+        sigma[i] = np.sqrt(ss)
+    delta = delta[sigma > eps]
+    sigma = sigma[sigma > eps]
+    return delta, sigma, delta / sigma
+
+
+def calcQ1(epsilon):
+    """core.py:839-841"""
+    return abs(np.sum(epsilon) / (epsilon.shape[0] - 1))
+
+
+def calcQ2(epsilon):
+    """core.py:844-846"""
+    return np.sum(epsilon**2) / (epsilon.shape[0] - 1)
+
+
+def calc_cR(Q2, sigma):
+    """core.py:849-851"""
+    return Q2 * np.exp(np.sum(np.log(sigma**2)) / sigma.shape[0])

@@ -1,0 +1,538 @@
+// api.cu — C ABI of libkrige_b200.so (include/krige_b200.h): handle, problem set-up,
+// orchestration of the factor kernels (factor.cu), the fused solve (solve.cu) and the
+// moving window (knn.cu). Host code only; no torch types, no CPU compute path.
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include <algorithm>
+#include "kernels.h"
+
+#define KB_VERSION 1001
+#define KB_CHUNK (128 * 1024)        // prediction points per solve launch (partials stay L2-sized)
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct kb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // description
+    bool described = false, ready = false, knn_ready = false;
+    int dim = 2, dtype = KB200_F64, n = 0, n_pad = 0, ld = 0, n_rl = 0, n_hd = 0, K1 = 1, na = 2, nrb = 0;
+    VgParams vg{};
+    Aniso an{};
+    DriftScale ds{};
+    PackMap pm{};
+    std::vector<double> hx, hy, hz, hval, hdrift;
+
+    // blob (one allocation): header | consts | ax | ay | az | tiles
+    DevBuf blob;
+    size_t off_consts = 0, off_ax = 0, off_ay = 0, off_az = 0, off_tiles = 0, blob_bytes = 0;
+
+    // factor workspace
+    DevBuf wC, wW, wT, wF, wRaw, wFlag;
+    // execute workspace
+    DevBuf wPart, wAux, wPts, wOut, wAxes, wDrift;
+    // knn workspace
+    DevBuf kSorted, kCells;
+    KnnParams kp{};
+
+    cudaEvent_t ev[16] = {};
+    double tm[12] = {};
+    long long launches = 0, solve_launches = 0;
+};
+
+static int fail(kb200_ctx* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+#define CU(h, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    return fail(h, _e == cudaErrorMemoryAllocation ? KB200_ENOMEM : KB200_ECUDA, \
+                std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int kb200_version(void) { return KB_VERSION; }
+
+extern "C" int kb200_create(kb200_handle* out, int device) {
+    if (!out) return KB200_EBADARG;
+    *out = nullptr;
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) return KB200_ECUDA;   // no CPU fallback by design
+    kb200_ctx* h = new kb200_ctx();
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= cnt) { delete h; return KB200_EBADARG; }
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return KB200_ECUDA; }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return KB200_ECUDA; }
+    h->own_stream = true;
+    for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete h; return KB200_ECUDA; }
+    if (kbk_factor_init() != cudaSuccess || kbk_solve_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
+    *out = h;
+    return KB200_OK;
+}
+
+extern "C" void kb200_destroy(kb200_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->blob, &h->wC, &h->wW, &h->wT, &h->wF, &h->wRaw, &h->wFlag, &h->wPart, &h->wAux,
+                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->kSorted, &h->kCells}) b->release();
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* kb200_last_error(kb200_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int kb200_set_stream(kb200_handle h, void* s) {
+    if (!h) return KB200_EBADARG;
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = reinterpret_cast<cudaStream_t>(s);
+    h->own_stream = false;
+    return KB200_OK;
+}
+
+extern "C" void kb200_reset_counters(kb200_handle h) {
+    if (!h) return;
+    h->launches = 0; h->solve_launches = 0;
+    for (double& t : h->tm) t = 0.0;
+}
+
+extern "C" int kb200_last_timings(kb200_handle h, double* ms, int n) {
+    if (!h || !ms) return KB200_EBADARG;
+    h->tm[10] = (double)h->solve_launches;
+    h->tm[11] = (double)h->launches;
+    int m = std::min(n, 12);
+    for (int i = 0; i < m; ++i) ms[i] = h->tm[i];
+    return m;
+}
+
+// gamma on the host (only to choose the covariance shift c0)
+static double host_gamma(const VgParams& v, double d) {
+    switch (v.model) {
+        case KB200_VG_LINEAR: return v.p0 * d + v.p1;
+        case KB200_VG_POWER: return v.p0 * std::pow(d, v.p1) + v.p2;
+        default: return v.p0 + v.p2;
+    }
+}
+
+// ---- description (shared by set_problem / describe_problem / set_problem_knn) ----
+static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
+                    const double* x, const double* y, const double* z, const double* values,
+                    const double* center, const double* aniso, int model, const double* vparams, int n_vparams,
+                    int exact_values, double eps, int n_rl, int n_hd, const double* drift_data) {
+    if (!h) return KB200_EBADARG;
+    h->described = false; h->ready = false; h->knn_ready = false;
+    if (dim != 2 && dim != 3) return fail(h, KB200_EBADARG, "dim must be 2 or 3");
+    if (dtype != KB200_F64 && dtype != KB200_F32) return fail(h, KB200_EBADARG, "dtype must be KB200_F64 or KB200_F32");
+    if (dtype == KB200_F32) return fail(h, KB200_EUNSUPPORTED, "fp32 contraction is not built yet (round 1: fp64 only)");
+    if (n < 1 || n > (int64_t)(KB_MAXRB - 1) * KB_BM) return fail(h, KB200_EBADARG, "n out of range");
+    if (!x || !y || (dim == 3 && !z) || !values || !center || !aniso || !vparams)
+        return fail(h, KB200_EBADARG, "null input array");
+    if (model < KB200_VG_LINEAR || model > KB200_VG_HOLE_EFFECT)
+        return fail(h, KB200_EUNSUPPORTED, "variogram model has no device implementation");
+    int need = (model == KB200_VG_LINEAR) ? 2 : 3;
+    if (n_vparams != need) return fail(h, KB200_EBADARG, "wrong number of variogram parameters");
+    if (!(n_rl == 0 || n_rl == dim)) return fail(h, KB200_EBADARG, "n_rl must be 0 or dim");
+    if (n_hd < 0 || n_rl + n_hd > KB200_MAX_DRIFT) return fail(h, KB200_EBADARG, "too many drift terms");
+    if (n_hd > 0 && !drift_data) return fail(h, KB200_EBADARG, "drift_data is null");
+    if (knn_only && (n_rl || n_hd)) return fail(h, KB200_EUNSUPPORTED, "moving window supports ordinary kriging only");
+
+    h->dim = dim; h->dtype = dtype; h->n = (int)n; h->n_rl = n_rl; h->n_hd = n_hd;
+    h->K1 = n_rl + n_hd + 1; h->na = h->K1 + 1;
+    h->vg.model = model;
+    h->vg.p0 = vparams[0]; h->vg.p1 = vparams[1]; h->vg.p2 = (need == 3) ? vparams[2] : 0.0;
+    h->vg.eps = eps; h->vg.exact = exact_values ? 1 : 0;
+    for (int i = 0; i < 9; ++i) h->an.m[i] = 0.0;
+    for (int i = 0; i < dim * dim; ++i) h->an.m[i] = aniso[i];
+    for (int i = 0; i < 3; ++i) h->an.c[i] = i < dim ? center[i] : 0.0;
+    h->hx.assign(x, x + n); h->hy.assign(y, y + n);
+    if (dim == 3) h->hz.assign(z, z + n); else h->hz.assign(n, 0.0);
+    h->hval.assign(values, values + n);
+    if (n_hd) h->hdrift.assign(drift_data, drift_data + (size_t)n_hd * n); else h->hdrift.clear();
+
+    // adjusted bounding box on the host (drift rescale + c0 for unbounded models)
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = 0; i < n; ++i) {
+        double d[3] = {x[i] - h->an.c[0], y[i] - h->an.c[1], dim == 3 ? z[i] - h->an.c[2] : 0.0};
+        for (int r = 0; r < dim; ++r) {
+            double v = h->an.c[r];
+            for (int c = 0; c < dim; ++c) v += h->an.m[r * dim + c] * d[c];
+            lo[r] = std::min(lo[r], v); hi[r] = std::max(hi[r], v);
+        }
+    }
+    double diag2 = 0.0;
+    for (int r = 0; r < dim; ++r) diag2 += (hi[r] - lo[r]) * (hi[r] - lo[r]);
+    double c0 = host_gamma(h->vg, std::sqrt(diag2));
+    if (!(c0 > 0.0) || !std::isfinite(c0)) c0 = 1.0;
+    h->vg.c0 = c0;
+    for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { h->ds.shift[c] = 0.0; h->ds.scale[c] = 1.0; }
+    for (int c = 0; c < n_rl; ++c) {
+        h->ds.shift[c] = 0.5 * (hi[c] + lo[c]);
+        double half = 0.5 * (hi[c] - lo[c]);
+        h->ds.scale[c] = half > 0.0 ? 1.0 / half : 1.0;
+    }
+    for (int c = 0; c < n_hd; ++c) {
+        const double* col = drift_data + (size_t)c * n;
+        double mean = 0.0;
+        for (int64_t i = 0; i < n; ++i) mean += col[i];
+        mean /= (double)n;
+        double amax = 0.0;
+        for (int64_t i = 0; i < n; ++i) amax = std::max(amax, std::fabs(col[i] - mean));
+        h->ds.shift[n_rl + c] = mean;
+        h->ds.scale[n_rl + c] = amax > 0.0 ? 1.0 / amax : 1.0;
+    }
+
+    // tile stream map
+    h->n_pad = (int)align_up((size_t)n, KB_BM);
+    h->ld = h->n_pad;
+    h->nrb = (int)((n + h->na + KB_BM - 1) / KB_BM);
+    int nk = (int)((n + KB_BK - 1) / KB_BK);
+    h->pm.nrb = h->nrb;
+    long long off = 0;
+    for (int I = 0; I < h->nrb; ++I) {
+        bool has_dual = (I + 1) * KB_BM > n;     // block holds rows >= n (dual rows live there)
+        int kt = has_dual ? nk : std::min(nk, (I + 1) * KB_BM / KB_BK);
+        h->pm.ktiles[I] = kt;
+        h->pm.tile_off[I] = off;
+        off += kt;
+    }
+    size_t esz = dtype == KB200_F64 ? 8 : 4;
+    size_t o = 0;
+    o += align_up(64 * sizeof(double), 256);
+    h->off_consts = o; o += align_up(512 * sizeof(double), 256);
+    h->off_ax = o; o += align_up((size_t)h->n_pad * 8, 256);
+    h->off_ay = o; o += align_up((size_t)h->n_pad * 8, 256);
+    h->off_az = o; o += align_up((size_t)h->n_pad * 8, 256);
+    h->off_tiles = o; o += (size_t)off * KB_BM * KB_BK * esz;
+    h->blob_bytes = knn_only ? h->off_tiles : o;
+    cudaSetDevice(h->device);
+    CU(h, h->blob.reserve(h->blob_bytes));
+    h->described = true;
+    return KB200_OK;
+}
+
+extern "C" int kb200_describe_problem(kb200_handle h, int dim, int dtype, int64_t n,
+                                      const double* x, const double* y, const double* z, const double* values,
+                                      const double* center, const double* aniso,
+                                      int model, const double* vparams, int n_vparams,
+                                      int exact_values, double eps, int n_rl, int n_hd, const double* drift_data) {
+    return describe(h, false, dim, dtype, n, x, y, z, values, center, aniso, model, vparams, n_vparams,
+                    exact_values, eps, n_rl, n_hd, drift_data);
+}
+
+extern "C" int64_t kb200_blob_bytes(kb200_handle h) { return (h && h->described) ? (int64_t)h->blob_bytes : 0; }
+extern "C" void* kb200_blob_ptr(kb200_handle h) { return (h && h->described) ? h->blob.p : nullptr; }
+
+// header layout (doubles): [0] magic, [1] c0, [2..18) shift, [18..34) scale
+static const double KB_MAGIC = 20260922.0;
+
+extern "C" int kb200_blob_commit(kb200_handle h) {
+    if (!h || !h->described) return fail(h, KB200_ESTATE, "describe the problem first");
+    cudaSetDevice(h->device);
+    double hdr[64];
+    CU(h, cudaMemcpyAsync(hdr, h->blob.p, sizeof(hdr), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (hdr[0] != KB_MAGIC) return fail(h, KB200_ESTATE, "blob does not hold a factored problem");
+    h->vg.c0 = hdr[1];
+    for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { h->ds.shift[c] = hdr[2 + c]; h->ds.scale[c] = hdr[18 + c]; }
+    h->ready = true;
+    return KB200_OK;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float t = 0.f; cudaEventElapsedTime(&t, a, b); return t; }
+
+extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
+                                 const double* x, const double* y, const double* z, const double* values,
+                                 const double* center, const double* aniso,
+                                 int model, const double* vparams, int n_vparams,
+                                 int exact_values, double eps, int n_rl, int n_hd, const double* drift_data) {
+    int rc = describe(h, false, dim, dtype, n, x, y, z, values, center, aniso, model, vparams, n_vparams,
+                      exact_values, eps, n_rl, n_hd, drift_data);
+    if (rc != KB200_OK) return rc;
+    cudaStream_t st = h->stream;
+    const int np = h->n_pad, ld = h->ld, nn = h->n;
+    const size_t mat = (size_t)np * ld * sizeof(double);
+    CU(h, h->wC.reserve(mat)); CU(h, h->wW.reserve(mat)); CU(h, h->wT.reserve(mat));
+    CU(h, h->wF.reserve((size_t)3 * KB_MAXAUX * np * sizeof(double)));
+    CU(h, h->wRaw.reserve((size_t)(4 + h->n_hd) * nn * sizeof(double)));
+    CU(h, h->wFlag.reserve(256));
+    double* raw = h->wRaw.as<double>();
+    double *rx = raw, *ry = raw + nn, *rz = raw + 2 * (size_t)nn, *rv = raw + 3 * (size_t)nn, *rh = raw + 4 * (size_t)nn;
+    char* blob = h->blob.as<char>();
+    double* ax = reinterpret_cast<double*>(blob + h->off_ax);
+    double* ay = reinterpret_cast<double*>(blob + h->off_ay);
+    double* az = reinterpret_cast<double*>(blob + h->off_az);
+    double* consts = reinterpret_cast<double*>(blob + h->off_consts);
+    int* flag = h->wFlag.as<int>();
+    int launches = 0;
+
+    CU(h, cudaEventRecord(h->ev[0], st));
+    CU(h, cudaMemcpyAsync(rx, h->hx.data(), nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(ry, h->hy.data(), nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(rz, h->hz.data(), nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(rv, h->hval.data(), nn * 8, cudaMemcpyHostToDevice, st));
+    if (h->n_hd) CU(h, cudaMemcpyAsync(rh, h->hdrift.data(), (size_t)h->n_hd * nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemsetAsync(ax, 0, (size_t)np * 8, st));
+    CU(h, cudaMemsetAsync(ay, 0, (size_t)np * 8, st));
+    CU(h, cudaMemsetAsync(az, 0, (size_t)np * 8, st));
+    CU(h, kbk_adjust_data(h->dim, h->an, nn, rx, ry, rz, ax, ay, az, st)); ++launches;
+    CU(h, cudaEventRecord(h->ev[1], st));
+
+    // covariance shift: c0 = sill for bounded models; for linear/power grow c0 until C is
+    // positive definite. A model that is not a valid variogram in this
+    // dimension (e.g. hole-effect in 2-D/3-D) never becomes positive definite.
+    const bool unbounded = (h->vg.model == KB200_VG_LINEAR || h->vg.model == KB200_VG_POWER);
+    const int max_try = unbounded ? 5 : 1;
+    int hflag = 0;
+    float t_asm = 0.f, t_chol = 0.f;
+    for (int attempt = 0; attempt < max_try; ++attempt) {
+        CU(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
+        CU(h, cudaEventRecord(h->ev[2], st));
+        CU(h, kbk_assemble(h->dim, h->vg, nn, np, ld, ax, ay, az, h->wC.as<double>(), st)); ++launches;
+        CU(h, cudaEventRecord(h->ev[3], st));
+        CU(h, kbk_cholesky(h->wC.as<double>(), h->wW.as<double>(), ld, np, flag, st, &launches));
+        CU(h, cudaEventRecord(h->ev[4], st));
+        CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        t_asm += ev_ms(h->ev[2], h->ev[3]); t_chol += ev_ms(h->ev[3], h->ev[4]);
+        if (hflag == 0) break;
+        h->vg.c0 *= 2.0;
+    }
+    if (hflag != 0) {
+        h->launches += launches;
+        return fail(h, KB200_ESINGULAR,
+                    "kriging matrix is not conditionally positive definite for this variogram/dimension "
+                    "(Cholesky pivot " + std::to_string(hflag - 1) + "); the general indefinite path is not built");
+    }
+    CU(h, kbk_trtri(h->wC.as<double>(), h->wW.as<double>(), h->wT.as<double>(), ld, np, st, &launches));
+    CU(h, cudaEventRecord(h->ev[5], st));
+    double* Fz = h->wF.as<double>();
+    double* Hz = Fz + (size_t)KB_MAXAUX * np;
+    double* Uz = Hz + (size_t)KB_MAXAUX * np;
+    CU(h, cudaMemsetAsync(consts, 0, 512 * sizeof(double), st));
+    CU(h, kbk_dual(h->wW.as<double>(), ld, nn, np, h->n_rl, h->n_hd, ax, ay, az, h->ds, rh, rv,
+                   Fz, Hz, Uz, consts, flag, st, &launches));
+    CU(h, kbk_pack(h->dtype, h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st)); ++launches;
+    double hdr[64] = {0};
+    hdr[0] = KB_MAGIC; hdr[1] = h->vg.c0;
+    for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { hdr[2 + c] = h->ds.shift[c]; hdr[18 + c] = h->ds.scale[c]; }
+    CU(h, cudaMemcpyAsync(blob, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+    CU(h, cudaEventRecord(h->ev[6], st));
+    CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    h->tm[6] += ev_ms(h->ev[0], h->ev[1]);
+    h->tm[0] += t_asm; h->tm[1] += t_chol;
+    h->tm[2] += ev_ms(h->ev[4], h->ev[5]);
+    h->tm[3] += ev_ms(h->ev[5], h->ev[6]);
+    h->launches += launches;
+    if (hflag != 0) return fail(h, KB200_ESINGULAR, "drift/unbiasedness block F^T C^-1 F is singular");
+    h->ready = true;
+    return KB200_OK;
+}
+
+// ---- execute --------------------------------------------------------------
+struct Src {
+    bool grid; int64_t nx, ny, nz;
+    const double *a, *b, *c;      // points (px,py,pz) or axes (gx,gy,gz), device pointers
+    int64_t first, count;
+    const double* d_drift; int64_t drift_stride, drift_first;
+};
+
+static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
+    cudaStream_t st = h->stream;
+    const int64_t chunk = KB_CHUNK;
+    int64_t cmax = std::min<int64_t>(chunk, (int64_t)align_up((size_t)s.count, KB_TN));
+    CU(h, h->wPart.reserve((size_t)h->nrb * cmax * sizeof(double)));
+    CU(h, h->wAux.reserve((size_t)h->na * cmax * sizeof(double)));
+    char* blob = h->blob.as<char>();
+    SolveParams sp{};
+    sp.vg = h->vg; sp.an = h->an;
+    sp.n = h->n; sp.n_pad = h->n_pad; sp.na = h->na; sp.nrb = h->nrb;
+    sp.ax = reinterpret_cast<double*>(blob + h->off_ax);
+    sp.ay = reinterpret_cast<double*>(blob + h->off_ay);
+    sp.az = reinterpret_cast<double*>(blob + h->off_az);
+    sp.tiles = blob + h->off_tiles; sp.pm = h->pm;
+    sp.partial = h->wPart.as<double>(); sp.auxout = h->wAux.as<double>();
+    FinalizeParams fp{};
+    fp.vg = h->vg; fp.an = h->an; fp.dim = h->dim; fp.n_rl = h->n_rl; fp.n_hd = h->n_hd; fp.nrb = h->nrb;
+    fp.ds = h->ds; fp.consts = reinterpret_cast<double*>(blob + h->off_consts);
+    fp.drift_pts = s.d_drift; fp.drift_stride = s.drift_stride;
+    fp.partial = sp.partial; fp.auxout = sp.auxout;
+    PointSource ps{};
+    ps.grid = s.grid ? 1 : 0;
+    ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
+    ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
+    CU(h, cudaEventRecord(h->ev[7], st));
+    for (int64_t o = 0; o < s.count; o += chunk) {
+        int64_t m = std::min(chunk, s.count - o);
+        ps.first = s.first + o;
+        sp.ps = ps; sp.m = m; sp.mpad = (long long)align_up((size_t)m, KB_TN);
+        CU(h, kbk_solve(h->dim, h->dtype, sp, st));
+        fp.ps = ps; fp.m = m; fp.mpad = sp.mpad; fp.drift_first = s.drift_first + o;
+        fp.z_out = d_z + o; fp.ss_out = d_ss + o;
+        CU(h, kbk_finalize(fp, st));
+        h->launches += 2; h->solve_launches += 1;
+    }
+    CU(h, cudaEventRecord(h->ev[8], st));
+    return KB200_OK;
+}
+
+static int check_ready(kb200_ctx* h) {
+    if (!h) return KB200_EBADARG;
+    if (!h->ready) return fail(h, KB200_ESTATE, "no factored problem: call kb200_set_problem (or blob_commit) first");
+    cudaSetDevice(h->device);
+    return KB200_OK;
+}
+
+extern "C" int kb200_execute_points_dev(kb200_handle h, int64_t m,
+                                        const double* d_px, const double* d_py, const double* d_pz,
+                                        const double* d_drift_pts, double* d_z, double* d_ss) {
+    int rc = check_ready(h); if (rc) return rc;
+    if (m <= 0) return KB200_OK;
+    if (!d_px || !d_py || (h->dim == 3 && !d_pz) || !d_z || !d_ss) return fail(h, KB200_EBADARG, "null pointer");
+    if (h->n_hd && !d_drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
+    Src s{false, 0, 0, 0, d_px, d_py, d_pz, 0, m, d_drift_pts, m, 0};
+    rc = run_solve(h, s, d_z, d_ss); if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
+    return KB200_OK;
+}
+
+extern "C" int kb200_execute_grid_dev(kb200_handle h, int64_t nx, int64_t ny, int64_t nz,
+                                      const double* d_gx, const double* d_gy, const double* d_gz,
+                                      const double* d_drift_pts, int64_t first, int64_t count,
+                                      double* d_z, double* d_ss) {
+    int rc = check_ready(h); if (rc) return rc;
+    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
+        return fail(h, KB200_EBADARG, "bad grid slice");
+    if (count == 0) return KB200_OK;
+    if (!d_gx || !d_gy || (h->dim == 3 && !d_gz) || !d_z || !d_ss) return fail(h, KB200_EBADARG, "null pointer");
+    if (h->dim == 2 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
+    if (h->n_hd && !d_drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
+    Src s{true, nx, ny, nz, d_gx, d_gy, d_gz, first, count, d_drift_pts, count, 0};
+    rc = run_solve(h, s, d_z, d_ss); if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
+    return KB200_OK;
+}
+
+extern "C" int kb200_execute_points(kb200_handle h, int64_t m,
+                                    const double* px, const double* py, const double* pz,
+                                    const double* drift_pts, double* z_out, double* ss_out) {
+    int rc = check_ready(h); if (rc) return rc;
+    if (m <= 0) return KB200_OK;
+    if (!px || !py || (h->dim == 3 && !pz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
+    if (h->n_hd && !drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
+    cudaStream_t st = h->stream;
+    CU(h, h->wPts.reserve((size_t)3 * m * 8));
+    CU(h, h->wOut.reserve((size_t)2 * m * 8));
+    double* dp = h->wPts.as<double>();
+    double* dout = h->wOut.as<double>();
+    CU(h, cudaEventRecord(h->ev[9], st));
+    CU(h, cudaMemcpyAsync(dp, px, m * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(dp + m, py, m * 8, cudaMemcpyHostToDevice, st));
+    if (h->dim == 3) CU(h, cudaMemcpyAsync(dp + 2 * m, pz, m * 8, cudaMemcpyHostToDevice, st));
+    const double* dd = nullptr;
+    if (h->n_hd) {
+        CU(h, h->wDrift.reserve((size_t)h->n_hd * m * 8));
+        CU(h, cudaMemcpyAsync(h->wDrift.p, drift_pts, (size_t)h->n_hd * m * 8, cudaMemcpyHostToDevice, st));
+        dd = h->wDrift.as<double>();
+    }
+    CU(h, cudaEventRecord(h->ev[10], st));
+    Src s{false, 0, 0, 0, dp, dp + m, dp + 2 * m, 0, m, dd, m, 0};
+    rc = run_solve(h, s, dout, dout + m); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(z_out, dout, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(ss_out, dout + m, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaEventRecord(h->ev[11], st));
+    CU(h, cudaStreamSynchronize(st));
+    h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
+    h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
+    h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
+    return KB200_OK;
+}
+
+extern "C" int kb200_execute_grid(kb200_handle h, int64_t nx, int64_t ny, int64_t nz,
+                                  const double* gx, const double* gy, const double* gz,
+                                  const double* drift_pts, int64_t first, int64_t count,
+                                  double* z_out, double* ss_out) {
+    int rc = check_ready(h); if (rc) return rc;
+    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
+        return fail(h, KB200_EBADARG, "bad grid slice");
+    if (count == 0) return KB200_OK;
+    if (!gx || !gy || (h->dim == 3 && !gz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
+    if (h->dim == 2 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
+    if (h->n_hd && !drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
+    cudaStream_t st = h->stream;
+    CU(h, h->wAxes.reserve((size_t)(nx + ny + nz) * 8));
+    CU(h, h->wOut.reserve((size_t)2 * count * 8));
+    double* da = h->wAxes.as<double>();
+    double* dout = h->wOut.as<double>();
+    CU(h, cudaEventRecord(h->ev[9], st));
+    CU(h, cudaMemcpyAsync(da, gx, nx * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(da + nx, gy, ny * 8, cudaMemcpyHostToDevice, st));
+    if (h->dim == 3) CU(h, cudaMemcpyAsync(da + nx + ny, gz, nz * 8, cudaMemcpyHostToDevice, st));
+    const double* dd = nullptr;
+    if (h->n_hd) {   // drift_pts: column-major [n_hd][count], values for this slice
+        CU(h, h->wDrift.reserve((size_t)h->n_hd * count * 8));
+        CU(h, cudaMemcpyAsync(h->wDrift.p, drift_pts, (size_t)h->n_hd * count * 8, cudaMemcpyHostToDevice, st));
+        dd = h->wDrift.as<double>();
+    }
+    CU(h, cudaEventRecord(h->ev[10], st));
+    Src s{true, nx, ny, nz, da, da + nx, da + nx + ny, first, count, dd, count, 0};
+    rc = run_solve(h, s, dout, dout + count); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(z_out, dout, count * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(ss_out, dout + count, count * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaEventRecord(h->ev[11], st));
+    CU(h, cudaStreamSynchronize(st));
+    h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
+    h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
+    h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
+    return KB200_OK;
+}
+
+// ---- debug taps (tests only) ------------------------------------------------
+extern "C" int64_t kb200_debug_fetch(kb200_handle h, int what, double* out, int64_t cap) {
+    if (!h || !out) return KB200_EBADARG;
+    if (!h->described) return KB200_ESTATE;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    const size_t mat = (size_t)h->n_pad * h->ld;
+    const void* src = nullptr; size_t cnt = 0;
+    if (what == 1) { src = h->wC.p; cnt = mat; }
+    else if (what == 2) { src = h->wW.p; cnt = mat; }
+    else if (what == 3) {
+        size_t nU = (size_t)h->na * h->n_pad;
+        size_t total = nU + (size_t)h->K1 * h->K1 + h->K1 + 1;
+        if ((int64_t)total > cap) return KB200_EBADARG;
+        const double* Uz = h->wF.as<double>() + (size_t)2 * KB_MAXAUX * h->n_pad;
+        if (cudaMemcpy(out, Uz, nU * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return KB200_ECUDA;
+        if (cudaMemcpy(out + nU, h->blob.as<char>() + h->off_consts, ((size_t)h->K1 * h->K1 + h->K1) * 8,
+                       cudaMemcpyDeviceToHost) != cudaSuccess) return KB200_ECUDA;
+        out[total - 1] = h->vg.c0;
+        return (int64_t)total;
+    } else return KB200_EBADARG;
+    if (!src) return KB200_ESTATE;
+    if ((int64_t)cnt > cap) return KB200_EBADARG;
+    if (cudaMemcpy(out, src, cnt * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return KB200_ECUDA;
+    return (int64_t)cnt;
+}

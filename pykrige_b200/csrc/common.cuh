@@ -1,0 +1,141 @@
+// common.cuh — shared device helpers for libkrige_b200 (sm_100a).
+//
+// Semantics follow the reference (cited per function); the code is written from
+// scratch for the GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/krige_b200.h"
+
+#define KB_WARP 32
+
+// ---- tile geometry of the fused solve kernel -------------
+#define KB_BM 256      // rows of W per CTA tile
+#define KB_TN 64       // prediction points per CTA tile
+#define KB_BK 16       // k extent of one staged tile
+#define KB_NB 64       // Cholesky / triangular-inverse block size
+#define KB_MAXAUX (KB200_MAX_DRIFT + 2)   // dual rows: U (K+1 columns) + zeta
+#define KB_MAXRB 128   // max row blocks (n_pad/KB_BM + 1) -> n up to ~32k
+
+struct VgParams {
+    int model;
+    double p0, p1, p2;   // stored (psill-form) parameters, variogram_models.py:25-81
+    double c0;           // covariance shift: cov(d) = c0 - gamma(d)
+    double eps;          // exact-hit cutoff, ok.py:177
+    int exact;           // ok.py:671-672
+};
+
+// Affine anisotropy map (core.py:120-193): adj = Mt (p - c) + c.
+// Explicit _rn intrinsics: data points and prediction points must go through the
+// *identical* instruction sequence so that coincident inputs give d == 0 exactly
+// (exact-hit semantics, ok.py:665-672) regardless of how nvcc contracts FMAs.
+struct Aniso {
+    double m[9];
+    double c[3];
+};
+
+template <int DIM>
+__device__ __forceinline__ void kb_adjust(const Aniso& a, double x, double y, double z,
+                                          double& ox, double& oy, double& oz) {
+    double dx = __dsub_rn(x, a.c[0]);
+    double dy = __dsub_rn(y, a.c[1]);
+    if (DIM == 2) {
+        double rx = __dadd_rn(__dmul_rn(a.m[0], dx), __dmul_rn(a.m[1], dy));
+        double ry = __dadd_rn(__dmul_rn(a.m[2], dx), __dmul_rn(a.m[3], dy));
+        ox = __dadd_rn(rx, a.c[0]);
+        oy = __dadd_rn(ry, a.c[1]);
+        oz = 0.0;
+    } else {
+        double dz = __dsub_rn(z, a.c[2]);
+        double rx = __dadd_rn(__dadd_rn(__dmul_rn(a.m[0], dx), __dmul_rn(a.m[1], dy)), __dmul_rn(a.m[2], dz));
+        double ry = __dadd_rn(__dadd_rn(__dmul_rn(a.m[3], dx), __dmul_rn(a.m[4], dy)), __dmul_rn(a.m[5], dz));
+        double rz = __dadd_rn(__dadd_rn(__dmul_rn(a.m[6], dx), __dmul_rn(a.m[7], dy)), __dmul_rn(a.m[8], dz));
+        ox = __dadd_rn(rx, a.c[0]);
+        oy = __dadd_rn(ry, a.c[1]);
+        oz = __dadd_rn(rz, a.c[2]);
+    }
+}
+
+// gamma(d) for the six built-in models, variogram_models.py:25-81 (same closed
+// forms; docs/source/variogram_models.rst:8-44).
+template <int MODEL>
+__device__ __forceinline__ double kb_gamma(const VgParams& v, double d) {
+    if (MODEL == KB200_VG_LINEAR) {
+        return v.p0 * d + v.p1;                                       // slope*d + nugget
+    } else if (MODEL == KB200_VG_POWER) {
+        return v.p0 * pow(d, v.p1) + v.p2;                            // scale*d^exponent + nugget
+    } else if (MODEL == KB200_VG_GAUSSIAN) {
+        double r = v.p1 * (4.0 / 7.0);
+        return v.p0 * (1.0 - exp(-(d * d) / (r * r))) + v.p2;
+    } else if (MODEL == KB200_VG_EXPONENTIAL) {
+        return v.p0 * (1.0 - exp(-d / (v.p1 / 3.0))) + v.p2;
+    } else if (MODEL == KB200_VG_SPHERICAL) {
+        if (d <= v.p1) {
+            double q = d / v.p1;
+            return v.p0 * (1.5 * q - 0.5 * q * q * q) + v.p2;
+        }
+        return v.p0 + v.p2;
+    } else {  // hole-effect
+        double q = d / (v.p1 / 3.0);
+        return v.p0 * (1.0 - (1.0 - q) * exp(-q)) + v.p2;
+    }
+}
+
+// Shifted covariance of a (data, prediction point) pair: the RHS entry.
+//   reference: b = -gamma(d), b = 0 on an exact hit when exact_values (ok.py:669-672)
+//   here:      c = c0 + b  
+template <int MODEL>
+__device__ __forceinline__ double kb_cov_rhs(const VgParams& v, double d) {
+    if (v.exact && fabs(d) <= v.eps) return v.c0;
+    return v.c0 - kb_gamma<MODEL>(v, d);
+}
+
+template <int DIM>
+__device__ __forceinline__ double kb_dist(double ax, double ay, double az,
+                                          double bx, double by, double bz) {
+    double dx = ax - bx, dy = ay - by;
+    double s = dx * dx + dy * dy;
+    if (DIM == 3) { double dz = az - bz; s += dz * dz; }
+    return sqrt(s);
+}
+
+// Where prediction points come from: explicit arrays or a rectangular grid
+// (2-D: x fastest, ok.py:864-866; 3-D: (z,y,x) 'ij' order, x fastest, ok3d.py:863-866).
+struct PointSource {
+    int grid;                 // 0 = explicit arrays, 1 = grid axes
+    const double* px; const double* py; const double* pz;   // explicit (original coords)
+    const double* gx; const double* gy; const double* gz;   // axes
+    long long nx, ny, nz;
+    long long first;          // offset of point 0 of this launch in the flattened grid / arrays
+};
+
+template <int DIM>
+__device__ __forceinline__ void kb_load_point(const PointSource& ps, const Aniso& an, long long p,
+                                              double& x, double& y, double& z) {
+    double rx, ry, rz = 0.0;
+    long long q = p + ps.first;
+    if (ps.grid) {
+        long long ix = q % ps.nx;
+        long long r = q / ps.nx;
+        long long iy = r % ps.ny;
+        rx = ps.gx[ix];
+        ry = ps.gy[iy];
+        if (DIM == 3) { long long iz = r / ps.ny; rz = ps.gz[iz]; }
+    } else {
+        rx = ps.px[q];
+        ry = ps.py[q];
+        if (DIM == 3) rz = ps.pz[q];
+    }
+    kb_adjust<DIM>(an, rx, ry, rz, x, y, z);
+}
+
+// ---- mma.sync m8n8k4 f64 (DMMA): the fp64 tensor path on sm_100a ------------
+// A 8x4 row: lane holds A[lane>>2][lane&3]; B 4x8 col: lane holds B[lane&3][lane>>2];
+// C 8x8: lane holds C[lane>>2][2*(lane&3) + {0,1}].
+__device__ __forceinline__ void kb_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+#define KB_CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)

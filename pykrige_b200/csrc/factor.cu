@@ -1,0 +1,537 @@
+// factor.cu — one-off (per problem) device work of the global kriging path:
+//   K1  assemble the shifted covariance matrix C = c0*11^T - Gamma     (ok.py:626-648, uk.py:861-875)
+//   K2a blocked Cholesky  C = L L^T  (DMMA trailing updates)            replaces scipy.linalg.inv, ok.py:663
+//   K2b blocked triangular inverse  W = L^-1 (DMMA GEMMs)
+//   K2c dual vectors  Uz = C^-1 [F | Z],  S = F^T C^-1 F, S^-1, phi
+//   K2d pack W (+ dual rows) into the fragment-ordered tile stream read by the solve kernel
+// See DESIGN.md §3-§4 for the algebra (covariance-form kriging; results equal the
+// reference's inverse x RHS, ok.py:679-681, to rounding).
+#include "common.cuh"
+#include "kernels.h"
+
+// ---------------------------------------------------------------------------
+// adjusted data coordinates (core.py:120-193 applied to the data, ok.py:284-289)
+template <int DIM>
+__global__ void adjust_data_kernel(Aniso an, int n, const double* __restrict__ x,
+                                   const double* __restrict__ y, const double* __restrict__ z,
+                                   double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ox, oy, oz;
+    kb_adjust<DIM>(an, x[i], y[i], DIM == 3 ? z[i] : 0.0, ox, oy, oz);
+    ax[i] = ox; ay[i] = oy; az[i] = oz;
+}
+
+// ---------------------------------------------------------------------------
+// K1: C[i][j] = c0 - gamma(|p_i - p_j|) (i != j), c0 on the diagonal; identity in the
+// padding. Only tiles on/below the diagonal are written (Cholesky reads the lower triangle).
+// HBM-write bound: n_pad^2/2 * 8 bytes.
+template <int DIM, int MODEL>
+__global__ void __launch_bounds__(256) assemble_kernel(VgParams vg, int n, int n_pad, int ld,
+                                                        const double* __restrict__ ax,
+                                                        const double* __restrict__ ay,
+                                                        const double* __restrict__ az,
+                                                        double* __restrict__ C) {
+    // blockIdx.x -> lower-triangular tile (it >= jt) of 64x64
+    int t = blockIdx.x;
+    int it = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)(it + 1) * (it + 2) / 2 <= t) ++it;
+    while ((long long)it * (it + 1) / 2 > t) --it;
+    int jt = t - (int)((long long)it * (it + 1) / 2);
+    __shared__ double sx[64], sy[64], sz[64];   // column (j) points
+    int tid = threadIdx.x;
+    if (tid < 64) {
+        int j = jt * 64 + tid;
+        bool ok = j < n;
+        sx[tid] = ok ? ax[j] : 0.0;
+        sy[tid] = ok ? ay[j] : 0.0;
+        sz[tid] = (ok && DIM == 3) ? az[j] : 0.0;
+    }
+    __syncthreads();
+    int jl = tid & 63;          // column within tile (contiguous -> coalesced stores)
+    int i0 = tid >> 6;          // 0..3
+    int j = jt * 64 + jl;
+    for (int r = i0; r < 64; r += 4) {
+        int i = it * 64 + r;
+        double v;
+        if (i < n && j < n) {
+            if (i == j) v = vg.c0;
+            else {
+                double d = kb_dist<DIM>(ax[i], ay[i], DIM == 3 ? az[i] : 0.0, sx[jl], sy[jl], sz[jl]);
+                v = vg.c0 - kb_gamma<MODEL>(vg, d);
+            }
+        } else {
+            v = (i == j) ? 1.0 : 0.0;
+        }
+        C[(size_t)i * ld + j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 64x64 DMMA GEMM tile core used by the Cholesky trailing update and the
+// triangular inverse: acc(64x64) += A(64 x [k0,k1)) * B([k0,k1) x 64).
+//   A row-major (lda).  B: NN -> B[k*ldb + j];  NT -> Bt[j*ldb + k].
+// 128 threads = 4 warps (2x2), each warp a 32x32 sub-tile = 4x4 m8n8k4 tiles.
+// smem rows are padded (+4 doubles) so the 8x4 / 4x8 fragment reads are conflict-free.
+#define GT_LDS_A 20
+#define GT_LDS_BN 68
+struct GemmSmem {
+    double a[64 * GT_LDS_A];
+    double b[64 * GT_LDS_A > 16 * GT_LDS_BN ? 64 * GT_LDS_A : 16 * GT_LDS_BN];
+};
+
+template <bool NT>
+__device__ __forceinline__ void gemm_tile_64(double (&acc)[4][4][2], GemmSmem& sm,
+                                             const double* __restrict__ A, int lda,
+                                             const double* __restrict__ B, int ldb,
+                                             int k0, int k1) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    // global->register staging: A (and NT-B) tile 64x16: thread -> row tid/2, half (tid&1)*8
+    const int ar = tid >> 1, ah = (tid & 1) * 8;
+    // NN-B tile 16x64: thread -> k = tid/8, j0 = (tid&7)*8
+    const int bk = tid >> 3, bj = (tid & 7) * 8;
+    double ra[8], rb[8];
+    auto gload = [&](int k) {
+        const double* pa = A + (size_t)ar * lda + k + ah;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ra[q] = pa[q];
+        if (NT) {
+            const double* pb = B + (size_t)ar * ldb + k + ah;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rb[q] = pb[q];
+        } else {
+            const double* pb = B + (size_t)(k + bk) * ldb + bj;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rb[q] = pb[q];
+        }
+    };
+    if (k0 >= k1) return;
+    gload(k0);
+    for (int k = k0; k < k1; k += 16) {
+        __syncthreads();   // previous tile fully consumed
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sm.a[ar * GT_LDS_A + ah + q] = ra[q];
+        if (NT) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sm.b[ar * GT_LDS_A + ah + q] = rb[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sm.b[bk * GT_LDS_BN + bj + q] = rb[q];
+        }
+        __syncthreads();
+        if (k + 16 < k1) gload(k + 16);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+                fa[mt] = sm.a[(wm * 32 + mt * 8 + (lane >> 2)) * GT_LDS_A + k4 * 4 + (lane & 3)];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                int col = wn * 32 + nt * 8 + (lane >> 2);
+                fb[nt] = NT ? sm.b[col * GT_LDS_A + k4 * 4 + (lane & 3)]
+                            : sm.b[(k4 * 4 + (lane & 3)) * GT_LDS_BN + col];
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    kb_dmma(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fb[nt]);
+        }
+    }
+}
+
+// out = alpha*acc + beta*out   (64x64 tile at `out`, row-major ldc)
+__device__ __forceinline__ void gemm_tile_store(const double (&acc)[4][4][2], double* out, int ldc,
+                                                double alpha, double beta) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            int r = wm * 32 + mt * 8 + (lane >> 2);
+            int c = wn * 32 + nt * 8 + 2 * (lane & 3);
+            double2* p = reinterpret_cast<double2*>(out + (size_t)r * ldc + c);
+            double2 v;
+            if (beta != 0.0) {
+                v = *p;
+                v.x = alpha * acc[mt][nt][0] + beta * v.x;
+                v.y = alpha * acc[mt][nt][1] + beta * v.y;
+            } else {
+                v.x = alpha * acc[mt][nt][0];
+                v.y = alpha * acc[mt][nt][1];
+            }
+            *p = v;
+        }
+}
+
+// ---------------------------------------------------------------------------
+// K2a.1  potf2 + inverse of one 64x64 diagonal block (one CTA, 256 threads).
+// Writes L_kk into C (strict upper part of the block zeroed) and L_kk^-1 into W's
+// diagonal block. A non-positive pivot sets *flag = 1 + global column index.
+__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ C, double* __restrict__ W,
+                                                         int ld, int kb, int* __restrict__ flag) {
+    extern __shared__ double dsm[];
+    double (*a)[65] = reinterpret_cast<double (*)[65]>(dsm);
+    double (*x)[65] = reinterpret_cast<double (*)[65]>(dsm + 64 * 65);
+    const int tid = threadIdx.x;
+    double* Cb = C + (size_t)kb * 64 * ld + kb * 64;
+    double* Wb = W + (size_t)kb * 64 * ld + kb * 64;
+    for (int e = tid; e < 64 * 64; e += 256) {
+        int r = e >> 6, c = e & 63;
+        a[r][c] = (c <= r) ? Cb[(size_t)r * ld + c] : 0.0;
+        x[r][c] = 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < 64; ++j) {
+        if (tid == 0) {
+            double d = a[j][j];
+            if (!(d > 0.0)) { if (*flag == 0) *flag = 1 + kb * 64 + j; d = 1.0; }
+            a[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        double dj = a[j][j];
+        if (tid > j && tid < 64) a[tid][j] /= dj;
+        __syncthreads();
+        // trailing update of the lower triangle: a[i][k] -= a[i][j]*a[k][j], j < k <= i
+        int m = 63 - j;                      // rows/cols j+1..63
+        for (int e = tid; e < m * m; e += 256) {
+            int i = j + 1 + e / m, k = j + 1 + e % m;
+            if (k <= i) a[i][k] -= a[i][j] * a[k][j];
+        }
+        __syncthreads();
+    }
+    // inverse by forward substitution: thread c owns column c of X = L^-1
+    if (tid < 64) {
+        int c = tid;
+        x[c][c] = 1.0 / a[c][c];
+        for (int i = c + 1; i < 64; ++i) {
+            double s0 = 0.0, s1 = 0.0;
+            int k = c;
+            for (; k + 1 < i; k += 2) { s0 += a[i][k] * x[k][c]; s1 += a[i][k + 1] * x[k + 1][c]; }
+            if (k < i) s0 += a[i][k] * x[k][c];
+            x[i][c] = -(s0 + s1) / a[i][i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < 64 * 64; e += 256) {
+        int r = e >> 6, c = e & 63;
+        Cb[(size_t)r * ld + c] = a[r][c];     // upper part is 0
+        Wb[(size_t)r * ld + c] = x[r][c];
+    }
+}
+
+// K2a.2  panel solve: rows below the diagonal block:  X <- X * L_kk^-T  (in place).
+// out[r][c] = sum_{j<=c} X[r][j] * Linv[c][j].  One CTA per 64 rows.
+__global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ C, const double* __restrict__ W,
+                                                          int ld, int kb) {
+    extern __shared__ double dsm[];
+    double (*xs)[65] = reinterpret_cast<double (*)[65]>(dsm);
+    double (*li)[65] = reinterpret_cast<double (*)[65]>(dsm + 64 * 65);
+    const int tid = threadIdx.x;
+    const int rb = kb + 1 + blockIdx.x;
+    double* Xb = C + (size_t)rb * 64 * ld + kb * 64;
+    const double* Wb = W + (size_t)kb * 64 * ld + kb * 64;
+    for (int e = tid; e < 64 * 64; e += 256) {
+        int r = e >> 6, c = e & 63;
+        xs[r][c] = Xb[(size_t)r * ld + c];
+        li[r][c] = Wb[(size_t)r * ld + c];
+    }
+    __syncthreads();
+    const int r = tid >> 2, cg = tid & 3;
+    double out[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        int c = cg + 4 * q;
+        double s = 0.0;
+        for (int j = 0; j <= c; ++j) s += xs[r][j] * li[c][j];
+        out[q] = s;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) Xb[(size_t)r * ld + cg + 4 * q] = out[q];
+}
+
+// K2a.3  trailing update (SYRK): C[it][jt] -= P_it * P_jt^T, kb < jt <= it.
+__global__ void __launch_bounds__(128) syrk_kernel(double* __restrict__ C, int ld, int kb) {
+    __shared__ GemmSmem sm;
+    int t = blockIdx.x;
+    int it = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)(it + 1) * (it + 2) / 2 <= t) ++it;
+    while ((long long)it * (it + 1) / 2 > t) --it;
+    int jt = t - (int)((long long)it * (it + 1) / 2);
+    it += kb + 1; jt += kb + 1;
+    const double* A = C + (size_t)it * 64 * ld + kb * 64;
+    const double* B = C + (size_t)jt * 64 * ld + kb * 64;
+    double acc[4][4][2] = {};
+    gemm_tile_64<true>(acc, sm, A, ld, B, ld, 0, 64);
+    gemm_tile_store(acc, C + (size_t)it * 64 * ld + jt * 64, ld, -1.0, 1.0);
+}
+
+// ---------------------------------------------------------------------------
+// K2b  triangular inverse by level doubling.  At level m (block size m = 64*2^s),
+// pair p covers rows [r0, r0+m) (top) and [r0+m, r0+m+m2) (bottom), r0 = 2*p*m:
+//     W21 = -W22 * (L21 * W11)
+// step 1: T1 = L21 * W11   (W11 lower-triangular: k >= first column of the tile)
+// step 2: W21 = -W22 * T1  (W22 lower-triangular: k <= last row of the tile)
+__global__ void __launch_bounds__(128) trtri_step1_kernel(const double* __restrict__ L, const double* __restrict__ W,
+                                                           double* __restrict__ T1, int ld, int n_pad, int m) {
+    __shared__ GemmSmem sm;
+    int r0 = 2 * blockIdx.z * m;
+    int m2 = min(m, n_pad - r0 - m);
+    int ti = blockIdx.y, tj = blockIdx.x;
+    if (m2 <= 0 || ti * 64 >= m2) return;
+    const double* A = L + (size_t)(r0 + m + ti * 64) * ld + r0;        // L21 rows
+    const double* B = W + (size_t)r0 * ld + r0 + tj * 64;              // W11 (NN), column tile tj
+    double acc[4][4][2] = {};
+    gemm_tile_64<false>(acc, sm, A, ld, B, ld, tj * 64, m);
+    gemm_tile_store(acc, T1 + (size_t)(r0 + m + ti * 64) * ld + r0 + tj * 64, ld, 1.0, 0.0);
+}
+
+__global__ void __launch_bounds__(128) trtri_step2_kernel(double* __restrict__ W, const double* __restrict__ T1,
+                                                           int ld, int n_pad, int m) {
+    __shared__ GemmSmem sm;
+    int r0 = 2 * blockIdx.z * m;
+    int m2 = min(m, n_pad - r0 - m);
+    int ti = blockIdx.y, tj = blockIdx.x;
+    if (m2 <= 0 || ti * 64 >= m2) return;
+    const double* A = W + (size_t)(r0 + m + ti * 64) * ld + (r0 + m);  // W22 rows of tile ti
+    const double* B = T1 + (size_t)(r0 + m) * ld + r0 + tj * 64;       // T1 (NN)
+    double acc[4][4][2] = {};
+    gemm_tile_64<false>(acc, sm, A, ld, B, ld, 0, ti * 64 + 64);
+    gemm_tile_store(acc, W + (size_t)(r0 + m + ti * 64) * ld + r0 + tj * 64, ld, -1.0, 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// K2c  dual vectors.  Fz (n x na, column-major, column stride n_pad) holds the drift
+// columns, the ones column and the data values.  Hz = W Fz ; Uz = W^T Hz = C^-1 Fz.
+// Regional-linear columns are built on device from the adjusted coordinates
+// (uk.py:877-883, uk3d.py:708-717) with an affine rescale (a change of drift basis,
+// which leaves lambda, z and sigma^2 unchanged because the constant is in the span).
+__global__ void build_fz_kernel(int n, int n_pad, int n_rl, int n_hd,
+                                const double* __restrict__ ax, const double* __restrict__ ay,
+                                const double* __restrict__ az,
+                                DriftScale ds, const double* __restrict__ hd, const double* __restrict__ values,
+                                double* __restrict__ Fz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    int K = n_rl + n_hd;
+    bool in = i < n;
+    for (int c = 0; c < n_rl; ++c) {
+        double v = c == 0 ? (in ? ax[i] : 0.0) : (c == 1 ? (in ? ay[i] : 0.0) : (in ? az[i] : 0.0));
+        Fz[(size_t)c * n_pad + i] = in ? (v - ds.shift[c]) * ds.scale[c] : 0.0;
+    }
+    for (int c = 0; c < n_hd; ++c)
+        Fz[(size_t)(n_rl + c) * n_pad + i] = in ? (hd[(size_t)c * n + i] - ds.shift[n_rl + c]) * ds.scale[n_rl + c] : 0.0;
+    Fz[(size_t)K * n_pad + i] = in ? 1.0 : 0.0;
+    Fz[(size_t)(K + 1) * n_pad + i] = in ? values[i] : 0.0;
+}
+
+// Hz[i][c] = sum_{k<=i} W[i][k] Fz[k][c]   (one warp per row)
+__global__ void __launch_bounds__(256) dual_h_kernel(const double* __restrict__ W, int ld, int n, int n_pad, int na,
+                                                      const double* __restrict__ Fz, double* __restrict__ Hz) {
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double acc[KB_MAXAUX];
+#pragma unroll
+    for (int c = 0; c < KB_MAXAUX; ++c) acc[c] = 0.0;
+    const double* wr = W + (size_t)row * ld;
+    for (int k = lane; k <= row; k += 32) {
+        double w = wr[k];
+#pragma unroll
+        for (int c = 0; c < KB_MAXAUX; ++c)
+            if (c < na) acc[c] += w * Fz[(size_t)c * n_pad + k];
+    }
+#pragma unroll
+    for (int c = 0; c < KB_MAXAUX; ++c) {
+        if (c < na) {
+            double v = acc[c];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) Hz[(size_t)c * n_pad + row] = v;
+        }
+    }
+}
+
+// Uz[k][c] = sum_{i>=k} W[i][k] Hz[i][c]   (block: 32 columns x 8 row slices)
+__global__ void __launch_bounds__(256) dual_u_kernel(const double* __restrict__ W, int ld, int n, int n_pad, int na,
+                                                      const double* __restrict__ Hz, double* __restrict__ Uz) {
+    __shared__ double red[8][32];
+    int kx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    int k = blockIdx.x * 32 + kx;
+    int kfirst = blockIdx.x * 32;
+    for (int c = 0; c < na; ++c) {
+        double s = 0.0;
+        if (k < n)
+            for (int i = kfirst + ty; i < n; i += 8)
+                if (i >= k) s += W[(size_t)i * ld + k] * Hz[(size_t)c * n_pad + i];
+        red[ty][kx] = s;
+        __syncthreads();
+        if (ty == 0) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v += red[q][kx];
+            if (k < n_pad) Uz[(size_t)c * n_pad + k] = (k < n) ? v : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+// S = F^T U (K1 x K1), phi = F^T zeta, S^-1 by Gauss-Jordan with partial pivoting.
+// consts layout: [0 .. K1*K1) Sinv, [K1*K1 .. K1*K1+K1) phi. Singular S sets *flag = -1.
+__global__ void __launch_bounds__(256) dual_small_kernel(int n, int n_pad, int K1,
+                                                          const double* __restrict__ Fz, const double* __restrict__ Uz,
+                                                          double* __restrict__ consts, int* __restrict__ flag) {
+    __shared__ double red[256];
+    __shared__ double S[16 * 17];
+    __shared__ double ph[16];
+    const int tid = threadIdx.x;
+    for (int a = 0; a < K1; ++a) {
+        for (int b = 0; b <= K1; ++b) {     // b == K1 -> zeta column
+            double s = 0.0;
+            for (int k = tid; k < n; k += 256) s += Fz[(size_t)a * n_pad + k] * Uz[(size_t)b * n_pad + k];
+            red[tid] = s;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+            if (tid == 0) { if (b < K1) S[a * 17 + b] = red[0]; else ph[a] = red[0]; }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        double M[16][32];
+        for (int a = 0; a < K1; ++a)
+            for (int b = 0; b < K1; ++b) {
+                M[a][b] = 0.5 * (S[a * 17 + b] + S[b * 17 + a]);
+                M[a][K1 + b] = (a == b) ? 1.0 : 0.0;
+            }
+        bool bad = false;
+        for (int c = 0; c < K1; ++c) {
+            int p = c; double best = fabs(M[c][c]);
+            for (int r = c + 1; r < K1; ++r) if (fabs(M[r][c]) > best) { best = fabs(M[r][c]); p = r; }
+            if (!(best > 0.0)) { bad = true; break; }
+            if (p != c) for (int q = 0; q < 2 * K1; ++q) { double t = M[c][q]; M[c][q] = M[p][q]; M[p][q] = t; }
+            double inv = 1.0 / M[c][c];
+            for (int q = 0; q < 2 * K1; ++q) M[c][q] *= inv;
+            for (int r = 0; r < K1; ++r) if (r != c) {
+                double f = M[r][c];
+                if (f != 0.0) for (int q = 0; q < 2 * K1; ++q) M[r][q] -= f * M[c][q];
+            }
+        }
+        if (bad) { if (*flag == 0) *flag = -1; }
+        for (int a = 0; a < K1; ++a) {
+            for (int b = 0; b < K1; ++b) consts[a * K1 + b] = bad ? 0.0 : M[a][K1 + b];
+            consts[K1 * K1 + a] = ph[a];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2d  pack: tile (row block I, k tile kt) -> 4096 values in fragment order
+//   element (r, k) of the tile lives at ((k/4)*32 + r/8)*32 + (r%8)*4 + k%4
+// rows < n: W (lower triangle); rows [n, n+na): dual rows Uz^T; other rows 0.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ W, int ld, int n, int n_pad, int na,
+                                                    const double* __restrict__ Uz, PackMap pm, T* __restrict__ out) {
+    int I = blockIdx.y, kt = blockIdx.x;
+    if (kt >= pm.ktiles[I]) return;
+    T* o = out + ((size_t)pm.tile_off[I] + kt) * (KB_BM * KB_BK);
+    for (int e = threadIdx.x; e < KB_BM * KB_BK; e += 256) {
+        int lane = e & 31, mt = (e >> 5) & 31, k4 = e >> 10;
+        int r = I * KB_BM + mt * 8 + (lane >> 2);
+        int k = kt * KB_BK + k4 * 4 + (lane & 3);
+        double v = 0.0;
+        if (r < n) { if (k <= r) v = W[(size_t)r * ld + k]; }
+        else if (r < n + na) { if (k < n) v = Uz[(size_t)(r - n) * n_pad + k]; }
+        o[e] = (T)v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+template <int DIM>
+static cudaError_t launch_assemble_dim(const VgParams& vg, int n, int n_pad, int ld,
+                                       const double* ax, const double* ay, const double* az, double* C,
+                                       cudaStream_t st) {
+    int nb = n_pad / 64;
+    int tiles = nb * (nb + 1) / 2;
+    switch (vg.model) {
+#define KB_CASE(M) case M: assemble_kernel<DIM, M><<<tiles, 256, 0, st>>>(vg, n, n_pad, ld, ax, ay, az, C); break;
+        KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+#undef KB_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_adjust_data(int dim, const Aniso& an, int n, const double* x, const double* y, const double* z,
+                            double* ax, double* ay, double* az, cudaStream_t st) {
+    int g = (n + 255) / 256;
+    if (dim == 2) adjust_data_kernel<2><<<g, 256, 0, st>>>(an, n, x, y, z, ax, ay, az);
+    else adjust_data_kernel<3><<<g, 256, 0, st>>>(an, n, x, y, z, ax, ay, az);
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_assemble(int dim, const VgParams& vg, int n, int n_pad, int ld,
+                         const double* ax, const double* ay, const double* az, double* C, cudaStream_t st) {
+    return dim == 2 ? launch_assemble_dim<2>(vg, n, n_pad, ld, ax, ay, az, C, st)
+                    : launch_assemble_dim<3>(vg, n, n_pad, ld, ax, ay, az, C, st);
+}
+
+#define KB_SM66 (2 * 64 * 65 * sizeof(double))
+cudaError_t kbk_factor_init() {
+    KB_CUDA_OK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SM66));
+    KB_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SM66));
+    return cudaSuccess;
+}
+
+// Blocked right-looking Cholesky + diagonal-block inverses (into W's diagonal blocks).
+cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, cudaStream_t st, int* launches) {
+    int nb = n_pad / 64;
+    for (int kb = 0; kb < nb; ++kb) {
+        potf2_inv_kernel<<<1, 256, KB_SM66, st>>>(C, W, ld, kb, flag);
+        ++*launches;
+        int below = nb - kb - 1;
+        if (below > 0) {
+            trsm_panel_kernel<<<below, 256, KB_SM66, st>>>(C, W, ld, kb);
+            syrk_kernel<<<below * (below + 1) / 2, 128, 0, st>>>(C, ld, kb);
+            *launches += 2;
+        }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_trtri(const double* L, double* W, double* T1, int ld, int n_pad, cudaStream_t st, int* launches) {
+    for (int m = 64; m < n_pad; m *= 2) {
+        int pairs = (n_pad + 2 * m - 1) / (2 * m);
+        dim3 grid(m / 64, m / 64, pairs);
+        trtri_step1_kernel<<<grid, 128, 0, st>>>(L, W, T1, ld, n_pad, m);
+        trtri_step2_kernel<<<grid, 128, 0, st>>>(W, T1, ld, n_pad, m);
+        *launches += 2;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_dual(const double* W, int ld, int n, int n_pad, int n_rl, int n_hd,
+                     const double* ax, const double* ay, const double* az, const DriftScale& ds,
+                     const double* hd, const double* values,
+                     double* Fz, double* Hz, double* Uz, double* consts, int* flag, cudaStream_t st, int* launches) {
+    int K1 = n_rl + n_hd + 1, na = K1 + 1;
+    build_fz_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, n_rl, n_hd, ax, ay, az, ds, hd, values, Fz);
+    dual_h_kernel<<<(n + 7) / 8, 256, 0, st>>>(W, ld, n, n_pad, na, Fz, Hz);
+    dual_u_kernel<<<(n_pad + 31) / 32, 256, 0, st>>>(W, ld, n, n_pad, na, Hz, Uz);
+    dual_small_kernel<<<1, 256, 0, st>>>(n, n_pad, K1, Fz, Uz, consts, flag);
+    *launches += 4;
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_pack(int dtype, const double* W, int ld, int n, int n_pad, int na, const double* Uz,
+                     const PackMap& pm, void* out, cudaStream_t st) {
+    int maxkt = 0;
+    for (int i = 0; i < pm.nrb; ++i) maxkt = pm.ktiles[i] > maxkt ? pm.ktiles[i] : maxkt;
+    dim3 grid(maxkt, pm.nrb);
+    if (dtype == KB200_F64) pack_kernel<double><<<grid, 256, 0, st>>>(W, ld, n, n_pad, na, Uz, pm, (double*)out);
+    else pack_kernel<float><<<grid, 256, 0, st>>>(W, ld, n, n_pad, na, Uz, pm, (float*)out);
+    return cudaGetLastError();
+}

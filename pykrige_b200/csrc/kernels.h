@@ -1,0 +1,85 @@
+// kernels.h — internal launcher interface between api.cu and the kernel files.
+#pragma once
+#include "common.cuh"
+
+struct DriftScale {            // f' = (f - shift) * scale  (change of drift basis)
+    double shift[KB200_MAX_DRIFT + 1];
+    double scale[KB200_MAX_DRIFT + 1];
+};
+
+// Tile stream layout of the packed inverse factor: row block I owns ktiles[I]
+// consecutive tiles of KB_BM x KB_BK values starting at tile index tile_off[I].
+struct PackMap {
+    int nrb;
+    int ktiles[KB_MAXRB];
+    long long tile_off[KB_MAXRB];
+};
+
+struct SolveParams {
+    VgParams vg;
+    Aniso an;
+    PointSource ps;
+    int n, n_pad, na, nrb;
+    const double* ax; const double* ay; const double* az;   // adjusted data coordinates
+    const void* tiles;
+    PackMap pm;
+    long long m;          // points in this launch
+    long long mpad;       // m rounded up to KB_TN (row stride of partial / auxout)
+    double* partial;      // [nrb][mpad]   per row block sum of squares
+    double* auxout;       // [na][mpad]    dual-row dot products
+};
+
+struct FinalizeParams {
+    VgParams vg;
+    Aniso an;
+    PointSource ps;
+    int dim, n_rl, n_hd, nrb;
+    DriftScale ds;
+    const double* consts;      // Sinv (K1*K1), phi (K1)
+    const double* drift_pts;   // device, column-major [n_hd][m_total] or null
+    long long drift_stride;    // column stride of drift_pts
+    long long drift_first;     // index of point 0 of this launch within drift_pts columns
+    long long m, mpad;
+    const double* partial; const double* auxout;
+    double* z_out; double* ss_out;   // already offset to this launch's first point
+};
+
+cudaError_t kbk_adjust_data(int dim, const Aniso& an, int n, const double* x, const double* y, const double* z,
+                            double* ax, double* ay, double* az, cudaStream_t st);
+cudaError_t kbk_assemble(int dim, const VgParams& vg, int n, int n_pad, int ld,
+                         const double* ax, const double* ay, const double* az, double* C, cudaStream_t st);
+cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, cudaStream_t st, int* launches);
+cudaError_t kbk_trtri(const double* L, double* W, double* T1, int ld, int n_pad, cudaStream_t st, int* launches);
+cudaError_t kbk_dual(const double* W, int ld, int n, int n_pad, int n_rl, int n_hd,
+                     const double* ax, const double* ay, const double* az, const DriftScale& ds,
+                     const double* hd, const double* values,
+                     double* Fz, double* Hz, double* Uz, double* consts, int* flag, cudaStream_t st, int* launches);
+cudaError_t kbk_pack(int dtype, const double* W, int ld, int n, int n_pad, int na, const double* Uz,
+                     const PackMap& pm, void* out, cudaStream_t st);
+
+cudaError_t kbk_factor_init();
+cudaError_t kbk_solve_init();   // opt-in shared memory attributes
+size_t      kbk_solve_smem(int dtype);
+cudaError_t kbk_solve(int dim, int dtype, const SolveParams& p, cudaStream_t st);
+cudaError_t kbk_finalize(const FinalizeParams& p, cudaStream_t st);
+
+// moving window (knn.cu)
+struct KnnParams {
+    VgParams vg;
+    Aniso an;
+    PointSource ps;
+    int dim, n, k;
+    const double* ax; const double* ay; const double* az; const double* values;  // adjusted data (cell-sorted order)
+    // uniform cell grid over the adjusted data
+    int gx, gy, gz;
+    double ox, oy, oz, inv_cell, cell;
+    const int* cell_start;     // [ncells+1]
+    long long m;
+    double* z_out; double* ss_out;
+    int* flag;                 // singular local system
+};
+cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, const double* az, const double* values,
+                          KnnParams& kp, double* sx, double* sy, double* sz, double* sv,
+                          int* cell_of, int* cell_start, int* cursor, int max_cells, cudaStream_t st, int* launches);
+cudaError_t kbk_knn_solve(const KnnParams& p, cudaStream_t st);
+size_t      kbk_knn_smem(int k);

@@ -1,0 +1,272 @@
+// solve.cu — K3: the per-grid-point hot kernel of the global kriging path, and the
+// tiny per-point finalize.
+//
+// Reference semantics (ok.py:665-681, uk.py:942-1007): for every prediction point j
+//     b_j = [-gamma(|p_j - x_k|) (0 on an exact hit) ; drift(p_j) ; 1],  x_j = A^-1 b_j,
+//     z_j = x_j[:n] . Z,   sigma2_j = -x_j . b_j .
+// Here, with c_j = c0 + b_j[:n] and W = chol(C)^-1:
+//     q_j  = || W c_j ||^2            <- the O(n^2) contraction, a triangular GEMM on the fp64 tensor pipe
+//     g_j  = U^T c_j, zc_j = zeta . c_j   <- extra dense "dual rows" appended to W (same GEMM)
+//     finalize: r = g - f_j, mu = S^-1 r, sigma2 = c0 - q + r.mu, z = zc - mu.phi
+//
+// One CTA = (row block I of KB_BM rows of W) x (tile of KB_TN points).  The RHS tile
+// c[k][j] is generated on the fly in shared memory from coordinates (never in HBM);
+// W tiles arrive as 32 KB fragment-ordered bulk copies (TMA engine, cp.async.bulk +
+// mbarrier) into a 3-stage ring; 8 warps issue m8n8k4 DMMA on a 32x64 sub-tile each.
+#include "common.cuh"
+#include "kernels.h"
+
+#define SV_STAGES 3
+#define SV_THREADS 256
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // bounded spin: a lost transaction traps instead of hanging the GPU
+    for (uint32_t it = 0; it < (1u << 26); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+// 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int DIM, int MODEL>
+__global__ void __launch_bounds__(SV_THREADS, 1) solve_kernel_f64(const __grid_constant__ SolveParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Ts = reinterpret_cast<double*>(smem_raw);                   // SV_STAGES * BM*BK
+    double* Bs = Ts + SV_STAGES * KB_BM * KB_BK;                        // SV_STAGES * BK*TN
+    double* red = Bs + SV_STAGES * KB_BK * KB_TN;                       // 8 * 64
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 8 * KB_TN);      // SV_STAGES
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int jt = blockIdx.x;
+    const int I = P.nrb - 1 - (int)blockIdx.y;          // heavy row blocks first
+    const int nkt = P.pm.ktiles[I];
+    const double* gt = reinterpret_cast<const double*>(P.tiles) + (size_t)P.pm.tile_off[I] * (KB_BM * KB_BK);
+    constexpr uint32_t TILE_BYTES = KB_BM * KB_BK * sizeof(double);
+
+    // the prediction point this thread generates RHS entries for
+    const long long pj = (long long)jt * KB_TN + warp * 8 + (lane >> 2);
+    const bool pvalid = pj < P.m;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (pvalid) kb_load_point<DIM>(P.ps, P.an, pj, px, py, pz);
+
+    if (tid == 0) {
+        for (int s = 0; s < SV_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // which k tiles this warp's 32 rows need: W rows are lower-triangular, dual rows are dense
+    const int r0w = I * KB_BM + warp * 32;
+    int warp_kmax;
+    if (r0w + 31 >= P.n && r0w < P.n + P.na) warp_kmax = 0x7fffffff;
+    else if (r0w >= P.n + P.na) warp_kmax = -1;
+    else warp_kmax = r0w + 31;
+
+    auto issue_load = [&](int t) {
+        int s = t % SV_STAGES;
+        mbar_expect_tx(&full[s], TILE_BYTES);
+        bulk_g2s(Ts + (size_t)s * KB_BM * KB_BK, gt + (size_t)t * KB_BM * KB_BK, TILE_BYTES, &full[s]);
+    };
+    auto gen_rhs = [&](int t) {
+        double* bs = Bs + (size_t)(t % SV_STAGES) * KB_BK * KB_TN;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            int k = t * KB_BK + 4 * s4 + (lane & 3);
+            double v = 0.0;
+            if (pvalid && k < P.n) {
+                double d = kb_dist<DIM>(P.ax[k], P.ay[k], DIM == 3 ? P.az[k] : 0.0, px, py, pz);
+                v = kb_cov_rhs<MODEL>(P.vg, d);
+            }
+            bs[(s4 * 8 + warp) * 32 + lane] = v;
+        }
+    };
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+
+    for (int t = 0; t < SV_STAGES - 1 && t < nkt; ++t) {
+        if (tid == 0) issue_load(t);
+        gen_rhs(t);
+    }
+    for (int it = 0; it < nkt; ++it) {
+        const int s = it % SV_STAGES;
+        mbar_wait(&full[s], (uint32_t)((it / SV_STAGES) & 1));
+        __syncthreads();      // everyone is done with tile it-1 (its stage is refilled below); RHS tile `it` is visible
+        const int tn = it + SV_STAGES - 1;
+        if (tn < nkt) {
+            if (tid == 0) issue_load(tn);
+            gen_rhs(tn);
+        }
+        if (it * KB_BK <= warp_kmax) {
+            const double* ts = Ts + (size_t)s * KB_BM * KB_BK;
+            const double* bs = Bs + (size_t)s * KB_BK * KB_TN;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                double fa[4], fb[8];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) fa[mt] = ts[(k4 * 32 + warp * 4 + mt) * 32 + lane];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) fb[nt] = bs[(k4 * 8 + nt) * 32 + lane];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+                        kb_dmma(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fb[nt]);
+            }
+        }
+    }
+
+    // epilogue: W rows -> sum of squares per point; dual rows -> direct output
+    double qs[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { qs[nt][0] = 0.0; qs[nt][1] = 0.0; }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int r = r0w + mt * 8 + (lane >> 2);
+        if (r < P.n) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                qs[nt][0] += acc[mt][nt][0] * acc[mt][nt][0];
+                qs[nt][1] += acc[mt][nt][1] * acc[mt][nt][1];
+            }
+        } else if (r < P.n + P.na) {
+            double* ao = P.auxout + (size_t)(r - P.n) * P.mpad + (size_t)jt * KB_TN + 2 * (lane & 3);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                ao[nt * 8] = acc[mt][nt][0];
+                ao[nt * 8 + 1] = acc[mt][nt][1];
+            }
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double v = qs[nt][i];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            qs[nt][i] = v;
+        }
+    if ((lane >> 2) == 0) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            red[warp * KB_TN + nt * 8 + 2 * lane] = qs[nt][0];
+            red[warp * KB_TN + nt * 8 + 2 * lane + 1] = qs[nt][1];
+        }
+    }
+    __syncthreads();
+    if (tid < KB_TN) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w * KB_TN + tid];     // fixed order: deterministic
+        P.partial[(size_t)I * P.mpad + (size_t)jt * KB_TN + tid] = v;
+    }
+}
+
+// Per-point finalize (deterministic reduction over row blocks + the (K+1)x(K+1) drift solve).
+template <int DIM>
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams P) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.m) return;
+    double q = 0.0;
+    for (int I = 0; I < P.nrb; ++I) q += P.partial[(size_t)I * P.mpad + p];
+    const int K = P.n_rl + P.n_hd, K1 = K + 1;
+    double r[KB200_MAX_DRIFT + 1];
+    double f[KB200_MAX_DRIFT + 1];
+    if (P.n_rl > 0) {
+        double x, y, z;
+        kb_load_point<DIM>(P.ps, P.an, p, x, y, z);
+        f[0] = (x - P.ds.shift[0]) * P.ds.scale[0];
+        f[1] = (y - P.ds.shift[1]) * P.ds.scale[1];
+        if (DIM == 3) f[2] = (z - P.ds.shift[2]) * P.ds.scale[2];
+    }
+    for (int c = 0; c < P.n_hd; ++c) {
+        double v = P.drift_pts[(size_t)c * P.drift_stride + P.drift_first + p];
+        f[P.n_rl + c] = (v - P.ds.shift[P.n_rl + c]) * P.ds.scale[P.n_rl + c];
+    }
+    f[K] = 1.0;
+    for (int a = 0; a < K1; ++a) r[a] = P.auxout[(size_t)a * P.mpad + p] - f[a];
+    const double zc = P.auxout[(size_t)K1 * P.mpad + p];
+    const double* Sinv = P.consts;
+    const double* phi = P.consts + K1 * K1;
+    double rmu = 0.0, muphi = 0.0;
+    for (int a = 0; a < K1; ++a) {
+        double mu = 0.0;
+        for (int b = 0; b < K1; ++b) mu += Sinv[a * K1 + b] * r[b];
+        rmu += r[a] * mu;
+        muphi += mu * phi[a];
+    }
+    P.ss_out[p] = P.vg.c0 - q + rmu;
+    P.z_out[p] = zc - muphi;
+}
+
+size_t kbk_solve_smem(int dtype) {
+    (void)dtype;
+    return (size_t)SV_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
+           SV_STAGES * sizeof(uint64_t) + 64;
+}
+
+template <int DIM, int MODEL>
+static cudaError_t solve_set_attr() {
+    return cudaFuncSetAttribute(solve_kernel_f64<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kbk_solve_smem(KB200_F64));
+}
+
+cudaError_t kbk_solve_init() {
+#define KB_ATTR(M) KB_CUDA_OK((solve_set_attr<2, M>())); KB_CUDA_OK((solve_set_attr<3, M>()));
+    KB_ATTR(KB200_VG_LINEAR) KB_ATTR(KB200_VG_POWER) KB_ATTR(KB200_VG_GAUSSIAN)
+    KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT)
+#undef KB_ATTR
+    return cudaSuccess;
+}
+
+template <int DIM>
+static cudaError_t solve_dim(int dtype, const SolveParams& p, cudaStream_t st) {
+    if (dtype != KB200_F64) return cudaErrorNotSupported;
+    dim3 grid((unsigned)(p.mpad / KB_TN), (unsigned)p.nrb);
+    size_t sm = kbk_solve_smem(dtype);
+    switch (p.vg.model) {
+#define KB_CASE(M) case M: solve_kernel_f64<DIM, M><<<grid, SV_THREADS, sm, st>>>(p); break;
+        KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+#undef KB_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_solve(int dim, int dtype, const SolveParams& p, cudaStream_t st) {
+    return dim == 2 ? solve_dim<2>(dtype, p, st) : solve_dim<3>(dtype, p, st);
+}
+
+cudaError_t kbk_finalize(const FinalizeParams& p, cudaStream_t st) {
+    unsigned g = (unsigned)((p.m + 255) / 256);
+    if (p.dim == 2) finalize_kernel<2><<<g, 256, 0, st>>>(p);
+    else finalize_kernel<3><<<g, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}

@@ -1,0 +1,406 @@
+"""UniversalKriging (2-D) with the B200 ``backend='cuda'`` execute() path.
+
+API mirror of the reference class (src/pykrige/uk.py:220-1328). Regional-linear drift is built
+on the device from the adjusted coordinates; point-log, external-Z, specified and functional
+drift terms are evaluated on the host (as in uk.py:884-910, 955-979) and shipped as extra
+drift columns of the same device system.
+"""
+import warnings
+import numpy as np
+
+from . import core
+from ._base import KrigeBase
+from .core import _adjust_for_anisotropy, _make_variogram_parameter_list, _initialize_variogram_model
+
+P_INV_TYPES = ("pinv", "pinvh")
+
+
+def _first_last_index(axis, v):
+    """(index of the first node >= v, index of the last node <= v) for every v — the node
+    selection rule of the reference's bilinear sampler (uk.py:556-559)."""
+    axis = np.asarray(axis, dtype=float)
+    ge = axis[None, :] >= v[:, None]
+    le = axis[None, :] <= v[:, None]
+    i2 = np.argmax(ge, axis=1)
+    i1 = axis.size - 1 - np.argmax(le[:, ::-1], axis=1)
+    return i1, i2
+
+
+class UniversalKriging(KrigeBase):
+    """Two-dimensional universal kriging; arguments as in the reference docstring (uk.py:40-205)."""
+
+    UNBIAS = True  # the unbiasedness row is always present on the device path (uk.py:208)
+    _ndim = 2
+
+    def __init__(
+        self,
+        x,
+        y,
+        z,
+        variogram_model="linear",
+        variogram_parameters=None,
+        variogram_function=None,
+        nlags=6,
+        weight=False,
+        anisotropy_scaling=1.0,
+        anisotropy_angle=0.0,
+        drift_terms=None,
+        point_drift=None,
+        external_drift=None,
+        external_drift_x=None,
+        external_drift_y=None,
+        specified_drift=None,
+        functional_drift=None,
+        verbose=False,
+        enable_plotting=False,
+        exact_values=True,
+        pseudo_inv=False,
+        pseudo_inv_type="pinv",
+    ):
+        self.pseudo_inv = bool(pseudo_inv)
+        self.pseudo_inv_type = str(pseudo_inv_type)
+        if self.pseudo_inv_type not in P_INV_TYPES:
+            raise ValueError("pseudo inv type not valid: " + str(pseudo_inv_type))
+        if drift_terms is None:
+            drift_terms = []
+        if specified_drift is None:
+            specified_drift = []
+        if functional_drift is None:
+            functional_drift = []
+        if not isinstance(exact_values, bool):
+            raise ValueError("exact_values has to be boolean True or False")
+        self.exact_values = exact_values
+        self.coordinates_type = "euclidean"
+
+        def _dim_ok(model):
+            from .compat_gstools import validate_gstools
+
+            validate_gstools(model)
+            if model.field_dim == 3:
+                raise ValueError("GSTools: model dim is not 1 or 2")
+
+        ov = self._select_variogram(variogram_model, variogram_function, _dim_ok)
+        if "gstools" in ov:
+            variogram_parameters = []
+            anisotropy_scaling = ov["gstools"].pykrige_anis
+            anisotropy_angle = ov["gstools"].pykrige_angle
+
+        self.X_ORIG = np.atleast_1d(np.squeeze(np.array(x, copy=True, dtype=np.float64)))
+        self.Y_ORIG = np.atleast_1d(np.squeeze(np.array(y, copy=True, dtype=np.float64)))
+        self.Z = np.atleast_1d(np.squeeze(np.array(z, copy=True, dtype=np.float64)))
+        self.verbose = verbose
+        self.enable_plotting = enable_plotting
+        if self.enable_plotting and self.verbose:
+            print("Plotting Enabled\n")
+
+        self.XCENTER = (np.amax(self.X_ORIG) + np.amin(self.X_ORIG)) / 2.0
+        self.YCENTER = (np.amax(self.Y_ORIG) + np.amin(self.Y_ORIG)) / 2.0
+        self.anisotropy_scaling = anisotropy_scaling
+        self.anisotropy_angle = anisotropy_angle
+        if self.verbose:
+            print("Adjusting data for anisotropy...")
+        self.X_ADJUSTED, self.Y_ADJUSTED = _adjust_for_anisotropy(
+            np.vstack((self.X_ORIG, self.Y_ORIG)).T,
+            [self.XCENTER, self.YCENTER],
+            [self.anisotropy_scaling],
+            [self.anisotropy_angle],
+        ).T
+
+        if self.verbose:
+            print("Initializing variogram model...")
+        vp_temp = _make_variogram_parameter_list(self.variogram_model, variogram_parameters)
+        self.lags, self.semivariance, self.variogram_model_parameters = _initialize_variogram_model(
+            np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T,
+            self.Z,
+            self.variogram_model,
+            vp_temp,
+            self.variogram_function,
+            nlags,
+            weight,
+            "euclidean",
+        )
+        if self.verbose:
+            self._print_variogram()
+        if self.enable_plotting:
+            self.display_variogram_model()
+        # statistics: computed on first access (the reference runs the O(N^4) loop here, uk.py:380)
+        self._stats_state = "lazy"
+
+        if self.verbose:
+            print("Initializing drift terms...")
+        self.regional_linear_drift = "regional_linear" in drift_terms
+        if self.regional_linear_drift and self.verbose:
+            print("Implementing regional linear drift.")
+
+        # external Z drift: sampled with the ORIGINAL coordinates (uk.py:413-446)
+        if "external_Z" in drift_terms:
+            if external_drift is None:
+                raise ValueError("Must specify external Z drift terms.")
+            if external_drift_x is None or external_drift_y is None:
+                raise ValueError("Must specify coordinates of external Z drift terms.")
+            self.external_Z_drift = True
+            if external_drift.shape[0] != external_drift_y.shape[0] or external_drift.shape[1] != external_drift_x.shape[0]:
+                if external_drift.shape[0] == external_drift_x.shape[0] and external_drift.shape[1] == external_drift_y.shape[0]:
+                    self.external_Z_array = np.array(external_drift.T)
+                else:
+                    raise ValueError("External drift dimensions do not match provided x- and y-coordinate dimensions.")
+            else:
+                self.external_Z_array = np.array(external_drift)
+            self.external_Z_array_x = np.array(external_drift_x).flatten()
+            self.external_Z_array_y = np.array(external_drift_y).flatten()
+            self.z_scalars = self._calculate_data_point_zscalars(self.X_ORIG, self.Y_ORIG)
+            if self.verbose:
+                print("Implementing external Z drift.")
+        else:
+            self.external_Z_drift = False
+
+        # point-logarithmic drift: well coordinates go to the adjusted frame (uk.py:448-474)
+        if "point_log" in drift_terms:
+            if point_drift is None:
+                raise ValueError("Must specify location(s) and strength(s) of point drift terms.")
+            self.point_log_drift = True
+            point_log = np.atleast_2d(np.squeeze(np.array(point_drift, copy=True)))
+            self.point_log_array = np.zeros(point_log.shape)
+            self.point_log_array[:, 2] = point_log[:, 2]
+            self.point_log_array[:, :2] = _adjust_for_anisotropy(
+                np.vstack((point_log[:, 0], point_log[:, 1])).T,
+                [self.XCENTER, self.YCENTER],
+                [self.anisotropy_scaling],
+                [self.anisotropy_angle],
+            )
+            if self.verbose:
+                print("Implementing external point-logarithmic drift; number of points =",
+                      self.point_log_array.shape[0], "\n")
+        else:
+            self.point_log_drift = False
+
+        if "specified" in drift_terms:
+            if type(specified_drift) is not list:
+                raise TypeError("Arrays for specified drift terms must be encapsulated in a list.")
+            if len(specified_drift) == 0:
+                raise ValueError("Must provide at least one drift-value array when using the 'specified' drift capability.")
+            self.specified_drift = True
+            self.specified_drift_data_arrays = []
+            for term in specified_drift:
+                specified = np.squeeze(np.array(term, copy=True))
+                if specified.size != self.X_ORIG.size:
+                    raise ValueError("Must specify the drift values for each data point when using the 'specified' drift capability.")
+                self.specified_drift_data_arrays.append(specified)
+        else:
+            self.specified_drift = False
+
+        # functional drift: callables evaluated with the adjusted coordinates (uk.py:496-510)
+        if "functional" in drift_terms:
+            if type(functional_drift) is not list:
+                raise TypeError("Callables for functional drift terms must be encapsulated in a list.")
+            if len(functional_drift) == 0:
+                raise ValueError("Must provide at least one callable object when using the 'functional' drift capability.")
+            self.functional_drift = True
+            self.functional_drift_terms = functional_drift
+        else:
+            self.functional_drift = False
+
+    def _stats_inputs(self):
+        return np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T, self.Z
+
+    def _calculate_data_point_zscalars(self, x, y, type_="array"):
+        """Bilinear sample of the external-Z grid at (x, y) (uk.py:512-628), vectorised; node
+        selection, degenerate (on-node / on-line) cases and the domain check follow the reference."""
+        xs = np.atleast_1d(np.asarray(x, dtype=float))
+        ys = np.atleast_1d(np.asarray(y, dtype=float))
+        shape = xs.shape
+        xs = xs.ravel()
+        ys = ys.ravel()
+        ax, ay, Zg = self.external_Z_array_x, self.external_Z_array_y, self.external_Z_array
+        if (np.any(xs > np.amax(ax)) or np.any(xs < np.amin(ax)) or np.any(ys > np.amax(ay)) or np.any(ys < np.amin(ay))):
+            raise ValueError("External drift array does not cover specified kriging domain.")
+        out = np.empty(xs.size)
+        step = max(1, 4_000_000 // max(ax.size, ay.size))
+        for s in range(0, xs.size, step):
+            xn, yn = xs[s:s + step], ys[s:s + step]
+            x1, x2 = _first_last_index(ax, xn)
+            y1, y2 = _first_last_index(ay, yn)
+            dx = ax[x2] - ax[x1]
+            dy = ay[y2] - ay[y1]
+            same_x = x1 == x2
+            same_y = y1 == y2
+            with np.errstate(divide="ignore", invalid="ignore"):
+                full = (Zg[y1, x1] * (ax[x2] - xn) * (ay[y2] - yn) + Zg[y1, x2] * (xn - ax[x1]) * (ay[y2] - yn)
+                        + Zg[y2, x1] * (ax[x2] - xn) * (yn - ay[y1]) + Zg[y2, x2] * (xn - ax[x1]) * (yn - ay[y1])) / (dx * dy)
+                along_x = (Zg[y1, x1] * (ax[x2] - xn) + Zg[y2, x2] * (xn - ax[x1])) / dx
+                along_y = (Zg[y1, x1] * (ay[y2] - yn) + Zg[y2, x2] * (yn - ay[y1])) / dy
+            z = np.where(same_y, np.where(same_x, Zg[y1, x1], along_x), np.where(same_x, along_y, full))
+            out[s:s + step] = z
+        if type_ == "scalar":
+            return out[0]
+        return out.reshape(shape)
+
+    def update_variogram_model(self, variogram_model, variogram_parameters=None, variogram_function=None,
+                               nlags=6, weight=False, anisotropy_scaling=1.0, anisotropy_angle=0.0):
+        """Change the variogram model and/or its parameters (uk.py:630-790)."""
+
+        def _dim_ok(model):
+            from .compat_gstools import validate_gstools
+
+            validate_gstools(model)
+            if model.field_dim == 3:
+                raise ValueError("GSTools: model dim is not 1 or 2")
+
+        ov = self._select_variogram(variogram_model, variogram_function, _dim_ok)
+        if "gstools" in ov:
+            variogram_parameters = []
+            anisotropy_scaling = ov["gstools"].pykrige_anis
+            anisotropy_angle = ov["gstools"].pykrige_angle
+        if anisotropy_scaling != self.anisotropy_scaling or anisotropy_angle != self.anisotropy_angle:
+            if self.verbose:
+                print("Adjusting data for anisotropy...")
+            self.anisotropy_scaling = anisotropy_scaling
+            self.anisotropy_angle = anisotropy_angle
+            self.X_ADJUSTED, self.Y_ADJUSTED = _adjust_for_anisotropy(
+                np.vstack((self.X_ORIG, self.Y_ORIG)).T,
+                [self.XCENTER, self.YCENTER],
+                [self.anisotropy_scaling],
+                [self.anisotropy_angle],
+            ).T
+        if self.verbose:
+            print("Updating variogram mode...")
+        vp_temp = _make_variogram_parameter_list(self.variogram_model, variogram_parameters)
+        self.lags, self.semivariance, self.variogram_model_parameters = _initialize_variogram_model(
+            np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T, self.Z, self.variogram_model, vp_temp,
+            self.variogram_function, nlags, weight, "euclidean",
+        )
+        if self.verbose:
+            self._print_variogram()
+        if self.enable_plotting:
+            self.display_variogram_model()
+        self._stats_state = "lazy"
+
+    # ---- device description -----------------------------------------------------------
+    def _data_arrays(self):
+        Mt = core.anisotropy_matrix(2, [self.anisotropy_scaling], [self.anisotropy_angle])
+        return self.X_ORIG, self.Y_ORIG, None, self.Z, [self.XCENTER, self.YCENTER], Mt
+
+    def _point_log_column(self, well, xa, ya):
+        """-strength * log(distance to the well), log(0) clamped to -100 (uk.py:885-896, 955-966)."""
+        with np.errstate(divide="ignore"):
+            ld = np.log(np.sqrt((xa - self.point_log_array[well, 0]) ** 2 + (ya - self.point_log_array[well, 1]) ** 2))
+        ld = np.where(np.isinf(ld), -100.0, ld)
+        return -self.point_log_array[well, 2] * ld
+
+    def _drift_spec(self):
+        """Host-evaluated drift columns at the data, in the reference's order (uk.py:884-910)."""
+        cols = []
+        if self.point_log_drift:
+            for w in range(self.point_log_array.shape[0]):
+                cols.append(self._point_log_column(w, self.X_ADJUSTED, self.Y_ADJUSTED))
+        if self.external_Z_drift:
+            cols.append(np.asarray(self.z_scalars, dtype=float))
+        if self.specified_drift:
+            for arr in self.specified_drift_data_arrays:
+                cols.append(np.asarray(arr, dtype=float))
+        if self.functional_drift:
+            for func in self.functional_drift_terms:
+                cols.append(np.asarray(func(self.X_ADJUSTED, self.Y_ADJUSTED), dtype=float))
+        return (2 if self.regional_linear_drift else 0), cols
+
+    def _problem_signature(self, dtype, knn):
+        sig = super()._problem_signature(dtype, knn)
+        _, cols = self._drift_spec()
+        return sig + tuple(float(np.sum(c)) for c in cols)
+
+    def execute(self, style, xpoints, ypoints, mask=None, backend="cuda", specified_drift_arrays=None,
+                dtype="float64"):
+        """Calculates a kriged grid and the associated variance (uk.py:1090-1328); ``backend='cuda'``."""
+        if self.verbose:
+            print("Executing Universal Kriging...\n")
+        if style != "grid" and style != "masked" and style != "points":
+            raise ValueError("style argument must be 'grid', 'points', or 'masked'")
+        xpts = np.atleast_1d(np.squeeze(np.array(xpoints, copy=True)))
+        ypts = np.atleast_1d(np.squeeze(np.array(ypoints, copy=True)))
+        nx = xpts.size
+        ny = ypts.size
+        flat_mask = None
+        if style in ["grid", "masked"]:
+            if style == "masked":
+                if mask is None:
+                    raise IOError("Must specify boolean masking array when style is 'masked'.")
+                if mask.shape[0] != ny or mask.shape[1] != nx:
+                    if mask.shape[0] == nx and mask.shape[1] == ny:
+                        mask = mask.T
+                    else:
+                        raise ValueError("Mask dimensions do not match specified grid dimensions.")
+                flat_mask = np.asarray(mask, dtype=bool).flatten()
+        elif style == "points":
+            if xpts.size != ypts.size:
+                raise ValueError("xpoints and ypoints must have same dimensions when treated as listing discrete points.")
+
+        # specified-drift validation (uk.py:1217-1274)
+        if specified_drift_arrays is None:
+            specified_drift_arrays = []
+        spec_drift_grids = []
+        if self.specified_drift:
+            if len(specified_drift_arrays) == 0:
+                raise ValueError("Must provide drift values for kriging points when using 'specified' drift capability.")
+            if type(specified_drift_arrays) is not list:
+                raise TypeError("Arrays for specified drift terms must be encapsulated in a list.")
+            for spec in specified_drift_arrays:
+                if style in ["grid", "masked"]:
+                    if spec.ndim < 2:
+                        raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
+                    elif spec.shape[0] != ny or spec.shape[1] != nx:
+                        if spec.shape[0] == nx and spec.shape[1] == ny:
+                            spec_drift_grids.append(np.squeeze(spec.T))
+                        else:
+                            raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
+                    else:
+                        spec_drift_grids.append(np.squeeze(spec))
+                elif style == "points":
+                    if spec.ndim != 1:
+                        raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
+                    elif spec.shape[0] != xpts.size:
+                        raise ValueError("Number of supplied drift values in array do not match specified number of kriging points.")
+                    else:
+                        spec_drift_grids.append(np.squeeze(spec))
+            if len(spec_drift_grids) != len(self.specified_drift_data_arrays):
+                raise ValueError("Inconsistent number of specified drift terms supplied.")
+        else:
+            if len(specified_drift_arrays) != 0:
+                warnings.warn(
+                    "Provided specified drift values, but 'specified' drift was not initialized during "
+                    "instantiation of UniversalKriging class.", RuntimeWarning,
+                )
+        self._check_backend(backend, "2D universal kriging")
+
+        host_terms = self.point_log_drift or self.external_Z_drift or self.specified_drift or self.functional_drift
+        drift_at = None
+        if host_terms:
+            def drift_at(pts, idx):
+                xo, yo = pts[0], pts[1]
+                xa, ya = _adjust_for_anisotropy(
+                    np.vstack((xo, yo)).T, [self.XCENTER, self.YCENTER],
+                    [self.anisotropy_scaling], [self.anisotropy_angle]).T
+                cols = []
+                if self.point_log_drift:
+                    for w in range(self.point_log_array.shape[0]):
+                        cols.append(self._point_log_column(w, xa, ya))
+                if self.external_Z_drift:
+                    cols.append(self._calculate_data_point_zscalars(xo, yo))
+                if self.specified_drift:
+                    for g in spec_drift_grids:
+                        flat = np.asarray(g, dtype=float).flatten()
+                        cols.append(flat if idx is None else flat[idx])
+                if self.functional_drift:
+                    for func in self.functional_drift_terms:
+                        cols.append(np.asarray(func(xa, ya), dtype=float) * np.ones(xa.shape))
+                return np.ascontiguousarray(np.vstack(cols), dtype=np.float64)
+
+        zvalues, sigmasq = self._run_cuda(
+            style, [xpts.astype(np.float64), ypts.astype(np.float64)], flat_mask, drift_at=drift_at, dtype=dtype,
+        )
+        if style == "masked":
+            zvalues = np.ma.array(zvalues, mask=flat_mask)
+            sigmasq = np.ma.array(sigmasq, mask=flat_mask)
+        if style in ["masked", "grid"]:
+            zvalues = zvalues.reshape((ny, nx))
+            sigmasq = sigmasq.reshape((ny, nx))
+        return zvalues, sigmasq

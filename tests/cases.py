@@ -1,0 +1,198 @@
+"""Seeded parity cases shared by tests/golden/make_golden.py (which runs the imported reference,
+in the build container only) and the test-suite (which replays them through the oracle on CPU and
+through backend='cuda' on the GPU). Synthetic inputs follow SURVEY.md §8(d): uniform random
+scatter, values with a non-zero mean, list-form variogram parameters [FULL sill, range, nugget],
+and the first 16 data coordinates appended as 'points' queries to exercise exact hits.
+"""
+import numpy as np
+
+
+def synth_data(seed, n, dim, box=(1000.0, 1000.0, 250.0)):
+    rng = np.random.default_rng(seed)
+    xyz = np.column_stack([rng.uniform(0.0, box[c], n) for c in range(dim)])
+    val = 50.0 + 10.0 * np.sin(xyz[:, 0] / 150.0) * np.cos(xyz[:, 1] / 200.0)
+    if dim == 3:
+        val = val + 5.0 * np.sin(xyz[:, 2] / 60.0)
+    val = val + rng.normal(0.0, 1.0, n)
+    return xyz, val
+
+
+def synth_points(seed, m, dim, data_xyz, box=(1000.0, 1000.0, 250.0), n_hits=16):
+    rng = np.random.default_rng(seed + 7919)
+    pts = np.column_stack([rng.uniform(0.0, box[c], m) for c in range(dim)])
+    hits = data_xyz[: min(n_hits, data_xyz.shape[0])]
+    return np.vstack([pts, hits])
+
+
+# functional drift terms by name (callables cannot be stored in fixtures)
+FUNCS = {
+    "fx": lambda x, y: x,
+    "fy": lambda x, y: y,
+    "fxy": lambda x, y: 1e-3 * x * y,
+    "fx3": lambda x, y, z: x,
+    "fy3": lambda x, y, z: y,
+    "fz3": lambda x, y, z: z,
+    "fr3": lambda x, y, z: np.sqrt(x * x + y * y + z * z),
+}
+
+MODELS = {
+    "linear": [0.004, 0.05],
+    "power": [0.002, 1.3, 0.05],
+    "gaussian": [1.0, 300.0, 0.05],
+    "exponential": [1.0, 300.0, 0.05],
+    "spherical": [1.0, 400.0, 0.05],
+    "hole-effect": [1.0, 300.0, 0.05],
+}
+
+
+def _c(name, cls, n, m, seed, model, params=None, **kw):
+    d = dict(name=name, cls=cls, n=n, m=m, seed=seed, model=model,
+             params=list(MODELS[model] if params is None else params),
+             dim=3 if cls.endswith("3D") else 2, style="points", ctor={}, k=None,
+             drift_terms=[], functional=[], n_specified=0, point_log=None, external_z=False,
+             exact_values=True, box=(1000.0, 1000.0, 250.0), ref_backend="vectorized")
+    d.update(kw)
+    return d
+
+
+CASES = []
+# config 1 of BASELINE.json: OK 2-D, N=100, 50x50 grid, spherical
+CASES.append(_c("cfg1_ok2d_n100_grid50", "OK", 100, 0, 1001, "spherical", style="grid",
+                grid=(50, 50, 1)))
+# every built-in variogram model, with anisotropy, points + exact hits
+for i, mname in enumerate(["linear", "power", "gaussian", "exponential", "spherical"]):
+    CASES.append(_c("ok2d_%s_aniso" % mname, "OK", 200, 300, 2000 + i, mname,
+                    ctor=dict(anisotropy_scaling=1.7, anisotropy_angle=30.0)))
+# hole-effect is not a valid (conditionally negative definite) model in 2-D for scattered data;
+# the reference still returns LU numbers for it. Kept as a fixture for the singular-path test.
+CASES.append(_c("ok2d_hole_effect_small", "OK", 12, 40, 2010, "hole-effect", params=[1.0, 900.0, 0.05]))
+CASES.append(_c("ok2d_nonexact", "OK", 150, 200, 2020, "exponential", exact_values=False))
+CASES.append(_c("ok2d_zero_nugget", "OK", 150, 200, 2021, "spherical", params=[2.0, 350.0, 0.0]))
+CASES.append(_c("ok2d_masked", "OK", 120, 0, 2022, "exponential", style="masked", grid=(23, 17, 1)))
+# reduced-size stand-ins for configs 2-4 that the reference can run in one call
+CASES.append(_c("cfg2r_ok2d_n1000", "OK", 1000, 2000, 1002, "exponential"))
+CASES.append(_c("cfg3r_ok3d_n800", "OK3D", 800, 1500, 1003, "gaussian"))
+CASES.append(_c("cfg4r_uk2d_n1000", "UK", 1000, 2000, 1004, "exponential", drift_terms=["regional_linear"]))
+# universal kriging drift kinds (uk.py:876-910)
+CASES.append(_c("uk2d_reglin_aniso", "UK", 180, 260, 3001, "spherical", drift_terms=["regional_linear"],
+                ctor=dict(anisotropy_scaling=0.6, anisotropy_angle=-20.0)))
+CASES.append(_c("uk2d_pointlog", "UK", 120, 200, 3002, "exponential", drift_terms=["point_log"],
+                point_log=[[300.0, 420.0, 1.0], [710.0, 150.0, -0.5]]))
+CASES.append(_c("uk2d_externalz", "UK", 120, 200, 3003, "exponential", drift_terms=["external_Z"], external_z=True))
+CASES.append(_c("uk2d_specified", "UK", 120, 200, 3004, "gaussian", drift_terms=["specified"], n_specified=2))
+CASES.append(_c("uk2d_functional", "UK", 120, 200, 3005, "linear", drift_terms=["functional"],
+                functional=["fx", "fy", "fxy"]))
+CASES.append(_c("uk2d_all_grid", "UK", 90, 0, 3006, "exponential", style="grid", grid=(19, 13, 1),
+                drift_terms=["regional_linear", "specified", "functional"], n_specified=1, functional=["fxy"]))
+CASES.append(_c("uk2d_masked", "UK", 90, 0, 3007, "spherical", style="masked", grid=(15, 21, 1),
+                drift_terms=["regional_linear"]))
+# 3-D
+CASES.append(_c("ok3d_linear_aniso", "OK3D", 200, 300, 4001, "linear",
+                ctor=dict(anisotropy_scaling_y=1.4, anisotropy_scaling_z=3.0, anisotropy_angle_x=10.0,
+                          anisotropy_angle_y=-25.0, anisotropy_angle_z=40.0)))
+CASES.append(_c("ok3d_grid", "OK3D", 150, 0, 4002, "exponential", style="grid", grid=(9, 8, 7)))
+CASES.append(_c("ok3d_masked", "OK3D", 100, 0, 4003, "spherical", style="masked", grid=(6, 7, 5)))
+CASES.append(_c("uk3d_reglin", "UK3D", 200, 300, 4004, "gaussian", drift_terms=["regional_linear"]))
+CASES.append(_c("uk3d_spec_func", "UK3D", 150, 200, 4005, "exponential", drift_terms=["specified", "functional"],
+                n_specified=1, functional=["fx3", "fr3"]))
+CASES.append(_c("uk3d_all_grid", "UK3D", 100, 0, 4006, "linear", style="grid", grid=(5, 6, 4),
+                drift_terms=["regional_linear", "functional"], functional=["fr3"]))
+# moving window (ok.py:722-758; reference backend 'loop')
+CASES.append(_c("knn2d_k8", "OK", 500, 300, 5001, "exponential", params=[1.0, 150.0, 0.05], k=8, ref_backend="loop"))
+CASES.append(_c("knn2d_k16_nonexact", "OK", 400, 200, 5002, "spherical", k=16, exact_values=False, ref_backend="loop"))
+CASES.append(_c("knn2d_k64_grid", "OK", 3000, 0, 1005, "exponential", params=[1.0, 50.0, 0.05], k=64,
+                style="grid", grid=(24, 20, 1), ref_backend="loop"))
+CASES.append(_c("knn3d_k10", "OK3D", 300, 200, 5003, "linear", k=10, ref_backend="loop"))
+CASES.append(_c("knn2d_k2", "OK", 60, 100, 5004, "linear", k=2, ref_backend="loop"))
+
+CASE_BY_NAME = {c["name"]: c for c in CASES}
+
+
+def build_inputs(case):
+    """Deterministic inputs of a case: data, values, prediction axes/points, mask, drift arrays."""
+    dim = case["dim"]
+    xyz, val = synth_data(case["seed"], case["n"], dim, case["box"])
+    out = dict(data=xyz, values=val)
+    rng = np.random.default_rng(case["seed"] + 31337)
+    if case["style"] == "points":
+        out["points"] = synth_points(case["seed"], case["m"], dim, xyz, case["box"])
+        npt = out["points"].shape[0]
+    else:
+        nx, ny, nz = case["grid"]
+        axes = [np.linspace(0.0, case["box"][0], nx), np.linspace(0.0, case["box"][1], ny)]
+        if dim == 3:
+            axes.append(np.linspace(0.0, case["box"][2], nz))
+        out["axes"] = axes
+        npt = nx * ny * (nz if dim == 3 else 1)
+        if case["style"] == "masked":
+            shape = (ny, nx) if dim == 2 else (nz, ny, nx)
+            out["mask"] = rng.uniform(size=shape) < 0.35
+    if case["n_specified"]:
+        # smooth specified drift fields evaluated at data and at prediction points
+        def field(j, P):
+            return np.cos(P[:, 0] / (180.0 + 40.0 * j)) + 0.5 * np.sin(P[:, 1] / (220.0 - 30.0 * j))
+        out["spec_data"] = [field(j, xyz) for j in range(case["n_specified"])]
+        if case["style"] == "points":
+            out["spec_pts"] = [field(j, out["points"]) for j in range(case["n_specified"])]
+        else:
+            if dim == 2:
+                gx, gy = np.meshgrid(out["axes"][0], out["axes"][1])
+                P = np.column_stack((gx.ravel(), gy.ravel()))
+                out["spec_pts"] = [field(j, P).reshape(gx.shape) for j in range(case["n_specified"])]
+            else:
+                gz, gy, gx = np.meshgrid(out["axes"][2], out["axes"][1], out["axes"][0], indexing="ij")
+                P = np.column_stack((gx.ravel(), gy.ravel(), gz.ravel()))
+                out["spec_pts"] = [field(j, P).reshape(gx.shape) for j in range(case["n_specified"])]
+    if case["external_z"]:
+        ex = np.linspace(-50.0, 1050.0, 45)
+        ey = np.linspace(-50.0, 1050.0, 38)
+        gx, gy = np.meshgrid(ex, ey)
+        out["ext_x"], out["ext_y"] = ex, ey
+        out["ext_z"] = 20.0 + 0.01 * gx + 5.0 * np.sin(gy / 170.0)
+    return out
+
+
+def make_model(module_ns, case, inp, reference=False):
+    """Instantiate the kriging class named by the case from `module_ns` (the reference package or
+    pykrige_b200)."""
+    cls = {"OK": "OrdinaryKriging", "UK": "UniversalKriging", "OK3D": "OrdinaryKriging3D",
+           "UK3D": "UniversalKriging3D"}[case["cls"]]
+    K = getattr(module_ns, cls)
+    xyz, val = inp["data"], inp["values"]
+    kw = dict(variogram_model=case["model"], variogram_parameters=list(case["params"]),
+              exact_values=case["exact_values"])
+    kw.update(case["ctor"])
+    if case["cls"] in ("UK", "UK3D"):
+        kw["drift_terms"] = list(case["drift_terms"])
+        if case["functional"]:
+            kw["functional_drift"] = [FUNCS[f] for f in case["functional"]]
+        if case["n_specified"]:
+            kw["specified_drift"] = [np.array(a) for a in inp["spec_data"]]
+        if case["point_log"] is not None:
+            kw["point_drift"] = np.array(case["point_log"])
+        if case["external_z"]:
+            kw["external_drift"] = inp["ext_z"]
+            kw["external_drift_x"] = inp["ext_x"]
+            kw["external_drift_y"] = inp["ext_y"]
+    if case["dim"] == 2:
+        return K(xyz[:, 0], xyz[:, 1], val, **kw)
+    return K(xyz[:, 0], xyz[:, 1], xyz[:, 2], val, **kw)
+
+
+def run_model(model, case, inp, backend):
+    """Call execute() the way a user would; returns (z, ss) as plain arrays + optional mask."""
+    style = case["style"]
+    kw = dict(backend=backend)
+    if case["k"] is not None:
+        kw["n_closest_points"] = case["k"]
+    if case["n_specified"]:
+        kw["specified_drift_arrays"] = [np.array(a) for a in inp["spec_pts"]]
+    if style == "points":
+        P = inp["points"]
+        args = [P[:, c] for c in range(case["dim"])]
+    else:
+        args = list(inp["axes"])
+    if style == "masked":
+        kw["mask"] = inp["mask"]
+    z, ss = model.execute(style, *args, **kw)
+    return z, ss

@@ -1,0 +1,77 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference (imported from
+/root/reference/src — only available in the build container, never on the GPU box).
+
+    python tests/golden/make_golden.py
+
+Writes
+  tests/golden/reference_goldens.npz : the reference's own test vectors (tests/test_core.py:28-42,
+      490-507, 707-725, 1957-1989): 15 data points, KT3D_H2O OK/UK answers on the 100x100 grid,
+      KT3D 3-D data + (z, sigma^2) answers.
+  tests/golden/ref_cases.npz : (z, sigmasq) of reference.execute(backend='vectorized'|'loop') for every
+      seeded case of tests/cases.py.
+The O(N^4) constructor statistics of OK3D/UK/UK3D are patched out; nothing else of the
+reference is touched.
+"""
+import os
+import sys
+import time
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, "/root/reference/src")
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import pykrige  # noqa: E402  (the reference)
+import pykrige.ok3d, pykrige.uk, pykrige.uk3d  # noqa: E402,E401
+import pykrige.kriging_tools as kt  # noqa: E402
+import cases  # noqa: E402
+
+assert pykrige.__file__.startswith("/root/reference"), pykrige.__file__
+
+
+def _no_stats(*a, **k):
+    return np.zeros(2), np.ones(2), np.zeros(2)
+
+
+for mod in (pykrige.ok3d, pykrige.uk, pykrige.uk3d):
+    mod._find_statistics = _no_stats
+
+
+def reference_goldens():
+    td = "/root/reference/tests/test_data"
+    data = np.genfromtxt(os.path.join(td, "test_data.txt"))
+    ok_ans, ok_gx, ok_gy, _, _ = kt.read_asc_grid(os.path.join(td, "test1_answer.asc"), footer=2)
+    uk_ans, uk_gx, uk_gy, _, _ = kt.read_asc_grid(os.path.join(td, "test2_answer.asc"), footer=2)
+    d3 = np.genfromtxt(os.path.join(td, "test3d_data.txt"), skip_header=1)
+    a3 = np.genfromtxt(os.path.join(td, "test3d_answer.txt"))
+    ext_ans, ext_gx, ext_gy, _, _ = kt.read_asc_grid(os.path.join(td, "test3_answer.asc"))
+    dem, dem_x, dem_y, _, _ = kt.read_asc_grid(os.path.join(td, "test3_dem.asc"))
+    np.savez_compressed(
+        os.path.join(HERE, "reference_goldens.npz"),
+        data=data, ok_answer=np.asarray(ok_ans), ok_gridx=ok_gx, ok_gridy=ok_gy,
+        uk_answer=np.asarray(uk_ans), uk_gridx=uk_gx, uk_gridy=uk_gy,
+        data3d=d3, answer3d=a3,
+        ext_answer=np.asarray(ext_ans), ext_gridx=ext_gx, ext_gridy=ext_gy,
+        dem=np.asarray(dem), dem_x=dem_x, dem_y=dem_y,
+    )
+
+
+def ref_cases():
+    out = {}
+    for case in cases.CASES:
+        t0 = time.time()
+        inp = cases.build_inputs(case)
+        model = cases.make_model(pykrige, case, inp, reference=True)
+        z, ss = cases.run_model(model, case, inp, case["ref_backend"])
+        out[case["name"] + "/z"] = np.asarray(np.ma.getdata(z), dtype=np.float64)
+        out[case["name"] + "/ss"] = np.asarray(np.ma.getdata(ss), dtype=np.float64)
+        # a cheap fingerprint of the inputs so a drifting RNG is detected by the tests
+        out[case["name"] + "/fp"] = np.array([inp["data"].sum(), inp["values"].sum()])
+        print("%-28s %6.2fs  z[%s] mean=%.6f" % (case["name"], time.time() - t0, z.shape, float(np.mean(z))))
+    np.savez_compressed(os.path.join(HERE, "ref_cases.npz"), **out)
+
+
+if __name__ == "__main__":
+    reference_goldens()
+    ref_cases()

@@ -1,0 +1,111 @@
+"""CPU tests: the oracle (oracle/krige_oracle.py) is pinned against (a) the reference's own golden
+vectors and (b) outputs of the imported reference for every seeded case (tests/golden/*.npz)."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import cases
+from conftest import assert_parity
+from oracle import krige_oracle as ko
+
+
+def _oracle_case(case, inp):
+    dim = case["dim"]
+    ctor = case["ctor"]
+    if dim == 2:
+        scaling = [ctor.get("anisotropy_scaling", 1.0)]
+        angle = [ctor.get("anisotropy_angle", 0.0)]
+    else:
+        scaling = [ctor.get("anisotropy_scaling_y", 1.0), ctor.get("anisotropy_scaling_z", 1.0)]
+        angle = [ctor.get("anisotropy_angle_x", 0.0), ctor.get("anisotropy_angle_y", 0.0),
+                 ctor.get("anisotropy_angle_z", 0.0)]
+    stored = ko.stored_parameters(case["model"], case["params"])
+    xyz = inp["data"]
+    pts = inp["points"] if case["style"] == "points" else ko.grid_points(inp["axes"])
+    center = (xyz.max(axis=0) + xyz.min(axis=0)) / 2.0
+    P = ko.adjust_for_anisotropy(xyz, center, scaling, angle)
+    Q = ko.adjust_for_anisotropy(pts, center, scaling, angle)
+    dd, pd = [], []
+    if case["point_log"] is not None:      # uk.py:884-896, 955-966 (wells in the adjusted frame)
+        wells = np.array(case["point_log"], dtype=float)
+        wxy = ko.adjust_for_anisotropy(wells[:, :2], center, scaling, angle)
+        for w in range(wells.shape[0]):
+            for X, lst in ((P, dd), (Q, pd)):
+                with np.errstate(divide="ignore"):
+                    ld = np.log(np.sqrt((X[:, 0] - wxy[w, 0]) ** 2 + (X[:, 1] - wxy[w, 1]) ** 2))
+                ld[np.isinf(ld)] = -100.0
+                lst.append(-wells[w, 2] * ld)
+    if case["external_z"]:                 # bilinear sample at ORIGINAL coordinates (uk.py:512-628)
+        from scipy.interpolate import RegularGridInterpolator
+        f = RegularGridInterpolator((inp["ext_y"], inp["ext_x"]), inp["ext_z"])
+        dd.append(f(np.column_stack((xyz[:, 1], xyz[:, 0]))))
+        pd.append(f(np.column_stack((pts[:, 1], pts[:, 0]))))
+    for j in range(case["n_specified"]):
+        dd.append(np.asarray(inp["spec_data"][j]).ravel())
+        pd.append(np.asarray(inp["spec_pts"][j]).ravel())
+    for fn in case["functional"]:          # evaluated with adjusted coordinates (uk.py:906-910)
+        f = cases.FUNCS[fn]
+        dd.append(f(*[P[:, c] for c in range(dim)]))
+        pd.append(f(*[Q[:, c] for c in range(dim)]))
+    z, ss = ko.krige(xyz, inp["values"], case["model"], stored, pts, scaling=scaling, angle=angle,
+                     regional_linear="regional_linear" in case["drift_terms"], data_drift=dd, point_drift=pd,
+                     exact_values=case["exact_values"], n_closest_points=case["k"])
+    return z, ss
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=[c["name"] for c in cases.CASES])
+def test_oracle_matches_reference_outputs(case, ref_cases):
+    inp = cases.build_inputs(case)
+    fp = ref_cases[case["name"] + "/fp"]
+    assert_allclose([inp["data"].sum(), inp["values"].sum()], fp, rtol=1e-13)
+    z, ss = _oracle_case(case, inp)
+    zr = ref_cases[case["name"] + "/z"].ravel()
+    sr = ref_cases[case["name"] + "/ss"].ravel()
+    if case["style"] == "masked":
+        keep = ~inp["mask"].ravel()
+        z, ss, zr, sr = z[keep], ss[keep], zr[keep], sr[keep]
+    # the oracle IS the reference's arithmetic: agreement to rounding of the dense inverse
+    assert_parity(z, zr, 1e-9, case["name"] + " z")
+    assert_parity(ss, sr, 1e-8, case["name"] + " ss")
+
+
+def test_oracle_vs_kt3d_ok(ref_goldens):
+    """tests/test_core.py:490-507: OK 2-D vs KT3D_H2O on the 100x100 grid."""
+    g = ref_goldens
+    d = g["data"]
+    pts = ko.grid_points([g["ok_gridx"], g["ok_gridy"]])
+    z, ss = ko.krige(d[:, :2], d[:, 2], "exponential", ko.stored_parameters("exponential", [500.0, 3000.0, 0.0]), pts)
+    assert_allclose(z.reshape(g["ok_answer"].shape), g["ok_answer"], rtol=1e-7)
+
+
+def test_oracle_vs_kt3d_uk(ref_goldens):
+    """tests/test_core.py:707-725: UK regional-linear vs KT3D_H2O."""
+    g = ref_goldens
+    d = g["data"]
+    pts = ko.grid_points([g["uk_gridx"], g["uk_gridy"]])
+    z, ss = ko.krige(d[:, :2], d[:, 2], "exponential", ko.stored_parameters("exponential", [500.0, 3000.0, 0.0]),
+                     pts, regional_linear=True)
+    assert_allclose(z.reshape(g["uk_answer"].shape), g["uk_answer"], rtol=1e-7)
+
+
+def test_oracle_vs_kt3d_3d(ref_goldens):
+    """tests/test_core.py:1957-1989: OK3D vs KT3D, z and sigma^2, rtol 1e-3; and the moving window
+    with k=10 equals the full answer (tests/test_core.py:1992-2017)."""
+    g = ref_goldens
+    d = g["data3d"]
+    ax = np.arange(10.0)
+    pts = ko.grid_points([ax, ax, ax])
+    z, ss = ko.krige(d[:, :3], d[:, 3], "linear", [1.0, 0.1], pts)
+    assert_allclose(z, g["answer3d"][:, 0], rtol=1e-3, atol=1e-8)
+    assert_allclose(ss, g["answer3d"][:, 1], rtol=1e-3, atol=1e-8)
+    z, ss = ko.krige(d[:, :3], d[:, 3], "linear", [1.0, 0.1], pts, n_closest_points=10)
+    assert_allclose(z, g["answer3d"][:, 0], rtol=1e-3)
+    assert_allclose(ss, g["answer3d"][:, 1], rtol=1e-3)
+
+
+def test_oracle_kitanidis():
+    """Kitanidis example 3.2 (tests/test_core.py:378-401): z = 1.6364, sigma^2 = 0.4201."""
+    data = np.array([[9.7, 47.6, 1.22], [43.8, 24.6, 2.822]])
+    z, ss = ko.krige(data[:, :2], data[:, 2], "linear", [0.006, 0.1], np.array([[18.8, 67.9]]))
+    assert z[0] == pytest.approx(1.6364, rel=1e-4)
+    assert ss[0] == pytest.approx(0.4201, rel=1e-4)
