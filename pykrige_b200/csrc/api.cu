@@ -41,6 +41,7 @@ struct kb200_ctx {
     DriftScale ds{};
     PackMap pm{};
     std::vector<double> hx, hy, hz, hval, hdrift;
+    double bb_lo[3] = {0, 0, 0}, bb_hi[3] = {0, 0, 0};   // adjusted bounding box of the data
 
     // blob (one allocation): header | consts | ax | ay | az | tiles
     DevBuf blob;
@@ -53,6 +54,7 @@ struct kb200_ctx {
     // knn workspace
     DevBuf kSorted, kCells;
     KnnParams kp{};
+    int k_ncells = 0;
 
     cudaEvent_t ev[16] = {};
     double tm[12] = {};
@@ -180,6 +182,7 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
             lo[r] = std::min(lo[r], v); hi[r] = std::max(hi[r], v);
         }
     }
+    for (int r = 0; r < 3; ++r) { h->bb_lo[r] = r < dim ? lo[r] : 0.0; h->bb_hi[r] = r < dim ? hi[r] : 0.0; }
     double diag2 = 0.0;
     for (int r = 0; r < dim; ++r) diag2 += (hi[r] - lo[r]) * (hi[r] - lo[r]);
     double c0 = host_gamma(h->vg, std::sqrt(diag2));
@@ -508,6 +511,185 @@ extern "C" int kb200_execute_grid(kb200_handle h, int64_t nx, int64_t ny, int64_
     h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
     h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
     return KB200_OK;
+}
+
+// ---- moving window ----------------------------------------------------------
+extern "C" int kb200_set_problem_knn(kb200_handle h, int dim, int64_t n,
+                                     const double* x, const double* y, const double* z, const double* values,
+                                     const double* center, const double* aniso,
+                                     int model, const double* vparams, int n_vparams, int exact_values, double eps) {
+    int rc = describe(h, true, dim, KB200_F64, n, x, y, z, values, center, aniso, model, vparams, n_vparams,
+                      exact_values, eps, 0, 0, nullptr);
+    if (rc != KB200_OK) return rc;
+    cudaStream_t st = h->stream;
+    const int nn = h->n, np = h->n_pad;
+    CU(h, h->wRaw.reserve((size_t)4 * nn * sizeof(double)));
+    double* raw = h->wRaw.as<double>();
+    double *rx = raw, *ry = raw + nn, *rz = raw + 2 * (size_t)nn, *rv = raw + 3 * (size_t)nn;
+    char* blob = h->blob.as<char>();
+    double* ax = reinterpret_cast<double*>(blob + h->off_ax);
+    double* ay = reinterpret_cast<double*>(blob + h->off_ay);
+    double* az = reinterpret_cast<double*>(blob + h->off_az);
+    int launches = 0;
+    CU(h, cudaEventRecord(h->ev[0], st));
+    CU(h, cudaMemcpyAsync(rx, h->hx.data(), nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(ry, h->hy.data(), nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(rz, h->hz.data(), nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(rv, h->hval.data(), nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemsetAsync(ax, 0, (size_t)np * 8, st));
+    CU(h, cudaMemsetAsync(ay, 0, (size_t)np * 8, st));
+    CU(h, cudaMemsetAsync(az, 0, (size_t)np * 8, st));
+    CU(h, kbk_adjust_data(h->dim, h->an, nn, rx, ry, rz, ax, ay, az, st)); ++launches;
+    CU(h, cudaEventRecord(h->ev[1], st));
+    // uniform cell grid with ~2 points per cell over the adjusted bounding box
+    KnnParams& kp = h->kp;
+    kp = KnnParams{};
+    double ext[3] = {0, 0, 0}, vol = 1.0; int live = 0;
+    for (int r = 0; r < h->dim; ++r) { ext[r] = h->bb_hi[r] - h->bb_lo[r]; if (ext[r] > 0.0) { vol *= ext[r]; ++live; } }
+    double cell = live ? std::pow(vol * 2.0 / (double)nn, 1.0 / live) : 1.0;
+    if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
+    int g[3] = {1, 1, 1};
+    for (;;) {
+        long long tot = 1;
+        for (int r = 0; r < h->dim; ++r) {
+            double cnt = std::floor(ext[r] / cell) + 1.0;
+            g[r] = (int)std::min(cnt, 4096.0);
+            tot *= g[r];
+        }
+        if (tot <= (1LL << 22)) break;
+        cell *= 1.5;
+    }
+    // a cell edge slightly larger than ext/g keeps every data point inside the grid after clamping
+    for (int r = 0; r < h->dim; ++r) if (g[r] == 4096) cell = std::max(cell, ext[r] / 4095.0);
+    kp.dim = h->dim; kp.n = nn; kp.gx = g[0]; kp.gy = g[1]; kp.gz = g[2];
+    kp.ox = h->bb_lo[0]; kp.oy = h->bb_lo[1]; kp.oz = h->bb_lo[2];
+    kp.cell = cell; kp.inv_cell = 1.0 / cell;
+    int ncells = g[0] * g[1] * g[2];
+    h->k_ncells = ncells;
+    CU(h, h->kSorted.reserve((size_t)nn * (4 * sizeof(double) + 2 * sizeof(int))));
+    CU(h, h->kCells.reserve((size_t)2 * (ncells + 1) * sizeof(int)));
+    CU(h, h->wFlag.reserve(256));
+    double* sx = h->kSorted.as<double>();
+    double *sy = sx + nn, *sz = sy + nn, *sv = sz + nn;
+    int* sorig = reinterpret_cast<int*>(sv + nn);
+    int* cell_of = sorig + nn;
+    int* cell_start = h->kCells.as<int>();
+    int* cursor = cell_start + (ncells + 1);
+    CU(h, kbk_knn_build(h->dim, nn, ax, ay, az, rv, kp, sx, sy, sz, sv, sorig, cell_of, cell_start, cursor,
+                        ncells, st, &launches));
+    CU(h, cudaEventRecord(h->ev[2], st));
+    CU(h, cudaStreamSynchronize(st));
+    h->tm[6] += ev_ms(h->ev[0], h->ev[1]);
+    h->tm[8] += ev_ms(h->ev[1], h->ev[2]);
+    h->launches += launches;
+    h->knn_ready = true;
+    return KB200_OK;
+}
+
+static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss) {
+    if (k < 2) return fail(h, KB200_EBADARG, "n_closest_points has to be at least two!");
+    if (k > h->n) return fail(h, KB200_EBADARG, "n_closest_points exceeds the number of data points");
+    if (kbk_knn_smem_per_warp(k) > 200 * 1024) return fail(h, KB200_EUNSUPPORTED, "n_closest_points too large for the shared-memory local solver");
+    cudaStream_t st = h->stream;
+    int* flag = h->wFlag.as<int>();
+    CU(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
+    KnnParams kp = h->kp;
+    kp.vg = h->vg; kp.an = h->an; kp.k = k;
+    PointSource ps{};
+    ps.grid = s.grid ? 1 : 0;
+    ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
+    ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz; ps.first = s.first;
+    kp.ps = ps; kp.m = s.count; kp.z_out = d_z; kp.ss_out = d_ss; kp.flag = flag;
+    CU(h, cudaEventRecord(h->ev[7], st));
+    CU(h, kbk_knn_solve(kp, st));
+    CU(h, cudaEventRecord(h->ev[8], st));
+    h->launches += 1; h->solve_launches += 1;
+    return KB200_OK;
+}
+
+static int knn_finish(kb200_ctx* h) {
+    int hflag = 0;
+    CU(h, cudaMemcpyAsync(&hflag, h->wFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->tm[9] += ev_ms(h->ev[7], h->ev[8]);
+    if (hflag) return fail(h, KB200_ESINGULAR, "Singular matrix");
+    return KB200_OK;
+}
+
+static int check_knn_ready(kb200_ctx* h) {
+    if (!h) return KB200_EBADARG;
+    if (!h->knn_ready) return fail(h, KB200_ESTATE, "call kb200_set_problem_knn first");
+    cudaSetDevice(h->device);
+    return KB200_OK;
+}
+
+extern "C" int kb200_execute_knn_grid_dev(kb200_handle h, int k, int64_t nx, int64_t ny, int64_t nz,
+                                          const double* d_gx, const double* d_gy, const double* d_gz,
+                                          int64_t first, int64_t count, double* d_z, double* d_ss) {
+    int rc = check_knn_ready(h); if (rc) return rc;
+    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
+        return fail(h, KB200_EBADARG, "bad grid slice");
+    if (count == 0) return KB200_OK;
+    if (!d_gx || !d_gy || (h->dim == 3 && !d_gz) || !d_z || !d_ss) return fail(h, KB200_EBADARG, "null pointer");
+    Src s{true, nx, ny, nz, d_gx, d_gy, d_gz, first, count, nullptr, 0, 0};
+    rc = run_knn(h, k, s, d_z, d_ss); if (rc) return rc;
+    return knn_finish(h);
+}
+
+extern "C" int kb200_execute_knn_grid(kb200_handle h, int k, int64_t nx, int64_t ny, int64_t nz,
+                                      const double* gx, const double* gy, const double* gz,
+                                      int64_t first, int64_t count, double* z_out, double* ss_out) {
+    int rc = check_knn_ready(h); if (rc) return rc;
+    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
+        return fail(h, KB200_EBADARG, "bad grid slice");
+    if (count == 0) return KB200_OK;
+    if (!gx || !gy || (h->dim == 3 && !gz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
+    cudaStream_t st = h->stream;
+    CU(h, h->wAxes.reserve((size_t)(nx + ny + nz) * 8));
+    CU(h, h->wOut.reserve((size_t)2 * count * 8));
+    double* da = h->wAxes.as<double>();
+    double* dout = h->wOut.as<double>();
+    CU(h, cudaEventRecord(h->ev[9], st));
+    CU(h, cudaMemcpyAsync(da, gx, nx * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(da + nx, gy, ny * 8, cudaMemcpyHostToDevice, st));
+    if (h->dim == 3) CU(h, cudaMemcpyAsync(da + nx + ny, gz, nz * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaEventRecord(h->ev[10], st));
+    Src s{true, nx, ny, nz, da, da + nx, da + nx + ny, first, count, nullptr, 0, 0};
+    rc = run_knn(h, k, s, dout, dout + count); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(z_out, dout, count * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(ss_out, dout + count, count * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaEventRecord(h->ev[11], st));
+    rc = knn_finish(h);
+    h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
+    h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
+    return rc;
+}
+
+extern "C" int kb200_execute_knn_points(kb200_handle h, int k, int64_t m,
+                                        const double* px, const double* py, const double* pz,
+                                        double* z_out, double* ss_out) {
+    int rc = check_knn_ready(h); if (rc) return rc;
+    if (m <= 0) return KB200_OK;
+    if (!px || !py || (h->dim == 3 && !pz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
+    cudaStream_t st = h->stream;
+    CU(h, h->wPts.reserve((size_t)3 * m * 8));
+    CU(h, h->wOut.reserve((size_t)2 * m * 8));
+    double* dp = h->wPts.as<double>();
+    double* dout = h->wOut.as<double>();
+    CU(h, cudaEventRecord(h->ev[9], st));
+    CU(h, cudaMemcpyAsync(dp, px, m * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(dp + m, py, m * 8, cudaMemcpyHostToDevice, st));
+    if (h->dim == 3) CU(h, cudaMemcpyAsync(dp + 2 * m, pz, m * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaEventRecord(h->ev[10], st));
+    Src s{false, 0, 0, 0, dp, dp + m, dp + 2 * m, 0, m, nullptr, 0, 0};
+    rc = run_knn(h, k, s, dout, dout + m); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(z_out, dout, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(ss_out, dout + m, m * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaEventRecord(h->ev[11], st));
+    rc = knn_finish(h);
+    h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
+    h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
+    return rc;
 }
 
 // ---- debug taps (tests only) ------------------------------------------------

@@ -69,7 +69,8 @@ struct KnnParams {
     Aniso an;
     PointSource ps;
     int dim, n, k;
-    const double* ax; const double* ay; const double* az; const double* values;  // adjusted data (cell-sorted order)
+    const double* ax; const double* ay; const double* az; const double* values;  // adjusted data, cell-sorted
+    const int* sorig;          // original index of each sorted point (deterministic tie-break)
     // uniform cell grid over the adjusted data
     int gx, gy, gz;
     double ox, oy, oz, inv_cell, cell;
@@ -79,7 +80,7 @@ struct KnnParams {
     int* flag;                 // singular local system
 };
 cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, const double* az, const double* values,
-                          KnnParams& kp, double* sx, double* sy, double* sz, double* sv,
-                          int* cell_of, int* cell_start, int* cursor, int max_cells, cudaStream_t st, int* launches);
+                          KnnParams& kp, double* sx, double* sy, double* sz, double* sv, int* sorig,
+                          int* cell_of, int* cell_start, int* cursor, int ncells, cudaStream_t st, int* launches);
 cudaError_t kbk_knn_solve(const KnnParams& p, cudaStream_t st);
-size_t      kbk_knn_smem(int k);
+size_t      kbk_knn_smem_per_warp(int k);

@@ -1,16 +1,352 @@
-// knn.cu — moving-window kriging (n_closest_points): exact kNN on a uniform cell grid +
-// per-point local (k+1)x(k+1) solve.  (ok.py:722-758, 929-986; cok.pyx:98-193)
+// knn.cu — moving-window kriging (n_closest_points = k).
+//
+// Reference semantics (ok.py:722-758, 929-986; native twin cok.pyx:98-193):
+//   per prediction point: the k nearest data points (cKDTree.query(k, eps=0.0): exact, sorted by
+//   distance), local system a = A_full[idx+{n}, idx+{n}] (zero diagonal, ones border), b = -gamma(d)
+//   (0 on exact hits), x = solve(a, b) (dgesv), z = x[:k].Z[idx], sigma2 = -x.b.
+// The reference gathers the local block from the full N x N matrix (80 GB at N = 1e5);
+// here the block is assembled on the fly from the neighbour coordinates.
+//
+// K4 (search): uniform cell grid over the adjusted data (counting sort by cell); one warp per
+//     prediction point grows a block of cells until the k-th candidate lies inside the visited
+//     region, then a warp bitonic sort yields the k nearest in ascending distance (ties by index).
+// K5 (solve): same warp assembles the k x k shifted covariance block C = c0 - gamma (diag c0) in
+//     shared memory and runs LU with partial pivoting (two right-hand sides c and 1); the ordinary
+//     kriging weights follow from the bordered-system identities.
 #include "common.cuh"
 #include "kernels.h"
+#include <cfloat>
+#include <algorithm>
 
-struct kb200_ctx;
-extern "C" int kb200_set_problem_knn(kb200_handle, int, int64_t, const double*, const double*, const double*,
-                                     const double*, const double*, const double*, int, const double*, int, int, double) {
-    return KB200_EUNSUPPORTED;
+#define KN_CAP 512          // candidate buffer (per warp)
+
+__global__ void knn_count_kernel(int dim, int n, const double* __restrict__ ax, const double* __restrict__ ay,
+                                 const double* __restrict__ az, KnnParams kp, int* __restrict__ cell_of,
+                                 int* __restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cx = min(kp.gx - 1, max(0, (int)floor((ax[i] - kp.ox) * kp.inv_cell)));
+    int cy = min(kp.gy - 1, max(0, (int)floor((ay[i] - kp.oy) * kp.inv_cell)));
+    int cz = dim == 3 ? min(kp.gz - 1, max(0, (int)floor((az[i] - kp.oz) * kp.inv_cell))) : 0;
+    int c = (cz * kp.gy + cy) * kp.gx + cx;
+    cell_of[i] = c;
+    atomicAdd(&counts[c], 1);
 }
-extern "C" int kb200_execute_knn_points(kb200_handle, int, int64_t, const double*, const double*, const double*,
-                                        double*, double*) { return KB200_EUNSUPPORTED; }
-extern "C" int kb200_execute_knn_grid(kb200_handle, int, int64_t, int64_t, int64_t, const double*, const double*,
-                                      const double*, int64_t, int64_t, double*, double*) { return KB200_EUNSUPPORTED; }
-extern "C" int kb200_execute_knn_grid_dev(kb200_handle, int, int64_t, int64_t, int64_t, const double*, const double*,
-                                          const double*, int64_t, int64_t, double*, double*) { return KB200_EUNSUPPORTED; }
+
+// exclusive scan of counts[0..ncells) into start[0..ncells], single block
+__global__ void __launch_bounds__(1024) knn_scan_kernel(int ncells, const int* __restrict__ counts, int* __restrict__ start) {
+    __shared__ int part[1024];
+    int tid = threadIdx.x;
+    int per = (ncells + 1023) / 1024;
+    int b = tid * per, e = min(ncells, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += counts[i];
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int run = tid ? part[tid - 1] : 0;
+    for (int i = b; i < e; ++i) { start[i] = run; run += counts[i]; }
+    if (tid == 1023) start[ncells] = part[1023];
+}
+
+// counting-sort scatter. The position inside a cell depends on atomics, but the neighbour ORDER used
+// by the solve is fixed by the final sort (distance, then original index), so results are deterministic.
+__global__ void knn_scatter_kernel(int n, const int* __restrict__ cell_of, const int* __restrict__ start,
+                                   int* __restrict__ cursor, const double* __restrict__ ax,
+                                   const double* __restrict__ ay, const double* __restrict__ az,
+                                   const double* __restrict__ val, double* __restrict__ sx, double* __restrict__ sy,
+                                   double* __restrict__ sz, double* __restrict__ sv, int* __restrict__ sorig) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cell_of[i];
+    int pos = start[c] + atomicAdd(&cursor[c], 1);
+    sx[pos] = ax[i]; sy[pos] = ay[i]; sz[pos] = az[i]; sv[pos] = val[i]; sorig[pos] = i;
+}
+
+// ---- warp helpers -----------------------------------------------------------
+__device__ __forceinline__ bool cand_less(double da, int ia, double db, int ib) {
+    return da < db || (da == db && ia < ib);
+}
+
+// ascending bitonic sort of (d2[], id[]) of length `len` (power of two) by one warp
+__device__ __forceinline__ void warp_bitonic(double* d2, int* id, const int* __restrict__ sorig, int len, int lane) {
+    for (int size = 2; size <= len; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (len >> 1); t += 32) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                double dl = d2[lo], dh = d2[hi];
+                int il = id[lo], ih = id[hi];
+                int ol = il >= 0 ? sorig[il] : 0x7fffffff, oh = ih >= 0 ? sorig[ih] : 0x7fffffff;
+                bool sw = up ? cand_less(dh, oh, dl, ol) : cand_less(dl, ol, dh, oh);
+                if (sw) { d2[lo] = dh; d2[hi] = dl; id[lo] = ih; id[hi] = il; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int DIM, int MODEL>
+__global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ KnnParams P, int warps_per_cta,
+                                                         int per_warp_doubles) {
+    extern __shared__ __align__(16) double ksm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= warps_per_cta) return;
+    const long long p = (long long)blockIdx.x * warps_per_cta + warp;
+    if (p >= P.m) return;
+    const int k = P.k;
+    const int S = k | 1;                       // odd row stride: conflict-free column walks
+    double* base = ksm + (size_t)warp * per_warp_doubles;
+    double* A = base;                          // k * S  (aliased by the candidate buffers during the search)
+    size_t a_doubles = (size_t)k * S;
+    size_t cand_doubles = KN_CAP + KN_CAP / 2; // d2[CAP] doubles + id[CAP] ints
+    size_t off = a_doubles > cand_doubles ? a_doubles : cand_doubles;
+    double* rc = base + off;                   // rhs c (becomes C^-1 c)
+    double* r1 = rc + k;                       // rhs 1 (becomes C^-1 1)
+    double* cv = r1 + k;                       // c kept for sigma^2
+    double* nx = cv + k; double* ny = nx + k; double* nz = ny + k; double* nv = nz + k;
+    double* cd2 = base;
+    int* cid = reinterpret_cast<int*>(base + KN_CAP);
+
+    double qx, qy, qz;
+    kb_load_point<DIM>(P.ps, P.an, p, qx, qy, qz);
+
+    // ---------------- K4: exact k nearest ----------------
+    const int cqx = min(P.gx - 1, max(0, (int)floor((qx - P.ox) * P.inv_cell)));
+    const int cqy = min(P.gy - 1, max(0, (int)floor((qy - P.oy) * P.inv_cell)));
+    const int cqz = DIM == 3 ? min(P.gz - 1, max(0, (int)floor((qz - P.oz) * P.inv_cell))) : 0;
+    int cnt = 0;
+    int r = 0;
+    int px0 = 0, px1 = -1, py0 = 0, py1 = -1, pz0 = 0, pz1 = -1;      // block already visited
+    auto compact = [&](int keep) {
+        int len = 1; while (len < cnt) len <<= 1;
+        for (int t = cnt + lane; t < len; t += 32) { cd2[t] = DBL_MAX; cid[t] = -1; }
+        __syncwarp();
+        warp_bitonic(cd2, cid, P.sorig, len, lane);
+        cnt = min(cnt, keep);
+    };
+    for (;;) {
+        const int x0 = max(0, cqx - r), x1 = min(P.gx - 1, cqx + r);
+        const int y0 = max(0, cqy - r), y1 = min(P.gy - 1, cqy + r);
+        const int z0 = DIM == 3 ? max(0, cqz - r) : 0, z1 = DIM == 3 ? min(P.gz - 1, cqz + r) : 0;
+        for (int cz = z0; cz <= z1; ++cz)
+            for (int cy = y0; cy <= y1; ++cy) {
+                const bool inner_row = (cz >= pz0 && cz <= pz1 && cy >= py0 && cy <= py1);
+                // cells of this row not visited before: [x0, px0) and (px1, x1] when the row was inside the old block
+                for (int seg = 0; seg < 2; ++seg) {
+                    int sx0, sx1;
+                    if (!inner_row) { if (seg) break; sx0 = x0; sx1 = x1; }
+                    else if (seg == 0) { sx0 = x0; sx1 = px0 - 1; }
+                    else { sx0 = px1 + 1; sx1 = x1; }
+                    if (sx0 > sx1) continue;
+                    const int rowbase = (cz * P.gy + cy) * P.gx;
+                    const int b = P.cell_start[rowbase + sx0], e = P.cell_start[rowbase + sx1 + 1];
+                    for (int i0 = b; i0 < e; i0 += 32) {
+                        int i = i0 + lane;
+                        bool ok = i < e;
+                        double d2 = 0.0;
+                        if (ok) {
+                            double dx = P.ax[i] - qx, dy = P.ay[i] - qy;
+                            d2 = dx * dx + dy * dy;
+                            if (DIM == 3) { double dz = P.az[i] - qz; d2 += dz * dz; }
+                        }
+                        unsigned msk = __ballot_sync(0xffffffffu, ok);
+                        int pos = cnt + __popc(msk & ((1u << lane) - 1u));
+                        if (ok) { cd2[pos] = d2; cid[pos] = i; }
+                        cnt += __popc(msk);
+                        __syncwarp();
+                        if (cnt > KN_CAP - 32) compact(k);
+                    }
+                }
+            }
+        px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
+        // distance from the query to the nearest face of the visited block that still has cells behind it
+        double dout = DBL_MAX;
+        if (x0 > 0) dout = fmin(dout, qx - (P.ox + x0 * P.cell));
+        if (x1 < P.gx - 1) dout = fmin(dout, (P.ox + (x1 + 1) * P.cell) - qx);
+        if (y0 > 0) dout = fmin(dout, qy - (P.oy + y0 * P.cell));
+        if (y1 < P.gy - 1) dout = fmin(dout, (P.oy + (y1 + 1) * P.cell) - qy);
+        if (DIM == 3) {
+            if (z0 > 0) dout = fmin(dout, qz - (P.oz + z0 * P.cell));
+            if (z1 < P.gz - 1) dout = fmin(dout, (P.oz + (z1 + 1) * P.cell) - qz);
+        }
+        if (dout == DBL_MAX) break;                    // whole grid visited
+        int inside = 0;
+        if (dout > 0.0) {
+            double lim = dout * dout;
+            for (int t = lane; t < cnt; t += 32) inside += (cd2[t] <= lim) ? 1 : 0;
+            for (int o = 16; o > 0; o >>= 1) inside += __shfl_xor_sync(0xffffffffu, inside, o);
+        }
+        if (inside >= k) break;
+        r += (r < 2) ? 1 : (r >> 1) + 1;               // grow the block
+    }
+    compact(k);                                        // ascending distance, first k are the neighbours
+    // neighbours -> per-warp arrays (these live outside the region the candidate buffers alias)
+    VgParams vg = P.vg;
+    if (MODEL == KB200_VG_LINEAR || MODEL == KB200_VG_POWER) {
+        // unbounded models: local shift c0 = gamma(2 d_k) >= gamma of any neighbour pair
+        double dk = sqrt(cd2[k - 1]);
+        double g = kb_gamma<MODEL>(vg, 2.0 * dk);
+        vg.c0 = g > 0.0 ? g : 1.0;
+    }
+    for (int t = lane; t < k; t += 32) {
+        int i = cid[t];
+        nx[t] = P.ax[i]; ny[t] = P.ay[i]; nz[t] = DIM == 3 ? P.az[i] : 0.0; nv[t] = P.values[i];
+        double c = kb_cov_rhs<MODEL>(vg, sqrt(cd2[t]));
+        rc[t] = c; cv[t] = c; r1[t] = 1.0;
+    }
+    __syncwarp();                                      // candidates consumed: A may be overwritten now
+
+    // ---------------- K5: local system ----------------
+    // C[i][j] = c0 - gamma(|x_i - x_j|), C[i][i] = c0   (ok.py:641-644 in covariance form)
+    for (int e = lane; e < k * k; e += 32) {
+        int i = e / k, j = e - i * k;
+        double v;
+        if (i == j) v = vg.c0;
+        else {
+            double d = kb_dist<DIM>(nx[i], ny[i], nz[i], nx[j], ny[j], nz[j]);
+            v = vg.c0 - kb_gamma<MODEL>(vg, d);
+        }
+        A[i * S + j] = v;
+    }
+    __syncwarp();
+    // LU with partial pivoting (dgesv semantics, cok.pyx:165-174), both right-hand sides carried along
+    bool singular = false;
+    for (int pcol = 0; pcol < k; ++pcol) {
+        double best = -1.0; int bi = pcol;
+        for (int i = pcol + lane; i < k; i += 32) {
+            double v = fabs(A[i * S + pcol]);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (!(best > 0.0)) { singular = true; break; }
+        if (bi != pcol) {
+            for (int j = lane; j < k; j += 32) {
+                double t = A[pcol * S + j]; A[pcol * S + j] = A[bi * S + j]; A[bi * S + j] = t;
+            }
+            if (lane == 0) {
+                double t = rc[pcol]; rc[pcol] = rc[bi]; rc[bi] = t;
+                t = r1[pcol]; r1[pcol] = r1[bi]; r1[bi] = t;
+            }
+            __syncwarp();
+        }
+        const double inv = 1.0 / A[pcol * S + pcol];
+        const double bc = rc[pcol], b1 = r1[pcol];
+        for (int i = pcol + 1 + lane; i < k; i += 32) {
+            double l = A[i * S + pcol] * inv;
+            A[i * S + pcol] = l;
+            rc[i] -= l * bc;
+            r1[i] -= l * b1;
+        }
+        __syncwarp();
+        // rank-1 update of the trailing block: lanes across columns, rows unrolled by 4
+        for (int j0 = pcol + 1; j0 < k; j0 += 32) {
+            int j = j0 + lane;
+            bool ok = j < k;
+            double u = ok ? A[pcol * S + j] : 0.0;
+            int i = pcol + 1;
+            for (; i + 3 < k; i += 4) {
+                double l0 = A[i * S + pcol], l1 = A[(i + 1) * S + pcol], l2 = A[(i + 2) * S + pcol], l3 = A[(i + 3) * S + pcol];
+                if (ok) {
+                    A[i * S + j] -= l0 * u; A[(i + 1) * S + j] -= l1 * u;
+                    A[(i + 2) * S + j] -= l2 * u; A[(i + 3) * S + j] -= l3 * u;
+                }
+            }
+            for (; i < k; ++i) { double l = A[i * S + pcol]; if (ok) A[i * S + j] -= l * u; }
+        }
+        __syncwarp();
+    }
+    if (singular) {
+        if (lane == 0) { atomicExch(P.flag, 1); P.z_out[p] = 0.0; P.ss_out[p] = 0.0; }
+        return;
+    }
+    // back substitution U x = y for both right-hand sides
+    for (int pcol = k - 1; pcol >= 0; --pcol) {
+        const double inv = 1.0 / A[pcol * S + pcol];
+        const double xc = rc[pcol] * inv, x1 = r1[pcol] * inv;
+        __syncwarp();
+        if (lane == 0) { rc[pcol] = xc; r1[pcol] = x1; }
+        for (int i = lane; i < pcol; i += 32) {
+            double u = A[i * S + pcol];
+            rc[i] -= u * xc;
+            r1[i] -= u * x1;
+        }
+        __syncwarp();
+    }
+    // bordered-system identities: mu = (1'C^-1 c - 1)/(1'C^-1 1); lambda = C^-1 c - mu C^-1 1
+    double s1 = 0.0, sc = 0.0;
+    for (int t = lane; t < k; t += 32) { s1 += r1[t]; sc += rc[t]; }
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); sc += __shfl_xor_sync(0xffffffffu, sc, o); }
+    const double mu = (sc - 1.0) / s1;
+    double zz = 0.0, lc = 0.0;
+    for (int t = lane; t < k; t += 32) {
+        double lam = rc[t] - mu * r1[t];
+        zz += lam * nv[t];
+        lc += lam * cv[t];
+    }
+    for (int o = 16; o > 0; o >>= 1) { zz += __shfl_xor_sync(0xffffffffu, zz, o); lc += __shfl_xor_sync(0xffffffffu, lc, o); }
+    if (lane == 0) {
+        P.z_out[p] = zz;                       // ok.py:755
+        P.ss_out[p] = vg.c0 - lc - mu;       // ok.py:756 (= -x.b) in covariance form
+    }
+}
+
+// ---- host side -------------------------------------------------------------
+size_t kbk_knn_smem_per_warp(int k) {
+    size_t S = (size_t)(k | 1);
+    size_t a = (size_t)k * S, c = KN_CAP + KN_CAP / 2;
+    return ((a > c ? a : c) + 7 * (size_t)k + 2) * sizeof(double);
+}
+
+template <int DIM>
+static cudaError_t knn_launch_dim(const KnnParams& p, cudaStream_t st) {
+    size_t per = kbk_knn_smem_per_warp(p.k);
+    int wpc = (int)std::min<size_t>(8, (200 * 1024) / per);
+    if (wpc < 1) return cudaErrorInvalidValue;
+    // keep several CTAs per SM resident when k is small
+    while (wpc > 1 && per * wpc > 100 * 1024) --wpc;
+    size_t smem = per * wpc;
+    unsigned grid = (unsigned)((p.m + wpc - 1) / wpc);
+    int per_d = (int)(per / sizeof(double));
+    switch (p.vg.model) {
+#define KB_CASE(M) case M: { \
+        cudaError_t e = cudaFuncSetAttribute(knn_solve_kernel<DIM, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e; \
+        knn_solve_kernel<DIM, M><<<grid, wpc * 32, smem, st>>>(p, wpc, per_d); } break;
+        KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+#undef KB_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_knn_solve(const KnnParams& p, cudaStream_t st) {
+    return p.dim == 2 ? knn_launch_dim<2>(p, st) : knn_launch_dim<3>(p, st);
+}
+
+cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, const double* az, const double* values,
+                          KnnParams& kp, double* sx, double* sy, double* sz, double* sv, int* sorig,
+                          int* cell_of, int* cell_start, int* cursor, int ncells, cudaStream_t st, int* launches) {
+    KB_CUDA_OK(cudaMemsetAsync(cursor, 0, (size_t)(ncells + 1) * sizeof(int), st));
+    KB_CUDA_OK(cudaMemsetAsync(cell_start, 0, (size_t)(ncells + 1) * sizeof(int), st));
+    int g = (n + 255) / 256;
+    // counts go to `cursor` first, the scan writes cell_start, then cursor is re-zeroed for the scatter
+    knn_count_kernel<<<g, 256, 0, st>>>(dim, n, ax, ay, az, kp, cell_of, cursor);
+    knn_scan_kernel<<<1, 1024, 0, st>>>(ncells, cursor, cell_start);
+    KB_CUDA_OK(cudaMemsetAsync(cursor, 0, (size_t)(ncells + 1) * sizeof(int), st));
+    knn_scatter_kernel<<<g, 256, 0, st>>>(n, cell_of, cell_start, cursor, ax, ay, az, values, sx, sy, sz, sv, sorig);
+    *launches += 3;
+    kp.ax = sx; kp.ay = sy; kp.az = sz; kp.values = sv; kp.sorig = sorig; kp.cell_start = cell_start;
+    return cudaGetLastError();
+}

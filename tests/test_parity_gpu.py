@@ -1,0 +1,181 @@
+"""GPU parity tests (run with -m gpu on a B200): backend='cuda' through the C ABI vs
+ (a) the committed outputs of the imported reference (tests/golden/ref_cases.npz),
+ (b) the reference's own golden vectors (tests/golden/reference_goldens.npz),
+ (c) the CPU oracle on fresh seeded inputs, and size-independent properties at larger sizes.
+Tolerance (BASELINE.json north_star / SURVEY.md §8d): rtol = 1e-5, atol = 1e-5*max|ref| for fp64.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import cases
+from conftest import assert_parity
+
+pytestmark = pytest.mark.gpu
+R64 = 1e-5
+
+GLOBAL_CASES = [c for c in cases.CASES if c["k"] is None and c["name"] != "ok2d_hole_effect_small"]
+KNN_CASES = [c for c in cases.CASES if c["k"] is not None]
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import pykrige_b200
+    return pykrige_b200
+
+
+def _run(pk, case):
+    inp = cases.build_inputs(case)
+    model = cases.make_model(pk, case, inp)
+    z, ss = cases.run_model(model, case, inp, "cuda")
+    return inp, z, ss
+
+
+@pytest.mark.parametrize("case", GLOBAL_CASES, ids=[c["name"] for c in GLOBAL_CASES])
+def test_global_cases_match_reference(pk, case, ref_cases):
+    inp, z, ss = _run(pk, case)
+    zr, sr = ref_cases[case["name"] + "/z"], ref_cases[case["name"] + "/ss"]
+    assert z.shape == zr.shape
+    if case["style"] == "masked":
+        assert np.ma.is_masked(z) and np.ma.is_masked(ss)
+        assert np.array_equal(np.ma.getmaskarray(z), inp["mask"])
+        keep = ~inp["mask"]
+        z, ss, zr, sr = np.ma.getdata(z)[keep], np.ma.getdata(ss)[keep], zr[keep], sr[keep]
+    assert_parity(z, zr, R64, case["name"] + " z")
+    assert_parity(ss, sr, R64, case["name"] + " ss")
+
+
+@pytest.mark.parametrize("case", KNN_CASES, ids=[c["name"] for c in KNN_CASES])
+def test_moving_window_cases_match_reference(pk, case, ref_cases):
+    inp, z, ss = _run(pk, case)
+    assert_parity(z, ref_cases[case["name"] + "/z"], R64, case["name"] + " z")
+    assert_parity(ss, ref_cases[case["name"] + "/ss"], R64, case["name"] + " ss")
+
+
+def test_kt3d_ok_golden(pk, ref_goldens):
+    """tests/test_core.py:490-507 through backend='cuda'."""
+    g = ref_goldens
+    d = g["data"]
+    ok = pk.OrdinaryKriging(d[:, 0], d[:, 1], d[:, 2], variogram_model="exponential",
+                            variogram_parameters=[500.0, 3000.0, 0.0])
+    z, ss = ok.execute("grid", g["ok_gridx"], g["ok_gridy"], backend="cuda")
+    assert_allclose(z, g["ok_answer"], rtol=1e-6)
+
+
+def test_kt3d_uk_golden(pk, ref_goldens):
+    """tests/test_core.py:707-725 through backend='cuda'."""
+    g = ref_goldens
+    d = g["data"]
+    uk = pk.UniversalKriging(d[:, 0], d[:, 1], d[:, 2], variogram_model="exponential",
+                             variogram_parameters=[500.0, 3000.0, 0.0], drift_terms=["regional_linear"])
+    z, ss = uk.execute("grid", g["uk_gridx"], g["uk_gridy"], backend="cuda")
+    assert_allclose(z, g["uk_answer"], rtol=1e-6)
+
+
+def test_kt3d_3d_golden(pk, ref_goldens):
+    """tests/test_core.py:1957-2017 through backend='cuda' (global and k=10 moving window)."""
+    g = ref_goldens
+    d = g["data3d"]
+    ax = np.arange(10.0)
+    k3 = pk.OrdinaryKriging3D(d[:, 0], d[:, 1], d[:, 2], d[:, 3], variogram_model="linear",
+                              variogram_parameters=[1.0, 0.1])
+    k, ss = k3.execute("grid", ax, ax, ax, backend="cuda")
+    assert_allclose(k, g["answer3d"][:, 0].reshape(10, 10, 10), rtol=1e-3, atol=1e-8)
+    assert_allclose(ss, g["answer3d"][:, 1].reshape(10, 10, 10), rtol=1e-3, atol=1e-8)
+
+
+def test_ok3d_equals_ok2d_on_a_plane(pk, ref_goldens):
+    """tests/test_core.py:1914-1956: 3-D kriging with z == 0 reproduces the 2-D KT3D_H2O answer."""
+    g = ref_goldens
+    d = g["data"]
+    k3 = pk.OrdinaryKriging3D(d[:, 0], d[:, 1], np.zeros(d.shape[0]), d[:, 2], variogram_model="exponential",
+                              variogram_parameters=[500.0, 3000.0, 0.0])
+    k, ss = k3.execute("grid", g["ok_gridx"], g["ok_gridy"], np.array([0.0]), backend="cuda")
+    assert_allclose(np.squeeze(k), g["ok_answer"], rtol=1e-6)
+
+
+def test_exact_hits_interpolate(pk):
+    """tests/test_core.py:1510-1836: at data locations z == data and sigma^2 == 0 when exact_values."""
+    xyz, val = cases.synth_data(77, 300, 2)
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential",
+                            variogram_parameters=[1.0, 300.0, 0.05])
+    z, ss = ok.execute("points", xyz[:40, 0], xyz[:40, 1], backend="cuda")
+    assert_allclose(z, val[:40], rtol=1e-9)
+    assert np.max(np.abs(ss)) < 1e-9
+    ok2 = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential",
+                             variogram_parameters=[1.0, 300.0, 0.05], exact_values=False)
+    z2, ss2 = ok2.execute("points", xyz[:40, 0], xyz[:40, 1], backend="cuda")
+    assert np.all(ss2 > 1e-3)   # nugget smoothing: no longer exact (tests/test_core.py:430-487)
+
+
+def test_full_size_properties_cfg2(pk):
+    """BASELINE config 2 data size (N=5000, exponential) on a slab of the 1000x1000 grid:
+    size-independent checks — linearity of z in the data values, invariance of sigma^2 to the values,
+    shard concatenation == single call bit-for-bit, oracle agreement on a subsample."""
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(1002, 5000, 2)
+    gx = np.linspace(0.0, 1000.0, 1000)
+    gy = np.linspace(0.0, 1000.0, 1000)[:8]           # 8000 points of the grid
+    params = [1.0, 300.0, 0.05]
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential", variogram_parameters=params)
+    z, ss = ok.execute("grid", gx, gy, backend="cuda")
+    # linearity: krige(a*Z + b) == a*krige(Z) + b ; sigma^2 unchanged
+    ok2 = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], 3.0 * val - 7.0, variogram_model="exponential",
+                             variogram_parameters=params)
+    z2, ss2 = ok2.execute("grid", gx, gy, backend="cuda")
+    assert_allclose(z2, 3.0 * z - 7.0, rtol=1e-9)
+    assert_allclose(ss2, ss, rtol=1e-12, atol=1e-14)
+    # sharding determinism: two half slices concatenated == one call, bit for bit
+    h = ok._ensure_problem()
+    za, sa = h.execute_grid(gx, gy, None, None, 0, 3000)
+    zb, sb = h.execute_grid(gx, gy, None, None, 3000, 5000)
+    assert np.array_equal(np.concatenate([za, zb]), z.ravel())
+    assert np.array_equal(np.concatenate([sa, sb]), ss.ravel())
+    # oracle on a subsample of 256 grid points + 16 exact hits
+    rng = np.random.default_rng(5)
+    pick = rng.choice(z.size, 256, replace=False)
+    G = ko.grid_points([gx, gy])
+    pts = np.vstack([G[pick], xyz[:16]])
+    zo, so = ko.krige(xyz, val, "exponential", ko.stored_parameters("exponential", params), pts)
+    zc, sc = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
+    assert_parity(zc, zo, R64, "cfg2 z")
+    assert_parity(sc, so, R64, "cfg2 ss")
+    assert_allclose(z.ravel()[pick], zc[:256], rtol=1e-12)
+
+
+def test_invalid_variogram_is_reported(pk):
+    """hole-effect is not conditionally negative definite in 2-D for dense scatter: the covariance-form
+    factorisation must fail loudly (LinAlgError), never return numbers silently."""
+    xyz, val = cases.synth_data(9, 600, 2)
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="hole-effect",
+                            variogram_parameters=[1.0, 300.0, 0.05])
+    with pytest.raises(np.linalg.LinAlgError):
+        ok.execute("points", xyz[:4, 0] + 1.0, xyz[:4, 1], backend="cuda")
+
+
+def test_custom_variogram_not_on_device(pk):
+    xyz, val = cases.synth_data(3, 30, 2)
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="custom", variogram_parameters=[1.0, 0.1],
+                            variogram_function=lambda m, d: m[0] * d + m[1])
+    with pytest.raises(NotImplementedError):
+        ok.execute("points", [1.0], [2.0], backend="cuda")
+
+
+def test_intermediates_match_scipy(pk):
+    """White-box: the device Cholesky factor and its inverse agree with scipy on the same matrix."""
+    import scipy.linalg as sl
+    from scipy.spatial.distance import cdist
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(11, 700, 2)
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="spherical",
+                            variogram_parameters=[1.0, 400.0, 0.05])
+    h = ok._ensure_problem()
+    n, n_pad = 700, 768
+    L = h.debug_fetch(1, n_pad * n_pad).reshape(n_pad, n_pad)[:n, :n]
+    W = h.debug_fetch(2, n_pad * n_pad).reshape(n_pad, n_pad)[:n, :n]
+    c0 = 1.0
+    C = c0 - ko.variogram("spherical", [0.95, 400.0, 0.05], cdist(xyz, xyz))
+    np.fill_diagonal(C, c0)
+    Lr = sl.cholesky(C, lower=True)
+    assert_allclose(np.tril(L), Lr, rtol=1e-9, atol=1e-12)
+    assert_allclose(np.tril(W), sl.solve_triangular(Lr, np.eye(n), lower=True), rtol=1e-7, atol=1e-10)
