@@ -15,6 +15,7 @@
 // mbarrier) into a 3-stage ring; 8 warps issue m8n8k4 DMMA on a 32x64 sub-tile each.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 #define SV_STAGES 3
 #define SV_THREADS 256
@@ -188,6 +189,173 @@ __global__ void __launch_bounds__(SV_THREADS, 1) solve_kernel_f64(const __grid_c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3 v2: warp-specialised.  Warps 0..WS_NPROD-1 are producers: they issue the 32 KB bulk copies of
+// the W tiles and generate the RHS tiles (sqrt + variogram on the fp64 FMA pipe); warps
+// WS_NPROD..WS_NPROD+7 are consumers: nothing but LDS + DMMA on the tensor pipe. Stages are handed
+// over with mbarriers (full: TMA transaction bytes + one arrival per producer warp; empty: one arrival
+// per consumer warp), so RHS generation overlaps the tensor work instead of alternating with it
+// (v1 measured 54 % DMMA-pipe active with both phases serialised by __syncthreads).
+#define WS_NPROD 4
+#define WS_STAGES 4
+#define WS_THREADS ((WS_NPROD + 8) * 32)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+
+template <int DIM, int MODEL>
+__global__ void __launch_bounds__(WS_THREADS, 1) solve_kernel_ws(const __grid_constant__ SolveParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Ts = reinterpret_cast<double*>(smem_raw);                   // WS_STAGES * BM*BK
+    double* Bs = Ts + WS_STAGES * KB_BM * KB_BK;                        // WS_STAGES * BK*TN
+    double* red = Bs + WS_STAGES * KB_BK * KB_TN;                       // 8 * 64
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 8 * KB_TN);      // WS_STAGES
+    uint64_t* empty = full + WS_STAGES;                                 // WS_STAGES
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int jt = blockIdx.x;
+    const int I = P.nrb - 1 - (int)blockIdx.y;
+    const int nkt = P.pm.ktiles[I];
+    const double* gt = reinterpret_cast<const double*>(P.tiles) + (size_t)P.pm.tile_off[I] * (KB_BM * KB_BK);
+    constexpr uint32_t TILE_BYTES = KB_BM * KB_BK * sizeof(double);
+
+    if (tid == 0) {
+        for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full[s], 1 + WS_NPROD); mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int cw = warp - WS_NPROD;                     // consumer warp index 0..7 (negative: producer)
+    double qs[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { qs[nt][0] = 0.0; qs[nt][1] = 0.0; }
+
+    if (warp < WS_NPROD) {
+        // ===================== producers =====================
+        // thread -> one prediction point of the tile; it evaluates all 16 k of every tile for that point
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;\n");
+        // 128 producer threads: thread -> (point nl = tid & 63, k half kh = tid >> 6 -> k4 in {2kh, 2kh+1})
+        const int nl = tid & 63;
+        const int kh = tid >> 6;
+        const long long pj = (long long)jt * KB_TN + nl;
+        const bool pvalid = pj < P.m;
+        double px = 0.0, py = 0.0, pz = 0.0;
+        if (pvalid) kb_load_point<DIM>(P.ps, P.an, pj, px, py, pz);
+        for (int t = 0; t < nkt; ++t) {
+            const int s = t % WS_STAGES;
+            mbar_wait(&empty[s], (uint32_t)(((t / WS_STAGES) & 1) ^ 1));
+            if (tid == 0) {
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                bulk_g2s(Ts + (size_t)s * KB_BM * KB_BK, gt + (size_t)t * KB_BM * KB_BK, TILE_BYTES, &full[s]);
+            }
+            double* bs = Bs + (size_t)s * KB_BK * KB_TN;
+#pragma unroll
+            for (int kq = 0; kq < 2; ++kq) {
+                const int k4 = kh * 2 + kq;
+                double v[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = t * KB_BK + k4 * 4 + kk;
+                    double val = 0.0;
+                    if (pvalid && k < P.n) {
+                        double d = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), DIM == 3 ? __ldg(P.az + k) : 0.0, px, py, pz);
+                        val = kb_cov_rhs<MODEL>(P.vg, d);
+                    }
+                    v[kk] = val;
+                }
+                // fragment order: ((k4*8 + n/8)*32 + (n%8)*4 + k%4): 4 consecutive k = 32 contiguous bytes
+                double2* dst = reinterpret_cast<double2*>(bs + (k4 * 8 + (nl >> 3)) * 32 + (nl & 7) * 4);
+                dst[0] = make_double2(v[0], v[1]);
+                dst[1] = make_double2(v[2], v[3]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);       // release: the tile written by this warp is visible
+        }
+    } else {
+        // ===================== consumers =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
+        const int r0w = I * KB_BM + cw * 32;
+        int warp_kmax;
+        if (r0w + 31 >= P.n && r0w < P.n + P.na) warp_kmax = 0x7fffffff;
+        else if (r0w >= P.n + P.na) warp_kmax = -1;
+        else warp_kmax = r0w + 31;
+        double acc[4][8][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+        for (int t = 0; t < nkt; ++t) {
+            const int s = t % WS_STAGES;
+            // every consumer waits for every tile (also the ones it skips): a warp that raced ahead could
+            // otherwise arrive twice on empty[s] within one phase and release a stage that is still being read
+            mbar_wait(&full[s], (uint32_t)((t / WS_STAGES) & 1));
+            if (t * KB_BK <= warp_kmax) {
+                const double* ts = Ts + (size_t)s * KB_BM * KB_BK;
+                const double* bs = Bs + (size_t)s * KB_BK * KB_TN;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    double fa[4], fb[8];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) fa[mt] = ts[(k4 * 32 + cw * 4 + mt) * 32 + lane];
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) fb[nt] = bs[(k4 * 8 + nt) * 32 + lane];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+                            kb_dmma(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fb[nt]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int r = r0w + mt * 8 + (lane >> 2);
+            if (r < P.n) {
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    qs[nt][0] += acc[mt][nt][0] * acc[mt][nt][0];
+                    qs[nt][1] += acc[mt][nt][1] * acc[mt][nt][1];
+                }
+            } else if (r < P.n + P.na) {
+                double* ao = P.auxout + (size_t)(r - P.n) * P.mpad + (size_t)jt * KB_TN + 2 * (lane & 3);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    ao[nt * 8] = acc[mt][nt][0];
+                    ao[nt * 8 + 1] = acc[mt][nt][1];
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                double v = qs[nt][i];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                qs[nt][i] = v;
+            }
+        if ((lane >> 2) == 0) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                red[cw * KB_TN + nt * 8 + 2 * lane] = qs[nt][0];
+                red[cw * KB_TN + nt * 8 + 2 * lane + 1] = qs[nt][1];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < KB_TN) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w * KB_TN + tid];     // fixed order: deterministic
+        P.partial[(size_t)I * P.mpad + (size_t)jt * KB_TN + tid] = v;
+    }
+}
+
 // Per-point finalize (deterministic reduction over row blocks + the (K+1)x(K+1) drift solve).
 template <int DIM>
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams P) {
@@ -230,9 +398,21 @@ size_t kbk_solve_smem(int dtype) {
     return (size_t)SV_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
            SV_STAGES * sizeof(uint64_t) + 64;
 }
+static size_t solve_smem_ws() {
+    return (size_t)WS_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
+           2 * WS_STAGES * sizeof(uint64_t) + 64;
+}
+// A/B switch for profiling only: KB200_SOLVE_V1=1 selects the non-specialised kernel.
+static bool use_v1() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KB200_SOLVE_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 
 template <int DIM, int MODEL>
 static cudaError_t solve_set_attr() {
+    KB_CUDA_OK(cudaFuncSetAttribute(solve_kernel_ws<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)solve_smem_ws()));
     return cudaFuncSetAttribute(solve_kernel_f64<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kbk_solve_smem(KB200_F64));
 }
@@ -251,7 +431,8 @@ static cudaError_t solve_dim(int dtype, const SolveParams& p, cudaStream_t st) {
     dim3 grid((unsigned)(p.mpad / KB_TN), (unsigned)p.nrb);
     size_t sm = kbk_solve_smem(dtype);
     switch (p.vg.model) {
-#define KB_CASE(M) case M: solve_kernel_f64<DIM, M><<<grid, SV_THREADS, sm, st>>>(p); break;
+#define KB_CASE(M) case M: if (use_v1()) solve_kernel_f64<DIM, M><<<grid, SV_THREADS, sm, st>>>(p); \
+                          else solve_kernel_ws<DIM, M><<<grid, WS_THREADS, solve_smem_ws(), st>>>(p); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
         KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
 #undef KB_CASE

@@ -1,0 +1,166 @@
+"""CPU tests of the host side: reference-facing API behaviour (the error checks of ok.py:834-874,
+uk.py:1169-1274, ok3d.py:833-876), parameter normalisation (core.py:196-376), anisotropy
+(core.py:120-193), and the C-ABI library (loads, exports every symbol of include/krige_b200.h,
+fails loudly without a GPU)."""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import pykrige_b200 as pk
+from pykrige_b200 import core, _cabi, multigpu, variogram_models as vm
+from oracle import krige_oracle as ko
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "krige_b200.h")).read()
+    declared = set(re.findall(r"\b(kb200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    lib = _cabi.load_library()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.kb200_version() >= 1000
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_cabi.KrigeB200Error):
+        _cabi.Handle()
+    ok = pk.OrdinaryKriging([0, 1, 2.0], [0, 1, 0.5], [1, 2, 3.0], variogram_parameters=[1.0, 0.1])
+    with pytest.raises(_cabi.KrigeB200Error):
+        ok.execute("points", [0.5], [0.5], backend="cuda")
+
+
+def test_variogram_models_match_oracle():
+    d = np.linspace(0.0, 900.0, 301)
+    for name, plist in cases.MODELS.items():
+        stored = ko.stored_parameters(name, plist)
+        f = pk.OrdinaryKriging.variogram_dict[name]
+        assert_allclose(f(stored, d), ko.variogram(name, stored, d), rtol=1e-14, atol=1e-15)
+        assert f.__name__ in vm.DEVICE_MODEL_IDS
+
+
+def test_parameter_list_normalisation():
+    """tests/test_core.py:114-181: list form is FULL sill -> psill; dict may give sill or psill."""
+    assert core._make_variogram_parameter_list("linear", [1.5, 0.2]) == [1.5, 0.2]
+    assert core._make_variogram_parameter_list("power", [1.5, 1.2, 0.2]) == [1.5, 1.2, 0.2]
+    for m in ("gaussian", "spherical", "exponential", "hole-effect"):
+        assert core._make_variogram_parameter_list(m, [2.0, 10.0, 0.5]) == [1.5, 10.0, 0.5]
+        assert core._make_variogram_parameter_list(m, {"sill": 2.0, "range": 10.0, "nugget": 0.5}) == [1.5, 10.0, 0.5]
+        assert core._make_variogram_parameter_list(m, {"psill": 1.5, "range": 10.0, "nugget": 0.5}) == [1.5, 10.0, 0.5]
+        with pytest.raises(KeyError):
+            core._make_variogram_parameter_list(m, {"range": 10.0, "nugget": 0.5})
+    assert core._make_variogram_parameter_list("linear", {"slope": 1.0, "nugget": 0.1}) == [1.0, 0.1]
+    with pytest.raises(ValueError):
+        core._make_variogram_parameter_list("linear", [1.0])
+    with pytest.raises(TypeError):
+        core._make_variogram_parameter_list("linear", (1.0, 0.1))
+    with pytest.raises(TypeError):
+        core._make_variogram_parameter_list("custom", {"a": 1})
+    assert core._make_variogram_parameter_list("exponential", None) is None
+
+
+def test_anisotropy_matches_oracle():
+    rng = np.random.default_rng(0)
+    X2 = rng.normal(size=(50, 2)) * 100
+    X3 = rng.normal(size=(50, 3)) * 100
+    assert_allclose(core._adjust_for_anisotropy(X2, [3.0, -2.0], [1.7], [33.0]),
+                    ko.adjust_for_anisotropy(X2, [3.0, -2.0], [1.7], [33.0]), rtol=1e-13, atol=1e-11)
+    assert_allclose(core._adjust_for_anisotropy(X3, [3.0, -2.0, 5.0], [1.4, 3.0], [10.0, -25.0, 40.0]),
+                    ko.adjust_for_anisotropy(X3, [3.0, -2.0, 5.0], [1.4, 3.0], [10.0, -25.0, 40.0]),
+                    rtol=1e-13, atol=1e-11)
+    # tests/test_core.py:83-111 known rotation
+    x = np.array([[1.0, 0.0], [0.0, 1.0]])
+    out = core._adjust_for_anisotropy(x, [0.0, 0.0], [2.0], [90.0])
+    assert_allclose(out, [[0.0, -2.0], [1.0, 0.0]], atol=1e-12)
+
+
+def test_fitted_variogram_is_reasonable():
+    xyz, val = cases.synth_data(5, 150, 2)
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="spherical", nlags=8)
+    p = ok.variogram_model_parameters
+    assert len(p) == 3 and p[0] >= 0 and p[1] > 0 and p[2] >= 0
+    assert ok.lags.size == ok.semivariance.size <= 8
+    lags, g = ok.get_variogram_points()
+    assert_allclose(g, vm.spherical_variogram_model(p, lags))
+
+
+def test_constructor_and_execute_argument_errors():
+    xyz, val = cases.synth_data(1, 20, 2)
+    with pytest.raises(ValueError):
+        pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="blurg")
+    with pytest.raises(ValueError):
+        pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, exact_values="blurg")
+    with pytest.raises(ValueError):
+        pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="custom")
+    with pytest.raises(ValueError):
+        pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, pseudo_inv_type="nope")
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_parameters=[1.0, 0.1])
+    gx, gy = np.arange(4.0), np.arange(3.0)
+    with pytest.raises(ValueError):
+        ok.execute("blurg", gx, gy)
+    with pytest.raises(IOError):
+        ok.execute("masked", gx, gy)
+    with pytest.raises(ValueError):
+        ok.execute("masked", gx, gy, mask=np.zeros((5, 5), bool))
+    with pytest.raises(ValueError):
+        ok.execute("points", np.arange(3.0), np.arange(4.0))
+    with pytest.raises(ValueError):
+        ok.execute("grid", gx, gy, n_closest_points=1)
+    with pytest.raises(ValueError):
+        ok.execute("grid", gx, gy, backend="vectorized")   # CPU backends live in the reference
+    uk = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, variogram_parameters=[1.0, 0.1], drift_terms=["specified"],
+                             specified_drift=[val])
+    with pytest.raises(ValueError):
+        uk.execute("grid", gx, gy)                          # specified drift arrays missing
+    with pytest.raises(TypeError):
+        pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, drift_terms=["functional"], functional_drift=lambda x, y: x,
+                            variogram_parameters=[1.0, 0.1])
+    with pytest.raises(ValueError):
+        pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, drift_terms=["external_Z"], variogram_parameters=[1.0, 0.1])
+    x3, v3 = cases.synth_data(2, 20, 3)
+    k3 = pk.OrdinaryKriging3D(x3[:, 0], x3[:, 1], x3[:, 2], v3, variogram_parameters=[1.0, 0.1])
+    with pytest.raises(ValueError):
+        k3.execute("masked", gx, gy, gx, mask=np.zeros((2, 2), bool))
+    with pytest.raises(IOError):
+        k3.execute("masked", gx, gy, gx)
+    assert k3._stats_state == "lazy"                        # O(N^4) statistics deferred
+    assert k3.Q1 is not None and k3._stats_state == "done"
+    assert ok.Q1 is None                                    # enable_statistics=False (ok.py:360-377)
+
+
+def test_external_z_sampler_matches_bilinear():
+    xyz, val = cases.synth_data(4, 30, 2)
+    case = cases.CASE_BY_NAME["uk2d_externalz"]
+    inp = cases.build_inputs(case)
+    uk = cases.make_model(pk, case, inp)
+    from scipy.interpolate import RegularGridInterpolator
+    f = RegularGridInterpolator((inp["ext_y"], inp["ext_x"]), inp["ext_z"])
+    P = inp["points"]
+    assert_allclose(uk._calculate_data_point_zscalars(P[:, 0], P[:, 1]), f(np.column_stack((P[:, 1], P[:, 0]))),
+                    rtol=1e-12)
+    # exactly on a node / on a grid line (degenerate branches of uk.py:560-595)
+    xs = np.array([inp["ext_x"][3], inp["ext_x"][3], 0.5 * (inp["ext_x"][3] + inp["ext_x"][4])])
+    ys = np.array([inp["ext_y"][5], 0.5 * (inp["ext_y"][5] + inp["ext_y"][6]), inp["ext_y"][5]])
+    assert_allclose(uk._calculate_data_point_zscalars(xs, ys), f(np.column_stack((ys, xs))), rtol=1e-12)
+    with pytest.raises(ValueError):
+        uk._calculate_data_point_zscalars(np.array([1e6]), np.array([0.0]))
+
+
+def test_shard_ranges_cover_exactly():
+    for count in (0, 1, 7, 1000, 10**6 + 3):
+        for world in (1, 2, 3, 4, 8):
+            spans = [multigpu.shard_range(count, r, world) for r in range(world)]
+            assert spans[0][0] == 0
+            for (f0, c0), (f1, c1) in zip(spans, spans[1:]):
+                assert f0 + c0 == f1
+            assert spans[-1][0] + spans[-1][1] == count
+            sizes = [c for _, c in spans]
+            assert max(sizes) - min(sizes) <= 1
