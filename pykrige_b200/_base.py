@@ -68,6 +68,27 @@ class KrigeBase:
             print("Range:", p[1])
             print("Nugget:", p[2], "\n")
 
+    # ---- experimental variogram: computed on first access when the parameters were given explicitly
+    #      (the reference always runs the O(N^2) pdist in the constructor, core.py:432-436) -------------
+    def _get_lags(self):
+        if callable(self._lags):
+            self._lags, self._semivariance = self._lags()
+        return self._lags
+
+    def _set_lags(self, v):
+        self._lags = v
+
+    def _get_semivariance(self):
+        self._get_lags()
+        return self._semivariance
+
+    def _set_semivariance(self, v):
+        if v is not None or not callable(getattr(self, "_lags", None)):
+            self._semivariance = v
+
+    lags = property(_get_lags, _set_lags)
+    semivariance = property(_get_semivariance, _set_semivariance)
+
     # ---- cross-validation statistics: lazy (the reference runs this O(N^4) loop in the
     #      constructor of OK3D/UK/UK3D, ok3d.py:352, uk.py:380, uk3d.py:380) -----
     def _stats_inputs(self):

@@ -101,20 +101,51 @@ def _make_variogram_parameter_list(variogram_model, variogram_model_parameters):
     raise TypeError("Variogram model parameters must be provided in either a list or a dict when they are explicitly specified.")
 
 
-def _experimental_variogram(X, y, nlags):
-    """Equal-width binned semivariogram (core.py:432-505), euclidean coordinates."""
-    d = pdist(X, metric="euclidean")
-    g = 0.5 * pdist(y[:, None], metric="sqeuclidean")
-    dmax, dmin = np.amax(d), np.amin(d)
-    dd = (dmax - dmin) / nlags
-    edges = [dmin + k * dd for k in range(nlags)] + [dmax + 0.001]
-    lags, semi = [], []
-    for k in range(nlags):
-        sel = (d >= edges[k]) & (d < edges[k + 1])
-        if np.any(sel):
-            lags.append(d[sel].mean())
-            semi.append(g[sel].mean())
-    return np.array(lags), np.array(semi)
+def _experimental_variogram(X, y, nlags, block=2048):
+    """Equal-width binned semivariogram (core.py:432-505), euclidean coordinates.
+
+    Same bins as the reference (nlags equal bins from dmin to dmax, last edge dmax + 0.001; lag = mean
+    distance and semivariance = mean 0.5*(dy)^2 of the pairs in the bin; empty bins dropped), but
+    accumulated over row blocks so that the O(N^2) pair list never exists (the reference's pdist needs
+    80 GB at N = 1e5)."""
+    n = X.shape[0]
+    if n * (n - 1) // 2 <= 20_000_000:
+        d = pdist(X, metric="euclidean")
+        g = 0.5 * pdist(y[:, None], metric="sqeuclidean")
+        dmax, dmin = np.amax(d), np.amin(d)
+        dd = (dmax - dmin) / nlags
+        edges = np.array([dmin + k * dd for k in range(nlags)] + [dmax + 0.001])
+        which = np.searchsorted(edges, d, side="right") - 1
+        ok = (which >= 0) & (which < nlags)
+        cnt = np.bincount(which[ok], minlength=nlags)
+        sd = np.bincount(which[ok], weights=d[ok], minlength=nlags)
+        sg = np.bincount(which[ok], weights=g[ok], minlength=nlags)
+    else:
+        from scipy.spatial.distance import cdist
+        dmin, dmax = np.inf, 0.0
+        for s in range(0, n, block):
+            D = cdist(X[s:s + block], X[s:])
+            iu = np.triu_indices(D.shape[0], 1, D.shape[1])
+            dv = D[iu]
+            if dv.size:
+                dmin, dmax = min(dmin, dv.min()), max(dmax, dv.max())
+        dd = (dmax - dmin) / nlags
+        edges = np.array([dmin + k * dd for k in range(nlags)] + [dmax + 0.001])
+        cnt = np.zeros(nlags)
+        sd = np.zeros(nlags)
+        sg = np.zeros(nlags)
+        for s in range(0, n, block):
+            D = cdist(X[s:s + block], X[s:])
+            iu = np.triu_indices(D.shape[0], 1, D.shape[1])
+            dv = D[iu]
+            gv = 0.5 * (y[s:s + block, None] - y[None, s:])[iu] ** 2
+            which = np.searchsorted(edges, dv, side="right") - 1
+            ok = (which >= 0) & (which < nlags)
+            cnt += np.bincount(which[ok], minlength=nlags)
+            sd += np.bincount(which[ok], weights=dv[ok], minlength=nlags)
+            sg += np.bincount(which[ok], weights=gv[ok], minlength=nlags)
+    keep = cnt > 0
+    return sd[keep] / cnt[keep], sg[keep] / cnt[keep]
 
 
 def _variogram_residuals(params, x, y, variogram_function, weight):
@@ -150,17 +181,24 @@ def _calculate_variogram_model(lags, semivariance, variogram_model, variogram_fu
 
 
 def _initialize_variogram_model(X, y, variogram_model, variogram_model_parameters,
-                                variogram_function, nlags, weight, coordinates_type):
-    """Returns (lags, semivariance, parameters) (core.py:379-535)."""
+                                variogram_function, nlags, weight, coordinates_type, lazy=False):
+    """Returns (lags, semivariance, parameters) (core.py:379-535). With lazy=True and explicit
+    parameters the experimental variogram (an O(N^2) pass that execute() never needs) is returned as
+    a zero-argument callable instead of arrays."""
     if coordinates_type != "euclidean":
         if coordinates_type == "geographic":
             raise NotImplementedError("coordinates_type='geographic' is not part of the B200 hot path (SURVEY.md §8f next-3)")
         raise ValueError("Specified coordinate type '%s' is not supported." % coordinates_type)
-    if X.shape[0] > 1:
+    p = variogram_model_parameters
+    deferred = None
+    if lazy and p is not None:
+        def deferred():
+            return _experimental_variogram(X, y, nlags) if X.shape[0] > 1 else (np.zeros(0), np.zeros(0))
+        lags, semivariance = None, None
+    elif X.shape[0] > 1:
         lags, semivariance = _experimental_variogram(X, y, nlags)
     else:
         lags, semivariance = np.zeros(0), np.zeros(0)
-    p = variogram_model_parameters
     if p is not None:
         if variogram_model == "linear" and len(p) != 2:
             raise ValueError("Exactly two parameters required for linear variogram model.")
@@ -170,6 +208,8 @@ def _initialize_variogram_model(X, y, variogram_model, variogram_model_parameter
         if variogram_model == "custom":
             raise ValueError("Variogram parameters must be specified when implementing custom variogram model.")
         p = _calculate_variogram_model(lags, semivariance, variogram_model, variogram_function, weight)
+    if deferred is not None:
+        return deferred, None, p
     return lags, semivariance, p
 
 

@@ -50,7 +50,8 @@ struct kb200_ctx {
     // factor workspace
     DevBuf wC, wW, wT, wF, wRaw, wFlag;
     // execute workspace
-    DevBuf wPart, wAux, wPts, wOut, wAxes, wDrift;
+    DevBuf wPart, wAux, wPts, wOut, wAxes, wDrift, wScratch;
+    int num_sms = 148;
     // knn workspace
     DevBuf kSorted, kCells;
     KnnParams kp{};
@@ -88,6 +89,7 @@ extern "C" int kb200_create(kb200_handle* out, int device) {
     h->own_stream = true;
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete h; return KB200_ECUDA; }
     if (kbk_factor_init() != cudaSuccess || kbk_solve_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
+    if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->num_sms < 1) h->num_sms = 148;
     *out = h;
     return KB200_OK;
 }
@@ -97,7 +99,7 @@ extern "C" void kb200_destroy(kb200_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->blob, &h->wC, &h->wW, &h->wT, &h->wF, &h->wRaw, &h->wFlag, &h->wPart, &h->wAux,
-                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->kSorted, &h->kCells}) b->release();
+                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->wScratch, &h->kSorted, &h->kCells}) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -147,7 +149,7 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     if (dim != 2 && dim != 3) return fail(h, KB200_EBADARG, "dim must be 2 or 3");
     if (dtype != KB200_F64 && dtype != KB200_F32) return fail(h, KB200_EBADARG, "dtype must be KB200_F64 or KB200_F32");
     if (dtype == KB200_F32) return fail(h, KB200_EUNSUPPORTED, "fp32 contraction is not built yet (round 1: fp64 only)");
-    if (n < 1 || n > (int64_t)(KB_MAXRB - 1) * KB_BM) return fail(h, KB200_EBADARG, "n out of range");
+    if (n < 1 || (!knn_only && n > (int64_t)(KB_MAXRB - 1) * KB_BM) || n > (1LL << 30)) return fail(h, KB200_EBADARG, "n out of range");
     if (!x || !y || (dim == 3 && !z) || !values || !center || !aniso || !vparams)
         return fail(h, KB200_EBADARG, "null input array");
     if (model < KB200_VG_LINEAR || model > KB200_VG_HOLE_EFFECT)
@@ -208,7 +210,7 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     // tile stream map
     h->n_pad = (int)align_up((size_t)n, KB_BM);
     h->ld = h->n_pad;
-    h->nrb = (int)((n + h->na + KB_BM - 1) / KB_BM);
+    h->nrb = knn_only ? 0 : (int)((n + h->na + KB_BM - 1) / KB_BM);
     int nk = (int)((n + KB_BK - 1) / KB_BK);
     h->pm.nrb = h->nrb;
     long long off = 0;
@@ -363,11 +365,37 @@ struct Src {
 
 static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     cudaStream_t st = h->stream;
+    char* blob = h->blob.as<char>();
+    PointSource ps{};
+    ps.grid = s.grid ? 1 : 0;
+    ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
+    ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
+    if (!kbk_solve_use_v1()) {
+        // K3 v3: one persistent launch for the whole slice (solve + finalize fused)
+        long long ntiles = (s.count + KB_TN - 1) / KB_TN;
+        int grid = (int)std::min<long long>(ntiles, h->num_sms);
+        CU(h, h->wScratch.reserve(kbk_solve_pt_scratch_doubles(h->n, grid) * sizeof(double)));
+        SolvePtParams pp{};
+        pp.vg = h->vg; pp.an = h->an; ps.first = s.first; pp.ps = ps;
+        pp.n = h->n; pp.na = h->na; pp.nrb = h->nrb; pp.n_rl = h->n_rl; pp.n_hd = h->n_hd;
+        pp.ax = reinterpret_cast<double*>(blob + h->off_ax);
+        pp.ay = reinterpret_cast<double*>(blob + h->off_ay);
+        pp.az = reinterpret_cast<double*>(blob + h->off_az);
+        pp.tiles = blob + h->off_tiles; pp.pm = h->pm; pp.ds = h->ds;
+        pp.consts = reinterpret_cast<double*>(blob + h->off_consts);
+        pp.drift_pts = s.d_drift; pp.drift_stride = s.drift_stride; pp.drift_first = s.drift_first;
+        pp.m = s.count; pp.scratch = h->wScratch.as<double>();
+        pp.z_out = d_z; pp.ss_out = d_ss;
+        CU(h, cudaEventRecord(h->ev[7], st));
+        CU(h, kbk_solve_pt(h->dim, pp, grid, st));
+        CU(h, cudaEventRecord(h->ev[8], st));
+        h->launches += 1; h->solve_launches += 1;
+        return KB200_OK;
+    }
     const int64_t chunk = KB_CHUNK;
     int64_t cmax = std::min<int64_t>(chunk, (int64_t)align_up((size_t)s.count, KB_TN));
     CU(h, h->wPart.reserve((size_t)h->nrb * cmax * sizeof(double)));
     CU(h, h->wAux.reserve((size_t)h->na * cmax * sizeof(double)));
-    char* blob = h->blob.as<char>();
     SolveParams sp{};
     sp.vg = h->vg; sp.an = h->an;
     sp.n = h->n; sp.n_pad = h->n_pad; sp.na = h->na; sp.nrb = h->nrb;
@@ -381,10 +409,6 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     fp.ds = h->ds; fp.consts = reinterpret_cast<double*>(blob + h->off_consts);
     fp.drift_pts = s.d_drift; fp.drift_stride = s.drift_stride;
     fp.partial = sp.partial; fp.auxout = sp.auxout;
-    PointSource ps{};
-    ps.grid = s.grid ? 1 : 0;
-    ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
-    ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
     CU(h, cudaEventRecord(h->ev[7], st));
     for (int64_t o = 0; o < s.count; o += chunk) {
         int64_t m = std::min(chunk, s.count - o);

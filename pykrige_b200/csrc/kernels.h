@@ -29,6 +29,23 @@ struct SolveParams {
     double* auxout;       // [na][mpad]    dual-row dot products
 };
 
+// K3 v3 (persistent point-tile kernel): solve + finalize in one launch
+struct SolvePtParams {
+    VgParams vg;
+    Aniso an;
+    PointSource ps;
+    int n, na, nrb, n_rl, n_hd;
+    const double* ax; const double* ay; const double* az;
+    const void* tiles;
+    PackMap pm;
+    DriftScale ds;
+    const double* consts;
+    const double* drift_pts; long long drift_stride, drift_first;
+    long long m;
+    double* scratch;          // [grid][ceil(n/16)][16*64]  RHS column blocks in fragment order
+    double* z_out; double* ss_out;
+};
+
 struct FinalizeParams {
     VgParams vg;
     Aniso an;
@@ -62,6 +79,9 @@ cudaError_t kbk_solve_init();   // opt-in shared memory attributes
 size_t      kbk_solve_smem(int dtype);
 cudaError_t kbk_solve(int dim, int dtype, const SolveParams& p, cudaStream_t st);
 cudaError_t kbk_finalize(const FinalizeParams& p, cudaStream_t st);
+cudaError_t kbk_solve_pt(int dim, const SolvePtParams& p, int grid, cudaStream_t st);
+bool        kbk_solve_use_v1();
+size_t      kbk_solve_pt_scratch_doubles(int n, int grid);
 
 // moving window (knn.cu)
 struct KnnParams {

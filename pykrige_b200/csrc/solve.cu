@@ -190,169 +190,231 @@ __global__ void __launch_bounds__(SV_THREADS, 1) solve_kernel_f64(const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 v2: warp-specialised.  Warps 0..WS_NPROD-1 are producers: they issue the 32 KB bulk copies of
-// the W tiles and generate the RHS tiles (sqrt + variogram on the fp64 FMA pipe); warps
-// WS_NPROD..WS_NPROD+7 are consumers: nothing but LDS + DMMA on the tensor pipe. Stages are handed
-// over with mbarriers (full: TMA transaction bytes + one arrival per producer warp; empty: one arrival
-// per consumer warp), so RHS generation overlaps the tensor work instead of alternating with it
-// (v1 measured 54 % DMMA-pipe active with both phases serialised by __syncthreads).
-#define WS_NPROD 4
-#define WS_STAGES 4
-#define WS_THREADS ((WS_NPROD + 8) * 32)
+// K3 v3: persistent, warp-specialised, one CTA = one tile of 64 prediction points x ALL rows of W.
+//
+// v1 (one CTA per (row block, point tile)) regenerates every RHS tile once per row block - a 10x
+// recompute of sqrt+exp at N=5000 - and alternates generation with the tensor work (measured: DMMA pipe
+// 54 % active). v2 (warp-specialised but still regenerating) was slower: four producer warps cannot
+// hide the fp64 sqrt/exp latency. v3 removes the recompute instead:
+//   phase G  all 12 warps evaluate the RHS column block c[k][j] of the tile ONCE (n x 64 values) and
+//            park it, already in MMA-fragment order, in a per-CTA scratch ring (L2-resident, re-used for
+//            every tile the CTA processes; size independent of M);
+//   phase M  warp 0 streams W tiles (32 KB) and RHS tiles (8 KB) with cp.async.bulk + mbarrier into a
+//            4-stage ring; warps 4..11 do nothing but LDS + DMMA, walking all row blocks and keeping the
+//            per-point sum of squares in registers;
+//   phase F  the (K+1)x(K+1) drift solve and the two outputs per point are produced in the same CTA:
+//            no partial buffers, no separate finalize pass, fixed summation order (deterministic).
+#define PT_STAGES 4
+#define PT_THREADS 384
+#define PT_STAGE_BYTES ((KB_BM * KB_BK + KB_BK * KB_TN) * 8)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
 
 template <int DIM, int MODEL>
-__global__ void __launch_bounds__(WS_THREADS, 1) solve_kernel_ws(const __grid_constant__ SolveParams P) {
+__global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_constant__ SolvePtParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* Ts = reinterpret_cast<double*>(smem_raw);                   // WS_STAGES * BM*BK
-    double* Bs = Ts + WS_STAGES * KB_BM * KB_BK;                        // WS_STAGES * BK*TN
-    double* red = Bs + WS_STAGES * KB_BK * KB_TN;                       // 8 * 64
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + 8 * KB_TN);      // WS_STAGES
-    uint64_t* empty = full + WS_STAGES;                                 // WS_STAGES
+    double* Ts = reinterpret_cast<double*>(smem_raw);                   // PT_STAGES * BM*BK
+    double* Bs = Ts + PT_STAGES * KB_BM * KB_BK;                        // PT_STAGES * BK*TN
+    double* qred = Bs + PT_STAGES * KB_BK * KB_TN;                      // 8 * 64
+    double* auxs = qred + 8 * KB_TN;                                    // KB_MAXAUX * 64
+    uint64_t* full = reinterpret_cast<uint64_t*>(auxs + KB_MAXAUX * KB_TN);   // PT_STAGES
+    uint64_t* empty = full + PT_STAGES;                                 // PT_STAGES
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int jt = blockIdx.x;
-    const int I = P.nrb - 1 - (int)blockIdx.y;
-    const int nkt = P.pm.ktiles[I];
-    const double* gt = reinterpret_cast<const double*>(P.tiles) + (size_t)P.pm.tile_off[I] * (KB_BM * KB_BK);
-    constexpr uint32_t TILE_BYTES = KB_BM * KB_BK * sizeof(double);
+    const int nk = (P.n + KB_BK - 1) / KB_BK;                           // k tiles of a full column block
+    double* scratch = P.scratch + (size_t)blockIdx.x * nk * (KB_BK * KB_TN);
+    const double* gt = reinterpret_cast<const double*>(P.tiles);
+    const long long ntiles = (P.m + KB_TN - 1) / KB_TN;
+    const int K = P.n_rl + P.n_hd, K1 = K + 1;
 
     if (tid == 0) {
-        for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full[s], 1 + WS_NPROD); mbar_init(&empty[s], 8); }
+        for (int s = 0; s < PT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     __syncthreads();
 
-    const int cw = warp - WS_NPROD;                     // consumer warp index 0..7 (negative: producer)
-    double qs[8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { qs[nt][0] = 0.0; qs[nt][1] = 0.0; }
+    uint32_t git = 0;                 // running stage counter (same sequence in producer and consumers)
+    const int cw = warp - 4;          // consumer warp 0..7
 
-    if (warp < WS_NPROD) {
-        // ===================== producers =====================
-        // thread -> one prediction point of the tile; it evaluates all 16 k of every tile for that point
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;\n");
-        // 128 producer threads: thread -> (point nl = tid & 63, k half kh = tid >> 6 -> k4 in {2kh, 2kh+1})
-        const int nl = tid & 63;
-        const int kh = tid >> 6;
-        const long long pj = (long long)jt * KB_TN + nl;
-        const bool pvalid = pj < P.m;
-        double px = 0.0, py = 0.0, pz = 0.0;
-        if (pvalid) kb_load_point<DIM>(P.ps, P.an, pj, px, py, pz);
-        for (int t = 0; t < nkt; ++t) {
-            const int s = t % WS_STAGES;
-            mbar_wait(&empty[s], (uint32_t)(((t / WS_STAGES) & 1) ^ 1));
-            if (tid == 0) {
-                mbar_expect_tx(&full[s], TILE_BYTES);
-                bulk_g2s(Ts + (size_t)s * KB_BM * KB_BK, gt + (size_t)t * KB_BM * KB_BK, TILE_BYTES, &full[s]);
-            }
-            double* bs = Bs + (size_t)s * KB_BK * KB_TN;
-#pragma unroll
-            for (int kq = 0; kq < 2; ++kq) {
-                const int k4 = kh * 2 + kq;
-                double v[4];
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int k = t * KB_BK + k4 * 4 + kk;
-                    double val = 0.0;
-                    if (pvalid && k < P.n) {
-                        double d = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), DIM == 3 ? __ldg(P.az + k) : 0.0, px, py, pz);
-                        val = kb_cov_rhs<MODEL>(P.vg, d);
-                    }
-                    v[kk] = val;
-                }
-                // fragment order: ((k4*8 + n/8)*32 + (n%8)*4 + k%4): 4 consecutive k = 32 contiguous bytes
-                double2* dst = reinterpret_cast<double2*>(bs + (k4 * 8 + (nl >> 3)) * 32 + (nl & 7) * 4);
-                dst[0] = make_double2(v[0], v[1]);
-                dst[1] = make_double2(v[2], v[3]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);       // release: the tile written by this warp is visible
-        }
-    } else {
-        // ===================== consumers =====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
-        const int r0w = I * KB_BM + cw * 32;
-        int warp_kmax;
-        if (r0w + 31 >= P.n && r0w < P.n + P.na) warp_kmax = 0x7fffffff;
-        else if (r0w >= P.n + P.na) warp_kmax = -1;
-        else warp_kmax = r0w + 31;
-        double acc[4][8][2];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
-        for (int t = 0; t < nkt; ++t) {
-            const int s = t % WS_STAGES;
-            // every consumer waits for every tile (also the ones it skips): a warp that raced ahead could
-            // otherwise arrive twice on empty[s] within one phase and release a stage that is still being read
-            mbar_wait(&full[s], (uint32_t)((t / WS_STAGES) & 1));
-            if (t * KB_BK <= warp_kmax) {
-                const double* ts = Ts + (size_t)s * KB_BM * KB_BK;
-                const double* bs = Bs + (size_t)s * KB_BK * KB_TN;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---------------- phase G: RHS column block of this tile, once ----------------
+        {
+            const int pl = tid & 63;                 // point within the tile
+            const int ks = tid >> 6;                 // 0..5: k-tile slice
+            const long long pj = tile * KB_TN + pl;
+            const bool pvalid = pj < P.m;
+            double px = 0.0, py = 0.0, pz = 0.0;
+            if (pvalid) kb_load_point<DIM>(P.ps, P.an, pj, px, py, pz);
+            for (int t = ks; t < nk; t += PT_THREADS / 64) {
+                double* bt = scratch + (size_t)t * (KB_BK * KB_TN);
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
-                    double fa[4], fb[8];
+                    double v[4];
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) fa[mt] = ts[(k4 * 32 + cw * 4 + mt) * 32 + lane];
-#pragma unroll
-                    for (int nt = 0; nt < 8; ++nt) fb[nt] = bs[(k4 * 8 + nt) * 32 + lane];
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < 8; ++nt)
-                            kb_dmma(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fb[nt]);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = t * KB_BK + k4 * 4 + kk;
+                        double val = 0.0;
+                        if (pvalid && k < P.n) {
+                            double d = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), DIM == 3 ? __ldg(P.az + k) : 0.0,
+                                                    px, py, pz);
+                            val = kb_cov_rhs<MODEL>(P.vg, d);
+                        }
+                        v[kk] = val;
+                    }
+                    // fragment order ((k4*8 + n/8)*32 + (n%8)*4 + k%4): 4 consecutive k = 32 contiguous bytes
+                    double2* dst = reinterpret_cast<double2*>(bt + (k4 * 8 + (pl >> 3)) * 32 + (pl & 7) * 4);
+                    dst[0] = make_double2(v[0], v[1]);
+                    dst[1] = make_double2(v[2], v[3]);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            // generic-proxy global writes -> later read by the async proxy (bulk copies) of this CTA
+            __threadfence();
+            asm volatile("fence.proxy.async.global;\n" ::: "memory");
         }
+        __syncthreads();
+
+        // ---------------- phase M ----------------
+        if (warp == 0) {
+            if (lane == 0) {
+                uint32_t g = git;
+                long long tau = 0;                   // W tiles are stored contiguously in (I, t) order
+                for (int I = 0; I < P.nrb; ++I) {
+                    const int kt = P.pm.ktiles[I];
+                    for (int t = 0; t < kt; ++t, ++tau, ++g) {
+                        const int s = g % PT_STAGES;
+                        mbar_wait(&empty[s], (uint32_t)(((g / PT_STAGES) & 1) ^ 1));
+                        mbar_expect_tx(&full[s], PT_STAGE_BYTES);
+                        bulk_g2s(Ts + (size_t)s * KB_BM * KB_BK, gt + (size_t)tau * (KB_BM * KB_BK),
+                                 KB_BM * KB_BK * 8, &full[s]);
+                        bulk_g2s(Bs + (size_t)s * KB_BK * KB_TN, scratch + (size_t)t * (KB_BK * KB_TN),
+                                 KB_BK * KB_TN * 8, &full[s]);
+                    }
+                }
+            }
+        } else if (warp >= 4) {
+            uint32_t g = git;
+            double qs[8][2];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            const int r = r0w + mt * 8 + (lane >> 2);
-            if (r < P.n) {
+            for (int nt = 0; nt < 8; ++nt) { qs[nt][0] = 0.0; qs[nt][1] = 0.0; }
+            for (int I = 0; I < P.nrb; ++I) {
+                const int kt = P.pm.ktiles[I];
+                const int r0w = I * KB_BM + cw * 32;
+                int warp_kmax;                       // W rows are lower-triangular, dual rows are dense
+                if (r0w + 31 >= P.n && r0w < P.n + P.na) warp_kmax = 0x7fffffff;
+                else if (r0w >= P.n + P.na) warp_kmax = -1;
+                else warp_kmax = r0w + 31;
+                double acc[4][8][2];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+                for (int t = 0; t < kt; ++t, ++g) {
+                    const int s = g % PT_STAGES;
+                    // every consumer waits for every stage (also the ones it skips) so that no warp can lap
+                    // the ring and arrive twice on empty[s] within one phase
+                    mbar_wait(&full[s], (uint32_t)((g / PT_STAGES) & 1));
+                    if (t * KB_BK <= warp_kmax) {
+                        const double* ts = Ts + (size_t)s * KB_BM * KB_BK;
+                        const double* bs = Bs + (size_t)s * KB_BK * KB_TN;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            double fa[4], fb[8];
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) fa[mt] = ts[(k4 * 32 + cw * 4 + mt) * 32 + lane];
+#pragma unroll
+                            for (int nt = 0; nt < 8; ++nt) fb[nt] = bs[(k4 * 8 + nt) * 32 + lane];
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                                for (int nt = 0; nt < 8; ++nt)
+                                    kb_dmma(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fb[nt]);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                }
+                // row-block epilogue: W rows -> running sum of squares; dual rows -> shared memory
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const int r = r0w + mt * 8 + (lane >> 2);
+                    if (r < P.n) {
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) {
+                            qs[nt][0] += acc[mt][nt][0] * acc[mt][nt][0];
+                            qs[nt][1] += acc[mt][nt][1] * acc[mt][nt][1];
+                        }
+                    } else if (r < P.n + P.na) {
+                        double* ao = auxs + (r - P.n) * KB_TN + 2 * (lane & 3);
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) {
+                            ao[nt * 8] = acc[mt][nt][0];
+                            ao[nt * 8 + 1] = acc[mt][nt][1];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    double v = qs[nt][i];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    qs[nt][i] = v;
+                }
+            if ((lane >> 2) == 0) {
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    qs[nt][0] += acc[mt][nt][0] * acc[mt][nt][0];
-                    qs[nt][1] += acc[mt][nt][1] * acc[mt][nt][1];
-                }
-            } else if (r < P.n + P.na) {
-                double* ao = P.auxout + (size_t)(r - P.n) * P.mpad + (size_t)jt * KB_TN + 2 * (lane & 3);
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    ao[nt * 8] = acc[mt][nt][0];
-                    ao[nt * 8 + 1] = acc[mt][nt][1];
+                    qred[cw * KB_TN + nt * 8 + 2 * lane] = qs[nt][0];
+                    qred[cw * KB_TN + nt * 8 + 2 * lane + 1] = qs[nt][1];
                 }
             }
         }
+        // every role advances the ring counter by the same amount
+        for (int I = 0; I < P.nrb; ++I) git += (uint32_t)P.pm.ktiles[I];
+        __syncthreads();
+
+        // ---------------- phase F: per-point finalize ----------------
+        if (tid < KB_TN) {
+            const long long pj = tile * KB_TN + tid;
+            if (pj < P.m) {
+                double q = 0.0;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                double v = qs[nt][i];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                qs[nt][i] = v;
-            }
-        if ((lane >> 2) == 0) {
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                red[cw * KB_TN + nt * 8 + 2 * lane] = qs[nt][0];
-                red[cw * KB_TN + nt * 8 + 2 * lane + 1] = qs[nt][1];
+                for (int w = 0; w < 8; ++w) q += qred[w * KB_TN + tid];     // fixed order: deterministic
+                double r[KB200_MAX_DRIFT + 1];
+                double f[KB200_MAX_DRIFT + 1];
+                if (P.n_rl > 0) {
+                    double x, y, z;
+                    kb_load_point<DIM>(P.ps, P.an, pj, x, y, z);
+                    f[0] = (x - P.ds.shift[0]) * P.ds.scale[0];
+                    f[1] = (y - P.ds.shift[1]) * P.ds.scale[1];
+                    if (DIM == 3) f[2] = (z - P.ds.shift[2]) * P.ds.scale[2];
+                }
+                for (int c = 0; c < P.n_hd; ++c) {
+                    double v = P.drift_pts[(size_t)c * P.drift_stride + P.drift_first + pj];
+                    f[P.n_rl + c] = (v - P.ds.shift[P.n_rl + c]) * P.ds.scale[P.n_rl + c];
+                }
+                f[K] = 1.0;
+                for (int a = 0; a < K1; ++a) r[a] = auxs[a * KB_TN + tid] - f[a];
+                const double zc = auxs[K1 * KB_TN + tid];
+                const double* Sinv = P.consts;
+                const double* phi = P.consts + K1 * K1;
+                double rmu = 0.0, muphi = 0.0;
+                for (int a = 0; a < K1; ++a) {
+                    double mu = 0.0;
+                    for (int b = 0; b < K1; ++b) mu += Sinv[a * K1 + b] * r[b];
+                    rmu += r[a] * mu;
+                    muphi += mu * phi[a];
+                }
+                P.ss_out[pj] = P.vg.c0 - q + rmu;
+                P.z_out[pj] = zc - muphi;
             }
         }
-    }
-    __syncthreads();
-    if (tid < KB_TN) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[w * KB_TN + tid];     // fixed order: deterministic
-        P.partial[(size_t)I * P.mpad + (size_t)jt * KB_TN + tid] = v;
+        __syncthreads();      // qred / auxs / scratch are re-used by the next tile
     }
 }
 
@@ -398,21 +460,26 @@ size_t kbk_solve_smem(int dtype) {
     return (size_t)SV_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
            SV_STAGES * sizeof(uint64_t) + 64;
 }
-static size_t solve_smem_ws() {
-    return (size_t)WS_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
-           2 * WS_STAGES * sizeof(uint64_t) + 64;
-}
 // A/B switch for profiling only: KB200_SOLVE_V1=1 selects the non-specialised kernel.
 static bool use_v1() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("KB200_SOLVE_V1"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
+static size_t solve_smem_pt() {
+    return (size_t)PT_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
+           KB_MAXAUX * KB_TN * sizeof(double) + 2 * PT_STAGES * sizeof(uint64_t) + 64;
+}
+bool kbk_solve_use_v1() { return use_v1(); }
+size_t kbk_solve_pt_scratch_doubles(int n, int grid) {
+    return (size_t)grid * ((n + KB_BK - 1) / KB_BK) * (KB_BK * KB_TN);
+}
+
 
 template <int DIM, int MODEL>
 static cudaError_t solve_set_attr() {
-    KB_CUDA_OK(cudaFuncSetAttribute(solve_kernel_ws<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)solve_smem_ws()));
+    KB_CUDA_OK(cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)solve_smem_pt()));
     return cudaFuncSetAttribute(solve_kernel_f64<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kbk_solve_smem(KB200_F64));
 }
@@ -431,8 +498,7 @@ static cudaError_t solve_dim(int dtype, const SolveParams& p, cudaStream_t st) {
     dim3 grid((unsigned)(p.mpad / KB_TN), (unsigned)p.nrb);
     size_t sm = kbk_solve_smem(dtype);
     switch (p.vg.model) {
-#define KB_CASE(M) case M: if (use_v1()) solve_kernel_f64<DIM, M><<<grid, SV_THREADS, sm, st>>>(p); \
-                          else solve_kernel_ws<DIM, M><<<grid, WS_THREADS, solve_smem_ws(), st>>>(p); break;
+#define KB_CASE(M) case M: solve_kernel_f64<DIM, M><<<grid, SV_THREADS, sm, st>>>(p); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
         KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
 #undef KB_CASE
@@ -443,6 +509,23 @@ static cudaError_t solve_dim(int dtype, const SolveParams& p, cudaStream_t st) {
 
 cudaError_t kbk_solve(int dim, int dtype, const SolveParams& p, cudaStream_t st) {
     return dim == 2 ? solve_dim<2>(dtype, p, st) : solve_dim<3>(dtype, p, st);
+}
+
+template <int DIM>
+static cudaError_t solve_pt_dim(const SolvePtParams& p, int grid, cudaStream_t st) {
+    size_t sm = solve_smem_pt();
+    switch (p.vg.model) {
+#define KB_CASE(M) case M: solve_kernel_pt<DIM, M><<<grid, PT_THREADS, sm, st>>>(p); break;
+        KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+#undef KB_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_solve_pt(int dim, const SolvePtParams& p, int grid, cudaStream_t st) {
+    return dim == 2 ? solve_pt_dim<2>(p, grid, st) : solve_pt_dim<3>(p, grid, st);
 }
 
 cudaError_t kbk_finalize(const FinalizeParams& p, cudaStream_t st) {

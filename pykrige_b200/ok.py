@@ -105,7 +105,7 @@ class OrdinaryKriging(KrigeBase):
             self.variogram_function,
             nlags,
             weight,
-            self.coordinates_type,
+            self.coordinates_type, lazy=True,
         )
         if self.verbose:
             print("Coordinates type: '%s'" % self.coordinates_type, "\n")
@@ -171,7 +171,7 @@ class OrdinaryKriging(KrigeBase):
             self.variogram_function,
             nlags,
             weight,
-            self.coordinates_type,
+            self.coordinates_type, lazy=True,
         )
         if self.verbose:
             self._print_variogram()

@@ -70,7 +70,7 @@ class _Krige3DMixin:
         vp_temp = _make_variogram_parameter_list(self.variogram_model, variogram_parameters)
         self.lags, self.semivariance, self.variogram_model_parameters = _initialize_variogram_model(
             np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED, self.Z_ADJUSTED)).T,
-            self.VALUES, self.variogram_model, vp_temp, self.variogram_function, nlags, weight, "euclidean",
+            self.VALUES, self.variogram_model, vp_temp, self.variogram_function, nlags, weight, "euclidean", lazy=True,
         )
         if self.verbose:
             self._print_variogram()
@@ -123,7 +123,7 @@ class _Krige3DMixin:
         vp_temp = _make_variogram_parameter_list(self.variogram_model, variogram_parameters)
         self.lags, self.semivariance, self.variogram_model_parameters = _initialize_variogram_model(
             np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED, self.Z_ADJUSTED)).T,
-            self.VALUES, self.variogram_model, vp_temp, self.variogram_function, nlags, weight, "euclidean",
+            self.VALUES, self.variogram_model, vp_temp, self.variogram_function, nlags, weight, "euclidean", lazy=True,
         )
         if self.verbose:
             self._print_variogram()

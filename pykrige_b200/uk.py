@@ -117,7 +117,7 @@ class UniversalKriging(KrigeBase):
             self.variogram_function,
             nlags,
             weight,
-            "euclidean",
+            "euclidean", lazy=True,
         )
         if self.verbose:
             self._print_variogram()
@@ -267,7 +267,7 @@ class UniversalKriging(KrigeBase):
         vp_temp = _make_variogram_parameter_list(self.variogram_model, variogram_parameters)
         self.lags, self.semivariance, self.variogram_model_parameters = _initialize_variogram_model(
             np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T, self.Z, self.variogram_model, vp_temp,
-            self.variogram_function, nlags, weight, "euclidean",
+            self.variogram_function, nlags, weight, "euclidean", lazy=True,
         )
         if self.verbose:
             self._print_variogram()
