@@ -318,7 +318,7 @@ def run_ours(args):
             except Exception:  # noqa: BLE001
                 traffic = None
         roofline = {
-            "bound": "tensor", "kernel": "solve_kernel_f64 (fp64 DMMA mma.sync.m8n8k4)",
+            "bound": "tensor", "kernel": "solve_kernel_pt (persistent point-tile kernel, fp64 DMMA mma.sync.m8n8k4; includes RHS generation and finalize)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "measured in this run: torch.matmul fp64 8192^3 (cuBLAS DGEMM), best of 3 "
                            "(MEASURED_PEAKS.json has no fp64 entry)",
