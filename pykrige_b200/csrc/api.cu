@@ -88,7 +88,7 @@ extern "C" int kb200_create(kb200_handle* out, int device) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return KB200_ECUDA; }
     h->own_stream = true;
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete h; return KB200_ECUDA; }
-    if (kbk_factor_init() != cudaSuccess || kbk_solve_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
+    if (kbk_factor_init() != cudaSuccess || kbk_solve_init() != cudaSuccess || kbk_solve_tf32_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->num_sms < 1) h->num_sms = 148;
     *out = h;
     return KB200_OK;
@@ -148,7 +148,6 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     h->described = false; h->ready = false; h->knn_ready = false;
     if (dim != 2 && dim != 3) return fail(h, KB200_EBADARG, "dim must be 2 or 3");
     if (dtype != KB200_F64 && dtype != KB200_F32) return fail(h, KB200_EBADARG, "dtype must be KB200_F64 or KB200_F32");
-    if (dtype == KB200_F32) return fail(h, KB200_EUNSUPPORTED, "fp32 contraction is not built yet (round 1: fp64 only)");
     if (n < 1 || (!knn_only && n > (int64_t)(KB_MAXRB - 1) * KB_BM) || n > (1LL << 30)) return fail(h, KB200_EBADARG, "n out of range");
     if (!x || !y || (dim == 3 && !z) || !values || !center || !aniso || !vparams)
         return fail(h, KB200_EBADARG, "null input array");
@@ -221,7 +220,7 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
         h->pm.tile_off[I] = off;
         off += kt;
     }
-    size_t esz = dtype == KB200_F64 ? 8 : 4;
+    size_t esz = 8;   // fp64 value, or TF32 hi + lo pair: both 8 bytes per element
     size_t o = 0;
     o += align_up(64 * sizeof(double), 256);
     h->off_consts = o; o += align_up(512 * sizeof(double), 256);
@@ -337,7 +336,9 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
     CU(h, cudaMemsetAsync(consts, 0, 512 * sizeof(double), st));
     CU(h, kbk_dual(h->wW.as<double>(), ld, nn, np, h->n_rl, h->n_hd, ax, ay, az, h->ds, rh, rv,
                    Fz, Hz, Uz, consts, flag, st, &launches));
-    CU(h, kbk_pack(h->dtype, h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st)); ++launches;
+    if (h->dtype == KB200_F32) CU(h, kbk_pack_tf32(h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
+    else CU(h, kbk_pack(h->dtype, h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
+    ++launches;
     double hdr[64] = {0};
     hdr[0] = KB_MAGIC; hdr[1] = h->vg.c0;
     for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { hdr[2 + c] = h->ds.shift[c]; hdr[18 + c] = h->ds.scale[c]; }
@@ -370,11 +371,14 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     ps.grid = s.grid ? 1 : 0;
     ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
     ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
-    if (!kbk_solve_use_v1()) {
-        // K3 v3: one persistent launch for the whole slice (solve + finalize fused)
-        long long ntiles = (s.count + KB_TN - 1) / KB_TN;
+    const bool f32 = h->dtype == KB200_F32;
+    if (f32 || !kbk_solve_use_v1()) {
+        // K3 v3 (fp64 DMMA) / tcgen05 TF32 kernel: one persistent launch for the whole slice
+        const int tp = f32 ? kbk_solve_tf32_tile_points() : KB_TN;
+        long long ntiles = (s.count + tp - 1) / tp;
         int grid = (int)std::min<long long>(ntiles, h->num_sms);
-        CU(h, h->wScratch.reserve(kbk_solve_pt_scratch_doubles(h->n, grid) * sizeof(double)));
+        CU(h, h->wScratch.reserve(f32 ? kbk_solve_tf32_scratch_bytes(h->n, grid)
+                                      : kbk_solve_pt_scratch_doubles(h->n, grid) * sizeof(double)));
         SolvePtParams pp{};
         pp.vg = h->vg; pp.an = h->an; ps.first = s.first; pp.ps = ps;
         pp.n = h->n; pp.na = h->na; pp.nrb = h->nrb; pp.n_rl = h->n_rl; pp.n_hd = h->n_hd;
@@ -387,7 +391,8 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
         pp.m = s.count; pp.scratch = h->wScratch.as<double>();
         pp.z_out = d_z; pp.ss_out = d_ss;
         CU(h, cudaEventRecord(h->ev[7], st));
-        CU(h, kbk_solve_pt(h->dim, pp, grid, st));
+        if (f32) CU(h, kbk_solve_tf32(h->dim, pp, grid, st));
+        else CU(h, kbk_solve_pt(h->dim, pp, grid, st));
         CU(h, cudaEventRecord(h->ev[8], st));
         h->launches += 1; h->solve_launches += 1;
         return KB200_OK;

@@ -83,6 +83,14 @@ cudaError_t kbk_solve_pt(int dim, const SolvePtParams& p, int grid, cudaStream_t
 bool        kbk_solve_use_v1();
 size_t      kbk_solve_pt_scratch_doubles(int n, int grid);
 
+// fp32 path (solve_tf32.cu): tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators
+cudaError_t kbk_solve_tf32_init();
+cudaError_t kbk_solve_tf32(int dim, const SolvePtParams& p, int grid, cudaStream_t st);
+cudaError_t kbk_pack_tf32(const double* W, int ld, int n, int n_pad, int na, const double* Uz, const PackMap& pm,
+                          void* out, cudaStream_t st);
+size_t      kbk_solve_tf32_scratch_bytes(int n, int grid);
+int         kbk_solve_tf32_tile_points();
+
 // moving window (knn.cu)
 struct KnnParams {
     VgParams vg;
