@@ -209,6 +209,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL prints its version) must not write to stdout: rank 0 prints exactly ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: backend='cuda' has no CPU fallback")
     torch.cuda.set_device(local)
@@ -351,7 +355,10 @@ def run_ours(args):
             "gpu_launches": int(launches.item()),
             "clocks": sampler.result(),
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -35,6 +35,7 @@ struct kb200_ctx {
 
     // description
     bool described = false, ready = false, knn_ready = false;
+    int gform = 0;            // 1: general (indefinite) fallback, tiles hold the symmetric inverse
     int dim = 2, dtype = KB200_F64, n = 0, n_pad = 0, ld = 0, n_rl = 0, n_hd = 0, K1 = 1, na = 2, nrb = 0;
     VgParams vg{};
     Aniso an{};
@@ -258,6 +259,7 @@ extern "C" int kb200_blob_commit(kb200_handle h) {
     CU(h, cudaStreamSynchronize(h->stream));
     if (hdr[0] != KB_MAGIC) return fail(h, KB200_ESTATE, "blob does not hold a factored problem");
     h->vg.c0 = hdr[1];
+    h->gform = (int)hdr[34];
     for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { h->ds.shift[c] = hdr[2 + c]; h->ds.scale[c] = hdr[18 + c]; }
     h->ready = true;
     return KB200_OK;
@@ -307,6 +309,7 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
     // dimension (e.g. hole-effect in 2-D/3-D) never becomes positive definite.
     const bool unbounded = (h->vg.model == KB200_VG_LINEAR || h->vg.model == KB200_VG_POWER);
     const int max_try = unbounded ? 5 : 1;
+    const double c0_first = h->vg.c0;
     int hflag = 0;
     float t_asm = 0.f, t_chol = 0.f;
     for (int attempt = 0; attempt < max_try; ++attempt) {
@@ -322,25 +325,53 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
         if (hflag == 0) break;
         h->vg.c0 *= 2.0;
     }
-    if (hflag != 0) {
-        h->launches += launches;
-        return fail(h, KB200_ESINGULAR,
-                    "kriging matrix is not conditionally positive definite for this variogram/dimension "
-                    "(Cholesky pivot " + std::to_string(hflag - 1) + "); the general indefinite path is not built");
-    }
-    CU(h, kbk_trtri(h->wC.as<double>(), h->wW.as<double>(), h->wT.as<double>(), ld, np, st, &launches));
-    CU(h, cudaEventRecord(h->ev[5], st));
+    h->gform = 0;
     double* Fz = h->wF.as<double>();
     double* Hz = Fz + (size_t)KB_MAXAUX * np;
     double* Uz = Hz + (size_t)KB_MAXAUX * np;
     CU(h, cudaMemsetAsync(consts, 0, 512 * sizeof(double), st));
+    if (hflag != 0) {
+        // C is not positive definite: the variogram is not conditionally negative definite in this
+        // dimension (e.g. hole-effect on dense scatter). General fallback: Gauss-Jordan inverse with
+        // partial pivoting + quadratic-form solve. fp64 only.
+        if (h->dtype != KB200_F64) {
+            h->launches += launches;
+            return fail(h, KB200_EUNSUPPORTED, "dtype=float32 needs a positive definite covariance form "
+                        "(the variogram is not valid in this dimension); use float64");
+        }
+        h->vg.c0 = c0_first;
+        CU(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
+        CU(h, cudaEventRecord(h->ev[3], st));
+        CU(h, kbk_assemble(h->dim, h->vg, nn, np, ld, ax, ay, az, h->wC.as<double>(), st)); ++launches;
+        double* rowbuf = h->wT.as<double>();
+        double* colbuf = rowbuf + np;
+        int* piv = reinterpret_cast<int*>(colbuf + np);
+        CU(h, kbk_general_inverse(h->wC.as<double>(), ld, nn, np, rowbuf, colbuf, piv, flag, st, &launches));
+        CU(h, cudaEventRecord(h->ev[4], st));
+        CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        t_chol += ev_ms(h->ev[3], h->ev[4]);
+        if (hflag != 0) {
+            h->launches += launches;
+            return fail(h, KB200_ESINGULAR, "kriging matrix is singular (zero pivot in column " +
+                        std::to_string(hflag - 1) + ")");
+        }
+        h->gform = 1;
+        CU(h, cudaEventRecord(h->ev[5], st));
+        CU(h, kbk_dual_gform(h->wC.as<double>(), ld, nn, np, h->n_rl, h->n_hd, ax, ay, az, h->ds, rh, rv,
+                             Fz, Uz, consts, flag, st, &launches));
+        CU(h, kbk_pack_gform(h->wC.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st)); ++launches;
+    } else {
+    CU(h, kbk_trtri(h->wC.as<double>(), h->wW.as<double>(), h->wT.as<double>(), ld, np, st, &launches));
+    CU(h, cudaEventRecord(h->ev[5], st));
     CU(h, kbk_dual(h->wW.as<double>(), ld, nn, np, h->n_rl, h->n_hd, ax, ay, az, h->ds, rh, rv,
                    Fz, Hz, Uz, consts, flag, st, &launches));
     if (h->dtype == KB200_F32) CU(h, kbk_pack_tf32(h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
     else CU(h, kbk_pack(h->dtype, h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
     ++launches;
+    }
     double hdr[64] = {0};
-    hdr[0] = KB_MAGIC; hdr[1] = h->vg.c0;
+    hdr[0] = KB_MAGIC; hdr[1] = h->vg.c0; hdr[34] = (double)h->gform;
     for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { hdr[2 + c] = h->ds.shift[c]; hdr[18 + c] = h->ds.scale[c]; }
     CU(h, cudaMemcpyAsync(blob, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
     CU(h, cudaEventRecord(h->ev[6], st));
@@ -388,7 +419,7 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
         pp.tiles = blob + h->off_tiles; pp.pm = h->pm; pp.ds = h->ds;
         pp.consts = reinterpret_cast<double*>(blob + h->off_consts);
         pp.drift_pts = s.d_drift; pp.drift_stride = s.drift_stride; pp.drift_first = s.drift_first;
-        pp.m = s.count; pp.scratch = h->wScratch.as<double>();
+        pp.m = s.count; pp.scratch = h->wScratch.as<double>(); pp.gform = h->gform;
         pp.z_out = d_z; pp.ss_out = d_ss;
         CU(h, cudaEventRecord(h->ev[7], st));
         if (f32) CU(h, kbk_solve_tf32(h->dim, pp, grid, st));
@@ -397,6 +428,7 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
         h->launches += 1; h->solve_launches += 1;
         return KB200_OK;
     }
+    if (h->gform) return fail(h, KB200_EUNSUPPORTED, "KB200_SOLVE_V1 does not implement the general fallback");
     const int64_t chunk = KB_CHUNK;
     int64_t cmax = std::min<int64_t>(chunk, (int64_t)align_up((size_t)s.count, KB_TN));
     CU(h, h->wPart.reserve((size_t)h->nrb * cmax * sizeof(double)));

@@ -535,3 +535,178 @@ cudaError_t kbk_pack(int dtype, const double* W, int ld, int n, int n_pad, int n
     else pack_kernel<float><<<grid, 256, 0, st>>>(W, ld, n, n_pad, na, Uz, pm, (float*)out);
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------
+// General fallback when C is not positive definite (a variogram that is not conditionally negative
+// definite in the working dimension, e.g. hole-effect on dense 2-D scatter; the reference's LU still
+// inverts such systems, ok.py:663). In-place Gauss-Jordan inversion with partial pivoting, two
+// launches per column (memory-bound, O(n^3) traffic: a slow path for a corner case):
+//   gj_pivot : pivot search in column k, row swap, scale of the pivot row, capture of column k
+//   gj_update: a[i][j] -= col[i] * row[j] for i != k
+// followed by the column swaps in reverse order. The result G = C^-1 is then used in the
+// quadratic-form variant of the solve kernel (q = c^T G c through the lower triangle with doubled
+// off-diagonals).
+__global__ void __launch_bounds__(1024) gj_pivot_kernel(double* __restrict__ A, int ld, int n, int k,
+                                                         double* __restrict__ rowbuf, double* __restrict__ colbuf,
+                                                         int* __restrict__ piv, int* __restrict__ flag) {
+    __shared__ double sval[1024];
+    __shared__ int sidx[1024];
+    const int tid = threadIdx.x;
+    double best = -1.0; int bi = k;
+    for (int i = k + tid; i < n; i += 1024) {
+        double v = fabs(A[(size_t)i * ld + k]);
+        if (v > best) { best = v; bi = i; }
+    }
+    sval[tid] = best; sidx[tid] = bi;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (tid < o) {
+            if (sval[tid + o] > sval[tid] || (sval[tid + o] == sval[tid] && sidx[tid + o] < sidx[tid])) {
+                sval[tid] = sval[tid + o]; sidx[tid] = sidx[tid + o];
+            }
+        }
+        __syncthreads();
+    }
+    const int p = sidx[0];
+    if (tid == 0) { piv[k] = p; if (!(sval[0] > 0.0) && *flag == 0) *flag = 1 + k; }
+    if (p != k) {
+        for (int j = tid; j < n; j += 1024) {
+            double t = A[(size_t)k * ld + j]; A[(size_t)k * ld + j] = A[(size_t)p * ld + j]; A[(size_t)p * ld + j] = t;
+        }
+    }
+    __syncthreads();
+    double d = A[(size_t)k * ld + k];
+    if (!(fabs(d) > 0.0)) d = 1.0;
+    const double inv = 1.0 / d;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {           // capture column k, then clear it
+        double c = (i == k) ? 0.0 : A[(size_t)i * ld + k];
+        colbuf[i] = c;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) if (i != k) A[(size_t)i * ld + k] = 0.0;
+    for (int j = tid; j < n; j += 1024) {
+        double v = (j == k) ? inv : A[(size_t)k * ld + j] * inv;
+        A[(size_t)k * ld + j] = v;
+        rowbuf[j] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) gj_update_kernel(double* __restrict__ A, int ld, int n, int k,
+                                                         const double* __restrict__ rowbuf,
+                                                         const double* __restrict__ colbuf) {
+    int j = blockIdx.x * 256 + threadIdx.x;
+    int i0 = blockIdx.y * 16;
+    if (j >= n) return;
+    double r = rowbuf[j];
+#pragma unroll 4
+    for (int ii = 0; ii < 16; ++ii) {
+        int i = i0 + ii;
+        if (i < n && i != k) {
+            double c = colbuf[i];
+            if (c != 0.0) A[(size_t)i * ld + j] -= c * r;
+        }
+    }
+}
+
+__global__ void gj_colswap_kernel(double* __restrict__ A, int ld, int n, const int* __restrict__ piv) {
+    // one thread per row: apply the recorded swaps as column swaps in reverse order
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* row = A + (size_t)i * ld;
+    for (int k = n - 1; k >= 0; --k) {
+        int p = piv[k];
+        if (p != k) { double t = row[k]; row[k] = row[p]; row[p] = t; }
+    }
+}
+
+// Uz[i][c] = sum_k G[i][k] Fz[k][c]  (full symmetric G; one warp per row)
+__global__ void __launch_bounds__(256) dual_g_kernel(const double* __restrict__ G, int ld, int n, int n_pad, int na,
+                                                      const double* __restrict__ Fz, double* __restrict__ Uz) {
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    double acc[KB_MAXAUX];
+#pragma unroll
+    for (int c = 0; c < KB_MAXAUX; ++c) acc[c] = 0.0;
+    if (row < n) {
+        const double* gr = G + (size_t)row * ld;
+        for (int k = lane; k < n; k += 32) {
+            double w = gr[k];
+#pragma unroll
+            for (int c = 0; c < KB_MAXAUX; ++c)
+                if (c < na) acc[c] += w * Fz[(size_t)c * n_pad + k];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < KB_MAXAUX; ++c) {
+        if (c < na) {
+            double v = acc[c];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) Uz[(size_t)c * n_pad + row] = v;
+        }
+    }
+}
+
+// pack for the quadratic-form variant: T = lower triangle of the symmetrised G with doubled off-diagonals
+__global__ void __launch_bounds__(256) pack_gform_kernel(const double* __restrict__ G, int ld, int n, int n_pad, int na,
+                                                          const double* __restrict__ Uz, PackMap pm,
+                                                          double* __restrict__ out) {
+    int I = blockIdx.y, kt = blockIdx.x;
+    if (kt >= pm.ktiles[I]) return;
+    double* o = out + ((size_t)pm.tile_off[I] + kt) * (KB_BM * KB_BK);
+    for (int e = threadIdx.x; e < KB_BM * KB_BK; e += 256) {
+        int lane = e & 31, mt = (e >> 5) & 31, k4 = e >> 10;
+        int r = I * KB_BM + mt * 8 + (lane >> 2);
+        int k = kt * KB_BK + k4 * 4 + (lane & 3);
+        double v = 0.0;
+        if (r < n) {
+            if (k < r) v = G[(size_t)r * ld + k] + G[(size_t)k * ld + r];
+            else if (k == r) v = G[(size_t)r * ld + r];
+        } else if (r < n + na) { if (k < n) v = Uz[(size_t)(r - n) * n_pad + k]; }
+        o[e] = v;
+    }
+}
+
+// full symmetric assemble for the fallback (upper tiles too): mirror the lower triangle
+__global__ void symmetrize_kernel(double* __restrict__ C, int ld, int n_pad) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j < n_pad && j > i) C[(size_t)i * ld + j] = C[(size_t)j * ld + i];
+}
+
+cudaError_t kbk_general_inverse(double* C, int ld, int n, int n_pad, double* rowbuf, double* colbuf, int* piv,
+                                int* flag, cudaStream_t st, int* launches) {
+    // C holds the assembled lower triangle (+ diagonal); build the full matrix, then invert the n x n part
+    symmetrize_kernel<<<dim3((n_pad + 255) / 256, n_pad), 256, 0, st>>>(C, ld, n_pad);
+    ++*launches;
+    dim3 ug((n + 255) / 256, (n + 15) / 16);
+    for (int k = 0; k < n; ++k) {
+        gj_pivot_kernel<<<1, 1024, 0, st>>>(C, ld, n, k, rowbuf, colbuf, piv, flag);
+        gj_update_kernel<<<ug, 256, 0, st>>>(C, ld, n, k, rowbuf, colbuf);
+    }
+    gj_colswap_kernel<<<(n + 127) / 128, 128, 0, st>>>(C, ld, n, piv);
+    *launches += 2 * n + 1;
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_dual_gform(const double* G, int ld, int n, int n_pad, int n_rl, int n_hd,
+                           const double* ax, const double* ay, const double* az, const DriftScale& ds,
+                           const double* hd, const double* values,
+                           double* Fz, double* Uz, double* consts, int* flag, cudaStream_t st, int* launches) {
+    int K1 = n_rl + n_hd + 1, na = K1 + 1;
+    build_fz_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, n_rl, n_hd, ax, ay, az, ds, hd, values, Fz);
+    dual_g_kernel<<<(n_pad + 7) / 8, 256, 0, st>>>(G, ld, n, n_pad, na, Fz, Uz);
+    dual_small_kernel<<<1, 256, 0, st>>>(n, n_pad, K1, Fz, Uz, consts, flag);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t kbk_pack_gform(const double* G, int ld, int n, int n_pad, int na, const double* Uz,
+                           const PackMap& pm, void* out, cudaStream_t st) {
+    int maxkt = 0;
+    for (int i = 0; i < pm.nrb; ++i) maxkt = pm.ktiles[i] > maxkt ? pm.ktiles[i] : maxkt;
+    dim3 grid(maxkt, pm.nrb);
+    pack_gform_kernel<<<grid, 256, 0, st>>>(G, ld, n, n_pad, na, Uz, pm, (double*)out);
+    return cudaGetLastError();
+}

@@ -42,6 +42,7 @@ struct SolvePtParams {
     const double* consts;
     const double* drift_pts; long long drift_stride, drift_first;
     long long m;
+    int gform;                // 1: tiles hold the symmetric inverse (quadratic form q = c^T G c), 0: W = chol(C)^-1
     double* scratch;          // [grid][ceil(n/16)][16*64]  RHS column blocks in fragment order
     double* z_out; double* ss_out;
 };
@@ -74,6 +75,14 @@ cudaError_t kbk_dual(const double* W, int ld, int n, int n_pad, int n_rl, int n_
 cudaError_t kbk_pack(int dtype, const double* W, int ld, int n, int n_pad, int na, const double* Uz,
                      const PackMap& pm, void* out, cudaStream_t st);
 
+cudaError_t kbk_general_inverse(double* C, int ld, int n, int n_pad, double* rowbuf, double* colbuf, int* piv,
+                                int* flag, cudaStream_t st, int* launches);
+cudaError_t kbk_dual_gform(const double* G, int ld, int n, int n_pad, int n_rl, int n_hd,
+                           const double* ax, const double* ay, const double* az, const DriftScale& ds,
+                           const double* hd, const double* values,
+                           double* Fz, double* Uz, double* consts, int* flag, cudaStream_t st, int* launches);
+cudaError_t kbk_pack_gform(const double* G, int ld, int n, int n_pad, int na, const double* Uz,
+                           const PackMap& pm, void* out, cudaStream_t st);
 cudaError_t kbk_factor_init();
 cudaError_t kbk_solve_init();   // opt-in shared memory attributes
 size_t      kbk_solve_smem(int dtype);

@@ -341,10 +341,22 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                 for (int mt = 0; mt < 4; ++mt) {
                     const int r = r0w + mt * 8 + (lane >> 2);
                     if (r < P.n) {
+                        if (!P.gform) {
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) {
-                            qs[nt][0] += acc[mt][nt][0] * acc[mt][nt][0];
-                            qs[nt][1] += acc[mt][nt][1] * acc[mt][nt][1];
+                            for (int nt = 0; nt < 8; ++nt) {
+                                qs[nt][0] += acc[mt][nt][0] * acc[mt][nt][0];
+                                qs[nt][1] += acc[mt][nt][1] * acc[mt][nt][1];
+                            }
+                        } else {
+                            // quadratic form c^T G c: multiply row r of T c by c[r] (read back from the
+                            // scratch ring: tile r/16, fragment order)
+                            const double* bt = scratch + (size_t)(r >> 4) * (KB_BK * KB_TN) + ((r & 15) >> 2) * 256 + (r & 3);
+#pragma unroll
+                            for (int nt = 0; nt < 8; ++nt) {
+                                const int c0i = nt * 8 + 2 * (lane & 3);
+                                qs[nt][0] += acc[mt][nt][0] * bt[(c0i >> 3) * 32 + (c0i & 7) * 4];
+                                qs[nt][1] += acc[mt][nt][1] * bt[((c0i + 1) >> 3) * 32 + ((c0i + 1) & 7) * 4];
+                            }
                         }
                     } else if (r < P.n + P.na) {
                         double* ao = auxs + (r - P.n) * KB_TN + 2 * (lane & 3);

@@ -143,14 +143,62 @@ def test_full_size_properties_cfg2(pk):
     assert_allclose(z.ravel()[pick], zc[:256], rtol=1e-12)
 
 
-def test_invalid_variogram_is_reported(pk):
-    """hole-effect is not conditionally negative definite in 2-D for dense scatter: the covariance-form
-    factorisation must fail loudly (LinAlgError), never return numbers silently."""
+def test_indefinite_variogram_takes_general_path(pk, ref_cases):
+    """hole-effect is not conditionally negative definite in 2-D on dense scatter: the covariance-form
+    Cholesky fails and the general (Gauss-Jordan + quadratic form) path must reproduce the reference's
+    LU-based numbers (the oracle inverts the same indefinite matrix, ok.py:663)."""
+    from oracle import krige_oracle as ko
     xyz, val = cases.synth_data(9, 600, 2)
-    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="hole-effect",
-                            variogram_parameters=[1.0, 300.0, 0.05])
+    params = [1.0, 300.0, 0.05]
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="hole-effect", variogram_parameters=params)
+    pts = cases.synth_points(9, 300, 2, xyz)
+    z, ss = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
+    zo, so = ko.krige(xyz, val, "hole-effect", ko.stored_parameters("hole-effect", params), pts)
+    assert_parity(z, zo, R64, "hole-effect z")
+    assert_parity(ss, so, R64, "hole-effect ss")
+    # universal kriging through the same fallback
+    uk = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="hole-effect", variogram_parameters=params,
+                             drift_terms=["regional_linear"])
+    z, ss = uk.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
+    zo, so = ko.krige(xyz, val, "hole-effect", ko.stored_parameters("hole-effect", params), pts, regional_linear=True)
+    assert_parity(z, zo, R64, "hole-effect uk z")
+    assert_parity(ss, so, R64, "hole-effect uk ss")
+    # the small committed reference case
+    case = cases.CASE_BY_NAME["ok2d_hole_effect_small"]
+    inp, z, ss = _run(pk, case)
+    assert_parity(z, ref_cases[case["name"] + "/z"], R64, "hole small z")
+    assert_parity(ss, ref_cases[case["name"] + "/ss"], R64, "hole small ss")
+    with pytest.raises(NotImplementedError):
+        ok.execute("points", pts[:4, 0], pts[:4, 1], backend="cuda", dtype="float32")
+
+
+def test_singular_system_is_reported(pk):
+    """Duplicate data points with a zero nugget make the kriging matrix exactly singular: the reference's
+    scipy.linalg.inv raises LinAlgError; so must backend='cuda' (never silent numbers)."""
+    xyz, val = cases.synth_data(10, 50, 2)
+    xyz = np.vstack([xyz, xyz[:3]])
+    val = np.concatenate([val, val[:3]])
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="spherical",
+                            variogram_parameters=[1.0, 300.0, 0.0])
     with pytest.raises(np.linalg.LinAlgError):
-        ok.execute("points", xyz[:4, 0] + 1.0, xyz[:4, 1], backend="cuda")
+        ok.execute("points", [10.0], [20.0], backend="cuda")
+
+
+def test_edge_sizes(pk):
+    """Empty and tiny inputs: zero prediction points, one prediction point, two data points."""
+    xyz, val = cases.synth_data(12, 40, 2)
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="linear", variogram_parameters=[0.01, 0.1])
+    z, ss = ok.execute("points", np.zeros(0), np.zeros(0), backend="cuda")
+    assert z.shape == (0,) and ss.shape == (0,)
+    z, ss = ok.execute("grid", [500.0], [500.0], backend="cuda")
+    assert z.shape == (1, 1)
+    from oracle import krige_oracle as ko
+    two = pk.OrdinaryKriging([0.0, 10.0], [0.0, 5.0], [1.0, 3.0], variogram_model="linear", variogram_parameters=[0.5, 0.1])
+    z, ss = two.execute("points", [2.0, 7.0], [1.0, 4.0], backend="cuda")
+    zo, so = ko.krige(np.array([[0.0, 0.0], [10.0, 5.0]]), np.array([1.0, 3.0]), "linear", [0.5, 0.1],
+                      np.array([[2.0, 1.0], [7.0, 4.0]]))
+    assert_allclose(z, zo, rtol=1e-10)
+    assert_allclose(ss, so, rtol=1e-10)
 
 
 def test_custom_variogram_not_on_device(pk):
