@@ -13,6 +13,13 @@
 #define KB_VERSION 1001
 #define KB_CHUNK (128 * 1024)        // prediction points per solve launch (partials stay L2-sized)
 
+struct Src {
+    bool grid; int64_t nx, ny, nz;
+    const double *a, *b, *c;      // points (px,py,pz) or axes (gx,gy,gz), device pointers
+    int64_t first, count;
+    const double* d_drift; int64_t drift_stride, drift_first;
+};
+
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
@@ -57,6 +64,7 @@ struct kb200_ctx {
     DevBuf kSorted, kCells;
     KnnParams kp{};
     int k_ncells = 0;
+    struct { int k; Src s; double* d_z; double* d_ss; } knn_last{};
 
     cudaEvent_t ev[16] = {};
     double tm[12] = {};
@@ -388,13 +396,6 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
 }
 
 // ---- execute --------------------------------------------------------------
-struct Src {
-    bool grid; int64_t nx, ny, nz;
-    const double *a, *b, *c;      // points (px,py,pz) or axes (gx,gy,gz), device pointers
-    int64_t first, count;
-    const double* d_drift; int64_t drift_stride, drift_first;
-};
-
 static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     cudaStream_t st = h->stream;
     char* blob = h->blob.as<char>();
@@ -647,10 +648,11 @@ extern "C" int kb200_set_problem_knn(kb200_handle h, int dim, int64_t n,
     return KB200_OK;
 }
 
-static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss) {
+static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss, int chol = 1) {
+    h->knn_last = {k, s, d_z, d_ss};
     if (k < 2) return fail(h, KB200_EBADARG, "n_closest_points has to be at least two!");
     if (k > h->n) return fail(h, KB200_EBADARG, "n_closest_points exceeds the number of data points");
-    if (kbk_knn_smem_per_warp(k) > 200 * 1024) return fail(h, KB200_EUNSUPPORTED, "n_closest_points too large for the shared-memory local solver");
+    if (kbk_knn_smem_per_warp(k, 0) > 200 * 1024) return fail(h, KB200_EUNSUPPORTED, "n_closest_points too large for the shared-memory local solver");
     cudaStream_t st = h->stream;
     int* flag = h->wFlag.as<int>();
     CU(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
@@ -662,7 +664,7 @@ static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss)
     ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz; ps.first = s.first;
     kp.ps = ps; kp.m = s.count; kp.z_out = d_z; kp.ss_out = d_ss; kp.flag = flag;
     CU(h, cudaEventRecord(h->ev[7], st));
-    CU(h, kbk_knn_solve(kp, st));
+    CU(h, kbk_knn_solve(kp, chol, st));
     CU(h, cudaEventRecord(h->ev[8], st));
     h->launches += 1; h->solve_launches += 1;
     return KB200_OK;
@@ -673,6 +675,15 @@ static int knn_finish(kb200_ctx* h) {
     CU(h, cudaMemcpyAsync(&hflag, h->wFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->tm[9] += ev_ms(h->ev[7], h->ev[8]);
+    if (hflag == 2) {
+        // a local covariance block was not positive definite (variogram not valid in this dimension):
+        // repeat the launch with the pivoted-LU solver (dgesv semantics)
+        int rc = run_knn(h, h->knn_last.k, h->knn_last.s, h->knn_last.d_z, h->knn_last.d_ss, 0);
+        if (rc) return rc;
+        CU(h, cudaMemcpyAsync(&hflag, h->wFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->tm[9] += ev_ms(h->ev[7], h->ev[8]);
+    }
     if (hflag) return fail(h, KB200_ESINGULAR, "Singular matrix");
     return KB200_OK;
 }

@@ -119,5 +119,5 @@ struct KnnParams {
 cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, const double* az, const double* values,
                           KnnParams& kp, double* sx, double* sy, double* sz, double* sv, int* sorig,
                           int* cell_of, int* cell_start, int* cursor, int ncells, cudaStream_t st, int* launches);
-cudaError_t kbk_knn_solve(const KnnParams& p, cudaStream_t st);
-size_t      kbk_knn_smem_per_warp(int k);
+cudaError_t kbk_knn_solve(const KnnParams& p, int chol, cudaStream_t st);
+size_t      kbk_knn_smem_per_warp(int k, int chol);

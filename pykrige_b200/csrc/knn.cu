@@ -92,8 +92,13 @@ __device__ __forceinline__ void warp_bitonic(double* d2, int* id, const int* __r
     }
 }
 
-template <int DIM, int MODEL>
-__global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ KnnParams P, int warps_per_cta,
+// CHOL = true : packed lower-triangular Cholesky of the local covariance block (no pivoting, half the
+//               updates, 20 KB of shared memory per point at k = 64 -> more points in flight); needs k <= 128.
+//               A non-positive pivot (variogram not valid in this dimension) sets *flag = 2 and the host
+//               re-runs the launch with CHOL = false.
+// CHOL = false: LU with partial pivoting on the full k x k block (dgesv semantics, cok.pyx:165-174).
+template <int DIM, int MODEL, bool CHOL>
+__global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ KnnParams P, int warps_per_cta,
                                                          int per_warp_doubles) {
     extern __shared__ __align__(16) double ksm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
     const int S = k | 1;                       // odd row stride: conflict-free column walks
     double* base = ksm + (size_t)warp * per_warp_doubles;
     double* A = base;                          // k * S  (aliased by the candidate buffers during the search)
-    size_t a_doubles = (size_t)k * S;
+    size_t a_doubles = CHOL ? (size_t)k * (k + 1) / 2 : (size_t)k * S;
     size_t cand_doubles = KN_CAP + KN_CAP / 2; // d2[CAP] doubles + id[CAP] ints
     size_t off = a_doubles > cand_doubles ? a_doubles : cand_doubles;
     double* rc = base + off;                   // rhs c (becomes C^-1 c)
@@ -203,6 +208,82 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
     }
     __syncwarp();                                      // candidates consumed: A may be overwritten now
 
+    if (CHOL) {
+        // ---------------- K5 (Cholesky): packed lower triangle, tri(i,j) = i(i+1)/2 + j ----------------
+        const int ntri = k * (k + 1) / 2;
+#pragma unroll 4
+        for (int e = lane; e < ntri; e += 32) {
+            int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            while (i * (i + 1) / 2 > e) --i;
+            const int j = e - i * (i + 1) / 2;
+            double v = vg.c0;
+            if (i != j) {
+                double d = kb_dist<DIM>(nx[i], ny[i], nz[i], nx[j], ny[j], nz[j]);
+                v = vg.c0 - kb_gamma<MODEL>(vg, d);
+            }
+            A[e] = v;
+        }
+        __syncwarp();
+        bool notpd = false;
+        for (int pc = 0; pc < k; ++pc) {
+            const int tp = pc * (pc + 1) / 2;
+            const double dpp = A[tp + pc];
+            if (!(dpp > 0.0)) { notpd = true; break; }
+            const double sq = sqrt(dpp);
+            const double inv = 1.0 / sq;
+            // forward substitution of both right-hand sides rides along (column pc is final here)
+            const double yc = rc[pc] * inv, y1 = r1[pc] * inv;
+            double lj[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = lane + 32 * q;
+                double l = 0.0;
+                if (j > pc && j < k) {
+                    const int idx = j * (j + 1) / 2 + pc;
+                    l = A[idx] * inv;
+                    A[idx] = l;
+                    rc[j] -= l * yc;
+                    r1[j] -= l * y1;
+                }
+                lj[q] = l;
+            }
+            __syncwarp();
+            if (lane == 0) { A[tp + pc] = sq; rc[pc] = yc; r1[pc] = y1; }
+            // trailing update of the lower triangle: a[i][j] -= l_i * l_j, pc < j <= i
+#pragma unroll 2
+            for (int i = pc + 1; i < k; ++i) {
+                const int ti = i * (i + 1) / 2;
+                const double li = A[ti + pc];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q * 32 <= i && q * 32 + 31 > pc) {
+                        const int j = lane + 32 * q;
+                        if (j > pc && j <= i) A[ti + j] -= li * lj[q];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (notpd) {
+            if (lane == 0) { atomicMax(P.flag, 2); P.z_out[p] = 0.0; P.ss_out[p] = 0.0; }
+            return;
+        }
+        // backward substitution L^T x = y (row walks: contiguous)
+        for (int pc = k - 1; pc >= 0; --pc) {
+            const int tp = pc * (pc + 1) / 2;
+            const double inv = 1.0 / A[tp + pc];
+            const double xc = rc[pc] * inv, x1 = r1[pc] * inv;
+            __syncwarp();
+            if (lane == 0) { rc[pc] = xc; r1[pc] = x1; }
+            for (int i = lane; i < pc; i += 32) {
+                const double u = A[tp + i];
+                rc[i] -= u * xc;
+                r1[i] -= u * x1;
+            }
+            __syncwarp();
+        }
+    } else {
     // ---------------- K5: local system ----------------
     // C[i][j] = c0 - gamma(|x_i - x_j|), C[i][i] = c0   (ok.py:641-644 in covariance form)
     for (int e = lane; e < k * k; e += 32) {
@@ -267,7 +348,7 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
         __syncwarp();
     }
     if (singular) {
-        if (lane == 0) { atomicExch(P.flag, 1); P.z_out[p] = 0.0; P.ss_out[p] = 0.0; }
+        if (lane == 0) { atomicMax(P.flag, 1); P.z_out[p] = 0.0; P.ss_out[p] = 0.0; }
         return;
     }
     // back substitution U x = y for both right-hand sides
@@ -283,6 +364,7 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
         }
         __syncwarp();
     }
+    }   // CHOL / LU
     // bordered-system identities: mu = (1'C^-1 c - 1)/(1'C^-1 1); lambda = C^-1 c - mu C^-1 1
     double s1 = 0.0, sc = 0.0;
     for (int t = lane; t < k; t += 32) { s1 += r1[t]; sc += rc[t]; }
@@ -302,27 +384,25 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
 }
 
 // ---- host side -------------------------------------------------------------
-size_t kbk_knn_smem_per_warp(int k) {
+size_t kbk_knn_smem_per_warp(int k, int chol) {
     size_t S = (size_t)(k | 1);
-    size_t a = (size_t)k * S, c = KN_CAP + KN_CAP / 2;
+    size_t a = chol ? (size_t)k * (k + 1) / 2 : (size_t)k * S, c = KN_CAP + KN_CAP / 2;
     return ((a > c ? a : c) + 7 * (size_t)k + 2) * sizeof(double);
 }
 
-template <int DIM>
+template <int DIM, bool CHOL>
 static cudaError_t knn_launch_dim(const KnnParams& p, cudaStream_t st) {
-    size_t per = kbk_knn_smem_per_warp(p.k);
-    int wpc = (int)std::min<size_t>(8, (200 * 1024) / per);
+    size_t per = kbk_knn_smem_per_warp(p.k, CHOL ? 1 : 0);
+    int wpc = (int)std::min<size_t>(16, (220 * 1024) / per);      // as many points in flight per SM as fit
     if (wpc < 1) return cudaErrorInvalidValue;
-    // keep several CTAs per SM resident when k is small
-    while (wpc > 1 && per * wpc > 100 * 1024) --wpc;
     size_t smem = per * wpc;
     unsigned grid = (unsigned)((p.m + wpc - 1) / wpc);
     int per_d = (int)(per / sizeof(double));
     switch (p.vg.model) {
 #define KB_CASE(M) case M: { \
-        cudaError_t e = cudaFuncSetAttribute(knn_solve_kernel<DIM, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = cudaFuncSetAttribute(knn_solve_kernel<DIM, M, CHOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e; \
-        knn_solve_kernel<DIM, M><<<grid, wpc * 32, smem, st>>>(p, wpc, per_d); } break;
+        knn_solve_kernel<DIM, M, CHOL><<<grid, wpc * 32, smem, st>>>(p, wpc, per_d); } break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
         KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
 #undef KB_CASE
@@ -331,8 +411,10 @@ static cudaError_t knn_launch_dim(const KnnParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t kbk_knn_solve(const KnnParams& p, cudaStream_t st) {
-    return p.dim == 2 ? knn_launch_dim<2>(p, st) : knn_launch_dim<3>(p, st);
+cudaError_t kbk_knn_solve(const KnnParams& p, int chol, cudaStream_t st) {
+    if (chol && p.k <= 128)
+        return p.dim == 2 ? knn_launch_dim<2, true>(p, st) : knn_launch_dim<3, true>(p, st);
+    return p.dim == 2 ? knn_launch_dim<2, false>(p, st) : knn_launch_dim<3, false>(p, st);
 }
 
 cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, const double* az, const double* values,

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) solve_kernel_f64(const __grid_c
 //            per-point sum of squares in registers;
 //   phase F  the (K+1)x(K+1) drift solve and the two outputs per point are produced in the same CTA:
 //            no partial buffers, no separate finalize pass, fixed summation order (deterministic).
-#define PT_STAGES 4
+#define PT_STAGES 5
 #define PT_THREADS 384
 #define PT_STAGE_BYTES ((KB_BM * KB_BK + KB_BK * KB_TN) * 8)
 
@@ -301,11 +301,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
             for (int nt = 0; nt < 8; ++nt) { qs[nt][0] = 0.0; qs[nt][1] = 0.0; }
             for (int I = 0; I < P.nrb; ++I) {
                 const int kt = P.pm.ktiles[I];
-                const int r0w = I * KB_BM + cw * 32;
-                int warp_kmax;                       // W rows are lower-triangular, dual rows are dense
-                if (r0w + 31 >= P.n && r0w < P.n + P.na) warp_kmax = 0x7fffffff;
-                else if (r0w >= P.n + P.na) warp_kmax = -1;
-                else warp_kmax = r0w + 31;
+                // this warp owns the m-tiles cw, cw+8, cw+16, cw+24 of the 256-row block (8 rows each):
+                // interleaving keeps the eight warps equally busy inside the triangular diagonal block and
+                // lets every m-tile skip the k tiles above the diagonal (W rows are lower-triangular, the
+                // dual rows are dense, padding rows need nothing)
+                int kmax[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r0 = I * KB_BM + (cw + 8 * q) * 8;
+                    if (r0 + 7 >= P.n && r0 < P.n + P.na) kmax[q] = 0x7fffffff;
+                    else if (r0 >= P.n + P.na) kmax[q] = -1;
+                    else kmax[q] = r0 + 7;
+                }
                 double acc[4][8][2];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -316,21 +323,24 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                     // every consumer waits for every stage (also the ones it skips) so that no warp can lap
                     // the ring and arrive twice on empty[s] within one phase
                     mbar_wait(&full[s], (uint32_t)((g / PT_STAGES) & 1));
-                    if (t * KB_BK <= warp_kmax) {
+                    const int k0 = t * KB_BK;
+                    if (k0 <= kmax[3] || k0 <= kmax[2] || k0 <= kmax[1] || k0 <= kmax[0]) {
                         const double* ts = Ts + (size_t)s * KB_BM * KB_BK;
                         const double* bs = Bs + (size_t)s * KB_BK * KB_TN;
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
-                            double fa[4], fb[8];
-#pragma unroll
-                            for (int mt = 0; mt < 4; ++mt) fa[mt] = ts[(k4 * 32 + cw * 4 + mt) * 32 + lane];
+                            double fb[8];
 #pragma unroll
                             for (int nt = 0; nt < 8; ++nt) fb[nt] = bs[(k4 * 8 + nt) * 32 + lane];
 #pragma unroll
-                            for (int mt = 0; mt < 4; ++mt)
+                            for (int q = 0; q < 4; ++q) {
+                                if (k0 <= kmax[q]) {
+                                    const double fa = ts[(k4 * 32 + cw + 8 * q) * 32 + lane];
 #pragma unroll
-                                for (int nt = 0; nt < 8; ++nt)
-                                    kb_dmma(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fb[nt]);
+                                    for (int nt = 0; nt < 8; ++nt)
+                                        kb_dmma(acc[q][nt][0], acc[q][nt][1], fa, fb[nt]);
+                                }
+                            }
                         }
                     }
                     __syncwarp();
@@ -339,7 +349,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                 // row-block epilogue: W rows -> running sum of squares; dual rows -> shared memory
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt) {
-                    const int r = r0w + mt * 8 + (lane >> 2);
+                    const int r = I * KB_BM + (cw + 8 * mt) * 8 + (lane >> 2);
                     if (r < P.n) {
                         if (!P.gform) {
 #pragma unroll

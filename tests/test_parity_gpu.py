@@ -258,3 +258,31 @@ def test_fp32_cases_match_reference(pk, case, ref_cases):
     # 3xTF32 keeps fp32-class accuracy: far inside the 1e-2 budget
     assert np.max(np.abs(np.ravel(z) - np.ravel(zr))) <= 2e-4 * np.max(np.abs(zr))
     assert np.max(np.abs(np.ravel(ss) - np.ravel(sr))) <= 2e-4 * np.max(np.abs(sr))
+
+
+def test_moving_window_goldens_and_fallback(pk, ref_goldens):
+    """tests/test_core.py:1992-2017: OK3D moving window k=10 reproduces the KT3D answer; and a variogram
+    that is not positive definite locally (hole-effect) goes through the pivoted-LU solver and still
+    matches the oracle's scipy.linalg.solve."""
+    from oracle import krige_oracle as ko
+    g = ref_goldens
+    d = g["data3d"]
+    ax = np.arange(10.0)
+    k3 = pk.OrdinaryKriging3D(d[:, 0], d[:, 1], d[:, 2], d[:, 3], variogram_model="linear",
+                              variogram_parameters=[1.0, 0.1])
+    k, ss = k3.execute("grid", ax, ax, ax, backend="cuda", n_closest_points=10)
+    assert_allclose(k, g["answer3d"][:, 0].reshape(10, 10, 10), rtol=1e-3)
+    assert_allclose(ss, g["answer3d"][:, 1].reshape(10, 10, 10), rtol=1e-3)
+    xyz, val = cases.synth_data(21, 800, 2)
+    params = [1.0, 120.0, 0.02]
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="hole-effect", variogram_parameters=params)
+    pts = cases.synth_points(21, 200, 2, xyz)
+    z, ss = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda", n_closest_points=24)
+    zo, so = ko.krige(xyz, val, "hole-effect", ko.stored_parameters("hole-effect", params), pts, n_closest_points=24)
+    assert_parity(z, zo, R64, "knn hole-effect z")
+    assert_parity(ss, so, R64, "knn hole-effect ss")
+    # k > 128 uses the LU solver directly
+    z, ss = ok.execute("points", pts[:20, 0], pts[:20, 1], backend="cuda", n_closest_points=130)
+    zo, so = ko.krige(xyz, val, "hole-effect", ko.stored_parameters("hole-effect", params), pts[:20], n_closest_points=130)
+    assert_parity(z, zo, 1e-4, "knn k130 z")
+    assert_parity(ss, so, 1e-4, "knn k130 ss")
