@@ -203,16 +203,20 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ C, 
         }
         __syncthreads();
     }
-    // inverse by forward substitution: thread c owns column c of X = L^-1
-    if (tid < 64) {
-        int c = tid;
-        x[c][c] = 1.0 / a[c][c];
-        for (int i = c + 1; i < 64; ++i) {
-            double s0 = 0.0, s1 = 0.0;
-            int k = c;
-            for (; k + 1 < i; k += 2) { s0 += a[i][k] * x[k][c]; s1 += a[i][k + 1] * x[k + 1][c]; }
-            if (k < i) s0 += a[i][k] * x[k][c];
-            x[i][c] = -(s0 + s1) / a[i][i];
+    // inverse by forward substitution: four threads (same warp) share column c of X = L^-1 and split the
+    // dot product over k; row i of every column is finished before row i+1 starts (lock-step over i)
+    {
+        const int c = tid >> 2, part = tid & 3;
+        if (part == 0) x[c][c] = 1.0 / a[c][c];
+        __syncwarp();
+        for (int i = 1; i < 64; ++i) {
+            double sacc = 0.0;
+            if (i > c)
+                for (int k = c + part; k < i; k += 4) sacc += a[i][k] * x[k][c];
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (i > c && part == 0) x[i][c] = -sacc / a[i][i];
+            __syncwarp();
         }
     }
     __syncthreads();
