@@ -64,7 +64,6 @@ struct kb200_ctx {
     DevBuf kSorted, kCells;
     KnnParams kp{};
     int k_ncells = 0;
-    struct { int k; Src s; double* d_z; double* d_ss; } knn_last{};
 
     cudaEvent_t ev[16] = {};
     double tm[12] = {};
@@ -648,8 +647,7 @@ extern "C" int kb200_set_problem_knn(kb200_handle h, int dim, int64_t n,
     return KB200_OK;
 }
 
-static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss, int chol = 1) {
-    h->knn_last = {k, s, d_z, d_ss};
+static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss, int chol) {
     if (k < 2) return fail(h, KB200_EBADARG, "n_closest_points has to be at least two!");
     if (k > h->n) return fail(h, KB200_EBADARG, "n_closest_points exceeds the number of data points");
     if (kbk_knn_smem_per_warp(k, 0) > 200 * 1024) return fail(h, KB200_EUNSUPPORTED, "n_closest_points too large for the shared-memory local solver");
@@ -670,15 +668,18 @@ static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss,
     return KB200_OK;
 }
 
-static int knn_finish(kb200_ctx* h) {
+// run the moving window, wait for it and handle the solver flag: 2 = a local covariance block was
+// not positive definite (variogram not valid in this dimension) -> repeat with the pivoted-LU solver
+// (dgesv semantics); 1 = exactly singular local system -> ValueError('Singular matrix').
+static int run_knn_checked(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss) {
+    int rc = run_knn(h, k, s, d_z, d_ss, 1);
+    if (rc) return rc;
     int hflag = 0;
     CU(h, cudaMemcpyAsync(&hflag, h->wFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->tm[9] += ev_ms(h->ev[7], h->ev[8]);
     if (hflag == 2) {
-        // a local covariance block was not positive definite (variogram not valid in this dimension):
-        // repeat the launch with the pivoted-LU solver (dgesv semantics)
-        int rc = run_knn(h, h->knn_last.k, h->knn_last.s, h->knn_last.d_z, h->knn_last.d_ss, 0);
+        rc = run_knn(h, k, s, d_z, d_ss, 0);
         if (rc) return rc;
         CU(h, cudaMemcpyAsync(&hflag, h->wFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
@@ -704,8 +705,7 @@ extern "C" int kb200_execute_knn_grid_dev(kb200_handle h, int k, int64_t nx, int
     if (count == 0) return KB200_OK;
     if (!d_gx || !d_gy || (h->dim == 3 && !d_gz) || !d_z || !d_ss) return fail(h, KB200_EBADARG, "null pointer");
     Src s{true, nx, ny, nz, d_gx, d_gy, d_gz, first, count, nullptr, 0, 0};
-    rc = run_knn(h, k, s, d_z, d_ss); if (rc) return rc;
-    return knn_finish(h);
+    return run_knn_checked(h, k, s, d_z, d_ss);
 }
 
 extern "C" int kb200_execute_knn_grid(kb200_handle h, int k, int64_t nx, int64_t ny, int64_t nz,
@@ -727,14 +727,15 @@ extern "C" int kb200_execute_knn_grid(kb200_handle h, int k, int64_t nx, int64_t
     if (h->dim == 3) CU(h, cudaMemcpyAsync(da + nx + ny, gz, nz * 8, cudaMemcpyHostToDevice, st));
     CU(h, cudaEventRecord(h->ev[10], st));
     Src s{true, nx, ny, nz, da, da + nx, da + nx + ny, first, count, nullptr, 0, 0};
-    rc = run_knn(h, k, s, dout, dout + count); if (rc) return rc;
+    rc = run_knn_checked(h, k, s, dout, dout + count); if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev[12], st));
     CU(h, cudaMemcpyAsync(z_out, dout, count * 8, cudaMemcpyDeviceToHost, st));
     CU(h, cudaMemcpyAsync(ss_out, dout + count, count * 8, cudaMemcpyDeviceToHost, st));
     CU(h, cudaEventRecord(h->ev[11], st));
-    rc = knn_finish(h);
+    CU(h, cudaStreamSynchronize(st));
     h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
-    h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
-    return rc;
+    h->tm[7] += ev_ms(h->ev[12], h->ev[11]);
+    return KB200_OK;
 }
 
 extern "C" int kb200_execute_knn_points(kb200_handle h, int k, int64_t m,
@@ -754,14 +755,15 @@ extern "C" int kb200_execute_knn_points(kb200_handle h, int k, int64_t m,
     if (h->dim == 3) CU(h, cudaMemcpyAsync(dp + 2 * m, pz, m * 8, cudaMemcpyHostToDevice, st));
     CU(h, cudaEventRecord(h->ev[10], st));
     Src s{false, 0, 0, 0, dp, dp + m, dp + 2 * m, 0, m, nullptr, 0, 0};
-    rc = run_knn(h, k, s, dout, dout + m); if (rc) return rc;
+    rc = run_knn_checked(h, k, s, dout, dout + m); if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev[12], st));
     CU(h, cudaMemcpyAsync(z_out, dout, m * 8, cudaMemcpyDeviceToHost, st));
     CU(h, cudaMemcpyAsync(ss_out, dout + m, m * 8, cudaMemcpyDeviceToHost, st));
     CU(h, cudaEventRecord(h->ev[11], st));
-    rc = knn_finish(h);
+    CU(h, cudaStreamSynchronize(st));
     h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
-    h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
-    return rc;
+    h->tm[7] += ev_ms(h->ev[12], h->ev[11]);
+    return KB200_OK;
 }
 
 // ---- debug taps (tests only) ------------------------------------------------
