@@ -58,6 +58,10 @@ extern "C" {
 #define KB200_F64 0
 #define KB200_F32 1   /* factorisation stays fp64; W and the RHS tile are fp32 */
 
+/* ---- coordinates (ok.py:292-318) -------------------------------------------- */
+#define KB200_EUCLIDEAN  0
+#define KB200_GEOGRAPHIC 1   /* (x, y) = (lon, lat) degrees; great-circle distances, core.py:36-97; OK 2-D only */
+
 #define KB200_MAX_DRIFT 15   /* drift columns (regional-linear + host supplied), excluding the unbiasedness column */
 
 typedef struct kb200_ctx* kb200_handle;
@@ -187,6 +191,11 @@ int kb200_describe_problem(kb200_handle h, int dim, int dtype, int64_t n,
                            int exact_values, double eps,
                            int n_rl, int n_hd, const double* drift_data);
 int kb200_blob_commit(kb200_handle h);
+
+/* Select the coordinate type of the NEXT kb200_set_problem / kb200_set_problem_knn / kb200_describe_problem
+ * call (default KB200_EUCLIDEAN). Geographic mode requires dim == 2 and no drift terms; anisotropy is ignored,
+ * as in the reference (ok.py:296-306). */
+int kb200_set_coordinates(kb200_handle h, int coordinates_type);
 
 /* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of the handle. */
 int kb200_set_stream(kb200_handle h, void* cuda_stream);

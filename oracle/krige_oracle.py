@@ -52,6 +52,71 @@ def stored_parameters(model, plist):
     return list(plist)
 
 
+# ---- geographic distances: core.py:36-97 -----------------------------------------------
+def great_circle_distance(lon1, lat1, lon2, lat2):
+    lat1 = np.array(lat1) * np.pi / 180.0
+    lat2 = np.array(lat2) * np.pi / 180.0
+    dlon = (lon1 - lon2) * np.pi / 180.0
+    c1, s1, c2, s2, cd = np.cos(lat1), np.sin(lat1), np.cos(lat2), np.sin(lat2), np.cos(dlon)
+    return 180.0 / np.pi * np.arctan2(np.sqrt((c2 * np.sin(dlon)) ** 2 + (c1 * s2 - s1 * c2 * cd) ** 2),
+                                      s1 * s2 + c1 * c2 * cd)
+
+
+def _unit_sphere(lonlat):
+    """lon/lat degrees -> 3-D unit vectors, the kd-tree coordinates of ok.py:936-956."""
+    lon = lonlat[:, 0] * np.pi / 180.0
+    lat = lonlat[:, 1] * np.pi / 180.0
+    return np.column_stack((np.cos(lon) * np.cos(lat), np.sin(lon) * np.cos(lat), np.sin(lat)))
+
+
+def krige_geographic(data_lonlat, values, model, plist_stored, points, *, exact_values=True, n_closest_points=None):
+    """coordinates_type='geographic' (OrdinaryKriging only; ok.py:634-640, 930-969, 990-996): great-circle
+    distances in degrees, no anisotropy; the moving window ranks neighbours by chord length on the unit
+    sphere and then uses great-circle distances."""
+    P = np.asarray(data_lonlat, dtype=np.float64)
+    Q = np.asarray(points, dtype=np.float64)
+    vals = np.asarray(values, dtype=np.float64)
+    n = P.shape[0]
+    def gmat(A, B):
+        return great_circle_distance(A[:, 0][:, None], A[:, 1][:, None], B[:, 0][None, :], B[:, 1][None, :])
+    if n_closest_points is None:
+        a = np.zeros((n + 1, n + 1))
+        a[:n, :n] = -variogram(model, plist_stored, gmat(P, P))
+        np.fill_diagonal(a, 0.0)
+        a[n, :n] = 1.0
+        a[:n, n] = 1.0
+        a_inv = scipy.linalg.inv(a)
+        bd = gmat(Q, P)
+        b = np.ones((Q.shape[0], n + 1))
+        b[:, :n] = -variogram(model, plist_stored, bd)
+        if exact_values:
+            b[:, :n][np.absolute(bd) <= EPS] = 0.0
+        x = a_inv @ b.T
+        return x[:n, :].T @ vals, np.sum(x.T * -b, axis=1)
+    k = n_closest_points
+    tree = cKDTree(_unit_sphere(P))
+    _, idx_all = tree.query(_unit_sphere(Q), k=k, eps=0.0)
+    z = np.zeros(Q.shape[0])
+    ss = np.zeros(Q.shape[0])
+    for i in range(Q.shape[0]):
+        sel = idx_all[i]
+        S = P[sel]
+        a = np.zeros((k + 1, k + 1))
+        a[:k, :k] = -variogram(model, plist_stored, gmat(S, S))
+        np.fill_diagonal(a, 0.0)
+        a[k, :k] = 1.0
+        a[:k, k] = 1.0
+        bd = great_circle_distance(Q[i, 0], Q[i, 1], S[:, 0], S[:, 1])
+        b = np.ones(k + 1)
+        b[:k] = -variogram(model, plist_stored, bd)
+        if exact_values:
+            b[:k][np.absolute(bd) <= EPS] = 0.0
+        x = scipy.linalg.solve(a, b)
+        z[i] = x[:k].dot(vals[sel])
+        ss[i] = -x.dot(b)
+    return z, ss
+
+
 # ---- anisotropy: core.py:120-193 -----------------------------------------------------
 def adjust_for_anisotropy(X, center, scaling, angle):
     X = np.array(X, dtype=np.float64, copy=True)

@@ -195,13 +195,11 @@ class KrigeBase:
         mid, vp = self._device_model()
         n_rl, cols = self._drift_spec()
         return (dtype, knn, mid, tuple(vp), bool(self.exact_values), tuple(np.ravel(Mt)), tuple(center),
-                n_rl, len(cols), x.size)
+                n_rl, len(cols), x.size, getattr(self, "coordinates_type", "euclidean"))
 
     def _ensure_problem(self, dtype="float64", knn=False):
         if getattr(self, "pseudo_inv", False):
             raise NotImplementedError("pseudo_inv=True is not supported by backend='cuda' (SURVEY.md §8f next-4)")
-        if getattr(self, "coordinates_type", "euclidean") != "euclidean":
-            raise NotImplementedError("backend='cuda' supports euclidean coordinates only (SURVEY.md §8f next-3)")
         dt = {"float64": _cabi.KB200_F64, "float32": _cabi.KB200_F32}.get(str(np.dtype(dtype)))
         if dt is None:
             raise ValueError("dtype must be float64 or float32")
@@ -213,6 +211,7 @@ class KrigeBase:
         mid, vp = self._device_model()
         n_rl, cols = self._drift_spec()
         self._kb_key = None
+        h.set_coordinates(getattr(self, "coordinates_type", "euclidean") == "geographic")
         if knn:
             h.set_problem_knn(self._ndim, x, y, z, v, center, Mt, mid, vp, self.exact_values, self.eps)
         else:

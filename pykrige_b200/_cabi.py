@@ -31,7 +31,7 @@ EXPORTS = [
     "kb200_execute_knn_points", "kb200_execute_knn_grid", "kb200_execute_knn_grid_dev",
     "kb200_set_problem_knn",
     "kb200_blob_bytes", "kb200_blob_ptr", "kb200_describe_problem", "kb200_blob_commit",
-    "kb200_set_stream", "kb200_last_timings", "kb200_reset_counters", "kb200_debug_fetch",
+    "kb200_set_coordinates", "kb200_set_stream", "kb200_last_timings", "kb200_reset_counters", "kb200_debug_fetch",
 ]
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -81,6 +81,7 @@ def load_library():
     lib.kb200_blob_ptr.argtypes = [h]
     lib.kb200_blob_ptr.restype = ctypes.c_void_p
     lib.kb200_blob_commit.argtypes = [h]
+    lib.kb200_set_coordinates.argtypes = [h, i32]
     lib.kb200_set_stream.argtypes = [h, ctypes.c_void_p]
     lib.kb200_last_timings.argtypes = [h, _c_double_p, i32]
     lib.kb200_reset_counters.argtypes = [h]
@@ -248,6 +249,9 @@ class Handle:
 
     def blob_commit(self):
         self._check(self.lib.kb200_blob_commit(self._h))
+
+    def set_coordinates(self, geographic):
+        self._check(self.lib.kb200_set_coordinates(self._h, 1 if geographic else 0))
 
     def set_stream(self, cuda_stream):
         self._check(self.lib.kb200_set_stream(self._h, ctypes.c_void_p(int(cuda_stream))))

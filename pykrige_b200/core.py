@@ -17,6 +17,23 @@ eps = 1.0e-10
 _BOUNDED = ("gaussian", "spherical", "exponential", "hole-effect")
 
 
+def great_circle_distance(lon1, lat1, lon2, lat2):
+    """Great-circle distance in DEGREES between points given as lon/lat degrees, numpy broadcasting
+    semantics (core.py:36-97: the arctan form, stable for small and near-antipodal separations)."""
+    lat1 = np.asarray(lat1, dtype=float) * np.pi / 180.0
+    lat2 = np.asarray(lat2, dtype=float) * np.pi / 180.0
+    dlon = (np.asarray(lon1, dtype=float) - np.asarray(lon2, dtype=float)) * np.pi / 180.0
+    c1, s1, c2, s2, cd = np.cos(lat1), np.sin(lat1), np.cos(lat2), np.sin(lat2), np.cos(dlon)
+    num = np.sqrt((c2 * np.sin(dlon)) ** 2 + (c1 * s2 - s1 * c2 * cd) ** 2)
+    return 180.0 / np.pi * np.arctan2(num, s1 * s2 + c1 * c2 * cd)
+
+
+def euclid3_to_great_circle(euclid3_distance):
+    """Chord length on the unit sphere -> great-circle distance in degrees (core.py:100-117)."""
+    e = np.minimum(np.asarray(euclid3_distance, dtype=float), 2.0)
+    return 180.0 - 360.0 / np.pi * np.arccos(0.5 * e)
+
+
 def anisotropy_matrix(ndim, scaling, angle):
     """Return Mt = stretch @ rot (ndim x ndim) of the reference's anisotropy map.
 
@@ -101,7 +118,14 @@ def _make_variogram_parameter_list(variogram_model, variogram_model_parameters):
     raise TypeError("Variogram model parameters must be provided in either a list or a dict when they are explicitly specified.")
 
 
-def _experimental_variogram(X, y, nlags, block=2048):
+def _pair_distances(XA, XB, coordinates_type):
+    if coordinates_type == "geographic":
+        return great_circle_distance(XA[:, 0][:, None], XA[:, 1][:, None], XB[:, 0][None, :], XB[:, 1][None, :])
+    from scipy.spatial.distance import cdist
+    return cdist(XA, XB)
+
+
+def _experimental_variogram(X, y, nlags, block=2048, coordinates_type="euclidean"):
     """Equal-width binned semivariogram (core.py:432-505), euclidean coordinates.
 
     Same bins as the reference (nlags equal bins from dmin to dmax, last edge dmax + 0.001; lag = mean
@@ -109,7 +133,9 @@ def _experimental_variogram(X, y, nlags, block=2048):
     accumulated over row blocks so that the O(N^2) pair list never exists (the reference's pdist needs
     80 GB at N = 1e5)."""
     n = X.shape[0]
-    if n * (n - 1) // 2 <= 20_000_000:
+    if coordinates_type == "geographic" and X.shape[1] != 2:
+        raise ValueError("Geographic coordinate type only supported for 2D datasets.")
+    if n * (n - 1) // 2 <= 20_000_000 and coordinates_type == "euclidean":
         d = pdist(X, metric="euclidean")
         g = 0.5 * pdist(y[:, None], metric="sqeuclidean")
         dmax, dmin = np.amax(d), np.amin(d)
@@ -121,10 +147,9 @@ def _experimental_variogram(X, y, nlags, block=2048):
         sd = np.bincount(which[ok], weights=d[ok], minlength=nlags)
         sg = np.bincount(which[ok], weights=g[ok], minlength=nlags)
     else:
-        from scipy.spatial.distance import cdist
         dmin, dmax = np.inf, 0.0
         for s in range(0, n, block):
-            D = cdist(X[s:s + block], X[s:])
+            D = _pair_distances(X[s:s + block], X[s:], coordinates_type)
             iu = np.triu_indices(D.shape[0], 1, D.shape[1])
             dv = D[iu]
             if dv.size:
@@ -135,7 +160,7 @@ def _experimental_variogram(X, y, nlags, block=2048):
         sd = np.zeros(nlags)
         sg = np.zeros(nlags)
         for s in range(0, n, block):
-            D = cdist(X[s:s + block], X[s:])
+            D = _pair_distances(X[s:s + block], X[s:], coordinates_type)
             iu = np.triu_indices(D.shape[0], 1, D.shape[1])
             dv = D[iu]
             gv = 0.5 * (y[s:s + block, None] - y[None, s:])[iu] ** 2
@@ -185,18 +210,17 @@ def _initialize_variogram_model(X, y, variogram_model, variogram_model_parameter
     """Returns (lags, semivariance, parameters) (core.py:379-535). With lazy=True and explicit
     parameters the experimental variogram (an O(N^2) pass that execute() never needs) is returned as
     a zero-argument callable instead of arrays."""
-    if coordinates_type != "euclidean":
-        if coordinates_type == "geographic":
-            raise NotImplementedError("coordinates_type='geographic' is not part of the B200 hot path (SURVEY.md §8f next-3)")
+    if coordinates_type not in ("euclidean", "geographic"):
         raise ValueError("Specified coordinate type '%s' is not supported." % coordinates_type)
     p = variogram_model_parameters
     deferred = None
     if lazy and p is not None:
         def deferred():
-            return _experimental_variogram(X, y, nlags) if X.shape[0] > 1 else (np.zeros(0), np.zeros(0))
+            return (_experimental_variogram(X, y, nlags, coordinates_type=coordinates_type)
+                    if X.shape[0] > 1 else (np.zeros(0), np.zeros(0)))
         lags, semivariance = None, None
     elif X.shape[0] > 1:
-        lags, semivariance = _experimental_variogram(X, y, nlags)
+        lags, semivariance = _experimental_variogram(X, y, nlags, coordinates_type=coordinates_type)
     else:
         lags, semivariance = np.zeros(0), np.zeros(0)
     if p is not None:
@@ -221,13 +245,13 @@ def _krige(X, y, coords, variogram_function, variogram_model_parameters, coordin
     import scipy.linalg
 
     n = X.shape[0]
-    d = cdist(X, X)
+    d = _pair_distances(X, X, coordinates_type)
     a = np.zeros((n + 1, n + 1))
     a[:n, :n] = -variogram_function(variogram_model_parameters, d)
     np.fill_diagonal(a, 0.0)
     a[n, :n] = 1.0
     a[:n, n] = 1.0
-    bd = np.sqrt(np.sum((X - np.asarray(coords)[None, :]) ** 2, axis=1))
+    bd = _pair_distances(X, np.asarray(coords, dtype=float)[None, :], coordinates_type).ravel()
     b = np.zeros(n + 1)
     b[:n] = -variogram_function(variogram_model_parameters, bd)
     b[np.nonzero(np.absolute(bd) <= 1e-10)[0]] = 0.0

@@ -43,6 +43,7 @@ struct kb200_ctx {
     // description
     bool described = false, ready = false, knn_ready = false;
     int gform = 0;            // 1: general (indefinite) fallback, tiles hold the symmetric inverse
+    int geo = 0;              // 1: coordinates_type='geographic' for the next problem description
     int dim = 2, dtype = KB200_F64, n = 0, n_pad = 0, ld = 0, n_rl = 0, n_hd = 0, K1 = 1, na = 2, nrb = 0;
     VgParams vg{};
     Aniso an{};
@@ -123,6 +124,15 @@ extern "C" int kb200_set_stream(kb200_handle h, void* s) {
     return KB200_OK;
 }
 
+extern "C" int kb200_set_coordinates(kb200_handle h, int coordinates_type) {
+    if (!h) return KB200_EBADARG;
+    if (coordinates_type != KB200_EUCLIDEAN && coordinates_type != KB200_GEOGRAPHIC)
+        return fail(h, KB200_EBADARG, "coordinates_type must be KB200_EUCLIDEAN or KB200_GEOGRAPHIC");
+    h->geo = coordinates_type == KB200_GEOGRAPHIC ? 1 : 0;
+    h->described = false; h->ready = false; h->knn_ready = false;
+    return KB200_OK;
+}
+
 extern "C" void kb200_reset_counters(kb200_handle h) {
     if (!h) return;
     h->launches = 0; h->solve_launches = 0;
@@ -155,6 +165,8 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     if (!h) return KB200_EBADARG;
     h->described = false; h->ready = false; h->knn_ready = false;
     if (dim != 2 && dim != 3) return fail(h, KB200_EBADARG, "dim must be 2 or 3");
+    if (h->geo && dim != 2) return fail(h, KB200_EBADARG, "geographic coordinates are two-dimensional (lon, lat)");
+    if (h->geo && (n_rl || n_hd)) return fail(h, KB200_EUNSUPPORTED, "universal kriging has no geographic mode (uk.py:337)");
     if (dtype != KB200_F64 && dtype != KB200_F32) return fail(h, KB200_EBADARG, "dtype must be KB200_F64 or KB200_F32");
     if (n < 1 || (!knn_only && n > (int64_t)(KB_MAXRB - 1) * KB_BM) || n > (1LL << 30)) return fail(h, KB200_EBADARG, "n out of range");
     if (!x || !y || (dim == 3 && !z) || !values || !center || !aniso || !vparams)
@@ -168,7 +180,8 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     if (n_hd > 0 && !drift_data) return fail(h, KB200_EBADARG, "drift_data is null");
     if (knn_only && (n_rl || n_hd)) return fail(h, KB200_EUNSUPPORTED, "moving window supports ordinary kriging only");
 
-    h->dim = dim; h->dtype = dtype; h->n = (int)n; h->n_rl = n_rl; h->n_hd = n_hd;
+    const int user_dim = dim;
+    h->dim = h->geo ? KB_GEO : dim; h->dtype = dtype; h->n = (int)n; h->n_rl = n_rl; h->n_hd = n_hd;
     h->K1 = n_rl + n_hd + 1; h->na = h->K1 + 1;
     h->vg.model = model;
     h->vg.p0 = vparams[0]; h->vg.p1 = vparams[1]; h->vg.p2 = (need == 3) ? vparams[2] : 0.0;
@@ -183,7 +196,16 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
 
     // adjusted bounding box on the host (drift rescale + c0 for unbounded models)
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    (void)user_dim;
+    const int sdim = h->geo ? 3 : dim;            // spatial dimensions of the device coordinates
     for (int64_t i = 0; i < n; ++i) {
+        if (h->geo) {
+            const double rad = 0.017453292519943295;
+            double u[3] = {std::cos(x[i] * rad) * std::cos(y[i] * rad), std::sin(x[i] * rad) * std::cos(y[i] * rad),
+                           std::sin(y[i] * rad)};
+            for (int r = 0; r < 3; ++r) { lo[r] = std::min(lo[r], u[r]); hi[r] = std::max(hi[r], u[r]); }
+            continue;
+        }
         double d[3] = {x[i] - h->an.c[0], y[i] - h->an.c[1], dim == 3 ? z[i] - h->an.c[2] : 0.0};
         for (int r = 0; r < dim; ++r) {
             double v = h->an.c[r];
@@ -191,10 +213,11 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
             lo[r] = std::min(lo[r], v); hi[r] = std::max(hi[r], v);
         }
     }
-    for (int r = 0; r < 3; ++r) { h->bb_lo[r] = r < dim ? lo[r] : 0.0; h->bb_hi[r] = r < dim ? hi[r] : 0.0; }
+    if (h->geo) for (int r = 0; r < 3; ++r) { lo[r] -= 1e-9; hi[r] += 1e-9; }   // device sincos may differ in the last ulp
+    for (int r = 0; r < 3; ++r) { h->bb_lo[r] = r < sdim ? lo[r] : 0.0; h->bb_hi[r] = r < sdim ? hi[r] : 0.0; }
     double diag2 = 0.0;
-    for (int r = 0; r < dim; ++r) diag2 += (hi[r] - lo[r]) * (hi[r] - lo[r]);
-    double c0 = host_gamma(h->vg, std::sqrt(diag2));
+    for (int r = 0; r < sdim; ++r) diag2 += (hi[r] - lo[r]) * (hi[r] - lo[r]);
+    double c0 = host_gamma(h->vg, h->geo ? 180.0 : std::sqrt(diag2));
     if (!(c0 > 0.0) || !std::isfinite(c0)) c0 = 1.0;
     h->vg.c0 = c0;
     for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { h->ds.shift[c] = 0.0; h->ds.scale[c] = 1.0; }
@@ -491,7 +514,7 @@ extern "C" int kb200_execute_grid_dev(kb200_handle h, int64_t nx, int64_t ny, in
         return fail(h, KB200_EBADARG, "bad grid slice");
     if (count == 0) return KB200_OK;
     if (!d_gx || !d_gy || (h->dim == 3 && !d_gz) || !d_z || !d_ss) return fail(h, KB200_EBADARG, "null pointer");
-    if (h->dim == 2 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
+    if (h->dim != 3 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
     if (h->n_hd && !d_drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
     Src s{true, nx, ny, nz, d_gx, d_gy, d_gz, first, count, d_drift_pts, count, 0};
     rc = run_solve(h, s, d_z, d_ss); if (rc) return rc;
@@ -544,7 +567,7 @@ extern "C" int kb200_execute_grid(kb200_handle h, int64_t nx, int64_t ny, int64_
         return fail(h, KB200_EBADARG, "bad grid slice");
     if (count == 0) return KB200_OK;
     if (!gx || !gy || (h->dim == 3 && !gz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
-    if (h->dim == 2 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
+    if (h->dim != 3 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
     if (h->n_hd && !drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
     cudaStream_t st = h->stream;
     CU(h, h->wAxes.reserve((size_t)(nx + ny + nz) * 8));
@@ -606,13 +629,14 @@ extern "C" int kb200_set_problem_knn(kb200_handle h, int dim, int64_t n,
     KnnParams& kp = h->kp;
     kp = KnnParams{};
     double ext[3] = {0, 0, 0}, vol = 1.0; int live = 0;
-    for (int r = 0; r < h->dim; ++r) { ext[r] = h->bb_hi[r] - h->bb_lo[r]; if (ext[r] > 0.0) { vol *= ext[r]; ++live; } }
+    const int sdim = h->dim == KB_GEO ? 3 : h->dim;
+    for (int r = 0; r < sdim; ++r) { ext[r] = h->bb_hi[r] - h->bb_lo[r]; if (ext[r] > 0.0) { vol *= ext[r]; ++live; } }
     double cell = live ? std::pow(vol * 2.0 / (double)nn, 1.0 / live) : 1.0;
     if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
     int g[3] = {1, 1, 1};
     for (;;) {
         long long tot = 1;
-        for (int r = 0; r < h->dim; ++r) {
+        for (int r = 0; r < sdim; ++r) {
             double cnt = std::floor(ext[r] / cell) + 1.0;
             g[r] = (int)std::min(cnt, 4096.0);
             tot *= g[r];
@@ -621,7 +645,7 @@ extern "C" int kb200_set_problem_knn(kb200_handle h, int dim, int64_t n,
         cell *= 1.5;
     }
     // a cell edge slightly larger than ext/g keeps every data point inside the grid after clamping
-    for (int r = 0; r < h->dim; ++r) if (g[r] == 4096) cell = std::max(cell, ext[r] / 4095.0);
+    for (int r = 0; r < sdim; ++r) if (g[r] == 4096) cell = std::max(cell, ext[r] / 4095.0);
     kp.dim = h->dim; kp.n = nn; kp.gx = g[0]; kp.gy = g[1]; kp.gz = g[2];
     kp.ox = h->bb_lo[0]; kp.oy = h->bb_lo[1]; kp.oz = h->bb_lo[2];
     kp.cell = cell; kp.inv_cell = 1.0 / cell;

@@ -35,9 +35,24 @@ struct Aniso {
     double c[3];
 };
 
+// DIM = 2, 3: euclidean coordinates.  DIM = KB_GEO (4): coordinates_type='geographic' (ok.py:292-306):
+// (x, y) = (lon, lat) in degrees, no anisotropy; on the device a point is its unit vector on the sphere
+// (the same conversion the reference uses for its kd-tree, ok.py:936-956) and distances are great-circle
+// degrees (core.py:36-97: atan2(|u x v|, u . v), which is that formula written with unit vectors).
+#define KB_GEO 4
+#define KB_HASZ(DIM) ((DIM) >= 3)
+
 template <int DIM>
 __device__ __forceinline__ void kb_adjust(const Aniso& a, double x, double y, double z,
                                           double& ox, double& oy, double& oz) {
+    if (DIM == KB_GEO) {
+        const double rad = 0.017453292519943295;     // pi / 180
+        double slon, clon, slat, clat;
+        sincos(x * rad, &slon, &clon);
+        sincos(y * rad, &slat, &clat);
+        ox = clon * clat; oy = slon * clat; oz = slat;
+        return;
+    }
     double dx = __dsub_rn(x, a.c[0]);
     double dy = __dsub_rn(y, a.c[1]);
     if (DIM == 2) {
@@ -94,6 +109,15 @@ __device__ __forceinline__ double kb_cov_rhs(const VgParams& v, double d) {
 template <int DIM>
 __device__ __forceinline__ double kb_dist(double ax, double ay, double az,
                                           double bx, double by, double bz) {
+    if (DIM == KB_GEO) {
+        // great-circle distance in degrees between unit vectors; coincident points give exactly 0
+        double cx = __dsub_rn(__dmul_rn(ay, bz), __dmul_rn(az, by));
+        double cy = __dsub_rn(__dmul_rn(az, bx), __dmul_rn(ax, bz));
+        double cz = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));
+        double s = sqrt(cx * cx + cy * cy + cz * cz);
+        double c = ax * bx + ay * by + az * bz;
+        return atan2(s, c) * 57.29577951308232;      // 180 / pi
+    }
     double dx = ax - bx, dy = ay - by;
     double s = dx * dx + dy * dy;
     if (DIM == 3) { double dz = az - bz; s += dz * dz; }

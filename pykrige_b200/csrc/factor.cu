@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(VgParams vg, int n, int n
         bool ok = j < n;
         sx[tid] = ok ? ax[j] : 0.0;
         sy[tid] = ok ? ay[j] : 0.0;
-        sz[tid] = (ok && DIM == 3) ? az[j] : 0.0;
+        sz[tid] = (ok && KB_HASZ(DIM)) ? az[j] : 0.0;
     }
     __syncthreads();
     int jl = tid & 63;          // column within tile (contiguous -> coalesced stores)
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(VgParams vg, int n, int n
         if (i < n && j < n) {
             if (i == j) v = vg.c0;
             else {
-                double d = kb_dist<DIM>(ax[i], ay[i], DIM == 3 ? az[i] : 0.0, sx[jl], sy[jl], sz[jl]);
+                double d = kb_dist<DIM>(ax[i], ay[i], KB_HASZ(DIM) ? az[i] : 0.0, sx[jl], sy[jl], sz[jl]);
                 v = vg.c0 - kb_gamma<MODEL>(vg, d);
             }
         } else {
@@ -473,14 +473,16 @@ cudaError_t kbk_adjust_data(int dim, const Aniso& an, int n, const double* x, co
                             double* ax, double* ay, double* az, cudaStream_t st) {
     int g = (n + 255) / 256;
     if (dim == 2) adjust_data_kernel<2><<<g, 256, 0, st>>>(an, n, x, y, z, ax, ay, az);
-    else adjust_data_kernel<3><<<g, 256, 0, st>>>(an, n, x, y, z, ax, ay, az);
+    else if (dim == 3) adjust_data_kernel<3><<<g, 256, 0, st>>>(an, n, x, y, z, ax, ay, az);
+    else adjust_data_kernel<KB_GEO><<<g, 256, 0, st>>>(an, n, x, y, z, ax, ay, az);
     return cudaGetLastError();
 }
 
 cudaError_t kbk_assemble(int dim, const VgParams& vg, int n, int n_pad, int ld,
                          const double* ax, const double* ay, const double* az, double* C, cudaStream_t st) {
-    return dim == 2 ? launch_assemble_dim<2>(vg, n, n_pad, ld, ax, ay, az, C, st)
-                    : launch_assemble_dim<3>(vg, n, n_pad, ld, ax, ay, az, C, st);
+    if (dim == 2) return launch_assemble_dim<2>(vg, n, n_pad, ld, ax, ay, az, C, st);
+    if (dim == 3) return launch_assemble_dim<3>(vg, n, n_pad, ld, ax, ay, az, C, st);
+    return launch_assemble_dim<KB_GEO>(vg, n, n_pad, ld, ax, ay, az, C, st);
 }
 
 #define KB_SM66 (2 * 64 * 65 * sizeof(double))

@@ -27,7 +27,7 @@ __global__ void knn_count_kernel(int dim, int n, const double* __restrict__ ax, 
     if (i >= n) return;
     int cx = min(kp.gx - 1, max(0, (int)floor((ax[i] - kp.ox) * kp.inv_cell)));
     int cy = min(kp.gy - 1, max(0, (int)floor((ay[i] - kp.oy) * kp.inv_cell)));
-    int cz = dim == 3 ? min(kp.gz - 1, max(0, (int)floor((az[i] - kp.oz) * kp.inv_cell))) : 0;
+    int cz = dim >= 3 ? min(kp.gz - 1, max(0, (int)floor((az[i] - kp.oz) * kp.inv_cell))) : 0;
     int c = (cz * kp.gy + cy) * kp.gx + cx;
     cell_of[i] = c;
     atomicAdd(&counts[c], 1);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
     // ---------------- K4: exact k nearest ----------------
     const int cqx = min(P.gx - 1, max(0, (int)floor((qx - P.ox) * P.inv_cell)));
     const int cqy = min(P.gy - 1, max(0, (int)floor((qy - P.oy) * P.inv_cell)));
-    const int cqz = DIM == 3 ? min(P.gz - 1, max(0, (int)floor((qz - P.oz) * P.inv_cell))) : 0;
+    const int cqz = KB_HASZ(DIM) ? min(P.gz - 1, max(0, (int)floor((qz - P.oz) * P.inv_cell))) : 0;
     int cnt = 0;
     int r = 0;
     int px0 = 0, px1 = -1, py0 = 0, py1 = -1, pz0 = 0, pz1 = -1;      // block already visited
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
     for (;;) {
         const int x0 = max(0, cqx - r), x1 = min(P.gx - 1, cqx + r);
         const int y0 = max(0, cqy - r), y1 = min(P.gy - 1, cqy + r);
-        const int z0 = DIM == 3 ? max(0, cqz - r) : 0, z1 = DIM == 3 ? min(P.gz - 1, cqz + r) : 0;
+        const int z0 = KB_HASZ(DIM) ? max(0, cqz - r) : 0, z1 = KB_HASZ(DIM) ? min(P.gz - 1, cqz + r) : 0;
         for (int cz = z0; cz <= z1; ++cz)
             for (int cy = y0; cy <= y1; ++cy) {
                 const bool inner_row = (cz >= pz0 && cz <= pz1 && cy >= py0 && cy <= py1);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
                         if (ok) {
                             double dx = P.ax[i] - qx, dy = P.ay[i] - qy;
                             d2 = dx * dx + dy * dy;
-                            if (DIM == 3) { double dz = P.az[i] - qz; d2 += dz * dz; }
+                            if (KB_HASZ(DIM)) { double dz = P.az[i] - qz; d2 += dz * dz; }
                         }
                         unsigned msk = __ballot_sync(0xffffffffu, ok);
                         int pos = cnt + __popc(msk & ((1u << lane) - 1u));
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
         if (x1 < P.gx - 1) dout = fmin(dout, (P.ox + (x1 + 1) * P.cell) - qx);
         if (y0 > 0) dout = fmin(dout, qy - (P.oy + y0 * P.cell));
         if (y1 < P.gy - 1) dout = fmin(dout, (P.oy + (y1 + 1) * P.cell) - qy);
-        if (DIM == 3) {
+        if (KB_HASZ(DIM)) {
             if (z0 > 0) dout = fmin(dout, qz - (P.oz + z0 * P.cell));
             if (z1 < P.gz - 1) dout = fmin(dout, (P.oz + (z1 + 1) * P.cell) - qz);
         }
@@ -197,13 +197,17 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
     if (MODEL == KB200_VG_LINEAR || MODEL == KB200_VG_POWER) {
         // unbounded models: local shift c0 = gamma(2 d_k) >= gamma of any neighbour pair
         double dk = sqrt(cd2[k - 1]);
+        if (DIM == KB_GEO) dk = 2.0 * asin(fmin(1.0, 0.5 * dk)) * 57.29577951308232;   // chord -> degrees
         double g = kb_gamma<MODEL>(vg, 2.0 * dk);
         vg.c0 = g > 0.0 ? g : 1.0;
     }
     for (int t = lane; t < k; t += 32) {
         int i = cid[t];
-        nx[t] = P.ax[i]; ny[t] = P.ay[i]; nz[t] = DIM == 3 ? P.az[i] : 0.0; nv[t] = P.values[i];
-        double c = kb_cov_rhs<MODEL>(vg, sqrt(cd2[t]));
+        nx[t] = P.ax[i]; ny[t] = P.ay[i]; nz[t] = KB_HASZ(DIM) ? P.az[i] : 0.0; nv[t] = P.values[i];
+        // euclidean: the search distance is the kriging distance; geographic: neighbours were ranked by chord
+        // length (ok.py:936-960), the kriging distance is the great-circle distance (ok.py:962-969)
+        const double dq = DIM == KB_GEO ? kb_dist<DIM>(nx[t], ny[t], nz[t], qx, qy, qz) : sqrt(cd2[t]);
+        double c = kb_cov_rhs<MODEL>(vg, dq);
         rc[t] = c; cv[t] = c; r1[t] = 1.0;
     }
     __syncwarp();                                      // candidates consumed: A may be overwritten now
@@ -413,8 +417,8 @@ static cudaError_t knn_launch_dim(const KnnParams& p, cudaStream_t st) {
 
 cudaError_t kbk_knn_solve(const KnnParams& p, int chol, cudaStream_t st) {
     if (chol && p.k <= 128)
-        return p.dim == 2 ? knn_launch_dim<2, true>(p, st) : knn_launch_dim<3, true>(p, st);
-    return p.dim == 2 ? knn_launch_dim<2, false>(p, st) : knn_launch_dim<3, false>(p, st);
+        return p.dim == 2 ? knn_launch_dim<2, true>(p, st) : (p.dim == 3 ? knn_launch_dim<3, true>(p, st) : knn_launch_dim<KB_GEO, true>(p, st));
+    return p.dim == 2 ? knn_launch_dim<2, false>(p, st) : (p.dim == 3 ? knn_launch_dim<3, false>(p, st) : knn_launch_dim<KB_GEO, false>(p, st));
 }
 
 cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, const double* az, const double* values,

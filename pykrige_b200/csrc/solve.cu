@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) solve_kernel_f64(const __grid_c
             int k = t * KB_BK + 4 * s4 + (lane & 3);
             double v = 0.0;
             if (pvalid && k < P.n) {
-                double d = kb_dist<DIM>(P.ax[k], P.ay[k], DIM == 3 ? P.az[k] : 0.0, px, py, pz);
+                double d = kb_dist<DIM>(P.ax[k], P.ay[k], KB_HASZ(DIM) ? P.az[k] : 0.0, px, py, pz);
                 v = kb_cov_rhs<MODEL>(P.vg, d);
             }
             bs[(s4 * 8 + warp) * 32 + lane] = v;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                         const int k = t * KB_BK + k4 * 4 + kk;
                         double val = 0.0;
                         if (pvalid && k < P.n) {
-                            double d = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), DIM == 3 ? __ldg(P.az + k) : 0.0,
+                            double d = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), KB_HASZ(DIM) ? __ldg(P.az + k) : 0.0,
                                                     px, py, pz);
                             val = kb_cov_rhs<MODEL>(P.vg, d);
                         }
@@ -507,7 +507,7 @@ static cudaError_t solve_set_attr() {
 }
 
 cudaError_t kbk_solve_init() {
-#define KB_ATTR(M) KB_CUDA_OK((solve_set_attr<2, M>())); KB_CUDA_OK((solve_set_attr<3, M>()));
+#define KB_ATTR(M) KB_CUDA_OK((solve_set_attr<2, M>())); KB_CUDA_OK((solve_set_attr<3, M>())); KB_CUDA_OK((solve_set_attr<KB_GEO, M>()));
     KB_ATTR(KB200_VG_LINEAR) KB_ATTR(KB200_VG_POWER) KB_ATTR(KB200_VG_GAUSSIAN)
     KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT)
 #undef KB_ATTR
@@ -530,6 +530,7 @@ static cudaError_t solve_dim(int dtype, const SolveParams& p, cudaStream_t st) {
 }
 
 cudaError_t kbk_solve(int dim, int dtype, const SolveParams& p, cudaStream_t st) {
+    if (dim == KB_GEO) return solve_dim<KB_GEO>(dtype, p, st);
     return dim == 2 ? solve_dim<2>(dtype, p, st) : solve_dim<3>(dtype, p, st);
 }
 
@@ -547,12 +548,14 @@ static cudaError_t solve_pt_dim(const SolvePtParams& p, int grid, cudaStream_t s
 }
 
 cudaError_t kbk_solve_pt(int dim, const SolvePtParams& p, int grid, cudaStream_t st) {
+    if (dim == KB_GEO) return solve_pt_dim<KB_GEO>(p, grid, st);
     return dim == 2 ? solve_pt_dim<2>(p, grid, st) : solve_pt_dim<3>(p, grid, st);
 }
 
 cudaError_t kbk_finalize(const FinalizeParams& p, cudaStream_t st) {
     unsigned g = (unsigned)((p.m + 255) / 256);
     if (p.dim == 2) finalize_kernel<2><<<g, 256, 0, st>>>(p);
-    else finalize_kernel<3><<<g, 256, 0, st>>>(p);
+    else if (p.dim == 3) finalize_kernel<3><<<g, 256, 0, st>>>(p);
+    else finalize_kernel<KB_GEO><<<g, 256, 0, st>>>(p);
     return cudaGetLastError();
 }

@@ -102,10 +102,10 @@ __global__ void __launch_bounds__(256) pack_tf32_kernel(const double* __restrict
 }
 
 template <int DIM, int MODEL>
-__device__ __forceinline__ float tf_cov_rhs(const VgParams& v, double d2) {
-    // exact hit on the fp64 squared distance (|d| <= eps, ok.py:665-672); the rest in fp32
-    if (v.exact && d2 <= v.eps * v.eps) return (float)v.c0;
-    float d = sqrtf((float)d2);
+__device__ __forceinline__ float tf_cov_rhs(const VgParams& v, double dd) {
+    // exact hit on the fp64 distance (|d| <= eps, ok.py:665-672); the variogram itself in fp32
+    if (v.exact && dd <= v.eps) return (float)v.c0;
+    float d = (float)dd;
     float c0 = (float)v.c0, p0 = (float)v.p0, p1 = (float)v.p1, p2 = (float)v.p2;
     float g;
     if (MODEL == KB200_VG_LINEAR) g = p0 * d + p1;
@@ -174,10 +174,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
                         const int k = t * TF_BK + kc * 4 + kk;
                         float c = 0.0f;
                         if (pvalid && k < P.n) {
-                            double dx = __ldg(P.ax + k) - px, dy = __ldg(P.ay + k) - py;
-                            double d2 = dx * dx + dy * dy;
-                            if (DIM == 3) { double dz = __ldg(P.az + k) - pz; d2 += dz * dz; }
-                            c = tf_cov_rhs<DIM, MODEL>(P.vg, d2);
+                            double dd = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), KB_HASZ(DIM) ? __ldg(P.az + k) : 0.0,
+                                                     px, py, pz);
+                            c = tf_cov_rhs<DIM, MODEL>(P.vg, dd);
                         }
                         hi[kk] = tf32_round(c);
                         lo[kk] = tf32_round(c - hi[kk]);
@@ -340,7 +339,7 @@ static cudaError_t tf32_attr() {
 }
 
 cudaError_t kbk_solve_tf32_init() {
-#define KB_ATTR(M) KB_CUDA_OK((tf32_attr<2, M>())); KB_CUDA_OK((tf32_attr<3, M>()));
+#define KB_ATTR(M) KB_CUDA_OK((tf32_attr<2, M>())); KB_CUDA_OK((tf32_attr<3, M>())); KB_CUDA_OK((tf32_attr<KB_GEO, M>()));
     KB_ATTR(KB200_VG_LINEAR) KB_ATTR(KB200_VG_POWER) KB_ATTR(KB200_VG_GAUSSIAN)
     KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT)
 #undef KB_ATTR
@@ -361,6 +360,7 @@ static cudaError_t tf32_dim(const SolvePtParams& p, int grid, cudaStream_t st) {
 }
 
 cudaError_t kbk_solve_tf32(int dim, const SolvePtParams& p, int grid, cudaStream_t st) {
+    if (dim == KB_GEO) return tf32_dim<KB_GEO>(p, grid, st);
     return dim == 2 ? tf32_dim<2>(p, grid, st) : tf32_dim<3>(p, grid, st);
 }
 

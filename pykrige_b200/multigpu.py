@@ -53,6 +53,7 @@ def prepare_sharded(model, dist=None, src=0, dtype="float64"):
         n_rl, cols = model._drift_spec()
         from . import _cabi
         dt = {"float64": _cabi.KB200_F64, "float32": _cabi.KB200_F32}[str(np.dtype(dtype))]
+        h.set_coordinates(getattr(model, "coordinates_type", "euclidean") == "geographic")
         h.describe_problem(model._ndim, dt, x, y, z, v, center, Mt, mid, vp, model.exact_values, model.eps,
                            n_rl=n_rl, drift_data=cols if cols else None)
         model._kb_key = None

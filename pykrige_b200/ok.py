@@ -88,9 +88,18 @@ class OrdinaryKriging(KrigeBase):
                 [self.anisotropy_angle],
             ).T
         elif self.coordinates_type == "geographic":
-            raise NotImplementedError(
-                "coordinates_type='geographic' is outside the B200 hot path (SURVEY.md §8f next-3)"
-            )
+            # lon/lat in degrees; anisotropy is ambiguous on the sphere and ignored (ok.py:292-306)
+            if anisotropy_scaling != 1.0:
+                warnings.warn(
+                    "Anisotropy is not compatible with geographic coordinates. Ignoring user set anisotropy.",
+                    UserWarning,
+                )
+            self.XCENTER = 0.0
+            self.YCENTER = 0.0
+            self.anisotropy_scaling = 1.0
+            self.anisotropy_angle = 0.0
+            self.X_ADJUSTED = self.X_ORIG
+            self.Y_ADJUSTED = self.Y_ORIG
         else:
             raise ValueError("Only 'euclidean' and 'geographic' are valid values for coordinates-keyword.")
 
@@ -149,7 +158,13 @@ class OrdinaryKriging(KrigeBase):
             variogram_parameters = []
             anisotropy_scaling = ov["gstools"].pykrige_anis
             anisotropy_angle = ov["gstools"].pykrige_angle
-        if anisotropy_scaling != self.anisotropy_scaling or anisotropy_angle != self.anisotropy_angle:
+        if self.coordinates_type == "geographic":
+            if anisotropy_scaling != 1.0:
+                warnings.warn(
+                    "Anisotropy is not compatible with geographic coordinates. Ignoring user set anisotropy.",
+                    UserWarning,
+                )
+        elif anisotropy_scaling != self.anisotropy_scaling or anisotropy_angle != self.anisotropy_angle:
             if self.verbose:
                 print("Adjusting data for anisotropy...")
             self.anisotropy_scaling = anisotropy_scaling

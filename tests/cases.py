@@ -50,7 +50,7 @@ def _c(name, cls, n, m, seed, model, params=None, **kw):
              params=list(MODELS[model] if params is None else params),
              dim=3 if cls.endswith("3D") else 2, style="points", ctor={}, k=None,
              drift_terms=[], functional=[], n_specified=0, point_log=None, external_z=False,
-             exact_values=True, box=(1000.0, 1000.0, 250.0), ref_backend="vectorized")
+             exact_values=True, box=(1000.0, 1000.0, 250.0), ref_backend="vectorized", geographic=False)
     d.update(kw)
     return d
 
@@ -105,6 +105,15 @@ CASES.append(_c("knn2d_k64_grid", "OK", 3000, 0, 1005, "exponential", params=[1.
 CASES.append(_c("knn3d_k10", "OK3D", 300, 200, 5003, "linear", k=10, ref_backend="loop"))
 CASES.append(_c("knn2d_k2", "OK", 60, 100, 5004, "linear", k=2, ref_backend="loop"))
 
+# coordinates_type='geographic' (ok.py:292-306, 634-640, 930-996): lon in [0, 60), lat in [0, 45) shifted to a
+# mid-latitude window; variogram ranges are in degrees
+_GEO = dict(geographic=True, box=(60.0, 45.0, 1.0), ctor=dict(coordinates_type="geographic"))
+CASES.append(_c("geo_ok_points", "OK", 250, 300, 6001, "exponential", params=[1.0, 25.0, 0.05], **_GEO))
+CASES.append(_c("geo_ok_grid_spherical", "OK", 150, 0, 6002, "spherical", params=[1.0, 30.0, 0.02], style="grid",
+                grid=(17, 12, 1), **_GEO))
+CASES.append(_c("geo_ok_nonexact_linear", "OK", 120, 150, 6003, "linear", params=[0.05, 0.1], exact_values=False, **_GEO))
+CASES.append(_c("geo_knn_k12", "OK", 400, 200, 6004, "exponential", params=[1.0, 20.0, 0.05], k=12, ref_backend="loop", **_GEO))
+
 CASE_BY_NAME = {c["name"]: c for c in CASES}
 
 
@@ -112,14 +121,23 @@ def build_inputs(case):
     """Deterministic inputs of a case: data, values, prediction axes/points, mask, drift arrays."""
     dim = case["dim"]
     xyz, val = synth_data(case["seed"], case["n"], dim, case["box"])
+    geo_shift = np.array([-20.0, 30.0]) if case.get("geographic") else None
+    if geo_shift is not None:
+        val = 50.0 + 10.0 * np.sin(xyz[:, 0] / 9.0) * np.cos(xyz[:, 1] / 7.0) + (val - np.round(val))
+        xyz = xyz + geo_shift
     out = dict(data=xyz, values=val)
     rng = np.random.default_rng(case["seed"] + 31337)
     if case["style"] == "points":
-        out["points"] = synth_points(case["seed"], case["m"], dim, xyz, case["box"])
+        out["points"] = synth_points(case["seed"], case["m"], dim, xyz - (geo_shift if geo_shift is not None else 0.0),
+                                     case["box"])
+        if geo_shift is not None:
+            out["points"] = out["points"] + geo_shift
         npt = out["points"].shape[0]
     else:
         nx, ny, nz = case["grid"]
         axes = [np.linspace(0.0, case["box"][0], nx), np.linspace(0.0, case["box"][1], ny)]
+        if geo_shift is not None:
+            axes = [axes[0] + geo_shift[0], axes[1] + geo_shift[1]]
         if dim == 3:
             axes.append(np.linspace(0.0, case["box"][2], nz))
         out["axes"] = axes

@@ -10,6 +10,11 @@ from oracle import krige_oracle as ko
 
 
 def _oracle_case(case, inp):
+    if case.get("geographic"):
+        pts = inp["points"] if case["style"] == "points" else ko.grid_points(inp["axes"])
+        return ko.krige_geographic(inp["data"], inp["values"], case["model"],
+                                   ko.stored_parameters(case["model"], case["params"]), pts,
+                                   exact_values=case["exact_values"], n_closest_points=case["k"])
     dim = case["dim"]
     ctor = case["ctor"]
     if dim == 2:

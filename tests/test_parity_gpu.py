@@ -14,7 +14,7 @@ from conftest import assert_parity
 pytestmark = pytest.mark.gpu
 R64 = 1e-5
 
-GLOBAL_CASES = [c for c in cases.CASES if c["k"] is None and c["name"] != "ok2d_hole_effect_small"]
+GLOBAL_CASES = [c for c in cases.CASES if c["k"] is None and c["name"] != "ok2d_hole_effect_small"]   # incl. geographic
 KNN_CASES = [c for c in cases.CASES if c["k"] is not None]
 
 
@@ -234,7 +234,7 @@ R32 = 1e-2
 F32_CASES = [c for c in GLOBAL_CASES if c["name"] in (
     "cfg1_ok2d_n100_grid50", "ok2d_exponential_aniso", "ok2d_gaussian_aniso", "ok2d_spherical_aniso",
     "ok2d_linear_aniso", "ok2d_masked", "cfg2r_ok2d_n1000", "cfg3r_ok3d_n800", "cfg4r_uk2d_n1000",
-    "uk2d_functional", "uk2d_all_grid", "uk3d_reglin", "ok3d_grid")]
+    "uk2d_functional", "uk2d_all_grid", "uk3d_reglin", "ok3d_grid", "geo_ok_points")]
 
 
 @pytest.mark.parametrize("case", F32_CASES, ids=[c["name"] for c in F32_CASES])
