@@ -426,7 +426,12 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
     ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
     const bool f32 = h->dtype == KB200_F32;
-    if (f32 || !kbk_solve_use_v1()) {
+    // few prediction points (fewer 64-point tiles than half the SMs): the persistent kernel would leave
+    // most SMs idle and each CTA would stream the whole factor alone; the row-block x tile kernel (v1)
+    // exposes nrb times more CTAs. Same arithmetic per point, so results do not depend on the choice
+    // beyond the summation order of the per-row-block partials (both deterministic).
+    const bool few = !f32 && !h->gform && h->nrb > 1 && ((s.count + KB_TN - 1) / KB_TN) * 2 < h->num_sms;
+    if (f32 || !(kbk_solve_use_v1() || few)) {
         // K3 v3 (fp64 DMMA) / tcgen05 TF32 kernel: one persistent launch for the whole slice
         const int tp = f32 ? kbk_solve_tf32_tile_points() : KB_TN;
         long long ntiles = (s.count + tp - 1) / tp;
