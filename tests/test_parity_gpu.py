@@ -286,3 +286,28 @@ def test_moving_window_goldens_and_fallback(pk, ref_goldens):
     zo, so = ko.krige(xyz, val, "hole-effect", ko.stored_parameters("hole-effect", params), pts[:20], n_closest_points=130)
     assert_parity(z, zo, 1e-4, "knn k130 z")
     assert_parity(ss, so, 1e-4, "knn k130 ss")
+
+
+def test_sklearn_krige_wrapper_routes_to_cuda(pk):
+    """The caller side (compat.py:251-291): Krige.fit / predict / GridSearchCV drive execute(style='points',
+    backend='cuda', n_closest_points=...) and reproduce the oracle's moving-window numbers."""
+    pytest.importorskip("sklearn")
+    from sklearn.model_selection import GridSearchCV
+    from pykrige_b200.compat import Krige
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(31, 160, 2)
+    est = Krige(method="ordinary", variogram_model="exponential", variogram_parameters=[1.0, 300.0, 0.05],
+                n_closest_points=12).fit(xyz[:120], val[:120])
+    pred = est.predict(xyz[120:])
+    zo, _ = ko.krige(xyz[:120], val[:120], "exponential", [0.95, 300.0, 0.05], xyz[120:], n_closest_points=12)
+    assert_allclose(pred, zo, rtol=1e-8)
+    search = GridSearchCV(Krige(variogram_parameters=None), {"method": ["ordinary", "universal"],
+                                                             "variogram_model": ["linear", "spherical"]}, cv=3)
+    search.fit(xyz, val)
+    assert set(search.best_params_) == {"method", "variogram_model"}
+    x3, v3 = cases.synth_data(32, 90, 3)
+    est3 = Krige(method="universal3d", variogram_model="linear", variogram_parameters=[0.01, 0.1],
+                 drift_terms=["regional_linear"]).fit(x3[:70], v3[:70])
+    z3 = est3.predict(x3[70:])
+    zo3, _ = ko.krige(x3[:70], v3[:70], "linear", [0.01, 0.1], x3[70:], regional_linear=True)
+    assert_allclose(z3, zo3, rtol=1e-7)
