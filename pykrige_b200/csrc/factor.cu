@@ -168,23 +168,20 @@ __device__ __forceinline__ void gemm_tile_store(const double (&acc)[4][4][2], do
 }
 
 // ---------------------------------------------------------------------------
-// K2a.1  potf2 + inverse of one 64x64 diagonal block (one CTA, 256 threads).
-// Writes L_kk into C (strict upper part of the block zeroed) and L_kk^-1 into W's
-// diagonal block. A non-positive pivot sets *flag = 1 + global column index.
-__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ C, double* __restrict__ W,
-                                                         int ld, int kb, int* __restrict__ flag) {
-    extern __shared__ double dsm[];
-    double (*a)[65] = reinterpret_cast<double (*)[65]>(dsm);
-    double (*x)[65] = reinterpret_cast<double (*)[65]>(dsm + 64 * 65);
+// K2a.1  potf2 of one 64x64 diagonal block (one CTA, 256 threads). Writes L_kk into C (strict upper part
+// of the block zeroed). A non-positive pivot sets *flag = 1 + global column index. The inverse of the
+// block (needed only by the triangular inverse, K2b) is computed later for all blocks at once
+// (diag_inv_kernel), off the critical path of the factorisation.
+__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ C, int ld, int kb, int* __restrict__ flag) {
+    __shared__ double a[64][65];
     const int tid = threadIdx.x;
     double* Cb = C + (size_t)kb * 64 * ld + kb * 64;
-    double* Wb = W + (size_t)kb * 64 * ld + kb * 64;
     for (int e = tid; e < 64 * 64; e += 256) {
         int r = e >> 6, c = e & 63;
         a[r][c] = (c <= r) ? Cb[(size_t)r * ld + c] : 0.0;
-        x[r][c] = 0.0;
     }
     __syncthreads();
+    const int ur = tid >> 2, uc = tid & 3;          // update mapping: row offset, column phase
     for (int j = 0; j < 64; ++j) {
         if (tid == 0) {
             double d = a[j][j];
@@ -192,19 +189,39 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ C, 
             a[j][j] = sqrt(d);
         }
         __syncthreads();
-        double dj = a[j][j];
+        const double dj = a[j][j];
         if (tid > j && tid < 64) a[tid][j] /= dj;
         __syncthreads();
         // trailing update of the lower triangle: a[i][k] -= a[i][j]*a[k][j], j < k <= i
-        int m = 63 - j;                      // rows/cols j+1..63
-        for (int e = tid; e < m * m; e += 256) {
-            int i = j + 1 + e / m, k = j + 1 + e % m;
-            if (k <= i) a[i][k] -= a[i][j] * a[k][j];
+        const int i = j + 1 + ur;
+        if (i < 64) {
+            const double lij = a[i][j];
+            for (int k = j + 1 + uc; k <= i; k += 4) a[i][k] -= lij * a[k][j];
         }
         __syncthreads();
     }
-    // inverse by forward substitution: four threads (same warp) share column c of X = L^-1 and split the
-    // dot product over k; row i of every column is finished before row i+1 starts (lock-step over i)
+    for (int e = tid; e < 64 * 64; e += 256) {
+        int r = e >> 6, c = e & 63;
+        Cb[(size_t)r * ld + c] = a[r][c];     // upper part is 0
+    }
+}
+
+// inverse of every 64x64 diagonal block of L into the diagonal blocks of W (one CTA per block).
+// Four threads (same warp) share column c of X = L^-1 and split the dot product over k; row i of every
+// column is finished before row i+1 starts.
+__global__ void __launch_bounds__(256) diag_inv_kernel(const double* __restrict__ C, double* __restrict__ W, int ld) {
+    extern __shared__ double dsm[];
+    double (*a)[65] = reinterpret_cast<double (*)[65]>(dsm);
+    double (*x)[65] = reinterpret_cast<double (*)[65]>(dsm + 64 * 65);
+    const int tid = threadIdx.x, kb = blockIdx.x;
+    const double* Cb = C + (size_t)kb * 64 * ld + kb * 64;
+    double* Wb = W + (size_t)kb * 64 * ld + kb * 64;
+    for (int e = tid; e < 64 * 64; e += 256) {
+        int r = e >> 6, c = e & 63;
+        a[r][c] = (c <= r) ? Cb[(size_t)r * ld + c] : 0.0;
+        x[r][c] = 0.0;
+    }
+    __syncthreads();
     {
         const int c = tid >> 2, part = tid & 3;
         if (part == 0) x[c][c] = 1.0 / a[c][c];
@@ -222,39 +239,38 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ C, 
     __syncthreads();
     for (int e = tid; e < 64 * 64; e += 256) {
         int r = e >> 6, c = e & 63;
-        Cb[(size_t)r * ld + c] = a[r][c];     // upper part is 0
         Wb[(size_t)r * ld + c] = x[r][c];
     }
 }
 
-// K2a.2  panel solve: rows below the diagonal block:  X <- X * L_kk^-T  (in place).
-// out[r][c] = sum_{j<=c} X[r][j] * Linv[c][j].  One CTA per 64 rows.
-__global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ C, const double* __restrict__ W,
-                                                          int ld, int kb) {
-    extern __shared__ double dsm[];
-    double (*xs)[65] = reinterpret_cast<double (*)[65]>(dsm);
-    double (*li)[65] = reinterpret_cast<double (*)[65]>(dsm + 64 * 65);
+// K2a.2  panel solve: rows below the diagonal block:  X <- X * L_kk^-T  (in place) by forward
+// substitution against L_kk itself: x[c] = (x[c] - sum_{j<c} x[j] L[c][j]) / L[c][c].  One thread per row,
+// the row lives in registers; L_kk is broadcast from shared memory.
+__global__ void __launch_bounds__(128) trsm_panel_kernel(double* __restrict__ C, int ld, int kb, int n_pad) {
+    __shared__ double l[64][65];
     const int tid = threadIdx.x;
-    const int rb = kb + 1 + blockIdx.x;
-    double* Xb = C + (size_t)rb * 64 * ld + kb * 64;
-    const double* Wb = W + (size_t)kb * 64 * ld + kb * 64;
-    for (int e = tid; e < 64 * 64; e += 256) {
+    const double* Lb = C + (size_t)kb * 64 * ld + kb * 64;
+    for (int e = tid; e < 64 * 64; e += 128) {
         int r = e >> 6, c = e & 63;
-        xs[r][c] = Xb[(size_t)r * ld + c];
-        li[r][c] = Wb[(size_t)r * ld + c];
+        l[r][c] = Lb[(size_t)r * ld + c];
     }
     __syncthreads();
-    const int r = tid >> 2, cg = tid & 3;
-    double out[16];
+    const int row = (kb + 1) * 64 + blockIdx.x * 128 + tid;
+    if (row >= n_pad) return;
+    double* xr = C + (size_t)row * ld + kb * 64;
+    double x[64];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        int c = cg + 4 * q;
-        double s = 0.0;
-        for (int j = 0; j <= c; ++j) s += xs[r][j] * li[c][j];
-        out[q] = s;
+    for (int c = 0; c < 64; ++c) x[c] = xr[c];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+        double s0 = x[c], s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j + 1 < c; j += 2) { s0 -= x[j] * l[c][j]; s1 -= x[j + 1] * l[c][j + 1]; }
+        if (c & 1) s0 -= x[c - 1] * l[c][c - 1];
+        x[c] = (s0 + s1) / l[c][c];
     }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) Xb[(size_t)r * ld + cg + 4 * q] = out[q];
+    for (int c = 0; c < 64; ++c) xr[c] = x[c];
 }
 
 // K2a.3  trailing update (SYRK): C[it][jt] -= P_it * P_jt^T, kb < jt <= it.
@@ -487,24 +503,24 @@ cudaError_t kbk_assemble(int dim, const VgParams& vg, int n, int n_pad, int ld,
 
 #define KB_SM66 (2 * 64 * 65 * sizeof(double))
 cudaError_t kbk_factor_init() {
-    KB_CUDA_OK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SM66));
-    KB_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SM66));
-    return cudaSuccess;
+    return cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SM66);
 }
 
 // Blocked right-looking Cholesky + diagonal-block inverses (into W's diagonal blocks).
 cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, cudaStream_t st, int* launches) {
     int nb = n_pad / 64;
     for (int kb = 0; kb < nb; ++kb) {
-        potf2_inv_kernel<<<1, 256, KB_SM66, st>>>(C, W, ld, kb, flag);
+        potf2_kernel<<<1, 256, 0, st>>>(C, ld, kb, flag);
         ++*launches;
         int below = nb - kb - 1;
         if (below > 0) {
-            trsm_panel_kernel<<<below, 256, KB_SM66, st>>>(C, W, ld, kb);
+            trsm_panel_kernel<<<(below * 64 + 127) / 128, 128, 0, st>>>(C, ld, kb, n_pad);
             syrk_kernel<<<below * (below + 1) / 2, 128, 0, st>>>(C, ld, kb);
             *launches += 2;
         }
     }
+    diag_inv_kernel<<<nb, 256, KB_SM66, st>>>(C, W, ld);
+    ++*launches;
     return cudaGetLastError();
 }
 
