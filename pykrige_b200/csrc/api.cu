@@ -426,12 +426,9 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
     ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
     const bool f32 = h->dtype == KB200_F32;
-    // few prediction points (fewer 64-point tiles than half the SMs): the persistent kernel would leave
-    // most SMs idle and each CTA would stream the whole factor alone; the row-block x tile kernel (v1)
-    // exposes nrb times more CTAs. Same arithmetic per point, so results do not depend on the choice
-    // beyond the summation order of the per-row-block partials (both deterministic).
-    const bool few = !f32 && !h->gform && h->nrb > 1 && ((s.count + KB_TN - 1) / KB_TN) * 2 < h->num_sms;
-    if (f32 || !(kbk_solve_use_v1() || few)) {
+    // NOTE: one kernel for every point count: the summation order per point must not depend on how the
+    // points are sharded (concatenated shards == single call, bit for bit).
+    if (f32 || !kbk_solve_use_v1()) {
         // K3 v3 (fp64 DMMA) / tcgen05 TF32 kernel: one persistent launch for the whole slice
         const int tp = f32 ? kbk_solve_tf32_tile_points() : KB_TN;
         long long ntiles = (s.count + tp - 1) / tp;
@@ -685,6 +682,14 @@ static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss,
     CU(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
     KnnParams kp = h->kp;
     kp.vg = h->vg; kp.an = h->an; kp.k = k;
+    {   // radius (in cells) of the ball expected to hold k points at the mean density
+        double ppc = (double)h->n / (double)std::max(1, h->k_ncells);
+        int live = 0;
+        if (kp.gx > 1) ++live; if (kp.gy > 1) ++live; if (kp.gz > 1) ++live;
+        double cells = (double)k / std::max(ppc, 1e-9);
+        double R = live >= 3 ? std::cbrt(cells * 3.0 / (4.0 * 3.14159265358979)) : (live == 2 ? std::sqrt(cells / 3.14159265358979) : 0.5 * cells);
+        kp.r0 = (int)std::min(64.0, std::max(1.0, std::ceil(R)));
+    }
     PointSource ps{};
     ps.grid = s.grid ? 1 : 0;
     ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;

@@ -110,6 +110,7 @@ struct KnnParams {
     const int* sorig;          // original index of each sorted point (deterministic tie-break)
     // uniform cell grid over the adjusted data
     int gx, gy, gz;
+    int r0;                    // start radius of the cell search (from the mean point density)
     double ox, oy, oz, inv_cell, cell;
     const int* cell_start;     // [ncells+1]
     long long m;

@@ -83,7 +83,11 @@ __device__ __forceinline__ void warp_bitonic(double* d2, int* id, const int* __r
                 bool up = ((lo & size) == 0);
                 double dl = d2[lo], dh = d2[hi];
                 int il = id[lo], ih = id[hi];
-                int ol = il >= 0 ? sorig[il] : 0x7fffffff, oh = ih >= 0 ? sorig[ih] : 0x7fffffff;
+                int ol = 0, oh = 0;
+                if (dl == dh) {        // ties are rare: only then fetch the original indices (deterministic order)
+                    ol = il >= 0 ? sorig[il] : 0x7fffffff;
+                    oh = ih >= 0 ? sorig[ih] : 0x7fffffff;
+                }
                 bool sw = up ? cand_less(dh, oh, dl, ol) : cand_less(dl, ol, dh, oh);
                 if (sw) { d2[lo] = dh; d2[hi] = dl; id[lo] = ih; id[hi] = il; }
             }
@@ -127,8 +131,7 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
     const int cqy = min(P.gy - 1, max(0, (int)floor((qy - P.oy) * P.inv_cell)));
     const int cqz = KB_HASZ(DIM) ? min(P.gz - 1, max(0, (int)floor((qz - P.oz) * P.inv_cell))) : 0;
     int cnt = 0;
-    int r = 0;
-    int px0 = 0, px1 = -1, py0 = 0, py1 = -1, pz0 = 0, pz1 = -1;      // block already visited
+    int r = P.r0;                                      // start radius (cells) from the mean point density
     auto compact = [&](int keep) {
         int len = 1; while (len < cnt) len <<= 1;
         for (int t = cnt + lane; t < len; t += 32) { cd2[t] = DBL_MAX; cid[t] = -1; }
@@ -140,37 +143,57 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
         const int x0 = max(0, cqx - r), x1 = min(P.gx - 1, cqx + r);
         const int y0 = max(0, cqy - r), y1 = min(P.gy - 1, cqy + r);
         const int z0 = KB_HASZ(DIM) ? max(0, cqz - r) : 0, z1 = KB_HASZ(DIM) ? min(P.gz - 1, cqz + r) : 0;
-        for (int cz = z0; cz <= z1; ++cz)
-            for (int cy = y0; cy <= y1; ++cy) {
-                const bool inner_row = (cz >= pz0 && cz <= pz1 && cy >= py0 && cy <= py1);
-                // cells of this row not visited before: [x0, px0) and (px1, x1] when the row was inside the old block
-                for (int seg = 0; seg < 2; ++seg) {
-                    int sx0, sx1;
-                    if (!inner_row) { if (seg) break; sx0 = x0; sx1 = x1; }
-                    else if (seg == 0) { sx0 = x0; sx1 = px0 - 1; }
-                    else { sx0 = px1 + 1; sx1 = x1; }
-                    if (sx0 > sx1) continue;
-                    const int rowbase = (cz * P.gy + cy) * P.gx;
-                    const int b = P.cell_start[rowbase + sx0], e = P.cell_start[rowbase + sx1 + 1];
-                    for (int i0 = b; i0 < e; i0 += 32) {
-                        int i = i0 + lane;
-                        bool ok = i < e;
-                        double d2 = 0.0;
-                        if (ok) {
-                            double dx = P.ax[i] - qx, dy = P.ay[i] - qy;
-                            d2 = dx * dx + dy * dy;
-                            if (KB_HASZ(DIM)) { double dz = P.az[i] - qz; d2 += dz * dz; }
-                        }
-                        unsigned msk = __ballot_sync(0xffffffffu, ok);
-                        int pos = cnt + __popc(msk & ((1u << lane) - 1u));
-                        if (ok) { cd2[pos] = d2; cid[pos] = i; }
-                        cnt += __popc(msk);
-                        __syncwarp();
-                        if (cnt > KN_CAP - 32) compact(k);
-                    }
-                }
+        cnt = 0;
+        const int nyr = y1 - y0 + 1;
+        const int nrows = nyr * (z1 - z0 + 1);
+        // every cell row of the block is one contiguous run of the cell-sorted points: 32 rows at a time,
+        // one lane per row fetches the run bounds (one round of independent loads), then the warp walks the
+        // concatenated runs with a flat index so that the coordinate loads of all candidates are independent
+        for (int row0 = 0; row0 < nrows; row0 += 32) {
+            const int rr = row0 + lane;
+            int rb = 0, rlen = 0;
+            if (rr < nrows) {
+                const int cy = y0 + rr % nyr, cz = z0 + rr / nyr;
+                const int rowbase = (cz * P.gy + cy) * P.gx;
+                rb = P.cell_start[rowbase + x0];
+                rlen = P.cell_start[rowbase + x1 + 1] - rb;
             }
-        px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
+            int incl = rlen;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int pre = incl - rlen;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int f0 = 0; f0 < total; f0 += 32) {
+                const int f = f0 + lane;
+                const bool ok = f < total;
+                int j = 0;
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) {
+                    const int cand = j + st;                               // <= 31
+                    const int pc = __shfl_sync(0xffffffffu, pre, cand);
+                    if (pc <= f) j = cand;
+                }
+                const int bj = __shfl_sync(0xffffffffu, rb, j);
+                const int pj = __shfl_sync(0xffffffffu, pre, j);
+                double d2 = 0.0;
+                int i = 0;
+                if (ok) {
+                    i = bj + (f - pj);
+                    double dx = P.ax[i] - qx, dy = P.ay[i] - qy;
+                    d2 = dx * dx + dy * dy;
+                    if (KB_HASZ(DIM)) { double dz = P.az[i] - qz; d2 += dz * dz; }
+                }
+                unsigned msk = __ballot_sync(0xffffffffu, ok);
+                int pos = cnt + __popc(msk & ((1u << lane) - 1u));
+                if (ok) { cd2[pos] = d2; cid[pos] = i; }
+                cnt += __popc(msk);
+                __syncwarp();
+                if (cnt > KN_CAP - 32) compact(k);
+            }
+        }
         // distance from the query to the nearest face of the visited block that still has cells behind it
         double dout = DBL_MAX;
         if (x0 > 0) dout = fmin(dout, qx - (P.ox + x0 * P.cell));
@@ -189,7 +212,7 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
             for (int o = 16; o > 0; o >>= 1) inside += __shfl_xor_sync(0xffffffffu, inside, o);
         }
         if (inside >= k) break;
-        r += (r < 2) ? 1 : (r >> 1) + 1;               // grow the block
+        r += (r < 2) ? 1 : (r >> 1);                   // not enough inside the inscribed sphere: larger block, start over
     }
     compact(k);                                        // ascending distance, first k are the neighbours
     // neighbours -> per-warp arrays (these live outside the region the candidate buffers alias)
@@ -255,7 +278,7 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
             __syncwarp();
             if (lane == 0) { A[tp + pc] = sq; rc[pc] = yc; r1[pc] = y1; }
             // trailing update of the lower triangle: a[i][j] -= l_i * l_j, pc < j <= i
-#pragma unroll 2
+#pragma unroll 4
             for (int i = pc + 1; i < k; ++i) {
                 const int ti = i * (i + 1) / 2;
                 const double li = A[ti + pc];
