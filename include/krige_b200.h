@@ -56,7 +56,9 @@ extern "C" {
 
 /* ---- arithmetic of the big contraction ---------------------------------- */
 #define KB200_F64 0
-#define KB200_F32 1   /* factorisation stays fp64; W and the RHS tile are fp32 */
+#define KB200_F32 1   /* factorisation stays fp64; contraction in 3xTF32 on tcgen05 (fp32-class accuracy) */
+#define KB200_F64X 2  /* fp64-class contraction on the INT8 tensor cores: error-free 6x7-bit slicing, exact int32
+                         accumulation (tcgen05 kind::i8), fp64 recombination; agrees with KB200_F64 to ~1e-10 */
 
 /* ---- coordinates (ok.py:292-318) -------------------------------------------- */
 #define KB200_EUCLIDEAN  0

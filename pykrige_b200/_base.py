@@ -200,9 +200,10 @@ class KrigeBase:
     def _ensure_problem(self, dtype="float64", knn=False):
         if getattr(self, "pseudo_inv", False):
             raise NotImplementedError("pseudo_inv=True is not supported by backend='cuda' (SURVEY.md §8f next-4)")
-        dt = {"float64": _cabi.KB200_F64, "float32": _cabi.KB200_F32}.get(str(np.dtype(dtype)))
+        name = dtype if isinstance(dtype, str) and dtype in _cabi.DTYPES else str(np.dtype(dtype))
+        dt = _cabi.DTYPES.get(name)
         if dt is None:
-            raise ValueError("dtype must be float64 or float32")
+            raise ValueError("dtype must be 'float64', 'float32' or 'float64x'")
         h = self._cuda_handle()
         key = self._problem_signature(dt, knn)
         if self._kb_key == key:

@@ -21,6 +21,8 @@ KB200_ESTATE = -6
 
 KB200_F64 = 0
 KB200_F32 = 1
+KB200_F64X = 2   # fp64-class contraction on the INT8 tensor cores (exact slice products)
+DTYPES = {"float64": KB200_F64, "float32": KB200_F32, "float64x": KB200_F64X}
 MAX_DRIFT = 15
 
 # every symbol include/krige_b200.h declares (checked by tests/test_cabi.py)

@@ -54,7 +54,7 @@ struct kb200_ctx {
 
     // blob (one allocation): header | consts | ax | ay | az | tiles
     DevBuf blob;
-    size_t off_consts = 0, off_ax = 0, off_ay = 0, off_az = 0, off_tiles = 0, blob_bytes = 0;
+    size_t off_consts = 0, off_ax = 0, off_ay = 0, off_az = 0, off_tiles = 0, off_rowscale = 0, blob_bytes = 0;
 
     // factor workspace
     DevBuf wC, wW, wT, wF, wRaw, wFlag;
@@ -97,7 +97,8 @@ extern "C" int kb200_create(kb200_handle* out, int device) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return KB200_ECUDA; }
     h->own_stream = true;
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete h; return KB200_ECUDA; }
-    if (kbk_factor_init() != cudaSuccess || kbk_solve_init() != cudaSuccess || kbk_solve_tf32_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
+    if (kbk_factor_init() != cudaSuccess || kbk_solve_init() != cudaSuccess || kbk_solve_tf32_init() != cudaSuccess ||
+        kbk_solve_i8_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->num_sms < 1) h->num_sms = 148;
     *out = h;
     return KB200_OK;
@@ -167,7 +168,8 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     if (dim != 2 && dim != 3) return fail(h, KB200_EBADARG, "dim must be 2 or 3");
     if (h->geo && dim != 2) return fail(h, KB200_EBADARG, "geographic coordinates are two-dimensional (lon, lat)");
     if (h->geo && (n_rl || n_hd)) return fail(h, KB200_EUNSUPPORTED, "universal kriging has no geographic mode (uk.py:337)");
-    if (dtype != KB200_F64 && dtype != KB200_F32) return fail(h, KB200_EBADARG, "dtype must be KB200_F64 or KB200_F32");
+    if (dtype != KB200_F64 && dtype != KB200_F32 && dtype != KB200_F64X)
+        return fail(h, KB200_EBADARG, "dtype must be KB200_F64, KB200_F32 or KB200_F64X");
     if (n < 1 || (!knn_only && n > (int64_t)(KB_MAXRB - 1) * KB_BM) || n > (1LL << 30)) return fail(h, KB200_EBADARG, "n out of range");
     if (!x || !y || (dim == 3 && !z) || !values || !center || !aniso || !vparams)
         return fail(h, KB200_EBADARG, "null input array");
@@ -258,7 +260,14 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     h->off_ax = o; o += align_up((size_t)h->n_pad * 8, 256);
     h->off_ay = o; o += align_up((size_t)h->n_pad * 8, 256);
     h->off_az = o; o += align_up((size_t)h->n_pad * 8, 256);
-    h->off_tiles = o; o += (size_t)off * KB_BM * KB_BK * esz;
+    h->off_tiles = o;
+    if (dtype == KB200_F64X) {
+        o += (size_t)kbk_i8_total_tiles((int)n, h->na, nullptr) * kbk_i8_tile_bytes();
+        o = align_up(o, 256);
+        h->off_rowscale = o; o += align_up((size_t)kbk_i8_nrb((int)n, h->na) * 64 * sizeof(double), 256);
+    } else {
+        o += (size_t)off * KB_BM * KB_BK * esz;
+    }
     h->blob_bytes = knn_only ? h->off_tiles : o;
     cudaSetDevice(h->device);
     CU(h, h->blob.reserve(h->blob_bytes));
@@ -396,8 +405,23 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
     CU(h, cudaEventRecord(h->ev[5], st));
     CU(h, kbk_dual(h->wW.as<double>(), ld, nn, np, h->n_rl, h->n_hd, ax, ay, az, h->ds, rh, rv,
                    Fz, Hz, Uz, consts, flag, st, &launches));
-    if (h->dtype == KB200_F32) CU(h, kbk_pack_tf32(h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
-    else CU(h, kbk_pack(h->dtype, h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
+    if (h->dtype == KB200_F32) {
+        CU(h, kbk_pack_tf32(h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
+    } else if (h->dtype == KB200_F64X) {
+        const int nrb8 = kbk_i8_nrb(nn, h->na);
+        std::vector<long long> toff(nrb8 + 1);
+        kbk_i8_total_tiles(nn, h->na, toff.data());
+        // workspace (T1 scratch is free now): tile offsets | row exponents
+        long long* d_toff = reinterpret_cast<long long*>(h->wT.as<char>());
+        int* d_rowexp = reinterpret_cast<int*>(h->wT.as<char>() + align_up((size_t)(nrb8 + 1) * sizeof(long long), 256));
+        CU(h, cudaMemcpyAsync(d_toff, toff.data(), (size_t)(nrb8 + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CU(h, kbk_pack_i8(h->wW.as<double>(), ld, nn, np, h->na, Uz, d_rowexp,
+                          reinterpret_cast<double*>(blob + h->off_rowscale), d_toff, blob + h->off_tiles, st));
+        CU(h, cudaStreamSynchronize(st));      // toff is a host temporary
+        ++launches;
+    } else {
+        CU(h, kbk_pack(h->dtype, h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
+    }
     ++launches;
     }
     double hdr[64] = {0};
@@ -425,15 +449,16 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     ps.grid = s.grid ? 1 : 0;
     ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
     ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
-    const bool f32 = h->dtype == KB200_F32;
+    const bool f32 = h->dtype == KB200_F32 || h->dtype == KB200_F64X;   // tcgen05 kernels (128-point tiles)
+    const bool i8 = h->dtype == KB200_F64X;
     // NOTE: one kernel for every point count: the summation order per point must not depend on how the
     // points are sharded (concatenated shards == single call, bit for bit).
     if (f32 || !kbk_solve_use_v1()) {
         // K3 v3 (fp64 DMMA) / tcgen05 TF32 kernel: one persistent launch for the whole slice
-        const int tp = f32 ? kbk_solve_tf32_tile_points() : KB_TN;
+        const int tp = i8 ? kbk_solve_i8_tile_points() : (f32 ? kbk_solve_tf32_tile_points() : KB_TN);
         long long ntiles = (s.count + tp - 1) / tp;
         int grid = (int)std::min<long long>(ntiles, h->num_sms);
-        CU(h, h->wScratch.reserve(f32 ? kbk_solve_tf32_scratch_bytes(h->n, grid)
+        CU(h, h->wScratch.reserve(i8 ? kbk_solve_i8_scratch_bytes(h->n, grid) : f32 ? kbk_solve_tf32_scratch_bytes(h->n, grid)
                                       : kbk_solve_pt_scratch_doubles(h->n, grid) * sizeof(double)));
         SolvePtParams pp{};
         pp.vg = h->vg; pp.an = h->an; ps.first = s.first; pp.ps = ps;
@@ -447,7 +472,9 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
         pp.m = s.count; pp.scratch = h->wScratch.as<double>(); pp.gform = h->gform;
         pp.z_out = d_z; pp.ss_out = d_ss;
         CU(h, cudaEventRecord(h->ev[7], st));
-        if (f32) CU(h, kbk_solve_tf32(h->dim, pp, grid, st));
+        pp.rowscale = reinterpret_cast<const double*>(blob + h->off_rowscale);
+        if (i8) CU(h, kbk_solve_i8(h->dim, pp, grid, st));
+        else if (f32) CU(h, kbk_solve_tf32(h->dim, pp, grid, st));
         else CU(h, kbk_solve_pt(h->dim, pp, grid, st));
         CU(h, cudaEventRecord(h->ev[8], st));
         h->launches += 1; h->solve_launches += 1;

@@ -43,6 +43,7 @@ struct SolvePtParams {
     const double* drift_pts; long long drift_stride, drift_first;
     long long m;
     int gform;                // 1: tiles hold the symmetric inverse (quadratic form q = c^T G c), 0: W = chol(C)^-1
+    const double* rowscale;   // int8-slice path only: 2^(ew_r - 12) per packed row
     double* scratch;          // [grid][ceil(n/16)][16*64]  RHS column blocks in fragment order
     double* z_out; double* ss_out;
 };
@@ -99,6 +100,17 @@ cudaError_t kbk_pack_tf32(const double* W, int ld, int n, int n_pad, int na, con
                           void* out, cudaStream_t st);
 size_t      kbk_solve_tf32_scratch_bytes(int n, int grid);
 int         kbk_solve_tf32_tile_points();
+
+// fp64-class path on the INT8 tensor cores (solve_i8.cu): error-free slicing + exact int32 accumulation
+cudaError_t kbk_solve_i8_init();
+cudaError_t kbk_solve_i8(int dim, const SolvePtParams& p, int grid, cudaStream_t st);
+cudaError_t kbk_pack_i8(const double* W, int ld, int n, int n_pad, int na, const double* Uz,
+                        int* rowexp, double* rowscale, const long long* tile_off_dev, void* out, cudaStream_t st);
+int         kbk_i8_nrb(int n, int na);
+long long   kbk_i8_total_tiles(int n, int na, long long* tile_off);
+size_t      kbk_i8_tile_bytes();
+size_t      kbk_solve_i8_scratch_bytes(int n, int grid);
+int         kbk_solve_i8_tile_points();
 
 // moving window (knn.cu)
 struct KnnParams {

@@ -52,7 +52,7 @@ def prepare_sharded(model, dist=None, src=0, dtype="float64"):
         mid, vp = model._device_model()
         n_rl, cols = model._drift_spec()
         from . import _cabi
-        dt = {"float64": _cabi.KB200_F64, "float32": _cabi.KB200_F32}[str(np.dtype(dtype))]
+        dt = _cabi.DTYPES[dtype if dtype in _cabi.DTYPES else str(np.dtype(dtype))]
         h.set_coordinates(getattr(model, "coordinates_type", "euclidean") == "geographic")
         h.describe_problem(model._ndim, dt, x, y, z, v, center, Mt, mid, vp, model.exact_values, model.eps,
                            n_rl=n_rl, drift_data=cols if cols else None)
@@ -62,8 +62,8 @@ def prepare_sharded(model, dist=None, src=0, dtype="float64"):
     torch.cuda.current_stream().synchronize()
     if rank != src:
         h.blob_commit()
-        model._kb_key = model._problem_signature(
-            {"float64": 0, "float32": 1}[str(np.dtype(dtype))], False)
+        from . import _cabi as _c
+        model._kb_key = model._problem_signature(_c.DTYPES[dtype if dtype in _c.DTYPES else str(np.dtype(dtype))], False)
     return h
 
 
