@@ -300,6 +300,27 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # informational: the same grid through dtype='float64x' (fp64-class int8-slice tensor-core path)
+    f64x = None
+    if world == 1:
+        try:
+            model._kb_key = None
+            zx, sx = model.execute("grid", gx, gy, backend="cuda", dtype="float64x")
+            h.reset_counters()
+            t0 = time.perf_counter()
+            model._kb_key = None
+            zx, sx = model.execute("grid", gx, gy, backend="cuda", dtype="float64x")
+            wall = time.perf_counter() - t0
+            tx = h.timings()
+            model._kb_key = None
+            z64, s64 = model.execute("grid", gx, gy, backend="cuda")
+            f64x = {"e2e_points_per_s": GRID * GRID / wall, "solve_only_points_per_s": GRID * GRID / (tx["solve_ms"] * 1e-3),
+                    "max_rel_dz_vs_float64": float(np.max(np.abs(zx - z64)) / np.max(np.abs(z64))),
+                    "max_rel_dss_vs_float64": float(np.max(np.abs(sx - s64)) / np.max(np.abs(s64))),
+                    "kernel": "solve_kernel_i8: tcgen05.mma kind::i8, 6x7-bit error-free slices, exact int32 accumulation in TMEM"}
+        except Exception as e:  # noqa: BLE001
+            f64x = {"error": "%s: %s" % (type(e).__name__, e)}
+
     strong = None
     if world > 1:
         step_dev(False)
@@ -345,6 +366,7 @@ def run_ours(args):
                                               "h2d_ms")},
                 "solve_only_points_per_s_rank0": count_w / (solve_ms * 1e-3),
                 "strong": strong,
+                "float64x_int8_slices": f64x,
             }),
             "roofline": roofline,
             "cpu_baseline": cpu,

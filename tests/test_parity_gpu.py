@@ -311,3 +311,32 @@ def test_sklearn_krige_wrapper_routes_to_cuda(pk):
     z3 = est3.predict(x3[70:])
     zo3, _ = ko.krige(x3[:70], v3[:70], "linear", [0.01, 0.1], x3[70:], regional_linear=True)
     assert_allclose(z3, zo3, rtol=1e-7)
+
+
+# ---- dtype='float64x': fp64-class contraction on the INT8 tensor cores (exact slice products) ---------
+F64X_CASES = [c for c in GLOBAL_CASES if c["name"] in (
+    "cfg1_ok2d_n100_grid50", "ok2d_exponential_aniso", "ok2d_linear_aniso", "ok2d_power_aniso", "ok2d_masked",
+    "cfg2r_ok2d_n1000", "cfg3r_ok3d_n800", "cfg4r_uk2d_n1000", "uk2d_all_grid", "uk3d_spec_func", "geo_ok_points")]
+
+
+@pytest.mark.parametrize("case", F64X_CASES, ids=[c["name"] for c in F64X_CASES])
+def test_float64x_cases_match_reference(pk, case, ref_cases):
+    inp = cases.build_inputs(case)
+    model = cases.make_model(pk, case, inp)
+    style = case["style"]
+    kw = dict(backend="cuda", dtype="float64x")
+    if case["n_specified"]:
+        kw["specified_drift_arrays"] = [np.array(a) for a in inp["spec_pts"]]
+    args = [inp["points"][:, c] for c in range(case["dim"])] if style == "points" else list(inp["axes"])
+    if style == "masked":
+        kw["mask"] = inp["mask"]
+    z, ss = model.execute(style, *args, **kw)
+    zr, sr = ref_cases[case["name"] + "/z"], ref_cases[case["name"] + "/ss"]
+    if style == "masked":
+        keep = ~inp["mask"]
+        z, ss, zr, sr = np.ma.getdata(z)[keep], np.ma.getdata(ss)[keep], zr[keep], sr[keep]
+    assert_parity(z, zr, R64, case["name"] + " z float64x")        # the fp64 tolerance, 1e-5
+    assert_parity(ss, sr, R64, case["name"] + " ss float64x")
+    # and fp64-class in fact: within 1e-8 of the reference
+    assert np.max(np.abs(np.ravel(z) - np.ravel(zr))) <= 1e-8 * np.max(np.abs(zr))
+    assert np.max(np.abs(np.ravel(ss) - np.ravel(sr))) <= 1e-8 * np.max(np.abs(sr))
