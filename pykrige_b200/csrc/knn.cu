@@ -102,7 +102,7 @@ __device__ __forceinline__ void warp_bitonic(double* d2, int* id, const int* __r
 //               re-runs the launch with CHOL = false.
 // CHOL = false: LU with partial pivoting on the full k x k block (dgesv semantics, cok.pyx:165-174).
 template <int DIM, int MODEL, bool CHOL>
-__global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ KnnParams P, int warps_per_cta,
+__global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ KnnParams P, int warps_per_cta,
                                                          int per_warp_doubles) {
     extern __shared__ __align__(16) double ksm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -113,13 +113,14 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
     const int S = k | 1;                       // odd row stride: conflict-free column walks
     double* base = ksm + (size_t)warp * per_warp_doubles;
     double* A = base;                          // k * S  (aliased by the candidate buffers during the search)
-    size_t a_doubles = CHOL ? (size_t)k * (k + 1) / 2 : (size_t)k * S;
+    const int kp = CHOL ? ((k + 31) & ~31) : k;      // padded system size of the blocked Cholesky
+    size_t a_doubles = CHOL ? (size_t)(kp / 32) * (kp / 32 + 1) / 2 * (32 * 33) : (size_t)k * S;
     size_t cand_doubles = KN_CAP + KN_CAP / 2; // d2[CAP] doubles + id[CAP] ints
     size_t off = a_doubles > cand_doubles ? a_doubles : cand_doubles;
     double* rc = base + off;                   // rhs c (becomes C^-1 c)
-    double* r1 = rc + k;                       // rhs 1 (becomes C^-1 1)
-    double* cv = r1 + k;                       // c kept for sigma^2
-    double* nx = cv + k; double* ny = nx + k; double* nz = ny + k; double* nv = nz + k;
+    double* r1 = rc + kp;                      // rhs 1 (becomes C^-1 1)
+    double* cv = r1 + kp;                      // c kept for sigma^2
+    double* nx = cv + kp; double* ny = nx + kp; double* nz = ny + kp; double* nv = nz + kp;
     double* cd2 = base;
     int* cid = reinterpret_cast<int*>(base + KN_CAP);
 
@@ -233,60 +234,109 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
         double c = kb_cov_rhs<MODEL>(vg, dq);
         rc[t] = c; cv[t] = c; r1[t] = 1.0;
     }
+    for (int t = k + lane; t < kp; t += 32) {          // identity padding of the blocked system
+        nx[t] = 0.0; ny[t] = 0.0; nz[t] = 0.0; nv[t] = 0.0; rc[t] = 0.0; cv[t] = 0.0; r1[t] = 0.0;
+    }
     __syncwarp();                                      // candidates consumed: A may be overwritten now
 
     if (CHOL) {
-        // ---------------- K5 (Cholesky): packed lower triangle, tri(i,j) = i(i+1)/2 + j ----------------
-        const int ntri = k * (k + 1) / 2;
+        // ---------------- K5 (Cholesky): 32x32 blocks, factorised in REGISTERS with warp shuffles ----------------
+        // lane r owns row r of the active block (32 doubles); L[c][q] of another row comes by __shfl_sync.
+        // One shuffle + one DFMA per multiply-add, no predicates or address arithmetic in the inner loops
+        // (the packed shared-memory update this replaces issued ~14 instructions per useful FMA).
+        // Blocks (bi, bj), bj <= bi, live in shared memory with row stride 33 (conflict-free for lane = row
+        // and for lane = column walks). Rows/cols >= k are identity padding with zero right-hand sides.
+        const int nbk = (k + 31) >> 5;
+#define KN_BLK(bi, bj) (A + (size_t)((bi) * ((bi) + 1) / 2 + (bj)) * (32 * 33))
+        for (int bi = 0; bi < nbk; ++bi)
+            for (int bj = 0; bj <= bi; ++bj) {
+                double* blk = KN_BLK(bi, bj);
 #pragma unroll 4
-        for (int e = lane; e < ntri; e += 32) {
-            int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-            while ((i + 1) * (i + 2) / 2 <= e) ++i;
-            while (i * (i + 1) / 2 > e) --i;
-            const int j = e - i * (i + 1) / 2;
-            double v = vg.c0;
-            if (i != j) {
-                double d = kb_dist<DIM>(nx[i], ny[i], nz[i], nx[j], ny[j], nz[j]);
-                v = vg.c0 - kb_gamma<MODEL>(vg, d);
+                for (int e = lane; e < 1024; e += 32) {
+                    const int li = e >> 5, lj = e & 31;
+                    const int i = bi * 32 + li, j = bj * 32 + lj;
+                    double v = 0.0;
+                    if (i == j) v = (i < k) ? vg.c0 : 1.0;
+                    else if (j < i && i < k) {
+                        double d = kb_dist<DIM>(nx[i], ny[i], nz[i], nx[j], ny[j], nz[j]);
+                        v = vg.c0 - kb_gamma<MODEL>(vg, d);
+                    }
+                    blk[li * 33 + lj] = v;
+                }
             }
-            A[e] = v;
-        }
         __syncwarp();
         bool notpd = false;
-        for (int pc = 0; pc < k; ++pc) {
-            const int tp = pc * (pc + 1) / 2;
-            const double dpp = A[tp + pc];
-            if (!(dpp > 0.0)) { notpd = true; break; }
-            const double sq = sqrt(dpp);
-            const double inv = 1.0 / sq;
-            // forward substitution of both right-hand sides rides along (column pc is final here)
-            const double yc = rc[pc] * inv, y1 = r1[pc] * inv;
-            double lj[4];
+        for (int b = 0; b < nbk; ++b) {
+            double* Dbb = KN_BLK(b, b);
+            double d[32];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int j = lane + 32 * q;
-                double l = 0.0;
-                if (j > pc && j < k) {
-                    const int idx = j * (j + 1) / 2 + pc;
-                    l = A[idx] * inv;
-                    A[idx] = l;
-                    rc[j] -= l * yc;
-                    r1[j] -= l * y1;
+            for (int c = 0; c < 32; ++c) d[c] = Dbb[lane * 33 + c];
+            double dinv = 1.0;
+#pragma unroll
+            for (int pc = 0; pc < 32; ++pc) {
+                const double piv = __shfl_sync(0xffffffffu, d[pc], pc);
+                if (!(piv > 0.0)) notpd = true;
+                const double inv = 1.0 / sqrt(piv);
+                const double l = d[pc] * inv;             // lane pc: sqrt(piv); lanes below: L[r][pc]
+                d[pc] = l;
+                if (lane == pc) dinv = inv;
+#pragma unroll
+                for (int c = pc + 1; c < 32; ++c) d[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), d[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) Dbb[lane * 33 + c] = d[c];
+            // forward substitution of both right-hand sides for this block (lane r <-> entry b*32 + r)
+            double yc = rc[b * 32 + lane], y1 = r1[b * 32 + lane];
+#pragma unroll
+            for (int pc = 0; pc < 32; ++pc) {
+                const double ip = __shfl_sync(0xffffffffu, dinv, pc);
+                const double tc = __shfl_sync(0xffffffffu, yc, pc) * ip;
+                const double t1 = __shfl_sync(0xffffffffu, y1, pc) * ip;
+                if (lane == pc) { yc = tc; y1 = t1; }
+                else if (lane > pc) { yc = fma(-d[pc], tc, yc); y1 = fma(-d[pc], t1, y1); }
+            }
+            rc[b * 32 + lane] = yc; r1[b * 32 + lane] = y1;
+            // panel: X = A(bi, b) L_bb^-T for the blocks below, and their right-hand side update
+            for (int bi = b + 1; bi < nbk; ++bi) {
+                double* Bib = KN_BLK(bi, b);
+                double x[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) x[c] = Bib[lane * 33 + c];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+#pragma unroll
+                    for (int q = 0; q < c; ++q) x[c] = fma(-x[q], __shfl_sync(0xffffffffu, d[q], c), x[c]);
+                    x[c] *= __shfl_sync(0xffffffffu, dinv, c);
                 }
-                lj[q] = l;
+                double tc = 0.0, t1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    Bib[lane * 33 + c] = x[c];
+                    tc = fma(x[c], __shfl_sync(0xffffffffu, yc, c), tc);
+                    t1 = fma(x[c], __shfl_sync(0xffffffffu, y1, c), t1);
+                }
+                rc[bi * 32 + lane] -= tc;
+                r1[bi * 32 + lane] -= t1;
             }
             __syncwarp();
-            if (lane == 0) { A[tp + pc] = sq; rc[pc] = yc; r1[pc] = y1; }
-            // trailing update of the lower triangle: a[i][j] -= l_i * l_j, pc < j <= i
-#pragma unroll 4
-            for (int i = pc + 1; i < k; ++i) {
-                const int ti = i * (i + 1) / 2;
-                const double li = A[ti + pc];
+            // trailing update: A(bi, bj) -= L(bi, b) L(bj, b)^T
+            for (int bi = b + 1; bi < nbk; ++bi) {
+                const double* Lib = KN_BLK(bi, b);
+                double xi[32];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (q * 32 <= i && q * 32 + 31 > pc) {
-                        const int j = lane + 32 * q;
-                        if (j > pc && j <= i) A[ti + j] -= li * lj[q];
+                for (int c = 0; c < 32; ++c) xi[c] = Lib[lane * 33 + c];
+                for (int bj = b + 1; bj <= bi; ++bj) {
+                    const double* Ljb = KN_BLK(bj, b);
+                    double* Aij = KN_BLK(bi, bj);
+                    double xj[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) xj[c] = Ljb[lane * 33 + c];
+#pragma unroll 4
+                    for (int c = 0; c < 32; ++c) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int pc = 0; pc < 32; ++pc) acc = fma(xi[pc], __shfl_sync(0xffffffffu, xj[pc], c), acc);
+                        Aij[lane * 33 + c] -= acc;
                     }
                 }
             }
@@ -296,20 +346,34 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
             if (lane == 0) { atomicMax(P.flag, 2); P.z_out[p] = 0.0; P.ss_out[p] = 0.0; }
             return;
         }
-        // backward substitution L^T x = y (row walks: contiguous)
-        for (int pc = k - 1; pc >= 0; --pc) {
-            const int tp = pc * (pc + 1) / 2;
-            const double inv = 1.0 / A[tp + pc];
-            const double xc = rc[pc] * inv, x1 = r1[pc] * inv;
-            __syncwarp();
-            if (lane == 0) { rc[pc] = xc; r1[pc] = x1; }
-            for (int i = lane; i < pc; i += 32) {
-                const double u = A[tp + i];
-                rc[i] -= u * xc;
-                r1[i] -= u * x1;
+        // backward substitution L^T x = y, block by block from the bottom
+        for (int b = nbk - 1; b >= 0; --b) {
+            double yc = rc[b * 32 + lane], y1 = r1[b * 32 + lane];
+            for (int bi = b + 1; bi < nbk; ++bi) {          // minus L(bi, b)^T x_bi : lane c walks column c
+                const double* Lib = KN_BLK(bi, b);
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const double lrc = Lib[r * 33 + lane];
+                    yc = fma(-lrc, rc[bi * 32 + r], yc);
+                    y1 = fma(-lrc, r1[bi * 32 + r], y1);
+                }
+            }
+            const double* Dbb = KN_BLK(b, b);
+            const double dinv = 1.0 / Dbb[lane * 33 + lane];
+#pragma unroll 4
+            for (int pc = 31; pc >= 0; --pc) {
+                const double ip = __shfl_sync(0xffffffffu, dinv, pc);
+                const double xc = __shfl_sync(0xffffffffu, yc, pc) * ip;
+                const double x1 = __shfl_sync(0xffffffffu, y1, pc) * ip;
+                const double lpq = Dbb[pc * 33 + lane];      // L[pc][lane]
+                if (lane == pc) { yc = xc; y1 = x1; }
+                else if (lane < pc) { yc = fma(-lpq, xc, yc); y1 = fma(-lpq, x1, y1); }
             }
             __syncwarp();
+            rc[b * 32 + lane] = yc; r1[b * 32 + lane] = y1;
+            __syncwarp();
         }
+#undef KN_BLK
     } else {
     // ---------------- K5: local system ----------------
     // C[i][j] = c0 - gamma(|x_i - x_j|), C[i][i] = c0   (ok.py:641-644 in covariance form)
@@ -413,14 +477,15 @@ __global__ void __launch_bounds__(512) knn_solve_kernel(const __grid_constant__ 
 // ---- host side -------------------------------------------------------------
 size_t kbk_knn_smem_per_warp(int k, int chol) {
     size_t S = (size_t)(k | 1);
-    size_t a = chol ? (size_t)k * (k + 1) / 2 : (size_t)k * S, c = KN_CAP + KN_CAP / 2;
-    return ((a > c ? a : c) + 7 * (size_t)k + 2) * sizeof(double);
+    size_t kp = chol ? (size_t)((k + 31) & ~31) : (size_t)k;
+    size_t a = chol ? (kp / 32) * (kp / 32 + 1) / 2 * (32 * 33) : (size_t)k * S, c = KN_CAP + KN_CAP / 2;
+    return ((a > c ? a : c) + 7 * kp + 2) * sizeof(double);
 }
 
 template <int DIM, bool CHOL>
 static cudaError_t knn_launch_dim(const KnnParams& p, cudaStream_t st) {
     size_t per = kbk_knn_smem_per_warp(p.k, CHOL ? 1 : 0);
-    int wpc = (int)std::min<size_t>(16, (220 * 1024) / per);      // as many points in flight per SM as fit
+    int wpc = (int)std::min<size_t>(8, (220 * 1024) / per);       // as many points in flight per SM as fit
     if (wpc < 1) return cudaErrorInvalidValue;
     size_t smem = per * wpc;
     unsigned grid = (unsigned)((p.m + wpc - 1) / wpc);
