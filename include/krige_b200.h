@@ -81,7 +81,7 @@ int  kb200_version(void);
  * (ok.py:626-648,663; uk.py:861-920,935).
  *
  *  dim            2 or 3
- *  dtype          KB200_F64 / KB200_F32
+ *  dtype          KB200_F64 (DMMA) / KB200_F32 (tcgen05 3xTF32) / KB200_F64X (tcgen05 INT8 slices, fp64-class)
  *  n              number of data points
  *  x,y,z          host, length n, ORIGINAL (un-adjusted) coordinates; z may be NULL when dim==2
  *  values         host, length n (self.Z / self.VALUES)
@@ -214,8 +214,7 @@ int  kb200_last_timings(kb200_handle h, double* ms, int n);
 void kb200_reset_counters(kb200_handle h);
 
 /* Debug/verification taps (used by tests only): copy device intermediates to host.
- *  what = 0: shifted covariance matrix C (n_pad x n_pad, row-major, lower triangle valid)
- *  what = 1: Cholesky factor L (same layout)
+ *  what = 1: Cholesky factor L of the shifted covariance matrix (n_pad x n_pad, row-major, lower triangle valid)
  *  what = 2: W = inv(L) (same layout)
  *  what = 3: dual block: Uz (n x (K+2), column-major), then Sinv ((K+1)^2), then phi (K+1), then c0
  * `cap` is the capacity of `out` in doubles; returns the number of doubles written or a negative code. */

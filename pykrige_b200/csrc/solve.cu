@@ -9,10 +9,13 @@
 //     g_j  = U^T c_j, zc_j = zeta . c_j   <- extra dense "dual rows" appended to W (same GEMM)
 //     finalize: r = g - f_j, mu = S^-1 r, sigma2 = c0 - q + r.mu, z = zc - mu.phi
 //
-// One CTA = (row block I of KB_BM rows of W) x (tile of KB_TN points).  The RHS tile
-// c[k][j] is generated on the fly in shared memory from coordinates (never in HBM);
-// W tiles arrive as 32 KB fragment-ordered bulk copies (TMA engine, cp.async.bulk +
-// mbarrier) into a 3-stage ring; 8 warps issue m8n8k4 DMMA on a 32x64 sub-tile each.
+// Kernels in this file (all fp64, mma.sync.m8n8k4 = SASS DMMA):
+//   solve_kernel_pt   (K3 v3, the product path) persistent CTAs, one CTA = 64 points x all rows of W, RHS column
+//                     block generated once per tile, W/RHS tiles streamed by cp.async.bulk + mbarrier, fused
+//                     finalize. See the comment above the kernel.
+//   solve_kernel_f64 + finalize_kernel (K3 v1) CTA = (row block x point tile), RHS regenerated per row block;
+//                     kept behind KB200_SOLVE_V1=1 for A/B profiling only.
+// The tcgen05 variants live in solve_tf32.cu (dtype float32) and solve_i8.cu (dtype float64x).
 #include "common.cuh"
 #include "kernels.h"
 #include <cstdlib>
