@@ -1,0 +1,29 @@
+"""CPU test of the bench.py contract for the reference arm (`--impl reference`): one JSON line on stdout with
+the keys the driver reads; non-zero ranks print nothing."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "points/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # a non-zero rank of the reference arm exits 0 without output
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"],
+                         capture_output=True, text=True, env=env, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == ""
