@@ -264,7 +264,7 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     if (dtype == KB200_F64X) {
         o += (size_t)kbk_i8_total_tiles((int)n, h->na, nullptr) * kbk_i8_tile_bytes();
         o = align_up(o, 256);
-        h->off_rowscale = o; o += align_up((size_t)kbk_i8_nrb((int)n, h->na) * 64 * sizeof(double), 256);
+        h->off_rowscale = o; o += align_up((size_t)kbk_i8_rows((int)n, h->na) * sizeof(double), 256);
     } else {
         o += (size_t)off * KB_BM * KB_BK * esz;
     }
@@ -413,7 +413,7 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
         kbk_i8_total_tiles(nn, h->na, toff.data());
         // workspace (T1 scratch is free now): tile offsets | row exponents
         long long* d_toff = reinterpret_cast<long long*>(h->wT.as<char>());
-        int* d_rowexp = reinterpret_cast<int*>(h->wT.as<char>() + align_up((size_t)(nrb8 + 1) * sizeof(long long), 256));
+        int* d_rowexp = reinterpret_cast<int*>(h->wT.as<char>() + align_up((size_t)(nrb8 + 1) * sizeof(long long), 256));   // kbk_i8_rows ints
         CU(h, cudaMemcpyAsync(d_toff, toff.data(), (size_t)(nrb8 + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
         CU(h, kbk_pack_i8(h->wW.as<double>(), ld, nn, np, h->na, Uz, d_rowexp,
                           reinterpret_cast<double*>(blob + h->off_rowscale), d_toff, blob + h->off_tiles, st));

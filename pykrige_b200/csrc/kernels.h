@@ -107,6 +107,7 @@ cudaError_t kbk_solve_i8(int dim, const SolvePtParams& p, int grid, cudaStream_t
 cudaError_t kbk_pack_i8(const double* W, int ld, int n, int n_pad, int na, const double* Uz,
                         int* rowexp, double* rowscale, const long long* tile_off_dev, void* out, cudaStream_t st);
 int         kbk_i8_nrb(int n, int na);
+int         kbk_i8_rows(int n, int na);
 long long   kbk_i8_total_tiles(int n, int na, long long* tile_off);
 size_t      kbk_i8_tile_bytes();
 size_t      kbk_solve_i8_scratch_bytes(int n, int grid);

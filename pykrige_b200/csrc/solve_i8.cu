@@ -10,8 +10,8 @@
 // in fp64 in the epilogue. The result agrees with the fp64 DMMA kernel to ~1e-10 (tests), at several
 // times its rate; dtype='float64' keeps the DMMA kernel as the default.
 //
-// Orientation as in solve_tf32.cu: D[point][W row], M = 128 points (TMEM lanes), N = 64 W rows per row
-// block, K = 32 per MMA; operands in the canonical no-swizzle K-major UMMA layout (8-row x 16-byte core
+// Orientation as in solve_tf32.cu: D[point][W row], M = 128 points (TMEM lanes), N = 80 W rows per row
+// block (as many as the six accumulators leave room for in TMEM: the RHS slices are re-read once per row block), K = 32 per MMA; operands in the canonical no-swizzle K-major UMMA layout (8-row x 16-byte core
 // matrices, k-chunks 128 B apart, 8-row groups 256 B apart), one stage = 32 k = one MMA k-step,
 // 21 MMAs per stage (all slice pairs with s + t <= 5).
 #include "common.cuh"
@@ -21,7 +21,7 @@
 #define I8_STAGES 5
 #define I8_THREADS 256
 #define I8_TM 128
-#define I8_BN 64
+#define I8_BN 80                               // 6 accumulators x 80 columns = 480 of the 512 TMEM columns
 #define I8_BK 32
 #define I8_W_SLICE (I8_BN * I8_BK)            // 2 KB
 #define I8_C_SLICE (I8_TM * I8_BK)            // 4 KB
@@ -282,30 +282,27 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t t_addr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    double v[32];
+                for (int ch = 0; ch < I8_BN / 16; ++ch) {
+                    double v[16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0.0;
+                    for (int j = 0; j < 16; ++j) v[j] = 0.0;
 #pragma unroll 1
                     for (int d = I8_S - 1; d >= 0; --d) {       // smallest contributions first
-                        uint32_t u[32];
+                        uint32_t u[16];
                         asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                             : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                              "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
-                              "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
-                              "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-                            : "r"(t_addr + (uint32_t)d * I8_BN + (uint32_t)half * 32u));
+                              "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                            : "r"(t_addr + (uint32_t)d * I8_BN + (uint32_t)ch * 16u));
                         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
                         const double sd = scalbn(1.0, -7 * d);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += (double)(int)u[j] * sd;
+                        for (int j = 0; j < 16; ++j) v[j] += (double)(int)u[j] * sd;
                     }
-                    const int r0 = J * I8_BN + half * 32;
+                    const int r0 = J * I8_BN + ch * 16;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         const int r = r0 + j;
                         if (r < P.n + P.na) {
                             const double x = v[j] * __ldg(P.rowscale + r) * pscale;
@@ -367,6 +364,7 @@ static size_t i8_smem() {
            (2 * I8_STAGES + 2) * sizeof(uint64_t) + 64;
 }
 int kbk_i8_nrb(int n, int na) { return (n + na + I8_BN - 1) / I8_BN; }
+int kbk_i8_rows(int n, int na) { return kbk_i8_nrb(n, na) * I8_BN; }
 long long kbk_i8_total_tiles(int n, int na, long long* tile_off /* [nrb+1] or null */) {
     int nk = (n + I8_BK - 1) / I8_BK, nrb = kbk_i8_nrb(n, na);
     long long off = 0;
