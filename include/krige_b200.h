@@ -213,6 +213,31 @@ int kb200_set_stream(kb200_handle h, void* cuda_stream);
 int  kb200_last_timings(kb200_handle h, double* ms, int n);
 void kb200_reset_counters(kb200_handle h);
 
+/* ---- constructor-side helpers ----------------------------------------------
+ *
+ * kb200_experimental_variogram replaces the pdist binning of core._initialize_variogram_model
+ * (core.py:432-505): over all n(n-1)/2 data pairs, d = pair distance (euclidean on the ALREADY
+ * ADJUSTED coordinates x, y[, z], dim = 2 | 3; great-circle degrees of (lon, lat) = (x, y) when the
+ * handle is in KB200_GEOGRAPHIC mode, dim = 2), g = 0.5 (v_i - v_j)^2, binned into `nlags` equal-width
+ * lags from dmin to dmax (last edge dmax + 0.001, core.py:471-476). Host arrays in and out:
+ *   counts[nlags], lag_sum[nlags] (sum of d), semi_sum[nlags] (sum of g), dminmax[2] = (dmin, dmax);
+ * the caller forms the means and drops empty lags (core.py:493-505). Stateless with respect to the
+ * factored problem of the handle. Returns KB200_EBADARG for n < 2, nlags < 1 or nlags > 4096.
+ */
+int kb200_experimental_variogram(kb200_handle h, int dim, int64_t n,
+                                 const double* x, const double* y, const double* z, const double* values,
+                                 int nlags, double* counts, double* lag_sum, double* semi_sum, double* dminmax);
+
+/* kb200_statistics replaces core._find_statistics (core.py:759-836): for every data point i >= 1 the
+ * ordinary-kriging estimate from points [0, i) and its variance, read off the Cholesky factor that
+ * kb200_set_problem computed on THIS handle (any dtype; not after kb200_blob_commit alone, not for the
+ * indefinite fallback -> KB200_EUNSUPPORTED, not for a kNN-only problem -> KB200_ESTATE).
+ * delta[i] = Z_i - zhat_i, sigma[i] = sqrt(sigmasq_i); entries 0 and points that coincide with an
+ * earlier point (distance <= 1e-10, core.py:729-731) are returned as 0 — the caller drops
+ * sigma <= eps entries exactly as core.py:829-831. Host arrays of length n.
+ */
+int kb200_statistics(kb200_handle h, double* delta, double* sigma);
+
 /* Debug/verification taps (used by tests only): copy device intermediates to host.
  *  what = 1: Cholesky factor L of the shifted covariance matrix (n_pad x n_pad, row-major, lower triangle valid)
  *  what = 2: W = inv(L) (same layout)

@@ -273,3 +273,80 @@ def krige_chunked(data_xyz, values, model, plist_stored, points, chunk=20000, **
         z[s:s + chunk] = x[:n, :].T @ vals
         ss[s:s + chunk] = -np.einsum("ij,ji->i", b, x)
     return z, ss
+
+
+# ---- constructor side ---------------------------------------------
+def experimental_variogram(X, y, nlags, coordinates_type="euclidean"):
+    """Binned experimental semivariogram, core.py:432-505: every pair's distance and half squared
+    value difference, nlags equal-width bins from dmin to dmax (last edge dmax + 0.001), per-bin means,
+    empty bins dropped. Materialises the full pair list like the reference does (small cases only)."""
+    from scipy.spatial.distance import pdist
+
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if coordinates_type == "euclidean":              # core.py:432-434
+        d = pdist(X, metric="euclidean")
+        g = 0.5 * pdist(y[:, None], metric="sqeuclidean")
+    elif coordinates_type == "geographic":           # core.py:440-453 (strict lower triangle)
+        if X.shape[1] != 2:
+            raise ValueError("Geographic coordinate type only supported for 2D datasets.")
+        D = great_circle_distance(X[:, 0][None, :], X[:, 1][None, :], X[:, 0][:, None], X[:, 1][:, None])
+        G = 0.5 * (y[None, :] - y[:, None]) ** 2.0
+        low = np.tril(np.ones(D.shape, dtype=bool), -1)
+        d, g = D[low], G[low]
+    else:
+        raise ValueError("Specified coordinate type '%s' is not supported." % coordinates_type)
+    dmax, dmin = np.amax(d), np.amin(d)              # core.py:471-476
+    dd = (dmax - dmin) / nlags
+    bins = [dmin + n * dd for n in range(nlags)]
+    bins.append(dmax + 0.001)
+    lags, semi = [], []
+    for n in range(nlags):                           # core.py:493-505
+        sel = (d >= bins[n]) & (d < bins[n + 1])
+        if np.any(sel):
+            lags.append(np.mean(d[sel]))
+            semi.append(np.mean(g[sel]))
+    return np.array(lags), np.array(semi)
+
+
+def krige_one(X, y, coords, model, m, coordinates_type="euclidean"):
+    """core._krige, core.py:654-756: one ordinary-kriging estimate and variance at `coords`."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    if coordinates_type == "euclidean":
+        d = cdist(X, X)
+        bd = cdist(X, np.asarray(coords, dtype=np.float64)[None, :]).ravel()
+    else:
+        d = great_circle_distance(X[:, 0][None, :], X[:, 1][None, :], X[:, 0][:, None], X[:, 1][:, None])
+        bd = great_circle_distance(X[:, 0], X[:, 1], coords[0] * np.ones(n), coords[1] * np.ones(n))
+    a = np.zeros((n + 1, n + 1))
+    a[:n, :n] = -variogram(model, m, d)
+    np.fill_diagonal(a, 0.0)
+    a[n, :] = 1.0
+    a[:, n] = 1.0
+    a[n, n] = 0.0
+    b = np.zeros(n + 1)
+    b[:n] = -variogram(model, m, bd)
+    if np.any(np.absolute(bd) <= 1e-10):             # core.py:729-731, 748-749
+        b[int(np.flatnonzero(bd <= 1e-10)[0])] = 0.0
+    b[n] = 1.0
+    res = np.linalg.solve(a, b)
+    return float(np.sum(res[:n] * y)), float(np.sum(res * -b))
+
+
+def find_statistics(X, y, model, m, coordinates_type="euclidean"):
+    """core._find_statistics, core.py:759-836: point i kriged from points [0, i); near-zero variances
+    are skipped. Returns (delta, sigma, epsilon)."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    delta = np.zeros(y.shape)
+    sigma = np.zeros(y.shape)
+    for i in range(1, y.shape[0]):
+        k, ss = krige_one(X[:i, :], y[:i], X[i, :], model, m, coordinates_type)
+        if np.absolute(ss) < EPS:
+            continue
+        delta[i] = y[i] - k
+        sigma[i] = np.sqrt(ss)
+    keep = sigma > EPS
+    delta, sigma = delta[keep], sigma[keep]
+    return delta, sigma, delta / sigma

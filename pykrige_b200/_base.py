@@ -94,12 +94,37 @@ class KrigeBase:
     def _stats_inputs(self):
         raise NotImplementedError
 
-    def _compute_statistics(self):
+    def _device_statistics(self):
+        """delta, sigma, epsilon from the Cholesky factor of the device problem (kb200_statistics,
+        csrc/variogram.cu: O(N) after the factorisation instead of the reference's N solves). Returns
+        None when this problem has no device twin (custom variogram, pseudo_inv, indefinite
+        covariance form, no CUDA device) — the caller then runs the reference's loop on the host."""
+        if not _cabi.device_available():
+            return None
+        try:
+            key = getattr(self, "_kb_key", None)
+            if key is not None and key[1] is False and key == self._problem_signature(key[0], False):
+                h = self._cuda_handle()           # the factor of the last global execute() is still there
+            else:
+                h = self._ensure_problem("float64")
+            delta, sigma = h.statistics(len(self._stats_inputs()[1]))
+        except (NotImplementedError, _cabi.KrigeB200Error, np.linalg.LinAlgError, ValueError, MemoryError):
+            return None
+        keep = (sigma * sigma >= core.eps) & (sigma > core.eps)      # core.py:818-819, 829-831
+        delta, sigma = delta[keep], sigma[keep]
+        return delta, sigma, delta / sigma
+
+    def _compute_statistics(self, device="auto"):
         X, y = self._stats_inputs()
-        self._delta, self._sigma, self._epsilon = core._find_statistics(
-            X, y, self.variogram_function, self.variogram_model_parameters, "euclidean",
-            getattr(self, "pseudo_inv", False),
-        )
+        res = self._device_statistics() if device in ("auto", True) else None
+        if res is None:
+            if device is True:
+                raise _cabi.KrigeB200Error("cross-validation statistics: this problem has no device route")
+            res = core._find_statistics(
+                X, y, self.variogram_function, self.variogram_model_parameters,
+                getattr(self, "coordinates_type", "euclidean"), getattr(self, "pseudo_inv", False),
+            )
+        self._delta, self._sigma, self._epsilon = res
         self._Q1 = core.calcQ1(self._epsilon)
         self._Q2 = core.calcQ2(self._epsilon)
         self._cR = core.calc_cR(self._Q2, self._sigma)

@@ -34,6 +34,7 @@ EXPORTS = [
     "kb200_set_problem_knn",
     "kb200_blob_bytes", "kb200_blob_ptr", "kb200_describe_problem", "kb200_blob_commit",
     "kb200_set_coordinates", "kb200_set_stream", "kb200_last_timings", "kb200_reset_counters", "kb200_debug_fetch",
+    "kb200_experimental_variogram", "kb200_statistics",
 ]
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -90,8 +91,38 @@ def load_library():
     lib.kb200_reset_counters.restype = None
     lib.kb200_debug_fetch.argtypes = [h, i32, dp, i64]
     lib.kb200_debug_fetch.restype = i64
+    lib.kb200_experimental_variogram.argtypes = [h, i32, i64, dp, dp, dp, dp, i32, dp, dp, dp, dp]
+    lib.kb200_statistics.argtypes = [h, dp, dp]
     _lib = lib
     return lib
+
+
+_aux = None
+_aux_error = None
+
+
+def aux_handle():
+    """One shared Handle for the constructor-side device helpers (experimental variogram). Raises
+    KrigeB200Error when the library or a CUDA device is missing (the failure is cached)."""
+    global _aux, _aux_error
+    if _aux is not None:
+        return _aux
+    if _aux_error is not None:
+        raise KrigeB200Error(_aux_error)
+    try:
+        _aux = Handle()
+    except KrigeB200Error as e:
+        _aux_error = str(e)
+        raise
+    return _aux
+
+
+def device_available():
+    try:
+        aux_handle()
+        return True
+    except KrigeB200Error:
+        return False
 
 
 def _ptr(a):
@@ -266,6 +297,29 @@ class Handle:
 
     def reset_counters(self):
         self.lib.kb200_reset_counters(self._h)
+
+    def experimental_variogram(self, X, values, nlags, geographic=False):
+        """Device twin of the pdist binning (core.py:432-505): X = (n, 2|3) ADJUSTED coordinates (or
+        lon/lat when geographic). Returns (counts, lag_sum, semi_sum, dmin, dmax)."""
+        X = np.asarray(X, dtype=np.float64)
+        dim = X.shape[1]
+        cols = [_f64(X[:, c]) for c in range(dim)]
+        v = _f64(values)
+        nl = int(nlags)
+        cnt, sd, sg, mm = (np.zeros(max(nl, 0)), np.zeros(max(nl, 0)), np.zeros(max(nl, 0)), np.zeros(2))
+        self._check(self.lib.kb200_set_coordinates(self._h, 1 if geographic else 0))
+        self._check(self.lib.kb200_experimental_variogram(
+            self._h, dim, X.shape[0], _ptr(cols[0]), _ptr(cols[1]), _ptr(cols[2]) if dim > 2 else None,
+            _ptr(v), nl, _ptr(cnt), _ptr(sd), _ptr(sg), _ptr(mm)))
+        return cnt, sd, sg, float(mm[0]), float(mm[1])
+
+    def statistics(self, n):
+        """(delta, sigma) of core._find_statistics (core.py:759-836) from the factor of the current
+        problem; skipped points are 0."""
+        delta = np.zeros(int(n))
+        sigma = np.zeros(int(n))
+        self._check(self.lib.kb200_statistics(self._h, _ptr(delta), _ptr(sigma)))
+        return delta, sigma
 
     def debug_fetch(self, what, count):
         out = np.empty(int(count), dtype=np.float64)

@@ -42,6 +42,7 @@ struct kb200_ctx {
 
     // description
     bool described = false, ready = false, knn_ready = false;
+    bool factor_live = false;  // L (wC) and the forward solves (wF) of the ready problem are still in the workspace
     int gform = 0;            // 1: general (indefinite) fallback, tiles hold the symmetric inverse
     int geo = 0;              // 1: coordinates_type='geographic' for the next problem description
     int dim = 2, dtype = KB200_F64, n = 0, n_pad = 0, ld = 0, n_rl = 0, n_hd = 0, K1 = 1, na = 2, nrb = 0;
@@ -63,6 +64,7 @@ struct kb200_ctx {
     int num_sms = 148;
     // knn workspace
     DevBuf kSorted, kCells;
+    DevBuf wVario;            // constructor-side helpers (experimental variogram, statistics)
     KnnParams kp{};
     int k_ncells = 0;
 
@@ -98,7 +100,7 @@ extern "C" int kb200_create(kb200_handle* out, int device) {
     h->own_stream = true;
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete h; return KB200_ECUDA; }
     if (kbk_factor_init() != cudaSuccess || kbk_solve_init() != cudaSuccess || kbk_solve_tf32_init() != cudaSuccess ||
-        kbk_solve_i8_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
+        kbk_solve_i8_init() != cudaSuccess || kbk_ev_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->num_sms < 1) h->num_sms = 148;
     *out = h;
     return KB200_OK;
@@ -109,7 +111,7 @@ extern "C" void kb200_destroy(kb200_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->blob, &h->wC, &h->wW, &h->wT, &h->wF, &h->wRaw, &h->wFlag, &h->wPart, &h->wAux,
-                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->wScratch, &h->kSorted, &h->kCells}) b->release();
+                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->wScratch, &h->kSorted, &h->kCells, &h->wVario}) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -130,7 +132,7 @@ extern "C" int kb200_set_coordinates(kb200_handle h, int coordinates_type) {
     if (coordinates_type != KB200_EUCLIDEAN && coordinates_type != KB200_GEOGRAPHIC)
         return fail(h, KB200_EBADARG, "coordinates_type must be KB200_EUCLIDEAN or KB200_GEOGRAPHIC");
     h->geo = coordinates_type == KB200_GEOGRAPHIC ? 1 : 0;
-    h->described = false; h->ready = false; h->knn_ready = false;
+    h->described = false; h->ready = false; h->knn_ready = false; h->factor_live = false;
     return KB200_OK;
 }
 
@@ -164,7 +166,7 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
                     const double* center, const double* aniso, int model, const double* vparams, int n_vparams,
                     int exact_values, double eps, int n_rl, int n_hd, const double* drift_data) {
     if (!h) return KB200_EBADARG;
-    h->described = false; h->ready = false; h->knn_ready = false;
+    h->described = false; h->ready = false; h->knn_ready = false; h->factor_live = false;
     if (dim != 2 && dim != 3) return fail(h, KB200_EBADARG, "dim must be 2 or 3");
     if (h->geo && dim != 2) return fail(h, KB200_EBADARG, "geographic coordinates are two-dimensional (lon, lat)");
     if (h->geo && (n_rl || n_hd)) return fail(h, KB200_EUNSUPPORTED, "universal kriging has no geographic mode (uk.py:337)");
@@ -438,6 +440,7 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
     h->launches += launches;
     if (hflag != 0) return fail(h, KB200_ESINGULAR, "drift/unbiasedness block F^T C^-1 F is singular");
     h->ready = true;
+    h->factor_live = !h->gform;
     return KB200_OK;
 }
 
@@ -828,6 +831,85 @@ extern "C" int kb200_execute_knn_points(kb200_handle h, int k, int64_t m,
 }
 
 // ---- debug taps (tests only) ------------------------------------------------
+// ---- constructor-side helpers -----------------------------------------------
+extern "C" int kb200_experimental_variogram(kb200_handle h, int dim, int64_t n,
+                                            const double* x, const double* y, const double* z, const double* values,
+                                            int nlags, double* counts, double* lag_sum, double* semi_sum,
+                                            double* dminmax) {
+    if (!h) return KB200_EBADARG;
+    if (dim != 2 && dim != 3) return fail(h, KB200_EBADARG, "dim must be 2 or 3");
+    if (h->geo && dim != 2) return fail(h, KB200_EBADARG, "Geographic coordinate type only supported for 2D datasets.");
+    if (n < 2 || n > 2000000000LL) return fail(h, KB200_EBADARG, "the experimental variogram needs 2 <= n < 2^31 points");
+    if (nlags < 1 || nlags > 4096) return fail(h, KB200_EBADARG, "nlags must be in [1, 4096]");
+    if (!x || !y || (dim == 3 && !z) || !values || !counts || !lag_sum || !semi_sum)
+        return fail(h, KB200_EBADARG, "null array");
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->stream;
+    const int nn = (int)n, kdim = h->geo ? KB_GEO : dim;
+    const int grid = kbk_ev_grid(nn, 2 * h->num_sms);
+    // workspace: x | y | z | v | edges | bmin | bmax | part | out
+    const size_t o_edges = 4 * (size_t)nn, o_bmin = o_edges + nlags + 1, o_bmax = o_bmin + grid,
+                 o_part = o_bmax + grid, o_out = o_part + (size_t)grid * 3 * nlags, total = o_out + 3 * (size_t)nlags;
+    CU(h, h->wVario.reserve(total * sizeof(double)));
+    double* w = h->wVario.as<double>();
+    double *dx = w, *dy = w + nn, *dz = w + 2 * (size_t)nn, *dv = w + 3 * (size_t)nn;
+    CU(h, cudaMemcpyAsync(dx, x, (size_t)nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(dy, y, (size_t)nn * 8, cudaMemcpyHostToDevice, st));
+    if (dim == 3) CU(h, cudaMemcpyAsync(dz, z, (size_t)nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(dv, values, (size_t)nn * 8, cudaMemcpyHostToDevice, st));
+    CU(h, kbk_ev_minmax(kdim, nn, dx, dy, dz, grid, w + o_bmin, w + o_bmax, st));
+    std::vector<double> mm(2 * (size_t)grid);
+    CU(h, cudaMemcpyAsync(mm.data(), w + o_bmin, 2 * (size_t)grid * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    double dmin = mm[0], dmax = mm[grid];
+    for (int b = 1; b < grid; ++b) { dmin = std::min(dmin, mm[b]); dmax = std::max(dmax, mm[grid + b]); }
+    if (!(dmax >= dmin)) return fail(h, KB200_EBADARG, "pair distances are not finite");
+    // equal-width lag edges exactly as core.py:471-476 (same fp64 expression, evaluated on the host)
+    const double dd = (dmax - dmin) / nlags;
+    std::vector<double> edges(nlags + 1);
+    for (int k = 0; k < nlags; ++k) edges[k] = dmin + k * dd;
+    edges[nlags] = dmax + 0.001;
+    CU(h, cudaMemcpyAsync(w + o_edges, edges.data(), (size_t)(nlags + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(h, kbk_ev_bin(kdim, nn, dx, dy, dz, dv, nlags, w + o_edges, dd > 0.0 ? 1.0 / dd : 0.0, grid,
+                     w + o_part, w + o_out, st));
+    std::vector<double> out(3 * (size_t)nlags);
+    CU(h, cudaMemcpyAsync(out.data(), w + o_out, out.size() * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    for (int k = 0; k < nlags; ++k) { counts[k] = out[k]; lag_sum[k] = out[nlags + k]; semi_sum[k] = out[2 * (size_t)nlags + k]; }
+    if (dminmax) { dminmax[0] = dmin; dminmax[1] = dmax; }
+    h->launches += 3;
+    return KB200_OK;
+}
+
+extern "C" int kb200_statistics(kb200_handle h, double* delta, double* sigma) {
+    if (!h || !delta || !sigma) return KB200_EBADARG;
+    if (!h->ready) return fail(h, KB200_ESTATE, "no factored problem: call kb200_set_problem first");
+    if (h->gform) return fail(h, KB200_EUNSUPPORTED, "cross-validation statistics need the positive definite "
+                              "covariance form (this problem runs on the general fallback)");
+    if (!h->factor_live) return fail(h, KB200_ESTATE, "the Cholesky factor is not on this handle "
+                                     "(problem received through kb200_blob_commit)");
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->stream;
+    const int nn = h->n, np = h->n_pad;
+    char* blob = h->blob.as<char>();
+    const double* ax = reinterpret_cast<double*>(blob + h->off_ax);
+    const double* ay = reinterpret_cast<double*>(blob + h->off_ay);
+    const double* az = reinterpret_cast<double*>(blob + h->off_az);
+    const double* Hz = h->wF.as<double>() + (size_t)KB_MAXAUX * np;
+    const int K = h->n_rl + h->n_hd;                       // Hz row K = L^-1 1, row K+1 = L^-1 Z
+    CU(h, h->wVario.reserve((size_t)nn * (2 * sizeof(double) + sizeof(int)) + 256));
+    double* d_delta = h->wVario.as<double>();
+    double* d_sigma = d_delta + nn;
+    int* d_dup = reinterpret_cast<int*>(d_sigma + nn);
+    CU(h, kbk_statistics(h->dim, nn, ax, ay, az, h->wC.as<double>(), h->ld,
+                         Hz + (size_t)K * np, Hz + (size_t)(K + 1) * np, d_dup, d_delta, d_sigma, st));
+    CU(h, cudaMemcpyAsync(delta, d_delta, (size_t)nn * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(sigma, d_sigma, (size_t)nn * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    h->launches += 2;
+    return KB200_OK;
+}
+
 extern "C" int64_t kb200_debug_fetch(kb200_handle h, int what, double* out, int64_t cap) {
     if (!h || !out) return KB200_EBADARG;
     if (!h->described) return KB200_ESTATE;

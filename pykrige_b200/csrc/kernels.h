@@ -135,3 +135,15 @@ cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, co
                           int* cell_of, int* cell_start, int* cursor, int ncells, cudaStream_t st, int* launches);
 cudaError_t kbk_knn_solve(const KnnParams& p, int chol, cudaStream_t st);
 size_t      kbk_knn_smem_per_warp(int k, int chol);
+
+// variogram.cu: constructor-side kernels (experimental variogram binning, cross-validation residuals)
+cudaError_t kbk_ev_init();
+int         kbk_ev_grid(int n, int num_sms);
+cudaError_t kbk_ev_minmax(int dim, int n, const double* x, const double* y, const double* z, int grid,
+                          double* bmin, double* bmax, cudaStream_t st);
+cudaError_t kbk_ev_bin(int dim, int n, const double* x, const double* y, const double* z, const double* v,
+                       int nlags, const double* edges, double inv_dd, int grid, double* part, double* out,
+                       cudaStream_t st);
+cudaError_t kbk_statistics(int dim, int n, const double* ax, const double* ay, const double* az,
+                           const double* L, int ld, const double* u, const double* zeta, int* dup,
+                           double* delta, double* sigma, cudaStream_t st);

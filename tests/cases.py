@@ -214,3 +214,75 @@ def run_model(model, case, inp, backend):
         kw["mask"] = inp["mask"]
     z, ss = model.execute(style, *args, **kw)
     return z, ss
+
+
+# ---- constructor-side cases: experimental variogram + cross-validation ----
+# X is what the reference hands to core._initialize_variogram_model / core._find_statistics: the
+# anisotropy-ADJUSTED coordinates (lon/lat for geographic); parameters in stored form.
+def _ctor_xy(case):
+    rng = np.random.default_rng(case["seed"])
+    kind, n, dim = case["layout"], case["n"], case["dim"]
+    if kind == "lattice":                       # many pair distances coincide with lag edges
+        side = int(round(n ** (1.0 / dim)))
+        ax = [np.arange(side, dtype=float) * 10.0 for _ in range(dim)]
+        X = np.column_stack([g.ravel() for g in np.meshgrid(*ax, indexing="ij")])
+        X = X[rng.permutation(X.shape[0])]
+    elif kind == "clusters":                    # two far clusters -> empty lags in between
+        a = rng.normal(0.0, 5.0, (n // 2, dim))
+        b = rng.normal(0.0, 5.0, (n - n // 2, dim)) + 1000.0
+        X = np.vstack([a, b])
+    elif kind == "geo":
+        X = np.column_stack([rng.uniform(-170.0, 170.0, n), rng.uniform(-75.0, 75.0, n)])
+    else:
+        box = (1000.0, 1000.0, 250.0)
+        X = np.column_stack([rng.uniform(0.0, box[c], n) for c in range(dim)])
+    if case.get("dups"):                        # exact duplicates of earlier points (distinct values)
+        for q in range(case["dups"]):
+            X[n - 1 - 3 * q] = X[2 * q]
+    s = 150.0 if kind != "geo" else 40.0
+    y = 50.0 + 10.0 * np.sin(X[:, 0] / s) * np.cos(X[:, 1] / (1.3 * s)) + rng.normal(0.0, 1.0, X.shape[0])
+    return X, y
+
+
+def _e(name, layout, n, dim, nlags, seed):
+    return dict(name=name, layout=layout, n=n, dim=dim, nlags=nlags, seed=seed,
+                coordinates_type="geographic" if layout == "geo" else "euclidean")
+
+
+VARIOGRAM_CASES = [
+    _e("ev2d_n300_l6", "uniform", 300, 2, 6, 4001),
+    _e("ev2d_n1500_l20", "uniform", 1500, 2, 20, 4002),
+    _e("ev3d_n400_l6", "uniform", 400, 3, 6, 4003),
+    _e("ev3d_n700_l50", "uniform", 700, 3, 50, 4004),       # more lags than the private-bin kernel holds
+    _e("ev2d_lattice_l8", "lattice", 400, 2, 8, 4005),
+    _e("ev3d_lattice_l5", "lattice", 343, 3, 5, 4006),
+    _e("ev2d_clusters_l10", "clusters", 200, 2, 10, 4007),
+    _e("ev2d_n2_l6", "uniform", 2, 2, 6, 4008),
+    _e("ev2d_n3_l1", "uniform", 3, 2, 1, 4009),
+    _e("evgeo_n250_l6", "geo", 250, 2, 6, 4010),
+    _e("ev2d_n777_l37", "uniform", 777, 2, 37, 4011),       # row count not a tile multiple, max private lags
+]
+
+
+def _s(name, layout, n, dim, model, params, seed, **kw):
+    d = dict(name=name, layout=layout, n=n, dim=dim, model=model, params=list(params), seed=seed,
+             coordinates_type="geographic" if layout == "geo" else "euclidean")
+    d.update(kw)
+    return d
+
+
+# parameters in STORED form ([psill, range, nugget] / [slope, nugget] / [scale, exponent, nugget])
+STATS_CASES = [
+    _s("st2d_exp_n120", "uniform", 120, 2, "exponential", [0.95, 100.0, 0.05], 5001),
+    _s("st2d_gau_n80", "uniform", 80, 2, "gaussian", [0.9, 60.0, 0.1], 5002),
+    _s("st3d_sph_n100", "uniform", 100, 3, "spherical", [1.0, 300.0, 0.0], 5003),
+    _s("st2d_lin_n90", "uniform", 90, 2, "linear", [0.004, 0.05], 5004),
+    _s("st2d_pow_n90", "uniform", 90, 2, "power", [0.002, 1.3, 0.05], 5005),
+    _s("st2d_dups_n60", "uniform", 60, 2, "exponential", [0.9, 200.0, 0.1], 5006, dups=3),
+    _s("stgeo_sph_n70", "geo", 70, 2, "spherical", [1.0, 60.0, 0.02], 5007),
+    _s("st2d_exp_n257", "uniform", 257, 2, "exponential", [2.0, 150.0, 0.0], 5008),
+]
+
+
+def build_ctor_inputs(case):
+    return _ctor_xy(case)

@@ -25,6 +25,12 @@ def ref_cases():
     return np.load(os.path.join(GOLDEN, "ref_cases.npz"))
 
 
+@pytest.fixture(scope="session")
+def ref_ctor():
+    """Reference outputs of core._initialize_variogram_model / core._find_statistics (make_golden.py ctor)."""
+    return np.load(os.path.join(GOLDEN, "ref_ctor.npz"))
+
+
 def assert_parity(out, ref, R, what=""):
     """allclose(out, ref, rtol=R, atol=R*max|ref|)."""
     out = np.asarray(np.ma.getdata(out), dtype=np.float64)

@@ -9,6 +9,8 @@ Writes
       KT3D 3-D data + (z, sigma^2) answers.
   tests/golden/ref_cases.npz : (z, sigmasq) of reference.execute(backend='vectorized'|'loop') for every
       seeded case of tests/cases.py.
+  tests/golden/ref_ctor.npz : lags/semivariance of core._initialize_variogram_model and delta/sigma/epsilon
+      of core._find_statistics for the constructor-side cases of tests/cases.py.
 The O(N^4) constructor statistics of OK3D/UK/UK3D are patched out; nothing else of the
 reference is touched.
 """
@@ -72,6 +74,41 @@ def ref_cases():
     np.savez_compressed(os.path.join(HERE, "ref_cases.npz"), **out)
 
 
+def ref_ctor():
+    """Outputs of the reference's constructor-side routines (core._initialize_variogram_model,
+    core._find_statistics) for tests/cases.py VARIOGRAM_CASES / STATS_CASES -> ref_ctor.npz."""
+    from pykrige import core as rcore
+    from pykrige import variogram_models as rvm
+    fn = {"linear": rvm.linear_variogram_model, "power": rvm.power_variogram_model,
+          "gaussian": rvm.gaussian_variogram_model, "exponential": rvm.exponential_variogram_model,
+          "spherical": rvm.spherical_variogram_model, "hole-effect": rvm.hole_effect_variogram_model}
+    out = {}
+    for case in cases.VARIOGRAM_CASES:
+        X, y = cases.build_ctor_inputs(case)
+        lags, semi, _ = rcore._initialize_variogram_model(
+            X, y, "linear", [1.0, 0.0], fn["linear"], case["nlags"], False, case["coordinates_type"])
+        out[case["name"] + "/lags"] = np.asarray(lags, dtype=np.float64)
+        out[case["name"] + "/semi"] = np.asarray(semi, dtype=np.float64)
+        out[case["name"] + "/fp"] = np.array([X.sum(), y.sum()])
+        print("%-22s lags=%d" % (case["name"], len(lags)))
+    for case in cases.STATS_CASES:
+        t0 = time.time()
+        X, y = cases.build_ctor_inputs(case)
+        delta, sigma, epsilon = rcore._find_statistics(
+            X, y, fn[case["model"]], case["params"], case["coordinates_type"])
+        out[case["name"] + "/delta"] = np.asarray(delta, dtype=np.float64)
+        out[case["name"] + "/sigma"] = np.asarray(sigma, dtype=np.float64)
+        out[case["name"] + "/epsilon"] = np.asarray(epsilon, dtype=np.float64)
+        out[case["name"] + "/fp"] = np.array([X.sum(), y.sum()])
+        print("%-22s %5.2fs kept=%d of %d" % (case["name"], time.time() - t0, len(delta), len(y)))
+    np.savez_compressed(os.path.join(HERE, "ref_ctor.npz"), **out)
+
+
 if __name__ == "__main__":
-    reference_goldens()
-    ref_cases()
+    which = sys.argv[1:] or ["goldens", "cases", "ctor"]
+    if "goldens" in which:
+        reference_goldens()
+    if "cases" in which:
+        ref_cases()
+    if "ctor" in which:
+        ref_ctor()

@@ -164,3 +164,26 @@ def test_shard_ranges_cover_exactly():
             assert spans[-1][0] + spans[-1][1] == count
             sizes = [c for _, c in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- constructor side: host mirror of the experimental variogram / statistics ------------------
+@pytest.mark.parametrize("case", cases.VARIOGRAM_CASES[:4] + cases.VARIOGRAM_CASES[6:10],
+                         ids=lambda c: c["name"])
+def test_host_experimental_variogram_matches_reference(case, ref_ctor):
+    from pykrige_b200 import core
+    X, y = cases.build_ctor_inputs(case)
+    for block in (2048, 97):             # the row-blocked accumulation must not depend on the block size
+        lags, semi = core._experimental_variogram(X, y, case["nlags"], block=block,
+                                                  coordinates_type=case["coordinates_type"], device=False)
+        assert_allclose(lags, ref_ctor[case["name"] + "/lags"], rtol=1e-10)
+        assert_allclose(semi, ref_ctor[case["name"] + "/semi"], rtol=1e-10)
+
+
+def test_host_statistics_match_reference(ref_ctor):
+    from pykrige_b200 import core, variogram_models as vm
+    case = cases.STATS_CASES[0]
+    X, y = cases.build_ctor_inputs(case)
+    d, s, e = core._find_statistics(X, y, vm.exponential_variogram_model, case["params"], "euclidean")
+    assert_allclose(d, ref_ctor[case["name"] + "/delta"], rtol=1e-8, atol=1e-10)
+    assert_allclose(s, ref_ctor[case["name"] + "/sigma"], rtol=1e-8)
+    assert_allclose(e, ref_ctor[case["name"] + "/epsilon"], rtol=1e-8, atol=1e-10)

@@ -114,3 +114,44 @@ def test_oracle_kitanidis():
     z, ss = ko.krige(data[:, :2], data[:, 2], "linear", [0.006, 0.1], np.array([[18.8, 67.9]]))
     assert z[0] == pytest.approx(1.6364, rel=1e-4)
     assert ss[0] == pytest.approx(0.4201, rel=1e-4)
+
+
+# ---- constructor side ------------------------------------------------
+def test_oracle_variogram_reference_known_answers():
+    """tests/test_core.py:226-236 and :283-301 (the reference's own known answers)."""
+    x = np.array([1.0 + n / np.sqrt(2) for n in range(4)])
+    lags, semi = ko.experimental_variogram(np.vstack((x, x)).T, np.arange(1.0, 5.0, 1.0), 6)
+    assert_allclose(lags, [1.0, 2.0, 3.0])
+    assert_allclose(semi, [0.5, 2.0, 4.5])
+    a = np.array([1.0, 2.0, 3.0, 4.0])
+    lags, semi = ko.experimental_variogram(np.vstack((a, a, a)).T, a, 3)
+    assert_allclose(lags, [np.sqrt(3.0), 2.0 * np.sqrt(3.0), 3.0 * np.sqrt(3.0)])
+    assert_allclose(semi, [0.5, 2.0, 4.5])
+
+
+@pytest.mark.parametrize("case", cases.VARIOGRAM_CASES, ids=[c["name"] for c in cases.VARIOGRAM_CASES])
+def test_oracle_variogram_matches_reference(case, ref_ctor):
+    X, y = cases.build_ctor_inputs(case)
+    assert_allclose([X.sum(), y.sum()], ref_ctor[case["name"] + "/fp"], rtol=1e-12)
+    lags, semi = ko.experimental_variogram(X, y, case["nlags"], case["coordinates_type"])
+    assert_allclose(lags, ref_ctor[case["name"] + "/lags"], rtol=1e-12)
+    assert_allclose(semi, ref_ctor[case["name"] + "/semi"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("case", cases.STATS_CASES, ids=[c["name"] for c in cases.STATS_CASES])
+def test_oracle_statistics_match_reference(case, ref_ctor):
+    X, y = cases.build_ctor_inputs(case)
+    assert_allclose([X.sum(), y.sum()], ref_ctor[case["name"] + "/fp"], rtol=1e-12)
+    delta, sigma, epsilon = ko.find_statistics(X, y, case["model"], case["params"], case["coordinates_type"])
+    assert delta.shape == ref_ctor[case["name"] + "/delta"].shape
+    assert_allclose(delta, ref_ctor[case["name"] + "/delta"], rtol=1e-8, atol=1e-10)
+    assert_allclose(sigma, ref_ctor[case["name"] + "/sigma"], rtol=1e-8)
+    assert_allclose(epsilon, ref_ctor[case["name"] + "/epsilon"], rtol=1e-8, atol=1e-10)
+
+
+def test_oracle_krige_one_kitanidis():
+    """tests/test_core.py:378-401: Kitanidis example 3.2 through core._krige."""
+    data = np.array([[9.7, 47.6, 1.22], [43.8, 24.6, 2.822]])
+    z, ss = ko.krige_one(data[:, :2], data[:, 2], np.array([18.8, 67.9]), "linear", [0.006, 0.1])
+    assert z == pytest.approx(1.6364, rel=1e-4)
+    assert ss == pytest.approx(0.4201, rel=1e-4)

@@ -340,3 +340,136 @@ def test_float64x_cases_match_reference(pk, case, ref_cases):
     # and fp64-class in fact: within 1e-8 of the reference
     assert np.max(np.abs(np.ravel(z) - np.ravel(zr))) <= 1e-8 * np.max(np.abs(zr))
     assert np.max(np.abs(np.ravel(ss) - np.ravel(sr))) <= 1e-8 * np.max(np.abs(sr))
+
+
+# ---- constructor side on the device: csrc/variogram.cu ----------------------
+def _list_params(case):
+    """stored -> list form of the constructors ([FULL sill, range, nugget], core.py:345-357)."""
+    p = list(case["params"])
+    if case["model"] in ("gaussian", "spherical", "exponential", "hole-effect"):
+        return [p[0] + p[2], p[1], p[2]]
+    return p
+
+
+@pytest.mark.parametrize("case", cases.VARIOGRAM_CASES, ids=[c["name"] for c in cases.VARIOGRAM_CASES])
+def test_device_experimental_variogram_matches_reference(pk, case, ref_ctor):
+    """kb200_experimental_variogram vs core._initialize_variogram_model of the imported reference. The
+    pair distances are computed in pdist's operation order, so bin assignment is identical; only the
+    order of the per-bin sums differs (rtol 1e-10)."""
+    from pykrige_b200 import core
+    X, y = cases.build_ctor_inputs(case)
+    lags, semi = core._experimental_variogram(X, y, case["nlags"], coordinates_type=case["coordinates_type"],
+                                              device=True)
+    assert lags.shape == ref_ctor[case["name"] + "/lags"].shape
+    assert_allclose(lags, ref_ctor[case["name"] + "/lags"], rtol=1e-10)
+    assert_allclose(semi, ref_ctor[case["name"] + "/semi"], rtol=1e-10)
+
+
+def test_device_experimental_variogram_large_vs_host(pk):
+    """N = 6000 (1.8e7 pairs): device vs the host mirror, counts exact, and run-to-run determinism of
+    the private-bin kernel."""
+    from pykrige_b200 import core, _cabi
+    rng = np.random.default_rng(77)
+    X = rng.uniform(0.0, 1000.0, (6000, 3))
+    y = rng.normal(0.0, 1.0, 6000) + 0.01 * X[:, 0]
+    h = _cabi.aux_handle()
+    cnt, sd, sg, dmin, dmax = h.experimental_variogram(X, y, 12)
+    cnt2, sd2, sg2, _, _ = h.experimental_variogram(X, y, 12)
+    assert np.array_equal(sd, sd2) and np.array_equal(sg, sg2) and np.array_equal(cnt, cnt2)
+    assert cnt.sum() == 6000 * 5999 // 2
+    lags_h, semi_h = core._experimental_variogram(X, y, 12, device=False)
+    keep = cnt > 0
+    assert_allclose(sd[keep] / cnt[keep], lags_h, rtol=1e-10)
+    assert_allclose(sg[keep] / cnt[keep], semi_h, rtol=1e-10)
+    with pytest.raises(ValueError):
+        h.experimental_variogram(X[:1], y[:1], 6)
+    with pytest.raises(ValueError):
+        h.experimental_variogram(X, y, 0)
+
+
+def _stats_model(pk, case, X, y, **kw):
+    params = _list_params(case)
+    if case["dim"] == 3:
+        return pk.OrdinaryKriging3D(X[:, 0], X[:, 1], X[:, 2], y, variogram_model=case["model"],
+                                    variogram_parameters=params, **kw)
+    return pk.OrdinaryKriging(X[:, 0], X[:, 1], y, variogram_model=case["model"], variogram_parameters=params,
+                              coordinates_type=case["coordinates_type"], **kw)
+
+
+@pytest.mark.parametrize("case", cases.STATS_CASES, ids=[c["name"] for c in cases.STATS_CASES])
+def test_device_statistics_match_reference(pk, case, ref_ctor):
+    """kb200_statistics (residuals from ONE Cholesky factor) vs core._find_statistics of the imported
+    reference (N growing solves), through the class attributes delta / sigma / epsilon / Q1 / Q2 / cR."""
+    from pykrige_b200 import core
+    X, y = cases.build_ctor_inputs(case)
+    m = _stats_model(pk, case, X, y)
+    res = m._device_statistics()
+    assert res is not None, "device route not taken"
+    delta, sigma, epsilon = res
+    dr, sr, er = (ref_ctor[case["name"] + "/" + k] for k in ("delta", "sigma", "epsilon"))
+    assert delta.shape == dr.shape
+    assert_allclose(delta, dr, rtol=1e-6, atol=1e-6 * np.abs(dr).max())
+    assert_allclose(sigma, sr, rtol=1e-6)
+    assert_allclose(epsilon, er, rtol=1e-6, atol=1e-6 * np.abs(er).max())
+    if case["dim"] == 3:
+        assert_allclose([m.Q1, m.Q2, m.cR], [core.calcQ1(er), core.calcQ2(er), core.calc_cR(core.calcQ2(er), sr)],
+                        rtol=1e-6)
+
+
+def test_device_statistics_reuse_factor_and_anisotropy(pk):
+    """After a global execute() the statistics come from the factor already on the handle (no second
+    factorisation); anisotropy goes through the adjusted coordinates like ok.py:361-368."""
+    from oracle import krige_oracle as ko
+    rng = np.random.default_rng(5)
+    x, y = rng.uniform(0, 1000, 150), rng.uniform(0, 1000, 150)
+    v = 3.0 + np.sin(x / 120.0) + rng.normal(0, 0.1, 150)
+    m = pk.OrdinaryKriging(x, y, v, variogram_model="spherical", variogram_parameters=[1.2, 350.0, 0.1],
+                           anisotropy_scaling=2.5, anisotropy_angle=35.0)
+    m.execute("grid", np.linspace(0, 1000, 20), np.linspace(0, 1000, 20), backend="cuda")
+    t0 = m._cuda_handle().timings()["launches"]
+    res = m._device_statistics()
+    assert m._cuda_handle().timings()["launches"] - t0 <= 2
+    X = np.vstack((m.X_ADJUSTED, m.Y_ADJUSTED)).T
+    d, s, e = ko.find_statistics(X, v, "spherical", [1.1, 350.0, 0.1])
+    assert_allclose(res[0], d, rtol=1e-6, atol=1e-6 * np.abs(d).max())
+    assert_allclose(res[1], s, rtol=1e-6)
+
+
+def test_device_statistics_large_vs_oracle_subsample(pk):
+    """N = 3000: the reference needs 3000 growing solves; check a few indices against core._krige's
+    restatement and that UK (drift columns present) reads the same ordinary-kriging residuals."""
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(808, 3000, 2)
+    params = [1.0, 300.0, 0.05]
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential", variogram_parameters=params)
+    h = ok._ensure_problem("float64")
+    delta, sigma = h.statistics(3000)
+    stored = ko.stored_parameters("exponential", params)
+    for i in (1, 2, 17, 500, 1999, 2999):
+        k, ss = ko.krige_one(xyz[:i], val[:i], xyz[i], "exponential", stored)
+        assert_allclose(delta[i], val[i] - k, rtol=1e-6, atol=1e-8)
+        assert_allclose(sigma[i], np.sqrt(ss), rtol=1e-6)
+    assert delta[0] == 0.0 and sigma[0] == 0.0
+    uk = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential", variogram_parameters=params,
+                             drift_terms=["regional_linear"])
+    d2, s2 = uk._ensure_problem("float64").statistics(3000)
+    assert_allclose(d2, delta, rtol=1e-9, atol=1e-12)
+    assert_allclose(s2, sigma, rtol=1e-9)
+
+
+def test_device_statistics_unsupported_routes(pk):
+    """Indefinite covariance form (general fallback) and kNN-only handles have no factor to read:
+    the C ABI says so and the class falls back to the reference's host loop."""
+    from pykrige_b200 import _cabi
+    xyz, val = cases.synth_data(9, 600, 2)
+    m = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="hole-effect",
+                           variogram_parameters=[1.0, 300.0, 0.05])
+    h = m._ensure_problem("float64")
+    with pytest.raises(NotImplementedError):
+        h.statistics(600)
+    assert m._device_statistics() is None
+    m._stats_state = "lazy"
+    assert m.epsilon is not None and np.all(np.isfinite(m.epsilon))      # host loop of core.py:759-836
+    hk = m._ensure_problem("float64", knn=True)
+    with pytest.raises(_cabi.KrigeB200Error):
+        hk.statistics(600)
