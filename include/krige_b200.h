@@ -213,6 +213,15 @@ int kb200_set_stream(kb200_handle h, void* cuda_stream);
 int  kb200_last_timings(kb200_handle h, double* ms, int n);
 void kb200_reset_counters(kb200_handle h);
 
+/* pseudo_inv=True (ok.py:156-165,660-661; uk.py:932-933; ok3d.py / uk3d.py likewise): the NEXT
+ * kb200_set_problem / kb200_describe_problem on this handle inverts the bordered kriging matrix with a
+ * pseudo-inverse (singular values below max(M,N)*eps*s_max dropped, as scipy.linalg.pinv / pinvh), so that
+ * redundant data points are averaged instead of raising KB200_ESINGULAR. float64 only
+ * (KB200_EUNSUPPORTED otherwise); the moving window ignores the flag, as the reference does
+ * (ok.py:753 always calls scipy.linalg.solve). Resets the handle's problem state.
+ */
+int kb200_set_pseudo_inverse(kb200_handle h, int enable);
+
 /* ---- constructor-side helpers ----------------------------------------------
  *
  * kb200_experimental_variogram replaces the pdist binning of core._initialize_variogram_model

@@ -155,13 +155,16 @@ def kriging_matrix(P, model, m, drift_cols=()):
 
 
 # ---- global solve: ok.py:650-683, uk.py:922-1009 --------------------------------------
-def exec_vector(a, P, Q, values, model, m, exact_values=True, drift_pts=()):
+def exec_vector(a, P, Q, values, model, m, exact_values=True, drift_pts=(), pseudo_inv=None):
     """Q: [npt, dim] adjusted prediction points; drift_pts: list of length-npt arrays.
     Returns (zvalues, sigmasq): inverse x RHS exactly as the reference's 'vectorized' backend."""
     n = P.shape[0]
     K = len(drift_pts)
     npt = Q.shape[0]
-    a_inv = scipy.linalg.inv(a)                   # ok.py:663
+    if pseudo_inv:                                # ok.py:660-661: P_INV[pseudo_inv_type](a), core.py:33
+        a_inv = {"pinv": scipy.linalg.pinv, "pinvh": scipy.linalg.pinvh}[pseudo_inv](a)
+    else:
+        a_inv = scipy.linalg.inv(a)               # ok.py:663
     bd = cdist(Q, P, "euclidean")                 # ok.py:989
     b = np.zeros((npt, n + K + 1))
     b[:, :n] = -variogram(model, m, bd)           # ok.py:670
@@ -212,8 +215,10 @@ def grid_points(axes):
 
 
 def krige(data_xyz, values, model, plist_stored, points, *, scaling=None, angle=None,
-          regional_linear=False, data_drift=(), point_drift=(), exact_values=True, n_closest_points=None):
+          regional_linear=False, data_drift=(), point_drift=(), exact_values=True, n_closest_points=None,
+          pseudo_inv=None):
     """End-to-end oracle for one execute() call on explicit points (original coordinates).
+    pseudo_inv: None | "pinv" | "pinvh" (ignored by the moving window, like ok.py:753).
 
     data_xyz [n, dim], points [npt, dim]; centre = (max+min)/2 of the data (ok.py:278-279);
     regional-linear drift uses the adjusted coordinates in x, y[, z] order (uk.py:877-883,
@@ -239,7 +244,7 @@ def krige(data_xyz, values, model, plist_stored, points, *, scaling=None, angle=
     dcols += [np.asarray(c, float) for c in data_drift]
     pcols += [np.asarray(c, float) for c in point_drift]
     a = kriging_matrix(P, model, plist_stored, dcols)
-    return exec_vector(a, P, Q, np.asarray(values, float), model, plist_stored, exact_values, pcols)
+    return exec_vector(a, P, Q, np.asarray(values, float), model, plist_stored, exact_values, pcols, pseudo_inv)
 
 
 def krige_chunked(data_xyz, values, model, plist_stored, points, chunk=20000, **kw):

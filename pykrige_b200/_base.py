@@ -99,8 +99,8 @@ class KrigeBase:
         csrc/variogram.cu: O(N) after the factorisation instead of the reference's N solves). Returns
         None when this problem has no device twin (custom variogram, pseudo_inv, indefinite
         covariance form, no CUDA device) — the caller then runs the reference's loop on the host."""
-        if not _cabi.device_available():
-            return None
+        if not _cabi.device_available() or getattr(self, "pseudo_inv", False):
+            return None                          # core._krige solves with lstsq under pseudo_inv (core.py:749-750)
         try:
             key = getattr(self, "_kb_key", None)
             if key is not None and key[1] is False and key == self._problem_signature(key[0], False):
@@ -220,11 +220,10 @@ class KrigeBase:
         mid, vp = self._device_model()
         n_rl, cols = self._drift_spec()
         return (dtype, knn, mid, tuple(vp), bool(self.exact_values), tuple(np.ravel(Mt)), tuple(center),
-                n_rl, len(cols), x.size, getattr(self, "coordinates_type", "euclidean"))
+                n_rl, len(cols), x.size, getattr(self, "coordinates_type", "euclidean"),
+                bool(getattr(self, "pseudo_inv", False)))
 
     def _ensure_problem(self, dtype="float64", knn=False):
-        if getattr(self, "pseudo_inv", False):
-            raise NotImplementedError("pseudo_inv=True is not supported by backend='cuda' (SURVEY.md §8f next-4)")
         name = dtype if isinstance(dtype, str) and dtype in _cabi.DTYPES else str(np.dtype(dtype))
         dt = _cabi.DTYPES.get(name)
         if dt is None:
@@ -238,6 +237,7 @@ class KrigeBase:
         n_rl, cols = self._drift_spec()
         self._kb_key = None
         h.set_coordinates(getattr(self, "coordinates_type", "euclidean") == "geographic")
+        h.set_pseudo_inverse(bool(getattr(self, "pseudo_inv", False)) and not knn)
         if knn:
             h.set_problem_knn(self._ndim, x, y, z, v, center, Mt, mid, vp, self.exact_values, self.eps)
         else:

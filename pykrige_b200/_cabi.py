@@ -34,7 +34,7 @@ EXPORTS = [
     "kb200_set_problem_knn",
     "kb200_blob_bytes", "kb200_blob_ptr", "kb200_describe_problem", "kb200_blob_commit",
     "kb200_set_coordinates", "kb200_set_stream", "kb200_last_timings", "kb200_reset_counters", "kb200_debug_fetch",
-    "kb200_experimental_variogram", "kb200_statistics",
+    "kb200_experimental_variogram", "kb200_statistics", "kb200_set_pseudo_inverse",
 ]
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -93,6 +93,7 @@ def load_library():
     lib.kb200_debug_fetch.restype = i64
     lib.kb200_experimental_variogram.argtypes = [h, i32, i64, dp, dp, dp, dp, i32, dp, dp, dp, dp]
     lib.kb200_statistics.argtypes = [h, dp, dp]
+    lib.kb200_set_pseudo_inverse.argtypes = [h, i32]
     _lib = lib
     return lib
 
@@ -297,6 +298,9 @@ class Handle:
 
     def reset_counters(self):
         self.lib.kb200_reset_counters(self._h)
+
+    def set_pseudo_inverse(self, enable):
+        self._check(self.lib.kb200_set_pseudo_inverse(self._h, 1 if enable else 0))
 
     def experimental_variogram(self, X, values, nlags, geographic=False):
         """Device twin of the pdist binning (core.py:432-505): X = (n, 2|3) ADJUSTED coordinates (or

@@ -45,6 +45,8 @@ struct kb200_ctx {
     bool factor_live = false;  // L (wC) and the forward solves (wF) of the ready problem are still in the workspace
     int gform = 0;            // 1: general (indefinite) fallback, tiles hold the symmetric inverse
     int geo = 0;              // 1: coordinates_type='geographic' for the next problem description
+    int pinv = 0;             // 1: pseudo_inv=True for the next problem description (global path only)
+    int pinv_sweeps = 0, pinv_rank = 0;
     int dim = 2, dtype = KB200_F64, n = 0, n_pad = 0, ld = 0, n_rl = 0, n_hd = 0, K1 = 1, na = 2, nrb = 0;
     VgParams vg{};
     Aniso an{};
@@ -100,7 +102,7 @@ extern "C" int kb200_create(kb200_handle* out, int device) {
     h->own_stream = true;
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete h; return KB200_ECUDA; }
     if (kbk_factor_init() != cudaSuccess || kbk_solve_init() != cudaSuccess || kbk_solve_tf32_init() != cudaSuccess ||
-        kbk_solve_i8_init() != cudaSuccess || kbk_ev_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
+        kbk_solve_i8_init() != cudaSuccess || kbk_ev_init() != cudaSuccess || kbk_pinv_init() != cudaSuccess) { delete h; return KB200_ECUDA; }
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->num_sms < 1) h->num_sms = 148;
     *out = h;
     return KB200_OK;
@@ -132,6 +134,13 @@ extern "C" int kb200_set_coordinates(kb200_handle h, int coordinates_type) {
     if (coordinates_type != KB200_EUCLIDEAN && coordinates_type != KB200_GEOGRAPHIC)
         return fail(h, KB200_EBADARG, "coordinates_type must be KB200_EUCLIDEAN or KB200_GEOGRAPHIC");
     h->geo = coordinates_type == KB200_GEOGRAPHIC ? 1 : 0;
+    h->described = false; h->ready = false; h->knn_ready = false; h->factor_live = false;
+    return KB200_OK;
+}
+
+extern "C" int kb200_set_pseudo_inverse(kb200_handle h, int enable) {
+    if (!h) return KB200_EBADARG;
+    h->pinv = enable ? 1 : 0;
     h->described = false; h->ready = false; h->knn_ready = false; h->factor_live = false;
     return KB200_OK;
 }
@@ -239,6 +248,15 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
         for (int64_t i = 0; i < n; ++i) amax = std::max(amax, std::fabs(col[i] - mean));
         h->ds.shift[n_rl + c] = mean;
         h->ds.scale[n_rl + c] = amax > 0.0 ? 1.0 / amax : 1.0;
+    }
+
+    if (h->pinv && !knn_only) {
+        // pseudo-inverse of the reference's own matrix: gamma form (c0 = 0), raw drift columns (pinv.cu)
+        if (dtype != KB200_F64) return fail(h, KB200_EUNSUPPORTED, "pseudo_inv=True runs in float64 only");
+        if (n + h->K1 > kbk_pinv_max_nt())
+            return fail(h, KB200_EUNSUPPORTED, "pseudo_inv=True supports at most " + std::to_string(kbk_pinv_max_nt() - h->K1) + " data points");
+        h->vg.c0 = 0.0;
+        for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { h->ds.shift[c] = 0.0; h->ds.scale[c] = 1.0; }
     }
 
     // tile stream map
@@ -358,6 +376,12 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
         CU(h, cudaEventRecord(h->ev[2], st));
         CU(h, kbk_assemble(h->dim, h->vg, nn, np, ld, ax, ay, az, h->wC.as<double>(), st)); ++launches;
         CU(h, cudaEventRecord(h->ev[3], st));
+        if (h->pinv) {                                  // no factorisation: the pseudo-inverse works on -Gamma itself
+            CU(h, cudaEventRecord(h->ev[4], st));
+            CU(h, cudaStreamSynchronize(st));
+            t_asm += ev_ms(h->ev[2], h->ev[3]);
+            break;
+        }
         CU(h, kbk_cholesky(h->wC.as<double>(), h->wW.as<double>(), ld, np, flag, st, &launches));
         CU(h, cudaEventRecord(h->ev[4], st));
         CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -371,7 +395,20 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
     double* Hz = Fz + (size_t)KB_MAXAUX * np;
     double* Uz = Hz + (size_t)KB_MAXAUX * np;
     CU(h, cudaMemsetAsync(consts, 0, 512 * sizeof(double), st));
-    if (hflag != 0) {
+    if (h->pinv) {
+        // pseudo_inv=True: A^+ of the bordered gamma-form matrix (pinv.cu), then the quadratic-form solve
+        const int nt = nn + h->K1;
+        CU(h, h->wVario.reserve(kbk_pinv_workspace_doubles(nt) * sizeof(double)));
+        CU(h, cudaEventRecord(h->ev[4], st));
+        CU(h, kbk_build_fz(nn, np, h->n_rl, h->n_hd, ax, ay, az, h->ds, rh, rv, Fz, st)); ++launches;
+        CU(h, kbk_pinv(nn, h->K1, np, h->wC.as<double>(), ld, Fz, rv, Uz, consts, h->wVario.as<double>(), flag, st,
+                       &launches, &h->pinv_sweeps, &h->pinv_rank));
+        if (h->pinv_sweeps < 0) { h->launches += launches; return fail(h, KB200_ESINGULAR, "pseudo-inverse: the Jacobi SVD did not converge"); }
+        CU(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
+        CU(h, cudaEventRecord(h->ev[5], st));
+        CU(h, kbk_pack_gform(h->wC.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st)); ++launches;
+        h->gform = 2;
+    } else if (hflag != 0) {
         // C is not positive definite: the variogram is not conditionally negative definite in this
         // dimension (e.g. hole-effect on dense scatter). General fallback: Gauss-Jordan inverse with
         // partial pivoting + quadratic-form solve. fp64 only.

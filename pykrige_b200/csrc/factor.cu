@@ -563,6 +563,12 @@ cudaError_t kbk_dual(const double* W, int ld, int n, int n_pad, int n_rl, int n_
     return cudaGetLastError();
 }
 
+cudaError_t kbk_build_fz(int n, int n_pad, int n_rl, int n_hd, const double* ax, const double* ay, const double* az,
+                         const DriftScale& ds, const double* hd, const double* values, double* Fz, cudaStream_t st) {
+    build_fz_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, n_rl, n_hd, ax, ay, az, ds, hd, values, Fz);
+    return cudaGetLastError();
+}
+
 cudaError_t kbk_pack(int dtype, const double* W, int ld, int n, int n_pad, int na, const double* Uz,
                      const PackMap& pm, void* out, cudaStream_t st) {
     int maxkt = 0;

@@ -147,3 +147,13 @@ cudaError_t kbk_ev_bin(int dim, int n, const double* x, const double* y, const d
 cudaError_t kbk_statistics(int dim, int n, const double* ax, const double* ay, const double* az,
                            const double* L, int ld, const double* u, const double* zeta, int* dup,
                            double* delta, double* sigma, cudaStream_t st);
+
+// pinv.cu: pseudo_inv=True (one-sided Jacobi SVD of the bordered kriging matrix)
+cudaError_t kbk_build_fz(int n, int n_pad, int n_rl, int n_hd, const double* ax, const double* ay, const double* az,
+                         const DriftScale& ds, const double* hd, const double* values, double* Fz, cudaStream_t st);
+cudaError_t kbk_pinv_init();
+int         kbk_pinv_max_nt();
+size_t      kbk_pinv_workspace_doubles(int nt);
+cudaError_t kbk_pinv(int n, int K1, int n_pad, double* C, int ldc, const double* Fz, const double* values,
+                     double* Uz, double* consts, double* work, int* counter, cudaStream_t st,
+                     int* launches, int* sweeps, int* rank);

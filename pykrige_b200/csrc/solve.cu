@@ -424,10 +424,23 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                     f[P.n_rl + c] = (v - P.ds.shift[P.n_rl + c]) * P.ds.scale[P.n_rl + c];
                 }
                 f[K] = 1.0;
-                for (int a = 0; a < K1; ++a) r[a] = auxs[a * KB_TN + tid] - f[a];
                 const double zc = auxs[K1 * KB_TN + tid];
                 const double* Sinv = P.consts;
                 const double* phi = P.consts + K1 * K1;
+                if (P.gform == 2) {
+                    // pseudo-inverse form (pinv.cu): b = [c; f], sigma^2 = -b^T A^+ b, z = w1.c + w2.f with
+                    // q = c^T G11 c, aux rows = G21 c, consts = G22 | w2
+                    double acc = q, zz = zc;
+                    for (int a = 0; a < K1; ++a) {
+                        double gf = 0.0;
+                        for (int b = 0; b < K1; ++b) gf += Sinv[a * K1 + b] * f[b];
+                        acc += f[a] * (2.0 * auxs[a * KB_TN + tid] + gf);
+                        zz += phi[a] * f[a];
+                    }
+                    P.ss_out[pj] = -acc;
+                    P.z_out[pj] = zz;
+                } else {
+                for (int a = 0; a < K1; ++a) r[a] = auxs[a * KB_TN + tid] - f[a];
                 double rmu = 0.0, muphi = 0.0;
                 for (int a = 0; a < K1; ++a) {
                     double mu = 0.0;
@@ -437,6 +450,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                 }
                 P.ss_out[pj] = P.vg.c0 - q + rmu;
                 P.z_out[pj] = zc - muphi;
+                }
             }
         }
         __syncthreads();      // qred / auxs / scratch are re-used by the next tile

@@ -54,6 +54,7 @@ def prepare_sharded(model, dist=None, src=0, dtype="float64"):
         from . import _cabi
         dt = _cabi.DTYPES[dtype if dtype in _cabi.DTYPES else str(np.dtype(dtype))]
         h.set_coordinates(getattr(model, "coordinates_type", "euclidean") == "geographic")
+        h.set_pseudo_inverse(bool(getattr(model, "pseudo_inv", False)))
         h.describe_problem(model._ndim, dt, x, y, z, v, center, Mt, mid, vp, model.exact_values, model.eps,
                            n_rl=n_rl, drift_data=cols if cols else None)
         model._kb_key = None

@@ -116,6 +116,26 @@ CASES.append(_c("geo_knn_k12", "OK", 400, 200, 6004, "exponential", params=[1.0,
 
 CASE_BY_NAME = {c["name"]: c for c in CASES}
 
+# pseudo_inv=True (ok.py:156-165,660-661; tests/test_core.py:2913-2949): redundant data points (exact
+# duplicates with different values, nugget 0 -> singular kriging matrix) are averaged. Kept out of CASES:
+# their reference outputs live in tests/golden/ref_pinv.npz.
+def _p(ptype="pinv"):
+    return dict(pseudo_inv=True, pseudo_inv_type=ptype)
+
+
+PINV_CASES = [
+    _c("pinv_ok2d_dups", "OK", 80, 120, 7001, "exponential", params=[1.0, 300.0, 0.0], dups=4, ctor=_p()),
+    _c("pinv_ok2d_dups_pinvh_linear", "OK", 60, 100, 7002, "linear", params=[0.004, 0.0], dups=3, ctor=_p("pinvh")),
+    _c("pinv_uk2d_rl_dups", "UK", 90, 120, 7003, "spherical", params=[1.0, 400.0, 0.0], dups=3,
+       drift_terms=["regional_linear"], ctor=_p()),
+    _c("pinv_ok3d_dups", "OK3D", 70, 100, 7004, "exponential", params=[1.0, 300.0, 0.0], dups=3, ctor=_p()),
+    _c("pinv_uk3d_rl_dups", "UK3D", 70, 100, 7005, "exponential", params=[1.0, 300.0, 0.0], dups=2,
+       drift_terms=["regional_linear"], ctor=_p("pinvh")),
+    _c("pinv_ok2d_regular_grid", "OK", 150, 0, 7006, "spherical", style="grid", grid=(19, 14, 1), ctor=_p()),
+    _c("pinv_ok2d_nonexact", "OK", 50, 80, 7007, "exponential", params=[1.0, 300.0, 0.0], dups=2, exact_values=False,
+       ctor=_p()),
+]
+
 
 def build_inputs(case):
     """Deterministic inputs of a case: data, values, prediction axes/points, mask, drift arrays."""
@@ -125,6 +145,8 @@ def build_inputs(case):
     if geo_shift is not None:
         val = 50.0 + 10.0 * np.sin(xyz[:, 0] / 9.0) * np.cos(xyz[:, 1] / 7.0) + (val - np.round(val))
         xyz = xyz + geo_shift
+    for q in range(case.get("dups", 0)):           # redundant data points (same place, different values)
+        xyz[case["n"] - 1 - 2 * q] = xyz[3 * q]
     out = dict(data=xyz, values=val)
     rng = np.random.default_rng(case["seed"] + 31337)
     if case["style"] == "points":

@@ -26,6 +26,12 @@ def ref_cases():
 
 
 @pytest.fixture(scope="session")
+def ref_pinv():
+    """Reference outputs with pseudo_inv=True (make_golden.py pinv)."""
+    return np.load(os.path.join(GOLDEN, "ref_pinv.npz"))
+
+
+@pytest.fixture(scope="session")
 def ref_ctor():
     """Reference outputs of core._initialize_variogram_model / core._find_statistics (make_golden.py ctor)."""
     return np.load(os.path.join(GOLDEN, "ref_ctor.npz"))

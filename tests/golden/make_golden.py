@@ -9,6 +9,7 @@ Writes
       KT3D 3-D data + (z, sigma^2) answers.
   tests/golden/ref_cases.npz : (z, sigmasq) of reference.execute(backend='vectorized'|'loop') for every
       seeded case of tests/cases.py.
+  tests/golden/ref_pinv.npz : (z, sigmasq) of the reference with pseudo_inv=True (redundant data points).
   tests/golden/ref_ctor.npz : lags/semivariance of core._initialize_variogram_model and delta/sigma/epsilon
       of core._find_statistics for the constructor-side cases of tests/cases.py.
 The O(N^4) constructor statistics of OK3D/UK/UK3D are patched out; nothing else of the
@@ -74,6 +75,20 @@ def ref_cases():
     np.savez_compressed(os.path.join(HERE, "ref_cases.npz"), **out)
 
 
+def ref_pinv():
+    """(z, sigmasq) of the reference with pseudo_inv=True for tests/cases.py PINV_CASES -> ref_pinv.npz."""
+    out = {}
+    for case in cases.PINV_CASES:
+        inp = cases.build_inputs(case)
+        model = cases.make_model(pykrige, case, inp, reference=True)
+        z, ss = cases.run_model(model, case, inp, case["ref_backend"])
+        out[case["name"] + "/z"] = np.asarray(np.ma.getdata(z), dtype=np.float64)
+        out[case["name"] + "/ss"] = np.asarray(np.ma.getdata(ss), dtype=np.float64)
+        out[case["name"] + "/fp"] = np.array([inp["data"].sum(), inp["values"].sum()])
+        print("%-30s z[%s] mean=%.6f ss mean=%.6f" % (case["name"], z.shape, float(np.mean(z)), float(np.mean(ss))))
+    np.savez_compressed(os.path.join(HERE, "ref_pinv.npz"), **out)
+
+
 def ref_ctor():
     """Outputs of the reference's constructor-side routines (core._initialize_variogram_model,
     core._find_statistics) for tests/cases.py VARIOGRAM_CASES / STATS_CASES -> ref_ctor.npz."""
@@ -105,10 +120,12 @@ def ref_ctor():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["goldens", "cases", "ctor"]
+    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv"]
     if "goldens" in which:
         reference_goldens()
     if "cases" in which:
         ref_cases()
     if "ctor" in which:
         ref_ctor()
+    if "pinv" in which:
+        ref_pinv()

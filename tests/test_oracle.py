@@ -155,3 +155,27 @@ def test_oracle_krige_one_kitanidis():
     z, ss = ko.krige_one(data[:, :2], data[:, 2], np.array([18.8, 67.9]), "linear", [0.006, 0.1])
     assert z == pytest.approx(1.6364, rel=1e-4)
     assert ss == pytest.approx(0.4201, rel=1e-4)
+
+
+# ---- pseudo_inv=True ---------------------------------------------------------
+@pytest.mark.parametrize("case", cases.PINV_CASES, ids=[c["name"] for c in cases.PINV_CASES])
+def test_oracle_pseudo_inverse_matches_reference(case, ref_pinv):
+    inp = cases.build_inputs(case)
+    assert_allclose([inp["data"].sum(), inp["values"].sum()], ref_pinv[case["name"] + "/fp"], rtol=1e-12)
+    pts = inp["points"] if case["style"] == "points" else ko.grid_points(inp["axes"])
+    z, ss = ko.krige(inp["data"], inp["values"], case["model"], ko.stored_parameters(case["model"], case["params"]),
+                     pts, regional_linear="regional_linear" in case["drift_terms"],
+                     exact_values=case["exact_values"], pseudo_inv=case["ctor"]["pseudo_inv_type"])
+    assert_parity(z, ref_pinv[case["name"] + "/z"].ravel(), 1e-9, "z")
+    assert_parity(ss, ref_pinv[case["name"] + "/ss"].ravel(), 1e-9, "ss")
+
+
+@pytest.mark.parametrize("ptype", ["pinv", "pinvh"])
+def test_oracle_pseudo_inverse_known_answer(ptype):
+    """tests/test_core.py:2913-2949: two redundant points (values 1 and 3) krige to their mean."""
+    data = np.array([[0.0, 0.0, 1.0], [0.0, 0.0, 3.0], [1.0, 0.0, 6.0]])
+    z, _ = ko.krige(data[:, :2], data[:, 2], "linear", [1.0, 0.0], np.array([[0.0, 0.0]]), pseudo_inv=ptype)
+    assert np.isclose(z[0], 2.0)
+    d3 = np.array([[0.0, 0.0, 0.0, 1.0], [0.0, 0.0, 0.0, 3.0], [1.0, 0.0, 0.0, 6.0]])
+    z, _ = ko.krige(d3[:, :3], d3[:, 3], "linear", [1.0, 0.0], np.array([[0.0, 0.0, 0.0]]), pseudo_inv=ptype)
+    assert np.isclose(z[0], 2.0)

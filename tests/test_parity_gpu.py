@@ -473,3 +473,63 @@ def test_device_statistics_unsupported_routes(pk):
     hk = m._ensure_problem("float64", knn=True)
     with pytest.raises(_cabi.KrigeB200Error):
         hk.statistics(600)
+
+
+# ---- pseudo_inv=True on the device: csrc/pinv.cu -------------------------------
+@pytest.mark.parametrize("case", cases.PINV_CASES, ids=[c["name"] for c in cases.PINV_CASES])
+def test_pseudo_inverse_cases_match_reference(pk, case, ref_pinv):
+    """Redundant data points make the kriging matrix singular; the Jacobi-SVD pseudo-inverse must give the
+    reference's scipy.linalg.pinv / pinvh numbers (both z and sigma^2)."""
+    inp, z, ss = _run(pk, case)
+    zr, sr = ref_pinv[case["name"] + "/z"], ref_pinv[case["name"] + "/ss"]
+    assert z.shape == zr.shape
+    assert_parity(np.asarray(z).ravel(), zr.ravel(), R64, "pinv z")
+    assert_parity(np.asarray(ss).ravel(), sr.ravel(), R64, "pinv ss")
+
+
+@pytest.mark.parametrize("ptype", ["pinv", "pinvh"])
+def test_pseudo_inverse_known_answers(pk, ptype):
+    """tests/test_core.py:2913-2949 (test_pseudo_2d / test_pseudo_3d) for all four classes."""
+    data = np.array([[0.0, 0.0, 1.0], [0.0, 0.0, 3.0], [1.0, 0.0, 6.0]])
+    for cls in (pk.OrdinaryKriging, pk.UniversalKriging):
+        m = cls(data[:, 0], data[:, 1], data[:, 2], variogram_parameters=[1.0, 0.0], pseudo_inv=True,
+                pseudo_inv_type=ptype)
+        z1, ss1 = m.execute("points", 0.0, 0.0, backend="cuda")
+        assert np.isclose(z1.item(), 2.0)
+    d3 = np.array([[0.0, 0.0, 0.0, 1.0], [0.0, 0.0, 0.0, 3.0], [1.0, 0.0, 0.0, 6.0]])
+    for cls in (pk.OrdinaryKriging3D, pk.UniversalKriging3D):
+        m = cls(d3[:, 0], d3[:, 1], d3[:, 2], d3[:, 3], variogram_parameters=[1.0, 0.0], pseudo_inv=True,
+                pseudo_inv_type=ptype)
+        z1, ss1 = m.execute("points", 0.0, 0.0, 0.0, backend="cuda")
+        assert np.isclose(z1.item(), 2.0)
+    # without the pseudo-inverse the same data is singular (what scipy.linalg.inv raises)
+    m = pk.OrdinaryKriging(data[:, 0], data[:, 1], data[:, 2], variogram_parameters=[1.0, 0.0])
+    with pytest.raises(np.linalg.LinAlgError):
+        m.execute("points", 0.0, 0.0, backend="cuda")
+
+
+def test_pseudo_inverse_medium_size_and_routes(pk):
+    """N = 700 with 20 redundant points vs the oracle; fp32 is refused; the moving window ignores the
+    flag like the reference (ok.py:753)."""
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(4242, 700, 2)
+    for q in range(20):
+        xyz[699 - q] = xyz[2 * q]
+    params = [1.0, 250.0, 0.0]
+    pts = cases.synth_points(4242, 500, 2, xyz)
+    m = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential", variogram_parameters=params,
+                           pseudo_inv=True)
+    z, ss = m.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
+    zo, so = ko.krige(xyz, val, "exponential", ko.stored_parameters("exponential", params), pts, pseudo_inv="pinv")
+    assert_parity(z, zo, R64, "pinv700 z")
+    assert_parity(ss, so, R64, "pinv700 ss")
+    with pytest.raises(NotImplementedError):
+        m.execute("points", pts[:, 0], pts[:, 1], backend="cuda", dtype="float32")
+    xyz2, val2 = cases.synth_data(4243, 400, 2)
+    mk = pk.OrdinaryKriging(xyz2[:, 0], xyz2[:, 1], val2, variogram_model="exponential",
+                            variogram_parameters=[1.0, 250.0, 0.05], pseudo_inv=True)
+    zk, sk = mk.execute("points", pts[:, 0], pts[:, 1], backend="cuda", n_closest_points=8)
+    zko, sko = ko.krige(xyz2, val2, "exponential", ko.stored_parameters("exponential", [1.0, 250.0, 0.05]), pts,
+                        n_closest_points=8)
+    assert_parity(zk, zko, R64, "pinv knn z")
+    assert_parity(sk, sko, R64, "pinv knn ss")
