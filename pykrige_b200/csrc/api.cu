@@ -382,7 +382,7 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
             t_asm += ev_ms(h->ev[2], h->ev[3]);
             break;
         }
-        CU(h, kbk_cholesky(h->wC.as<double>(), h->wW.as<double>(), ld, np, flag, st, &launches));
+        CU(h, kbk_cholesky(h->wC.as<double>(), h->wW.as<double>(), ld, np, flag, 3.6e-15 * h->vg.c0, st, &launches));
         CU(h, cudaEventRecord(h->ev[4], st));
         CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
@@ -424,7 +424,7 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
         double* rowbuf = h->wT.as<double>();
         double* colbuf = rowbuf + np;
         int* piv = reinterpret_cast<int*>(colbuf + np);
-        CU(h, kbk_general_inverse(h->wC.as<double>(), ld, nn, np, rowbuf, colbuf, piv, flag, st, &launches));
+        CU(h, kbk_general_inverse(h->wC.as<double>(), ld, nn, np, rowbuf, colbuf, piv, flag, 3.6e-15 * h->vg.c0, st, &launches));
         CU(h, cudaEventRecord(h->ev[4], st));
         CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));

@@ -169,10 +169,11 @@ __device__ __forceinline__ void gemm_tile_store(const double (&acc)[4][4][2], do
 
 // ---------------------------------------------------------------------------
 // K2a.1  potf2 of one 64x64 diagonal block (one CTA, 256 threads). Writes L_kk into C (strict upper part
-// of the block zeroed). A non-positive pivot sets *flag = 1 + global column index. The inverse of the
+// of the block zeroed). A pivot at or below dtol (16 eps c0: the rounding noise of c0 - sum l^2, so exactly
+// redundant points are caught like scipy's exact zero pivot) sets *flag = 1 + global column index. The inverse of the
 // block (needed only by the triangular inverse, K2b) is computed later for all blocks at once
 // (diag_inv_kernel), off the critical path of the factorisation.
-__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ C, int ld, int kb, int* __restrict__ flag) {
+__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ C, int ld, int kb, int* __restrict__ flag, double dtol) {
     __shared__ double a[64][65];
     const int tid = threadIdx.x;
     double* Cb = C + (size_t)kb * 64 * ld + kb * 64;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ C, int 
     for (int j = 0; j < 64; ++j) {
         if (tid == 0) {
             double d = a[j][j];
-            if (!(d > 0.0)) { if (*flag == 0) *flag = 1 + kb * 64 + j; d = 1.0; }
+            if (!(d > dtol)) { if (*flag == 0) *flag = 1 + kb * 64 + j; d = 1.0; }   // dtol: rounding noise of the diagonal
             a[j][j] = sqrt(d);
         }
         __syncthreads();
@@ -509,13 +510,13 @@ cudaError_t kbk_factor_init() {
 }
 
 // Blocked right-looking Cholesky + diagonal-block inverses (into W's diagonal blocks).
-cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, cudaStream_t st, int* launches) {
+cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, double dtol, cudaStream_t st, int* launches) {
     const int nb = n_pad / 64;
     const int OW = 4;                                   // outer panel = 4 x 64 columns
     for (int ob = 0; ob < nb; ob += OW) {
         const int oe = ob + OW < nb ? ob + OW : nb;     // end of the outer panel (tile units)
         for (int kb = ob; kb < oe; ++kb) {
-            potf2_kernel<<<1, 256, 0, st>>>(C, ld, kb, flag);
+            potf2_kernel<<<1, 256, 0, st>>>(C, ld, kb, flag, dtol);
             ++*launches;
             const int below = nb - kb - 1;
             if (below > 0) {
@@ -591,7 +592,7 @@ cudaError_t kbk_pack(int dtype, const double* W, int ld, int n, int n_pad, int n
 // off-diagonals).
 __global__ void __launch_bounds__(1024) gj_pivot_kernel(double* __restrict__ A, int ld, int n, int k,
                                                          double* __restrict__ rowbuf, double* __restrict__ colbuf,
-                                                         int* __restrict__ piv, int* __restrict__ flag) {
+                                                         int* __restrict__ piv, int* __restrict__ flag, double ptol) {
     __shared__ double sval[1024];
     __shared__ int sidx[1024];
     const int tid = threadIdx.x;
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(1024) gj_pivot_kernel(double* __restrict__ A, 
         __syncthreads();
     }
     const int p = sidx[0];
-    if (tid == 0) { piv[k] = p; if (!(sval[0] > 0.0) && *flag == 0) *flag = 1 + k; }
+    if (tid == 0) { piv[k] = p; if (!(sval[0] > ptol) && *flag == 0) *flag = 1 + k; }   // ptol: rounding noise (this variant scales the pivot row, so redundant rows cancel to ~1 ulp, not 0)
     if (p != k) {
         for (int j = tid; j < n; j += 1024) {
             double t = A[(size_t)k * ld + j]; A[(size_t)k * ld + j] = A[(size_t)p * ld + j]; A[(size_t)p * ld + j] = t;
@@ -719,13 +720,13 @@ __global__ void symmetrize_kernel(double* __restrict__ C, int ld, int n_pad) {
 }
 
 cudaError_t kbk_general_inverse(double* C, int ld, int n, int n_pad, double* rowbuf, double* colbuf, int* piv,
-                                int* flag, cudaStream_t st, int* launches) {
+                                int* flag, double ptol, cudaStream_t st, int* launches) {
     // C holds the assembled lower triangle (+ diagonal); build the full matrix, then invert the n x n part
     symmetrize_kernel<<<dim3((n_pad + 255) / 256, n_pad), 256, 0, st>>>(C, ld, n_pad);
     ++*launches;
     dim3 ug((n + 255) / 256, (n + 15) / 16);
     for (int k = 0; k < n; ++k) {
-        gj_pivot_kernel<<<1, 1024, 0, st>>>(C, ld, n, k, rowbuf, colbuf, piv, flag);
+        gj_pivot_kernel<<<1, 1024, 0, st>>>(C, ld, n, k, rowbuf, colbuf, piv, flag, ptol);
         gj_update_kernel<<<ug, 256, 0, st>>>(C, ld, n, k, rowbuf, colbuf);
     }
     gj_colswap_kernel<<<(n + 127) / 128, 128, 0, st>>>(C, ld, n, piv);

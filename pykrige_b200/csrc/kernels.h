@@ -67,7 +67,7 @@ cudaError_t kbk_adjust_data(int dim, const Aniso& an, int n, const double* x, co
                             double* ax, double* ay, double* az, cudaStream_t st);
 cudaError_t kbk_assemble(int dim, const VgParams& vg, int n, int n_pad, int ld,
                          const double* ax, const double* ay, const double* az, double* C, cudaStream_t st);
-cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, cudaStream_t st, int* launches);
+cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, double dtol, cudaStream_t st, int* launches);
 cudaError_t kbk_trtri(const double* L, double* W, double* T1, int ld, int n_pad, cudaStream_t st, int* launches);
 cudaError_t kbk_dual(const double* W, int ld, int n, int n_pad, int n_rl, int n_hd,
                      const double* ax, const double* ay, const double* az, const DriftScale& ds,
@@ -77,7 +77,7 @@ cudaError_t kbk_pack(int dtype, const double* W, int ld, int n, int n_pad, int n
                      const PackMap& pm, void* out, cudaStream_t st);
 
 cudaError_t kbk_general_inverse(double* C, int ld, int n, int n_pad, double* rowbuf, double* colbuf, int* piv,
-                                int* flag, cudaStream_t st, int* launches);
+                                int* flag, double ptol, cudaStream_t st, int* launches);
 cudaError_t kbk_dual_gform(const double* G, int ld, int n, int n_pad, int n_rl, int n_hd,
                            const double* ax, const double* ay, const double* az, const DriftScale& ds,
                            const double* hd, const double* values,

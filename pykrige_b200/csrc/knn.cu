@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
             }
         __syncwarp();
         bool notpd = false;
+        const double ptol = 3.6e-15 * vg.c0;       // 16 eps: exact duplicates (nugget 0) give a pivot of +-1 ulp, not 0
         for (int b = 0; b < nbk; ++b) {
             double* Dbb = KN_BLK(b, b);
             double d[32];
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
 #pragma unroll
             for (int pc = 0; pc < 32; ++pc) {
                 const double piv = __shfl_sync(0xffffffffu, d[pc], pc);
-                if (!(piv > 0.0)) notpd = true;
+                if (!(piv > ptol)) notpd = true;        // at or below the rounding noise of c0 - sum l^2: not PD
                 const double inv = 1.0 / sqrt(piv);
                 const double l = d[pc] * inv;             // lane pc: sqrt(piv); lanes below: L[r][pc]
                 d[pc] = l;
