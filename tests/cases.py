@@ -308,3 +308,81 @@ STATS_CASES = [
 
 def build_ctor_inputs(case):
     return _ctor_xy(case)
+
+
+# ---- whole-chain scenarios on the reference's own small fixtures (tests/test_core.py:28-80): the
+# variogram is FITTED (no parameters given), so constructor binning + least squares + execute() are all
+# exercised. Reference outputs: tests/golden/ref_scenarios.npz (make_golden.py scenarios).
+SAMPLE_2D = np.array([[0.3, 1.2, 0.47], [1.9, 0.6, 0.56], [1.1, 3.2, 0.74], [3.3, 4.4, 1.47], [4.7, 3.8, 1.74]])
+SAMPLE_3D = np.array([[0.1, 0.1, 0.3, 0.9], [0.2, 0.1, 0.4, 0.8], [0.1, 0.3, 0.1, 0.9], [0.5, 0.4, 0.4, 0.5],
+                      [0.3, 0.3, 0.2, 0.7]])
+
+
+def _sc(name, cls, data, style, **kw):
+    d = dict(name=name, cls=cls, data=data, style=style, ctor={}, exec={}, dim=3 if cls.endswith("3D") else 2)
+    d.update(kw)
+    return d
+
+
+SCENARIOS = []
+for _m in ("linear", "power", "gaussian", "spherical", "exponential"):
+    SCENARIOS.append(_sc("val_ok_fit_" + _m, "OK", "validation", "grid", ctor=dict(variogram_model=_m)))
+SCENARIOS.append(_sc("val_uk_fit_linear_rl", "UK", "validation", "grid",
+                     ctor=dict(variogram_model="linear", drift_terms=["regional_linear"])))
+SCENARIOS.append(_sc("val_ok_fit_spherical_weight_aniso", "OK", "validation", "grid",
+                     ctor=dict(variogram_model="spherical", weight=True, nlags=8, anisotropy_scaling=2.0,
+                               anisotropy_angle=30.0)))
+SCENARIOS.append(_sc("val_ok_fit_exponential_stats", "OK", "validation", "grid",
+                     ctor=dict(variogram_model="exponential", enable_statistics=True), stats=True))
+SCENARIOS.append(_sc("s2d_ok_fit_linear_grid", "OK", "sample2d", "grid", ctor=dict(variogram_model="linear")))
+SCENARIOS.append(_sc("s2d_ok_fit_linear_masked", "OK", "sample2d", "masked", ctor=dict(variogram_model="linear")))
+SCENARIOS.append(_sc("s2d_ok_fit_linear_points", "OK", "sample2d", "points", ctor=dict(variogram_model="linear")))
+SCENARIOS.append(_sc("s2d_uk_three_drifts", "UK", "sample2d", "grid",
+                     ctor=dict(variogram_model="linear", drift_terms=["regional_linear", "external_Z", "point_log"]),
+                     three_drifts=True))
+SCENARIOS.append(_sc("s3d_ok_fit_linear_grid", "OK3D", "sample3d", "grid", ctor=dict(variogram_model="linear")))
+SCENARIOS.append(_sc("s3d_uk_fit_linear_rl_masked", "UK3D", "sample3d", "masked",
+                     ctor=dict(variogram_model="linear", drift_terms=["regional_linear"]), stats=True))
+SCENARIOS.append(_sc("s3d_ok_fit_power_points", "OK3D", "sample3d", "points", ctor=dict(variogram_model="power"),
+                     stats=True))
+
+
+def scenario_inputs(sc, validation_data):
+    """(data array, execute args, execute kwargs) of a scenario; `validation_data` is the 15-point KT3D_H2O
+    set stored in reference_goldens.npz (tests/test_core.py:28-31)."""
+    if sc["data"] == "validation":
+        data = np.asarray(validation_data)
+        args = [np.linspace(1067000.0, 1072000.0, 40), np.linspace(241500.0, 244000.0, 30)]
+    elif sc["data"] == "sample2d":
+        data = SAMPLE_2D
+        args = [np.arange(0.0, 6.0, 1.0), np.arange(0.0, 5.5, 0.5)]
+    else:
+        data = SAMPLE_3D
+        args = [np.arange(0.0, 0.6, 0.05), np.arange(0.0, 0.6, 0.01), np.arange(0.0, 0.6, 0.1)]
+    kw = {}
+    if sc["style"] == "masked":
+        if sc["dim"] == 2:
+            xi, yi = np.meshgrid(args[0], args[1])
+            kw["mask"] = np.array(xi == yi)
+        else:
+            zi, yi, xi = np.meshgrid(args[2], args[1], args[0], indexing="ij")
+            kw["mask"] = np.array((xi == yi) & (yi == zi))
+    if sc["style"] == "points":
+        rng = np.random.default_rng(99)
+        lo, hi = data[:, :sc["dim"]].min(axis=0), data[:, :sc["dim"]].max(axis=0)
+        P = rng.uniform(lo, hi, (25, sc["dim"]))
+        P[:3] = data[:3, :sc["dim"]]                      # exact hits
+        args = [P[:, c] for c in range(sc["dim"])]
+    return data, args, kw
+
+
+def scenario_model(module_ns, sc, data):
+    cls = {"OK": "OrdinaryKriging", "UK": "UniversalKriging", "OK3D": "OrdinaryKriging3D",
+           "UK3D": "UniversalKriging3D"}[sc["cls"]]
+    kw = dict(sc["ctor"])
+    if sc.get("three_drifts"):                            # tests/test_core.py:1222-1238
+        dem = np.repeat(np.arange(0.0, 5.1, 0.1)[np.newaxis, :], 6, axis=0)
+        kw.update(point_drift=np.array([[1.1, 1.1, -1.0]]), external_drift=dem,
+                  external_drift_x=np.arange(0.0, 5.1, 0.1), external_drift_y=np.arange(0.0, 6.0, 1.0))
+    cols = [data[:, c] for c in range(data.shape[1])]
+    return getattr(module_ns, cls)(*cols, **kw)

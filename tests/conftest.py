@@ -32,6 +32,12 @@ def ref_pinv():
 
 
 @pytest.fixture(scope="session")
+def ref_scenarios():
+    """Reference outputs of the whole-chain scenarios (make_golden.py scenarios)."""
+    return np.load(os.path.join(GOLDEN, "ref_scenarios.npz"))
+
+
+@pytest.fixture(scope="session")
 def ref_ctor():
     """Reference outputs of core._initialize_variogram_model / core._find_statistics (make_golden.py ctor)."""
     return np.load(os.path.join(GOLDEN, "ref_ctor.npz"))

@@ -10,6 +10,8 @@ Writes
   tests/golden/ref_cases.npz : (z, sigmasq) of reference.execute(backend='vectorized'|'loop') for every
       seeded case of tests/cases.py.
   tests/golden/ref_pinv.npz : (z, sigmasq) of the reference with pseudo_inv=True (redundant data points).
+  tests/golden/ref_scenarios.npz : fitted parameters, lags, (z, sigmasq) and statistics of the reference for the
+      whole-chain scenarios (no variogram parameters given) on the reference's own small fixtures.
   tests/golden/ref_ctor.npz : lags/semivariance of core._initialize_variogram_model and delta/sigma/epsilon
       of core._find_statistics for the constructor-side cases of tests/cases.py.
 The O(N^4) constructor statistics of OK3D/UK/UK3D are patched out; nothing else of the
@@ -89,6 +91,33 @@ def ref_pinv():
     np.savez_compressed(os.path.join(HERE, "ref_pinv.npz"), **out)
 
 
+def ref_scenarios():
+    """Whole-chain scenarios (fitted variograms) of tests/cases.py SCENARIOS -> ref_scenarios.npz."""
+    gold = np.load(os.path.join(HERE, "reference_goldens.npz"))
+    out = {}
+    for sc in cases.SCENARIOS:
+        data, args, kw = cases.scenario_inputs(sc, gold["data"])
+        import importlib
+        if sc.get("stats") and sc["cls"] != "OK":           # un-patch the statistics for this scenario
+            from pykrige import core as rcore
+            for mod in (pykrige.ok3d, pykrige.uk, pykrige.uk3d):
+                mod._find_statistics = rcore._find_statistics
+        model = cases.scenario_model(pykrige, sc, data)
+        z, ss = model.execute(sc["style"], *args, backend="vectorized", **kw)
+        out[sc["name"] + "/params"] = np.asarray(model.variogram_model_parameters, dtype=np.float64)
+        out[sc["name"] + "/lags"] = np.asarray(model.lags, dtype=np.float64)
+        out[sc["name"] + "/semi"] = np.asarray(model.semivariance, dtype=np.float64)
+        out[sc["name"] + "/z"] = np.asarray(np.ma.getdata(z), dtype=np.float64)
+        out[sc["name"] + "/ss"] = np.asarray(np.ma.getdata(ss), dtype=np.float64)
+        if sc.get("stats"):
+            out[sc["name"] + "/Q"] = np.array([model.Q1, model.Q2, model.cR], dtype=np.float64)
+            out[sc["name"] + "/epsilon"] = np.asarray(model.epsilon, dtype=np.float64)
+        print("%-36s params=%s" % (sc["name"], np.array2string(out[sc["name"] + "/params"], precision=5)))
+        for mod in (pykrige.ok3d, pykrige.uk, pykrige.uk3d):
+            mod._find_statistics = _no_stats
+    np.savez_compressed(os.path.join(HERE, "ref_scenarios.npz"), **out)
+
+
 def ref_ctor():
     """Outputs of the reference's constructor-side routines (core._initialize_variogram_model,
     core._find_statistics) for tests/cases.py VARIOGRAM_CASES / STATS_CASES -> ref_ctor.npz."""
@@ -120,7 +149,7 @@ def ref_ctor():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv"]
+    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios"]
     if "goldens" in which:
         reference_goldens()
     if "cases" in which:
@@ -129,3 +158,5 @@ if __name__ == "__main__":
         ref_ctor()
     if "pinv" in which:
         ref_pinv()
+    if "scenarios" in which:
+        ref_scenarios()

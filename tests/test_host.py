@@ -187,3 +187,17 @@ def test_host_statistics_match_reference(ref_ctor):
     assert_allclose(d, ref_ctor[case["name"] + "/delta"], rtol=1e-8, atol=1e-10)
     assert_allclose(s, ref_ctor[case["name"] + "/sigma"], rtol=1e-8)
     assert_allclose(e, ref_ctor[case["name"] + "/epsilon"], rtol=1e-8, atol=1e-10)
+
+
+# ---- whole-chain scenarios: constructor (binning + least-squares fit) vs the imported reference ----
+@pytest.mark.parametrize("sc", cases.SCENARIOS, ids=[s["name"] for s in cases.SCENARIOS])
+def test_fitted_variogram_matches_reference(sc, ref_scenarios, ref_goldens):
+    """No variogram parameters given: lags, semivariances and the soft-L1 fit must reproduce the
+    reference's constructor (ok.py:326-346 -> core.py:379-651). Runs the host binning on a CPU-only
+    box and the device binning where a GPU is present; both must land on the same fit."""
+    data, _, _ = cases.scenario_inputs(sc, ref_goldens["data"])
+    m = cases.scenario_model(pk, sc, data)
+    assert_allclose(m.lags, ref_scenarios[sc["name"] + "/lags"], rtol=1e-10)
+    assert_allclose(m.semivariance, ref_scenarios[sc["name"] + "/semi"], rtol=1e-10)
+    pr = ref_scenarios[sc["name"] + "/params"]
+    assert_allclose(m.variogram_model_parameters, pr, rtol=1e-6, atol=1e-7 * np.abs(pr).max())

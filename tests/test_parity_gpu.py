@@ -533,3 +533,32 @@ def test_pseudo_inverse_medium_size_and_routes(pk):
                         n_closest_points=8)
     assert_parity(zk, zko, R64, "pinv knn z")
     assert_parity(sk, sko, R64, "pinv knn ss")
+
+
+# ---- whole-chain scenarios on the reference's own fixtures (fitted variograms) ------------------------
+@pytest.mark.parametrize("sc", cases.SCENARIOS, ids=[s["name"] for s in cases.SCENARIOS])
+def test_whole_chain_scenarios_match_reference(pk, sc, ref_scenarios, ref_goldens):
+    """Constructor (device binning + least-squares fit) -> execute(backend='cuda') -> statistics against the
+    imported reference run the same way (tests/test_core.py:565-666, 1020-1067, 1219-1255, 2205-2353 are the
+    scenarios these replay). The three-drift case is exactly determined by its drift terms (5 points, 5
+    constraints; the reference's own matrix has rcond 2e-33) — like the reference's test it is checked for
+    shape and finiteness only."""
+    data, args, kw = cases.scenario_inputs(sc, ref_goldens["data"])
+    m = cases.scenario_model(pk, sc, data)
+    z, ss = m.execute(sc["style"], *args, backend="cuda", **kw)
+    zr, sr = ref_scenarios[sc["name"] + "/z"], ref_scenarios[sc["name"] + "/ss"]
+    assert z.shape == zr.shape and ss.shape == sr.shape
+    if sc["style"] == "masked":
+        assert np.ma.is_masked(z)
+        keep = ~np.ma.getmaskarray(z)
+        z, ss, zr, sr = np.ma.getdata(z)[keep], np.ma.getdata(ss)[keep], zr[keep], sr[keep]
+    if sc.get("three_drifts"):
+        assert np.all(np.isfinite(z)) and np.all(np.isfinite(ss))
+        return
+    assert_parity(np.ravel(z), np.ravel(zr), R64, sc["name"] + " z")
+    assert_parity(np.ravel(ss), np.ravel(sr), R64, sc["name"] + " ss")
+    if sc.get("stats"):
+        Q = ref_scenarios[sc["name"] + "/Q"]
+        assert_allclose([m.Q1, m.Q2, m.cR], Q, rtol=1e-5)
+        assert_allclose(m.epsilon, ref_scenarios[sc["name"] + "/epsilon"], rtol=1e-5,
+                        atol=1e-5 * np.abs(ref_scenarios[sc["name"] + "/epsilon"]).max())
