@@ -47,44 +47,97 @@ __device__ __forceinline__ void pj_reduce3(double& a, double& b, double& g, doub
     for (int q = 0; q < PJ_T / 32; ++q) { a += red[q]; b += red[8 + q]; g += red[16 + q]; }   // same order in every thread
 }
 
-// One round of the round-robin ordering: m/2 disjoint column pairs, one CTA per pair.
+// One round of the round-robin ordering over column BLOCKS: the columns are cut into blocks of NC/2; a CTA
+// takes a pair of blocks (NC columns), stages them in shared memory, orthogonalises every pair among them
+// (exact one-sided rotations: three dot products and one plane rotation per pair, all from shared memory)
+// and writes them back once; the accumulated NC x NC rotation is then applied to the same columns of V in
+// one streaming pass. Per pair of columns this moves 4 nt / (NC - 1) doubles instead of 8 nt (NC = 2 is
+// the plain one-sided Jacobi). mb = number of blocks (even).
+template <int NC>
 __global__ void __launch_bounds__(PJ_T) pinv_jacobi_round_kernel(int nt, int ld, double* __restrict__ Bt,
-                                                                 double* __restrict__ Vt, int r, int m,
+                                                                 double* __restrict__ Vt, int r, int mb,
                                                                  double tol, double thr2, int* __restrict__ counter) {
-    extern __shared__ double pj_sm[];      // rows p and q of Bt
+    extern __shared__ double pj_sm[];      // NC columns of B, each nt long
     __shared__ double red[24];
+    __shared__ double M[NC][NC];           // rows_new = M rows_old (accumulated rotations)
+    __shared__ int any_rot;
+    constexpr int HB = NC / 2;
     const int k = blockIdx.x, tid = threadIdx.x;
-    int p, q;
-    if (k == 0) { p = m - 1; q = r; }
-    else { p = (r + k) % (m - 1); q = (r - k + (m - 1)) % (m - 1); }
-    if (p > q) { int t = p; p = q; q = t; }
-    if (q >= nt) return;                   // the dummy player of an odd-sized tournament
-    double* bp = Bt + (size_t)p * ld;
-    double* bq = Bt + (size_t)q * ld;
-    double a = 0.0, b = 0.0, g = 0.0;
-    for (int i = tid; i < nt; i += PJ_T) {
-        const double x = bp[i], y = bq[i];
-        pj_sm[i] = x; pj_sm[nt + i] = y;
-        a += x * x; b += y * y; g += x * y;
+    int I, J;
+    if (k == 0) { I = mb - 1; J = r; }
+    else { I = (r + k) % (mb - 1); J = (r - k + (mb - 1)) % (mb - 1); }
+    if (mb == 1) { I = 0; J = 0; }
+    int col[NC];
+#pragma unroll
+    for (int a = 0; a < NC; ++a) {
+        const int c = (a < HB ? I * HB + a : J * HB + (a - HB));
+        col[a] = (c < nt && !(mb == 1 && a >= HB)) ? c : -1;
     }
-    pj_reduce3(a, b, g, red);
-    const double ab = a * b;
-    if (!(ab > 1e-280) || !(fabs(g) > tol * sqrt(ab))) return;        // already orthogonal (block-uniform)
-    if (tid == 0 && a >= thr2 && b >= thr2) atomicAdd(counter, 1);     // only live columns count for convergence
-    const double zeta = (b - a) / (2.0 * g);
-    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-    for (int i = tid; i < nt; i += PJ_T) {
-        const double x = pj_sm[i], y = pj_sm[nt + i];
-        bp[i] = c * x - s * y;
-        bq[i] = s * x + c * y;
+    if (tid < NC * NC) M[tid / NC][tid % NC] = (tid / NC == tid % NC) ? 1.0 : 0.0;
+    if (tid == 0) any_rot = 0;
+#pragma unroll
+    for (int a = 0; a < NC; ++a)
+        if (col[a] >= 0) {
+            const double* src = Bt + (size_t)col[a] * ld;
+            for (int i = tid; i < nt; i += PJ_T) pj_sm[(size_t)a * nt + i] = src[i];
+        }
+    __syncthreads();
+    for (int a = 0; a < NC - 1; ++a) {
+        if (col[a] < 0) continue;
+        for (int c = a + 1; c < NC; ++c) {
+            if (col[c] < 0) continue;
+            double* xa = pj_sm + (size_t)a * nt;
+            double* xc = pj_sm + (size_t)c * nt;
+            double al = 0.0, be = 0.0, ga = 0.0;
+            for (int i = tid; i < nt; i += PJ_T) {
+                const double x = xa[i], y = xc[i];
+                al += x * x; be += y * y; ga += x * y;
+            }
+            __syncthreads();               // red[] of the previous pair has been consumed
+            pj_reduce3(al, be, ga, red);
+            const double ab = al * be;
+            if (!(ab > 1e-280) || !(fabs(ga) > tol * sqrt(ab))) continue;          // block-uniform
+            const double zeta = (be - al) / (2.0 * ga);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+            for (int i = tid; i < nt; i += PJ_T) {
+                const double x = xa[i], y = xc[i];
+                xa[i] = cs * x - sn * y;
+                xc[i] = sn * x + cs * y;
+            }
+            if (tid < NC) {
+                const double x = M[a][tid], y = M[c][tid];
+                M[a][tid] = cs * x - sn * y;
+                M[c][tid] = sn * x + cs * y;
+            }
+            if (tid == 0) {
+                any_rot = 1;
+                if (al >= thr2 && be >= thr2) atomicAdd(counter, 1);              // only live columns count
+            }
+        }
     }
-    double* vp = Vt + (size_t)p * ld;
-    double* vq = Vt + (size_t)q * ld;
+    __syncthreads();
+    if (!any_rot) return;
+#pragma unroll
+    for (int a = 0; a < NC; ++a)
+        if (col[a] >= 0) {
+            double* dst = Bt + (size_t)col[a] * ld;
+            for (int i = tid; i < nt; i += PJ_T) dst[i] = pj_sm[(size_t)a * nt + i];
+        }
     for (int i = tid; i < nt; i += PJ_T) {
-        const double x = vp[i], y = vq[i];
-        vp[i] = c * x - s * y;
-        vq[i] = s * x + c * y;
+        double v[NC], w[NC];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) v[a] = col[a] >= 0 ? Vt[(size_t)col[a] * ld + i] : 0.0;
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc = fma(M[a][c], v[c], acc);
+            w[a] = acc;
+        }
+#pragma unroll
+        for (int a = 0; a < NC; ++a)
+            if (col[a] >= 0) Vt[(size_t)col[a] * ld + i] = w[a];
     }
 }
 
@@ -194,14 +247,19 @@ __global__ void pinv_pad_kernel(int n, int K1, int n_pad, int ldc, double* __res
     if (blockIdx.y == 0 && j >= n && j < n_pad) Uz[(size_t)K1 * n_pad + j] = 0.0;
 }
 
-int kbk_pinv_max_nt() { return (227 * 1024 - 1024) / 16; }
+int kbk_pinv_max_nt() { return (227 * 1024 - 4096) / 16; }
 size_t kbk_pinv_workspace_doubles(int nt) {
     const size_t ld = ((size_t)nt + 7) / 8 * 8;
     return 3 * (size_t)nt * ld + 2 * (size_t)nt + 64;
 }
 
 cudaError_t kbk_pinv_init() {
-    return cudaFuncSetAttribute(pinv_jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    const int mx = 227 * 1024 - 4096;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(pinv_jacobi_round_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pinv_jacobi_round_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pinv_jacobi_round_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pinv_jacobi_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
 }
 
 // Runs the whole pseudo-inverse. C (n_pad x ldc): assembled with c0 = 0; on return it holds G11.
@@ -231,14 +289,25 @@ cudaError_t kbk_pinv(int n, int K1, int n_pad, double* C, int ldc, const double*
     const double epsm = 2.220446049250313e-16;
     const double thr2 = (nt * epsm) * (nt * epsm) * fro2;
     const double tol = nt * epsm > 1e-15 ? nt * epsm : 1e-15;     // dgesvj-style orthogonality threshold
-    const int m = (nt + 1) / 2 * 2;
-    const size_t sm = 2 * (size_t)nt * sizeof(double);
+    // columns per CTA: as many as fit in shared memory (16 / 8 / 4 / 2)
+    const size_t smax = 227 * 1024 - 4096;
+    int nc = 16;
+    while (nc > 2 && (size_t)nc * nt * sizeof(double) > smax) nc /= 2;
+    const int hb = nc / 2;
+    int mb = (nt + hb - 1) / hb;                        // column blocks
+    if (mb > 1) mb = (mb + 1) / 2 * 2;                  // even number of players (the last may be a dummy)
+    const int rounds = mb > 1 ? mb - 1 : 1, ctas = mb > 1 ? mb / 2 : 1;
+    const size_t sm = (size_t)nc * nt * sizeof(double);
     *sweeps = -1;
     for (int sweep = 0; sweep < 40 && nt > 1; ++sweep) {
         if ((e = cudaMemsetAsync(counter, 0, sizeof(int), st)) != cudaSuccess) return e;
-        for (int r = 0; r < m - 1; ++r)
-            pinv_jacobi_round_kernel<<<m / 2, PJ_T, sm, st>>>(nt, ld, Bt, Vt, r, m, tol, thr2, counter);
-        *launches += m - 1;
+        for (int r = 0; r < rounds; ++r) {
+            if (nc == 16) pinv_jacobi_round_kernel<16><<<ctas, PJ_T, sm, st>>>(nt, ld, Bt, Vt, r, mb, tol, thr2, counter);
+            else if (nc == 8) pinv_jacobi_round_kernel<8><<<ctas, PJ_T, sm, st>>>(nt, ld, Bt, Vt, r, mb, tol, thr2, counter);
+            else if (nc == 4) pinv_jacobi_round_kernel<4><<<ctas, PJ_T, sm, st>>>(nt, ld, Bt, Vt, r, mb, tol, thr2, counter);
+            else pinv_jacobi_round_kernel<2><<<ctas, PJ_T, sm, st>>>(nt, ld, Bt, Vt, r, mb, tol, thr2, counter);
+        }
+        *launches += rounds;
         int rot = 0;
         if ((e = cudaMemcpyAsync(&rot, counter, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
