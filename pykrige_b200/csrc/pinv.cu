@@ -48,86 +48,105 @@ __device__ __forceinline__ void pj_reduce3(double& a, double& b, double& g, doub
 }
 
 // One round of the round-robin ordering over column BLOCKS: the columns are cut into blocks of NC/2; a CTA
-// takes a pair of blocks (NC columns), stages them in shared memory, orthogonalises every pair among them
-// (exact one-sided rotations: three dot products and one plane rotation per pair, all from shared memory)
-// and writes them back once; the accumulated NC x NC rotation is then applied to the same columns of V in
-// one streaming pass. Per pair of columns this moves 4 nt / (NC - 1) doubles instead of 8 nt (NC = 2 is
-// the plain one-sided Jacobi). mb = number of blocks (even).
+// takes a pair of blocks (NC columns), stages them in shared memory and runs one full inner tournament on
+// them: NC-1 steps of NC/2 disjoint column pairs, each pair owned by a group of 8/(NC/2) warps (exact
+// one-sided rotations: three dot products and one plane rotation per pair, all from shared memory). The
+// columns are written back once; the accumulated NC x NC rotation is then applied to the same columns of V
+// in one streaming pass. Per pair of columns this moves 8 nt / (NC - 1) doubles instead of 8 nt (NC = 2 is
+// the plain one-sided Jacobi). mb = number of blocks (even, or 1).
 template <int NC>
 __global__ void __launch_bounds__(PJ_T) pinv_jacobi_round_kernel(int nt, int ld, double* __restrict__ Bt,
                                                                  double* __restrict__ Vt, int r, int mb,
                                                                  double tol, double thr2, int* __restrict__ counter) {
     extern __shared__ double pj_sm[];      // NC columns of B, each nt long
-    __shared__ double red[24];
+    constexpr int HB = NC / 2;             // columns per block = pairs per inner step
+    constexpr int WPP = (PJ_T / 32) / HB;  // warps per pair
+    constexpr int GS = 32 * WPP;           // threads per pair
+    __shared__ double part[HB][WPP][3];
     __shared__ double M[NC][NC];           // rows_new = M rows_old (accumulated rotations)
+    __shared__ int scol[NC];
     __shared__ int any_rot;
-    constexpr int HB = NC / 2;
     const int k = blockIdx.x, tid = threadIdx.x;
-    int I, J;
-    if (k == 0) { I = mb - 1; J = r; }
-    else { I = (r + k) % (mb - 1); J = (r - k + (mb - 1)) % (mb - 1); }
-    if (mb == 1) { I = 0; J = 0; }
-    int col[NC];
-#pragma unroll
-    for (int a = 0; a < NC; ++a) {
-        const int c = (a < HB ? I * HB + a : J * HB + (a - HB));
-        col[a] = (c < nt && !(mb == 1 && a >= HB)) ? c : -1;
+    const int grp = tid / GS, lg = tid % GS, wig = lg >> 5, lane = tid & 31;
+    if (tid < NC) {
+        int I, J;
+        if (mb == 1) { I = 0; J = 0; }
+        else if (k == 0) { I = mb - 1; J = r; }
+        else { I = (r + k) % (mb - 1); J = (r - k + (mb - 1)) % (mb - 1); }
+        const int c = (tid < HB ? I * HB + tid : J * HB + (tid - HB));
+        scol[tid] = (c < nt && !(mb == 1 && tid >= HB)) ? c : -1;
     }
     if (tid < NC * NC) M[tid / NC][tid % NC] = (tid / NC == tid % NC) ? 1.0 : 0.0;
     if (tid == 0) any_rot = 0;
-#pragma unroll
-    for (int a = 0; a < NC; ++a)
-        if (col[a] >= 0) {
-            const double* src = Bt + (size_t)col[a] * ld;
+    __syncthreads();
+    for (int a = 0; a < NC; ++a) {
+        const int ca = scol[a];
+        if (ca >= 0) {
+            const double* src = Bt + (size_t)ca * ld;
             for (int i = tid; i < nt; i += PJ_T) pj_sm[(size_t)a * nt + i] = src[i];
         }
+    }
     __syncthreads();
-    for (int a = 0; a < NC - 1; ++a) {
-        if (col[a] < 0) continue;
-        for (int c = a + 1; c < NC; ++c) {
-            if (col[c] < 0) continue;
-            double* xa = pj_sm + (size_t)a * nt;
-            double* xc = pj_sm + (size_t)c * nt;
-            double al = 0.0, be = 0.0, ga = 0.0;
-            for (int i = tid; i < nt; i += PJ_T) {
+    for (int step = 0; step < NC - 1; ++step) {
+        // inner round robin on NC players: group 0 pairs (NC-1, step), group g pairs ((step+g), (step-g)) mod NC-1
+        int a, c;
+        if (NC == 2) { a = 0; c = 1; }
+        else if (grp == 0) { a = NC - 1; c = step; }
+        else { a = (step + grp) % (NC - 1); c = (step - grp + (NC - 1)) % (NC - 1); }
+        if (a > c) { const int t = a; a = c; c = t; }
+        const bool valid = scol[a] >= 0 && scol[c] >= 0;
+        double* xa = pj_sm + (size_t)a * nt;
+        double* xc = pj_sm + (size_t)c * nt;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        if (valid)
+            for (int i = lg; i < nt; i += GS) {
                 const double x = xa[i], y = xc[i];
                 al += x * x; be += y * y; ga += x * y;
             }
-            __syncthreads();               // red[] of the previous pair has been consumed
-            pj_reduce3(al, be, ga, red);
-            const double ab = al * be;
-            if (!(ab > 1e-280) || !(fabs(ga) > tol * sqrt(ab))) continue;          // block-uniform
+        for (int o = 16; o > 0; o >>= 1) {
+            al += __shfl_xor_sync(0xffffffffu, al, o);
+            be += __shfl_xor_sync(0xffffffffu, be, o);
+            ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        if (lane == 0) { part[grp][wig][0] = al; part[grp][wig][1] = be; part[grp][wig][2] = ga; }
+        __syncthreads();
+        al = be = ga = 0.0;
+#pragma unroll
+        for (int w = 0; w < WPP; ++w) { al += part[grp][w][0]; be += part[grp][w][1]; ga += part[grp][w][2]; }
+        const double ab = al * be;
+        if (valid && ab > 1e-280 && fabs(ga) > tol * sqrt(ab)) {                  // uniform within the group
             const double zeta = (be - al) / (2.0 * ga);
             const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
             const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-            for (int i = tid; i < nt; i += PJ_T) {
+            for (int i = lg; i < nt; i += GS) {
                 const double x = xa[i], y = xc[i];
                 xa[i] = cs * x - sn * y;
                 xc[i] = sn * x + cs * y;
             }
-            if (tid < NC) {
-                const double x = M[a][tid], y = M[c][tid];
-                M[a][tid] = cs * x - sn * y;
-                M[c][tid] = sn * x + cs * y;
+            if (lg < NC) {
+                const double x = M[a][lg], y = M[c][lg];
+                M[a][lg] = cs * x - sn * y;
+                M[c][lg] = sn * x + cs * y;
             }
-            if (tid == 0) {
+            if (lg == 0) {
                 any_rot = 1;
                 if (al >= thr2 && be >= thr2) atomicAdd(counter, 1);              // only live columns count
             }
         }
+        __syncthreads();                   // the next step pairs the columns differently
     }
-    __syncthreads();
     if (!any_rot) return;
-#pragma unroll
-    for (int a = 0; a < NC; ++a)
-        if (col[a] >= 0) {
-            double* dst = Bt + (size_t)col[a] * ld;
+    for (int a = 0; a < NC; ++a) {
+        const int ca = scol[a];
+        if (ca >= 0) {
+            double* dst = Bt + (size_t)ca * ld;
             for (int i = tid; i < nt; i += PJ_T) dst[i] = pj_sm[(size_t)a * nt + i];
         }
+    }
     for (int i = tid; i < nt; i += PJ_T) {
         double v[NC], w[NC];
 #pragma unroll
-        for (int a = 0; a < NC; ++a) v[a] = col[a] >= 0 ? Vt[(size_t)col[a] * ld + i] : 0.0;
+        for (int a = 0; a < NC; ++a) v[a] = scol[a] >= 0 ? Vt[(size_t)scol[a] * ld + i] : 0.0;
 #pragma unroll
         for (int a = 0; a < NC; ++a) {
             double acc = 0.0;
@@ -137,7 +156,7 @@ __global__ void __launch_bounds__(PJ_T) pinv_jacobi_round_kernel(int nt, int ld,
         }
 #pragma unroll
         for (int a = 0; a < NC; ++a)
-            if (col[a] >= 0) Vt[(size_t)col[a] * ld + i] = w[a];
+            if (scol[a] >= 0) Vt[(size_t)scol[a] * ld + i] = w[a];
     }
 }
 
