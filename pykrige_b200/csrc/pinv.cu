@@ -16,6 +16,35 @@
 
 #define PJ_T 256
 
+// 1-D bulk copies through the TMA engine (SASS UBLKCP): a single CTA per SM cannot keep enough plain
+// loads in flight to stream its columns at HBM speed.
+__device__ __forceinline__ uint32_t pj_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pj_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(pj_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pj_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(pj_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pj_mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 26); ++it) {          // bounded spin: trap instead of hanging the GPU
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(pj_smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void pj_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(pj_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pj_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pj_bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 :: "l"(dst), "r"(pj_smem_u32(src)), "r"(bytes) : "memory");
+}
+
 // Bt (row p = column p of B) := A, Vt := I. C: assembled with c0 = 0 (lower triangle valid, zero
 // diagonal); Fz: drift columns 0..K-1 then ones (column K), each n_pad long.
 __global__ void pinv_build_kernel(int n, int K1, int nt, int ld, const double* __restrict__ C, int ldc,
@@ -58,7 +87,7 @@ template <int NC>
 __global__ void __launch_bounds__(PJ_T) pinv_jacobi_round_kernel(int nt, int ld, double* __restrict__ Bt,
                                                                  double* __restrict__ Vt, int r, int mb,
                                                                  double tol, double thr2, int* __restrict__ counter) {
-    extern __shared__ double pj_sm[];      // NC columns of B, each nt long
+    extern __shared__ __align__(128) double pj_sm[];      // NC columns of B, stride nts
     constexpr int HB = NC / 2;             // columns per block = pairs per inner step
     constexpr int WPP = (PJ_T / 32) / HB;  // warps per pair
     constexpr int GS = 32 * WPP;           // threads per pair
@@ -66,6 +95,7 @@ __global__ void __launch_bounds__(PJ_T) pinv_jacobi_round_kernel(int nt, int ld,
     __shared__ double M[NC][NC];           // rows_new = M rows_old (accumulated rotations)
     __shared__ int scol[NC];
     __shared__ int any_rot;
+    __shared__ __align__(8) uint64_t bar;
     const int k = blockIdx.x, tid = threadIdx.x;
     const int grp = tid / GS, lg = tid % GS, wig = lg >> 5, lane = tid & 31;
     if (tid < NC) {
@@ -77,16 +107,23 @@ __global__ void __launch_bounds__(PJ_T) pinv_jacobi_round_kernel(int nt, int ld,
         scol[tid] = (c < nt && !(mb == 1 && tid >= HB)) ? c : -1;
     }
     if (tid < NC * NC) M[tid / NC][tid % NC] = (tid / NC == tid % NC) ? 1.0 : 0.0;
-    if (tid == 0) any_rot = 0;
-    __syncthreads();
-    for (int a = 0; a < NC; ++a) {
-        const int ca = scol[a];
-        if (ca >= 0) {
-            const double* src = Bt + (size_t)ca * ld;
-            for (int i = tid; i < nt; i += PJ_T) pj_sm[(size_t)a * nt + i] = src[i];
-        }
+    if (tid == 0) {
+        any_rot = 0;
+        pj_mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     __syncthreads();
+    const int nts = (nt + 1) & ~1;                       // column stride in shared memory (16-byte multiple)
+    const uint32_t cb = (uint32_t)nts * 8u;              // bytes per column copy (<= ld * 8: rows are padded to 8)
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int a = 0; a < NC; ++a) if (scol[a] >= 0) total += cb;
+        pj_mbar_expect_tx(&bar, total);
+        for (int a = 0; a < NC; ++a)
+            if (scol[a] >= 0) pj_bulk_g2s(pj_sm + (size_t)a * nts, Bt + (size_t)scol[a] * ld, cb, &bar);
+    }
+    pj_mbar_wait(&bar, 0);
     for (int step = 0; step < NC - 1; ++step) {
         // inner round robin on NC players: group 0 pairs (NC-1, step), group g pairs ((step+g), (step-g)) mod NC-1
         int a, c;
@@ -95,8 +132,8 @@ __global__ void __launch_bounds__(PJ_T) pinv_jacobi_round_kernel(int nt, int ld,
         else { a = (step + grp) % (NC - 1); c = (step - grp + (NC - 1)) % (NC - 1); }
         if (a > c) { const int t = a; a = c; c = t; }
         const bool valid = scol[a] >= 0 && scol[c] >= 0;
-        double* xa = pj_sm + (size_t)a * nt;
-        double* xc = pj_sm + (size_t)c * nt;
+        double* xa = pj_sm + (size_t)a * nts;
+        double* xc = pj_sm + (size_t)c * nts;
         double al = 0.0, be = 0.0, ga = 0.0;
         if (valid)
             for (int i = lg; i < nt; i += GS) {
@@ -136,28 +173,39 @@ __global__ void __launch_bounds__(PJ_T) pinv_jacobi_round_kernel(int nt, int ld,
         __syncthreads();                   // the next step pairs the columns differently
     }
     if (!any_rot) return;
-    for (int a = 0; a < NC; ++a) {
-        const int ca = scol[a];
-        if (ca >= 0) {
-            double* dst = Bt + (size_t)ca * ld;
-            for (int i = tid; i < nt; i += PJ_T) dst[i] = pj_sm[(size_t)a * nt + i];
-        }
-    }
-    for (int i = tid; i < nt; i += PJ_T) {
-        double v[NC], w[NC];
-#pragma unroll
-        for (int a = 0; a < NC; ++a) v[a] = scol[a] >= 0 ? Vt[(size_t)scol[a] * ld + i] : 0.0;
-#pragma unroll
-        for (int a = 0; a < NC; ++a) {
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) acc = fma(M[a][c], v[c], acc);
-            w[a] = acc;
-        }
-#pragma unroll
+    // rotated columns: generic-proxy writes to shared memory -> bulk stores (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
         for (int a = 0; a < NC; ++a)
-            if (scol[a] >= 0) Vt[(size_t)scol[a] * ld + i] = w[a];
+            if (scol[a] >= 0) pj_bulk_s2g(Bt + (size_t)scol[a] * ld, pj_sm + (size_t)a * nts, cb);
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
     }
+    // V: rows_new = M rows_old, streamed; UV elements per thread and trip keep >= 16 loads in flight
+    constexpr int UV = NC >= 16 ? 1 : 16 / NC;
+    for (int i0 = tid; i0 < nt; i0 += PJ_T * UV) {
+        double v[UV][NC];
+#pragma unroll
+        for (int u = 0; u < UV; ++u) {
+            const int i = i0 + u * PJ_T;
+#pragma unroll
+            for (int a = 0; a < NC; ++a) v[u][a] = (i < nt && scol[a] >= 0) ? Vt[(size_t)scol[a] * ld + i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UV; ++u) {
+            const int i = i0 + u * PJ_T;
+            if (i < nt) {
+#pragma unroll
+                for (int a = 0; a < NC; ++a) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) acc = fma(M[a][c], v[u][c], acc);
+                    if (scol[a] >= 0) Vt[(size_t)scol[a] * ld + i] = acc;
+                }
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // the stores have left shared memory and landed
 }
 
 // s2[p] = ||b_p||^2
@@ -266,7 +314,7 @@ __global__ void pinv_pad_kernel(int n, int K1, int n_pad, int ldc, double* __res
     if (blockIdx.y == 0 && j >= n && j < n_pad) Uz[(size_t)K1 * n_pad + j] = 0.0;
 }
 
-int kbk_pinv_max_nt() { return (227 * 1024 - 4096) / 16; }
+int kbk_pinv_max_nt() { return (227 * 1024 - 4096) / 16 - 1; }
 size_t kbk_pinv_workspace_doubles(int nt) {
     const size_t ld = ((size_t)nt + 7) / 8 * 8;
     return 3 * (size_t)nt * ld + 2 * (size_t)nt + 64;
@@ -311,12 +359,13 @@ cudaError_t kbk_pinv(int n, int K1, int n_pad, double* C, int ldc, const double*
     // columns per CTA: as many as fit in shared memory (16 / 8 / 4 / 2)
     const size_t smax = 227 * 1024 - 4096;
     int nc = 16;
-    while (nc > 2 && (size_t)nc * nt * sizeof(double) > smax) nc /= 2;
+    const size_t nts_h = ((size_t)nt + 1) & ~(size_t)1;  // column stride in shared memory
+    while (nc > 2 && (size_t)nc * nts_h * sizeof(double) > smax) nc /= 2;
     const int hb = nc / 2;
     int mb = (nt + hb - 1) / hb;                        // column blocks
     if (mb > 1) mb = (mb + 1) / 2 * 2;                  // even number of players (the last may be a dummy)
     const int rounds = mb > 1 ? mb - 1 : 1, ctas = mb > 1 ? mb / 2 : 1;
-    const size_t sm = (size_t)nc * nt * sizeof(double);
+    const size_t sm = (size_t)nc * nts_h * sizeof(double);
     *sweeps = -1;
     for (int sweep = 0; sweep < 40 && nt > 1; ++sweep) {
         if ((e = cudaMemsetAsync(counter, 0, sizeof(int), st)) != cudaSuccess) return e;
