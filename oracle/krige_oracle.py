@@ -9,7 +9,9 @@ Parity pinning: this oracle is checked in tests/test_oracle.py against
   * the reference's own golden vectors (KT3D_H2O / KT3D answers of tests/test_core.py:490-507,
     707-725, 1957-1989, stored in tests/golden/reference_goldens.npz), and
   * outputs of the imported reference itself (backend='vectorized' / 'loop'), generated here by
-    tests/golden/make_golden.py and stored in tests/golden/*.npz.
+    tests/golden/make_golden.py and stored in tests/golden/*.npz, and
+  * the reference's own compiled native twins (lib/cok.pyx) built into oracle/_ref by
+    oracle/build_ref.py and driven by oracle/ref_native.py (same inputs, fresh seeds).
 
 The arithmetic deliberately stays in the reference's form (gamma-form matrix with zero diagonal,
 explicit inverse, inverse x RHS) — NOT the covariance/Cholesky form the CUDA path uses — so that

@@ -179,3 +179,38 @@ def test_oracle_pseudo_inverse_known_answer(ptype):
     d3 = np.array([[0.0, 0.0, 0.0, 1.0], [0.0, 0.0, 0.0, 3.0], [1.0, 0.0, 0.0, 6.0]])
     z, _ = ko.krige(d3[:, :3], d3[:, 3], "linear", [1.0, 0.0], np.array([[0.0, 0.0, 0.0]]), pseudo_inv=ptype)
     assert np.isclose(z[0], 2.0)
+
+
+# ---- the reference's compiled native twins (oracle/_ref, built by oracle/build_ref.py) ----------------
+def _native():
+    from oracle import ref_native
+    if not ref_native.available():
+        pytest.skip("oracle/_ref is not built (python oracle/build_ref.py, needs /root/reference)")
+    return ref_native
+
+
+@pytest.mark.parametrize("model", ["linear", "power", "gaussian", "exponential", "spherical"])
+def test_oracle_matches_compiled_reference_twin(model):
+    """The numpy restatement vs the reference's own compiled `_c_exec_loop` (cok.pyx:14-96), same inputs."""
+    rn = _native()
+    xyz, val = cases.synth_data(11, 300, 2)
+    pts = cases.synth_points(11, 200, 2, xyz)
+    stored = ko.stored_parameters(model, cases.MODELS[model])
+    for exact in (True, False):
+        z, ss = rn.exec_loop(xyz, pts, val, model, stored, exact_values=exact)
+        zo, so = ko.krige(xyz, val, model, stored, pts, exact_values=exact)
+        assert_parity(zo, z, 1e-8, "z")
+        assert_parity(so, ss, 1e-8, "ss")
+
+
+def test_oracle_moving_window_matches_compiled_reference_twin():
+    """... and `_c_exec_loop_moving_window` (cok.pyx:98-193), 2-D and 3-D."""
+    rn = _native()
+    for dim, k in ((2, 8), (3, 12)):
+        xyz, val = cases.synth_data(12 + dim, 400, dim)
+        pts = cases.synth_points(12 + dim, 150, dim, xyz)
+        stored = ko.stored_parameters("exponential", [1.0, 150.0, 0.05])
+        z, ss = rn.exec_loop_moving_window(xyz, pts, val, "exponential", stored, k)
+        zo, so = ko.krige(xyz, val, "exponential", stored, pts, n_closest_points=k)
+        assert_parity(zo, z, 1e-9, "z")
+        assert_parity(so, ss, 1e-9, "ss")
