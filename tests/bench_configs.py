@@ -1,6 +1,6 @@
 """Time the other BASELINE.json configs on ONE GPU (full data size, points sharded as one slice) and
 spot-check parity against the CPU oracle on a subsample. Prints one JSON line per config.
-    python scripts/bench_configs.py [cfg1 cfg3 cfg4 cfg5 ...] [--frac F]   (F = fraction of the grid to krige)
+    python tests/bench_configs.py [cfg1 cfg3 cfg4 cfg5 ...] [--frac F]   (F = fraction of the grid to krige)
 """
 import json
 import os
@@ -10,7 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # lives under tests/: it checks parity against the oracle
 import cases  # noqa: E402
 import pykrige_b200 as pk  # noqa: E402
 from oracle import krige_oracle as ko  # noqa: E402
