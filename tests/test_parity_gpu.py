@@ -587,3 +587,92 @@ def test_cuda_matches_compiled_reference_twins(pk):
                                         ko.stored_parameters("exponential", [1.0, 150.0, 0.05]), 16)
     assert_parity(z, zr, R64, "knn z vs cok._c_exec_loop_moving_window")
     assert_parity(ss, sr, R64, "knn ss vs cok._c_exec_loop_moving_window")
+
+
+# ---- BASELINE configs 3, 4, 5 at their full data sizes: size-independent properties + oracle subsample ----
+def test_full_size_properties_cfg3(pk):
+    """Config 3 (OK3D, N=8000, gaussian [1, 300, 0.05]) on 4096 random points of the 200x200x50 grid + 16
+    exact hits: linearity in the values, sigma^2 independent of the values, shard concatenation bit for bit,
+    grid call == points call, oracle (full 8001^2 inverse) on a subsample."""
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(1003, 8000, 3)
+    params = [1.0, 300.0, 0.05]
+    gx, gy, gz = np.linspace(0, 1000, 200), np.linspace(0, 1000, 200), np.linspace(0, 250, 50)
+    mk = lambda v: pk.OrdinaryKriging3D(xyz[:, 0], xyz[:, 1], xyz[:, 2], v, variogram_model="gaussian",
+                                        variogram_parameters=params)
+    ok = mk(val)
+    rng = np.random.default_rng(33)
+    pts = np.column_stack([rng.choice(gx, 4096), rng.choice(gy, 4096), rng.choice(gz, 4096)])
+    pts = np.vstack([pts, xyz[:16]])
+    z, ss = ok.execute("points", pts[:, 0], pts[:, 1], pts[:, 2], backend="cuda")
+    z2, ss2 = mk(-2.0 * val + 11.0).execute("points", pts[:, 0], pts[:, 1], pts[:, 2], backend="cuda")
+    assert_allclose(z2, -2.0 * z + 11.0, rtol=1e-8)
+    assert_allclose(ss2, ss, rtol=1e-12, atol=1e-14)
+    assert_allclose(z[-16:], val[:16], rtol=1e-9)                       # exact hits interpolate
+    assert np.all(np.abs(ss[-16:]) < 1e-9)
+    h = ok._ensure_problem()
+    zg, sg = h.execute_grid(gx, gy, gz, None, 777, 5000)               # a slice of the real grid
+    za, sa = h.execute_grid(gx, gy, gz, None, 777, 1234)
+    zb, sb = h.execute_grid(gx, gy, gz, None, 777 + 1234, 5000 - 1234)
+    assert np.array_equal(np.concatenate([za, zb]), zg) and np.array_equal(np.concatenate([sa, sb]), sg)
+    G = ko.grid_points([gx, gy, gz])[777:777 + 5000]
+    zp, sp = ok.execute("points", G[:, 0], G[:, 1], G[:, 2], backend="cuda")
+    assert_allclose(zg, zp, rtol=1e-12)
+    assert_allclose(sg, sp, rtol=1e-10, atol=1e-13)
+    sub = np.r_[0:48, 4096:4112]
+    zo, so = ko.krige(xyz, val, "gaussian", ko.stored_parameters("gaussian", params), pts[sub])
+    assert_parity(z[sub], zo, R64, "cfg3 z")
+    assert_parity(ss[sub], so, R64, "cfg3 ss")
+
+
+def test_full_size_properties_cfg4(pk):
+    """Config 4 (UK regional_linear, N=10000, exponential, fp32 device math): float32 vs float64 device paths
+    within the fp32 tolerance, float64 vs the oracle (10003^2 inverse) on a subsample, drift reproduction
+    (a field that IS a linear trend is returned exactly with zero-mean residual structure)."""
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(1004, 10000, 2)
+    params = [1.0, 300.0, 0.05]
+    uk = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential", variogram_parameters=params,
+                             drift_terms=["regional_linear"])
+    rng = np.random.default_rng(44)
+    pts = np.vstack([rng.uniform(0, 1000, (4096, 2)), xyz[:16]])
+    z64, s64 = uk.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
+    z32, s32 = uk.execute("points", pts[:, 0], pts[:, 1], backend="cuda", dtype="float32")
+    assert_parity(z32, z64, 1e-2, "cfg4 fp32 z")
+    assert_parity(s32, s64, 1e-2, "cfg4 fp32 ss")
+    sub = np.r_[0:32, 4096:4112]
+    zo, so = ko.krige(xyz, val, "exponential", ko.stored_parameters("exponential", params), pts[sub],
+                      regional_linear=True)
+    assert_parity(z64[sub], zo, R64, "cfg4 z")
+    assert_parity(s64[sub], so, R64, "cfg4 ss")
+    trend = 3.0 + 0.01 * xyz[:, 0] - 0.02 * xyz[:, 1]
+    ut = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], trend, variogram_model="exponential", variogram_parameters=params,
+                             drift_terms=["regional_linear"])
+    zt, _ = ut.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
+    assert_allclose(zt, 3.0 + 0.01 * pts[:, 0] - 0.02 * pts[:, 1], rtol=1e-8, atol=1e-8)
+
+
+def test_full_size_properties_cfg5(pk):
+    """Config 5 (OK 2-D, N=100000, k=64 moving window, exponential [1, 50, 0.05]): 4096 grid points + 16
+    exact hits against the oracle's kd-tree + (k+1)^2 solves, shard concatenation bit for bit, linearity."""
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(1005, 100000, 2)
+    params = [1.0, 50.0, 0.05]
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential", variogram_parameters=params)
+    g = np.linspace(0, 1000, 4000)
+    rng = np.random.default_rng(55)
+    pts = np.vstack([np.column_stack([rng.choice(g, 4096), rng.choice(g, 4096)]), xyz[:16]])
+    z, ss = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda", n_closest_points=64)
+    zo, so = ko.krige(xyz, val, "exponential", ko.stored_parameters("exponential", params), pts, n_closest_points=64)
+    assert_parity(z, zo, R64, "cfg5 z")
+    assert_parity(ss, so, R64, "cfg5 ss")
+    h = ok._ensure_problem("float64", knn=True)
+    zg, sg = h.execute_knn_grid(64, g, g, None, 123456, 6000)
+    za, sa = h.execute_knn_grid(64, g, g, None, 123456, 2500)
+    zb, sb = h.execute_knn_grid(64, g, g, None, 123456 + 2500, 3500)
+    assert np.array_equal(np.concatenate([za, zb]), zg) and np.array_equal(np.concatenate([sa, sb]), sg)
+    ok2 = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], 0.5 * val + 4.0, variogram_model="exponential",
+                             variogram_parameters=params)
+    z2, ss2 = ok2.execute("points", pts[:, 0], pts[:, 1], backend="cuda", n_closest_points=64)
+    assert_allclose(z2, 0.5 * z + 4.0, rtol=1e-9)
+    assert_allclose(ss2, ss, rtol=1e-12, atol=1e-14)
