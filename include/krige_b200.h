@@ -53,6 +53,7 @@ extern "C" {
 #define KB200_VG_EXPONENTIAL  3  /* params [psill, range, nugget]     variogram_models.py:48 */
 #define KB200_VG_SPHERICAL    4  /* params [psill, range, nugget]     variogram_models.py:56 */
 #define KB200_VG_HOLE_EFFECT  5  /* params [psill, range, nugget]     variogram_models.py:73 */
+#define KB200_VG_TABLE        6  /* 'custom' / GSTools callables (ok.py:224-253): tabulated by the host, see kb200_set_variogram_table; no params */
 
 /* ---- arithmetic of the big contraction ---------------------------------- */
 #define KB200_F64 0
@@ -212,6 +213,19 @@ int kb200_set_stream(kb200_handle h, void* cuda_stream);
  */
 int  kb200_last_timings(kb200_handle h, double* ms, int n);
 void kb200_reset_counters(kb200_handle h);
+
+/* 'custom' variogram callables and GSTools covariance models (variogram_function f(params, d), ok.py:224-253;
+ * the reference's own native backend refuses them, lib/variogram_models.pyx:20-21). A Python callable cannot
+ * run on the device, so the host samples it once: gamma_nodes[i] = f(params, d_i) at the n_nodes (>= 16)
+ * square-root-spaced distances d_i = dmax * (i / (n_nodes - 1))^2, i = 0 .. n_nodes-1 (dense near 0, where
+ * variograms bend). The device evaluates model KB200_VG_TABLE by cubic Hermite interpolation in sqrt(d)
+ * (<= 3e-12 relative for smooth models at 2^20 nodes). Every distance that the following
+ * problem evaluates must be <= dmax (data-data and data-prediction); the host wrapper sizes dmax from the
+ * bounding boxes. All nodes must be finite (KB200_EBADARG otherwise). The table is copied; it stays
+ * attached to the handle until replaced. Call before kb200_set_problem / kb200_describe_problem /
+ * kb200_set_problem_knn with model = KB200_VG_TABLE (vparams may be NULL, n_vparams = 0).
+ */
+int kb200_set_variogram_table(kb200_handle h, int64_t n_nodes, double dmax, const double* gamma_nodes);
 
 /* pseudo_inv=True (ok.py:156-165,660-661; uk.py:932-933; ok3d.py / uk3d.py likewise): the NEXT
  * kb200_set_problem / kb200_describe_problem on this handle inverts the bordered kriging matrix with a

@@ -28,6 +28,8 @@ EPS = 1.0e-10  # ok.py:177
 # ---- variogram models: variogram_models.py:25-81 ------------------------------------
 def variogram(model, m, d):
     d = np.asarray(d, dtype=np.float64)
+    if callable(model):          # variogram_model='custom': user callable f(params, d), ok.py:247-253
+        return np.asarray(model(m, d), dtype=np.float64)
     if model == "linear":        # variogram_models.py:25-29
         return float(m[0]) * d + float(m[1])
     if model == "power":         # :32-37

@@ -187,17 +187,67 @@ class KrigeBase:
         print("cR =", self.cR)
 
     # ---- the backend='cuda' arm ---------------------------------------------------------
+    TABLE_MODEL_ID = 6          # KB200_VG_TABLE
+    TABLE_NODES = (1 << 20) + 1
+
     def _device_model(self):
-        """model id + stored parameters for the device; custom / GSTools callables have no device
-        twin -> NotImplementedError (the reference's 'C' backend convention, variogram_models.pyx:20-21)."""
+        """model id + stored parameters for the device. Built-in models run as closed forms; a 'custom'
+        callable or a GSTools model (which the reference's native 'C' backend refuses,
+        variogram_models.pyx:20-21) is tabulated by the host and interpolated on the device
+        (KB200_VG_TABLE, include/krige_b200.h: kb200_set_variogram_table)."""
         name = getattr(self.variogram_function, "__name__", None)
         mid = variogram_models.DEVICE_MODEL_IDS.get(name)
         if mid is None or self.variogram_function is not self.variogram_dict.get(self.variogram_model):
-            raise NotImplementedError(
-                "backend='cuda' evaluates the built-in variogram models on the device; "
-                "'custom' / GSTools variogram callables are not supported (no CPU fallback)."
-            )
+            if not callable(self.variogram_function):
+                raise NotImplementedError("backend='cuda' needs a built-in variogram model or a callable f(params, d)")
+            return self.TABLE_MODEL_ID, []
         return mid, [float(v) for v in self.variogram_model_parameters]
+
+    def _adjusted_corners(self, lo, hi):
+        """Corners of the axis-aligned box [lo, hi] (original coordinates) in the adjusted frame."""
+        nd = self._ndim
+        x, y, z, v, center, Mt = self._data_arrays()
+        Mt = np.asarray(Mt, dtype=float).reshape(nd, nd)
+        c = np.asarray(center, dtype=float)
+        corners = np.array(np.meshgrid(*[[lo[k], hi[k]] for k in range(nd)], indexing="ij")).reshape(nd, -1).T
+        return (corners - c) @ Mt.T + c
+
+    def _table_dmax(self, pred_lo=None, pred_hi=None):
+        """Upper bound of every distance the device will evaluate: data-data and data-prediction (the
+        distance between two boxes is largest at a pair of corners; the affine anisotropy map keeps them
+        corners), with head-room for the moving window's local shift gamma(2 d_k)."""
+        if getattr(self, "coordinates_type", "euclidean") == "geographic":
+            return 360.0
+        x, y, z = self._data_arrays()[:3]
+        cols = [x, y] + ([z] if self._ndim == 3 else [])
+        dlo = [float(np.min(c)) for c in cols]
+        dhi = [float(np.max(c)) for c in cols]
+        D = self._adjusted_corners(dlo, dhi)
+        pts = D if pred_lo is None else np.vstack([D, self._adjusted_corners(pred_lo, pred_hi)])
+        span = np.sqrt(((pts[:, None, :] - D[None, :, :]) ** 2).sum(axis=2)).max()
+        need = 2.2 * max(float(span), 1e-300)
+        have = getattr(self, "_kb_table_dmax", 0.0)
+        if need > have:                       # grow geometrically so that moving prediction windows do not re-tabulate
+            self._kb_table_dmax = need if have == 0.0 else max(need, 2.0 * have)
+        return self._kb_table_dmax
+
+    def _variogram_table(self, dmax):
+        """gamma at the sqrt-spaced nodes d_i = dmax (i/(n-1))^2, cached per (callable, parameters, dmax)."""
+        key = (id(self.variogram_function), tuple(np.ravel(np.asarray(self.variogram_model_parameters, dtype=float))),
+               float(dmax))
+        cached = getattr(self, "_kb_table", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        n = self.TABLE_NODES
+        d = dmax * (np.arange(n, dtype=np.float64) / (n - 1)) ** 2
+        with np.errstate(all="ignore"):
+            g = np.asarray(self.variogram_function(self.variogram_model_parameters, d), dtype=np.float64)
+        if g.shape != d.shape:
+            g = np.broadcast_to(g, d.shape).copy()
+        if not np.all(np.isfinite(g)):
+            raise ValueError("the custom variogram function must be finite on [0, %g]" % dmax)
+        self._kb_table = (key, g)
+        return g
 
     def _data_arrays(self):
         """(x, y, z|None, values, center, Mt) in ORIGINAL coordinates."""
@@ -219,6 +269,9 @@ class KrigeBase:
         x, y, z, v, center, Mt = self._data_arrays()
         mid, vp = self._device_model()
         n_rl, cols = self._drift_spec()
+        if mid == self.TABLE_MODEL_ID:      # the table itself is part of the problem
+            vp = ("table", id(self.variogram_function), getattr(self, "_kb_table_dmax", 0.0)) + tuple(
+                np.ravel(np.asarray(self.variogram_model_parameters, dtype=float)))
         return (dtype, knn, mid, tuple(vp), bool(self.exact_values), tuple(np.ravel(Mt)), tuple(center),
                 n_rl, len(cols), x.size, getattr(self, "coordinates_type", "euclidean"),
                 bool(getattr(self, "pseudo_inv", False)))
@@ -229,6 +282,8 @@ class KrigeBase:
         if dt is None:
             raise ValueError("dtype must be 'float64', 'float32' or 'float64x'")
         h = self._cuda_handle()
+        if self._device_model()[0] == self.TABLE_MODEL_ID:
+            self._table_dmax()                  # fixes the tabulated range before it enters the signature
         key = self._problem_signature(dt, knn)
         if self._kb_key == key:
             return h
@@ -238,6 +293,9 @@ class KrigeBase:
         self._kb_key = None
         h.set_coordinates(getattr(self, "coordinates_type", "euclidean") == "geographic")
         h.set_pseudo_inverse(bool(getattr(self, "pseudo_inv", False)) and not knn)
+        if mid == self.TABLE_MODEL_ID:
+            dmax = self._table_dmax()
+            h.set_variogram_table(self._variogram_table(dmax), dmax)
         if knn:
             h.set_problem_knn(self._ndim, x, y, z, v, center, Mt, mid, vp, self.exact_values, self.eps)
         else:
@@ -252,8 +310,10 @@ class KrigeBase:
         host-supplied drift values at the given points, or None.
         Returns flat (z, ss) of length npt in the reference's flattened order."""
         knn = n_closest_points is not None
-        h = self._ensure_problem(dtype, knn)
         nd = self._ndim
+        if self._device_model()[0] == self.TABLE_MODEL_ID and all(np.size(a) for a in axes[:nd]):
+            self._table_dmax([float(np.min(a)) for a in axes[:nd]], [float(np.max(a)) for a in axes[:nd]])
+        h = self._ensure_problem(dtype, knn)
         if style == "points":
             pts = [np.ascontiguousarray(a, dtype=np.float64) for a in axes]
             dv = drift_at(pts, None) if drift_at is not None else None

@@ -35,6 +35,7 @@ EXPORTS = [
     "kb200_blob_bytes", "kb200_blob_ptr", "kb200_describe_problem", "kb200_blob_commit",
     "kb200_set_coordinates", "kb200_set_stream", "kb200_last_timings", "kb200_reset_counters", "kb200_debug_fetch",
     "kb200_experimental_variogram", "kb200_statistics", "kb200_set_pseudo_inverse",
+    "kb200_set_variogram_table",
 ]
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -94,6 +95,7 @@ def load_library():
     lib.kb200_experimental_variogram.argtypes = [h, i32, i64, dp, dp, dp, dp, i32, dp, dp, dp, dp]
     lib.kb200_statistics.argtypes = [h, dp, dp]
     lib.kb200_set_pseudo_inverse.argtypes = [h, i32]
+    lib.kb200_set_variogram_table.argtypes = [h, i64, ctypes.c_double, dp]
     _lib = lib
     return lib
 
@@ -298,6 +300,11 @@ class Handle:
 
     def reset_counters(self):
         self.lib.kb200_reset_counters(self._h)
+
+    def set_variogram_table(self, nodes, dmax):
+        """nodes[i] = gamma at d_i = dmax * (i / (len - 1))**2 (KB200_VG_TABLE, 'custom' callables)."""
+        nodes = _f64(nodes)
+        self._check(self.lib.kb200_set_variogram_table(self._h, nodes.size, float(dmax), _ptr(nodes)))
 
     def set_pseudo_inverse(self, enable):
         self._check(self.lib.kb200_set_pseudo_inverse(self._h, 1 if enable else 0))

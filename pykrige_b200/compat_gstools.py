@@ -1,5 +1,6 @@
 """GSTools interface check (reference: src/pykrige/compat_gstools.py:21-36). GSTools models reach
-the kriging classes as 'custom' callables, which backend='cuda' rejects (NotImplementedError)."""
+the kriging classes as 'custom' callables; backend='cuda' tabulates such callables on the host and
+interpolates them on the device (KB200_VG_TABLE)."""
 
 
 class GSToolsException(Exception):

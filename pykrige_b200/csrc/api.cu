@@ -67,6 +67,9 @@ struct kb200_ctx {
     // knn workspace
     DevBuf kSorted, kCells;
     DevBuf wVario;            // constructor-side helpers (experimental variogram, statistics)
+    DevBuf wTab;              // KB200_VG_TABLE: (value, slope) pairs on the device
+    std::vector<double> htab; // ... and on the host (value, slope interleaved), for the covariance shift
+    double tab_dmax = 0.0; int tab_n = 0;
     KnnParams kp{};
     int k_ncells = 0;
 
@@ -113,7 +116,7 @@ extern "C" void kb200_destroy(kb200_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->blob, &h->wC, &h->wW, &h->wT, &h->wF, &h->wRaw, &h->wFlag, &h->wPart, &h->wAux,
-                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->wScratch, &h->kSorted, &h->kCells, &h->wVario}) b->release();
+                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->wScratch, &h->kSorted, &h->kCells, &h->wVario, &h->wTab}) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -161,12 +164,48 @@ extern "C" int kb200_last_timings(kb200_handle h, double* ms, int n) {
 }
 
 // gamma on the host (only to choose the covariance shift c0)
-static double host_gamma(const VgParams& v, double d) {
+static double host_gamma(const kb200_ctx* h, const VgParams& v, double d) {
     switch (v.model) {
         case KB200_VG_LINEAR: return v.p0 * d + v.p1;
         case KB200_VG_POWER: return v.p0 * std::pow(d, v.p1) + v.p2;
+        case KB200_VG_TABLE: {
+            // same cubic Hermite as kb_gamma<KB200_VG_TABLE>; the largest tabulated value up to d, so that the
+            // shift also covers non-monotone callables
+            if (h->tab_n < 2) return 1.0;
+            const double inv_h = (h->tab_n - 1) / std::sqrt(h->tab_dmax);
+            int last = (int)std::min<double>(h->tab_n - 1, std::ceil(std::sqrt(std::max(d, 0.0)) * inv_h));
+            double g = h->htab[0];
+            for (int i = 0; i <= last; ++i) g = std::max(g, h->htab[2 * (size_t)i]);
+            return g;
+        }
         default: return v.p0 + v.p2;
     }
+}
+
+extern "C" int kb200_set_variogram_table(kb200_handle h, int64_t n_nodes, double dmax, const double* gamma_nodes) {
+    if (!h) return KB200_EBADARG;
+    if (n_nodes < 16 || n_nodes > (1LL << 26) || !gamma_nodes || !(dmax > 0.0) || !std::isfinite(dmax))
+        return fail(h, KB200_EBADARG, "variogram table: 16 <= n_nodes <= 2^26, dmax > 0");
+    const int n = (int)n_nodes;
+    for (int i = 0; i < n; ++i)
+        if (!std::isfinite(gamma_nodes[i])) return fail(h, KB200_EBADARG, "variogram table: the callable must be finite on [0, dmax] (node " + std::to_string(i) + ")");
+    h->described = false; h->ready = false; h->knn_ready = false; h->factor_live = false;
+    // slopes per unit node index: centred differences, second-order one-sided at the two ends
+    h->htab.resize(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        double m;
+        if (i == 0) m = -1.5 * gamma_nodes[0] + 2.0 * gamma_nodes[1] - 0.5 * gamma_nodes[2];
+        else if (i == n - 1) m = 1.5 * gamma_nodes[n - 1] - 2.0 * gamma_nodes[n - 2] + 0.5 * gamma_nodes[n - 3];
+        else m = 0.5 * (gamma_nodes[i + 1] - gamma_nodes[i - 1]);
+        h->htab[2 * (size_t)i] = gamma_nodes[i];
+        h->htab[2 * (size_t)i + 1] = m;
+    }
+    h->tab_n = n; h->tab_dmax = dmax;
+    cudaSetDevice(h->device);
+    CU(h, h->wTab.reserve(h->htab.size() * sizeof(double)));
+    CU(h, cudaMemcpyAsync(h->wTab.p, h->htab.data(), h->htab.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return KB200_OK;
 }
 
 // ---- description (shared by set_problem / describe_problem / set_problem_knn) ----
@@ -182,12 +221,15 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     if (dtype != KB200_F64 && dtype != KB200_F32 && dtype != KB200_F64X)
         return fail(h, KB200_EBADARG, "dtype must be KB200_F64, KB200_F32 or KB200_F64X");
     if (n < 1 || (!knn_only && n > (int64_t)(KB_MAXRB - 1) * KB_BM) || n > (1LL << 30)) return fail(h, KB200_EBADARG, "n out of range");
-    if (!x || !y || (dim == 3 && !z) || !values || !center || !aniso || !vparams)
+    if (!x || !y || (dim == 3 && !z) || !values || !center || !aniso || (!vparams && model != KB200_VG_TABLE))
         return fail(h, KB200_EBADARG, "null input array");
-    if (model < KB200_VG_LINEAR || model > KB200_VG_HOLE_EFFECT)
+    if (model < KB200_VG_LINEAR || model > KB200_VG_TABLE)
         return fail(h, KB200_EUNSUPPORTED, "variogram model has no device implementation");
-    int need = (model == KB200_VG_LINEAR) ? 2 : 3;
-    if (n_vparams != need) return fail(h, KB200_EBADARG, "wrong number of variogram parameters");
+    int need = (model == KB200_VG_TABLE) ? 0 : (model == KB200_VG_LINEAR) ? 2 : 3;
+    if (model == KB200_VG_TABLE) {
+        if (h->tab_n < 16) return fail(h, KB200_ESTATE, "KB200_VG_TABLE: call kb200_set_variogram_table first");
+        if (n_vparams != 0 && !vparams) return fail(h, KB200_EBADARG, "null input array");
+    } else if (n_vparams != need) return fail(h, KB200_EBADARG, "wrong number of variogram parameters");
     if (!(n_rl == 0 || n_rl == dim)) return fail(h, KB200_EBADARG, "n_rl must be 0 or dim");
     if (n_hd < 0 || n_rl + n_hd > KB200_MAX_DRIFT) return fail(h, KB200_EBADARG, "too many drift terms");
     if (n_hd > 0 && !drift_data) return fail(h, KB200_EBADARG, "drift_data is null");
@@ -197,7 +239,9 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     h->dim = h->geo ? KB_GEO : dim; h->dtype = dtype; h->n = (int)n; h->n_rl = n_rl; h->n_hd = n_hd;
     h->K1 = n_rl + n_hd + 1; h->na = h->K1 + 1;
     h->vg.model = model;
-    h->vg.p0 = vparams[0]; h->vg.p1 = vparams[1]; h->vg.p2 = (need == 3) ? vparams[2] : 0.0;
+    h->vg.p0 = need > 0 ? vparams[0] : 0.0; h->vg.p1 = need > 1 ? vparams[1] : 0.0; h->vg.p2 = (need == 3) ? vparams[2] : 0.0;
+    h->vg.tab = h->wTab.as<double2>(); h->vg.tab_n = h->tab_n;
+    h->vg.tab_inv_h = h->tab_n > 1 ? (h->tab_n - 1) / std::sqrt(h->tab_dmax) : 0.0;
     h->vg.eps = eps; h->vg.exact = exact_values ? 1 : 0;
     for (int i = 0; i < 9; ++i) h->an.m[i] = 0.0;
     for (int i = 0; i < dim * dim; ++i) h->an.m[i] = aniso[i];
@@ -230,7 +274,9 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     for (int r = 0; r < 3; ++r) { h->bb_lo[r] = r < sdim ? lo[r] : 0.0; h->bb_hi[r] = r < sdim ? hi[r] : 0.0; }
     double diag2 = 0.0;
     for (int r = 0; r < sdim; ++r) diag2 += (hi[r] - lo[r]) * (hi[r] - lo[r]);
-    double c0 = host_gamma(h->vg, h->geo ? 180.0 : std::sqrt(diag2));
+    if (model == KB200_VG_TABLE && h->tab_dmax < (h->geo ? 180.0 : std::sqrt(diag2)))
+        return fail(h, KB200_EBADARG, "variogram table: dmax is smaller than the extent of the data");
+    double c0 = host_gamma(h, h->vg, h->geo ? 180.0 : std::sqrt(diag2));
     if (!(c0 > 0.0) || !std::isfinite(c0)) c0 = 1.0;
     h->vg.c0 = c0;
     for (int c = 0; c <= KB200_MAX_DRIFT; ++c) { h->ds.shift[c] = 0.0; h->ds.scale[c] = 1.0; }
@@ -366,7 +412,7 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
     // covariance shift: c0 = sill for bounded models; for linear/power grow c0 until C is
     // positive definite. A model that is not a valid variogram in this
     // dimension (e.g. hole-effect in 2-D/3-D) never becomes positive definite.
-    const bool unbounded = (h->vg.model == KB200_VG_LINEAR || h->vg.model == KB200_VG_POWER);
+    const bool unbounded = (h->vg.model == KB200_VG_LINEAR || h->vg.model == KB200_VG_POWER || h->vg.model == KB200_VG_TABLE);
     const int max_try = unbounded ? 5 : 1;
     const double c0_first = h->vg.c0;
     int hflag = 0;

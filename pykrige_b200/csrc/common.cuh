@@ -24,6 +24,10 @@ struct VgParams {
     double c0;           // covariance shift: cov(d) = c0 - gamma(d)
     double eps;          // exact-hit cutoff, ok.py:177
     int exact;           // ok.py:671-672
+    // KB200_VG_TABLE: (value, slope per node) pairs at sqrt-spaced nodes, see kb200_set_variogram_table
+    const double2* tab;
+    double tab_inv_h;    // (n_nodes - 1) / sqrt(dmax)
+    int tab_n;
 };
 
 // Affine anisotropy map (core.py:120-193): adj = Mt (p - c) + c.
@@ -73,7 +77,7 @@ __device__ __forceinline__ void kb_adjust(const Aniso& a, double x, double y, do
 }
 
 // gamma(d) for the six built-in models, variogram_models.py:25-81 (same closed
-// forms; docs/source/variogram_models.rst:8-44).
+// forms; docs/source/variogram_models.rst:8-44), and the tabulated model for custom callables.
 template <int MODEL>
 __device__ __forceinline__ double kb_gamma(const VgParams& v, double d) {
     if (MODEL == KB200_VG_LINEAR) {
@@ -91,6 +95,16 @@ __device__ __forceinline__ double kb_gamma(const VgParams& v, double d) {
             return v.p0 * (1.5 * q - 0.5 * q * q * q) + v.p2;
         }
         return v.p0 + v.p2;
+    } else if (MODEL == KB200_VG_TABLE) {
+        // tabulated callable: cubic Hermite in u = sqrt(d) * (n-1)/sqrt(dmax); one 32-byte read per evaluation
+        const double u = sqrt(d) * v.tab_inv_h;
+        int i = (int)u;
+        i = i > v.tab_n - 2 ? v.tab_n - 2 : i;
+        const double t = u - (double)i;
+        const double2 a = __ldg(v.tab + i), b = __ldg(v.tab + i + 1);
+        const double t2 = t * t, t3 = t2 * t;
+        return (2.0 * t3 - 3.0 * t2 + 1.0) * a.x + (t3 - 2.0 * t2 + t) * a.y
+             + (3.0 * t2 - 2.0 * t3) * b.x + (t3 - t2) * b.y;
     } else {  // hole-effect
         double q = d / (v.p1 / 3.0);
         return v.p0 * (1.0 - (1.0 - q) * exp(-q)) + v.p2;

@@ -481,7 +481,7 @@ static cudaError_t launch_assemble_dim(const VgParams& vg, int n, int n_pad, int
     switch (vg.model) {
 #define KB_CASE(M) case M: assemble_kernel<DIM, M><<<tiles, 256, 0, st>>>(vg, n, n_pad, ld, ax, ay, az, C); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
-        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
 #undef KB_CASE
         default: return cudaErrorInvalidValue;
     }

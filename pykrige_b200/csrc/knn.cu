@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
     compact(k);                                        // ascending distance, first k are the neighbours
     // neighbours -> per-warp arrays (these live outside the region the candidate buffers alias)
     VgParams vg = P.vg;
-    if (MODEL == KB200_VG_LINEAR || MODEL == KB200_VG_POWER) {
-        // unbounded models: local shift c0 = gamma(2 d_k) >= gamma of any neighbour pair
+    if (MODEL == KB200_VG_LINEAR || MODEL == KB200_VG_POWER || MODEL == KB200_VG_TABLE) {
+        // unbounded (or unknown: tabulated) models: local shift c0 = gamma(2 d_k) >= gamma of any neighbour pair
         double dk = sqrt(cd2[k - 1]);
         if (DIM == KB_GEO) dk = 2.0 * asin(fmin(1.0, 0.5 * dk)) * 57.29577951308232;   // chord -> degrees
         double g = kb_gamma<MODEL>(vg, 2.0 * dk);
@@ -497,7 +497,7 @@ static cudaError_t knn_launch_dim(const KnnParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return e; \
         knn_solve_kernel<DIM, M, CHOL><<<grid, wpc * 32, smem, st>>>(p, wpc, per_d); } break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
-        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
 #undef KB_CASE
         default: return cudaErrorInvalidValue;
     }

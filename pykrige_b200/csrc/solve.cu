@@ -526,7 +526,7 @@ static cudaError_t solve_set_attr() {
 cudaError_t kbk_solve_init() {
 #define KB_ATTR(M) KB_CUDA_OK((solve_set_attr<2, M>())); KB_CUDA_OK((solve_set_attr<3, M>())); KB_CUDA_OK((solve_set_attr<KB_GEO, M>()));
     KB_ATTR(KB200_VG_LINEAR) KB_ATTR(KB200_VG_POWER) KB_ATTR(KB200_VG_GAUSSIAN)
-    KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT)
+    KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT) KB_ATTR(KB200_VG_TABLE)
 #undef KB_ATTR
     return cudaSuccess;
 }
@@ -539,7 +539,7 @@ static cudaError_t solve_dim(int dtype, const SolveParams& p, cudaStream_t st) {
     switch (p.vg.model) {
 #define KB_CASE(M) case M: solve_kernel_f64<DIM, M><<<grid, SV_THREADS, sm, st>>>(p); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
-        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
 #undef KB_CASE
         default: return cudaErrorInvalidValue;
     }
@@ -557,7 +557,7 @@ static cudaError_t solve_pt_dim(const SolvePtParams& p, int grid, cudaStream_t s
     switch (p.vg.model) {
 #define KB_CASE(M) case M: solve_kernel_pt<DIM, M><<<grid, PT_THREADS, sm, st>>>(p); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
-        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
 #undef KB_CASE
         default: return cudaErrorInvalidValue;
     }

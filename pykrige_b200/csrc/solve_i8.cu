@@ -383,7 +383,7 @@ static cudaError_t i8_attr() {
 cudaError_t kbk_solve_i8_init() {
 #define KB_ATTR(M) KB_CUDA_OK((i8_attr<2, M>())); KB_CUDA_OK((i8_attr<3, M>())); KB_CUDA_OK((i8_attr<KB_GEO, M>()));
     KB_ATTR(KB200_VG_LINEAR) KB_ATTR(KB200_VG_POWER) KB_ATTR(KB200_VG_GAUSSIAN)
-    KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT)
+    KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT) KB_ATTR(KB200_VG_TABLE)
 #undef KB_ATTR
     return cudaSuccess;
 }
@@ -394,7 +394,7 @@ static cudaError_t i8_dim(const SolvePtParams& p, int grid, cudaStream_t st) {
     switch (p.vg.model) {
 #define KB_CASE(M) case M: solve_kernel_i8<DIM, M><<<grid, I8_THREADS, sm, st>>>(p); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
-        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
 #undef KB_CASE
         default: return cudaErrorInvalidValue;
     }

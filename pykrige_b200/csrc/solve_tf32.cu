@@ -341,7 +341,7 @@ static cudaError_t tf32_attr() {
 cudaError_t kbk_solve_tf32_init() {
 #define KB_ATTR(M) KB_CUDA_OK((tf32_attr<2, M>())); KB_CUDA_OK((tf32_attr<3, M>())); KB_CUDA_OK((tf32_attr<KB_GEO, M>()));
     KB_ATTR(KB200_VG_LINEAR) KB_ATTR(KB200_VG_POWER) KB_ATTR(KB200_VG_GAUSSIAN)
-    KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT)
+    KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT) KB_ATTR(KB200_VG_TABLE)
 #undef KB_ATTR
     return cudaSuccess;
 }
@@ -352,7 +352,7 @@ static cudaError_t tf32_dim(const SolvePtParams& p, int grid, cudaStream_t st) {
     switch (p.vg.model) {
 #define KB_CASE(M) case M: solve_kernel_tf32<DIM, M><<<grid, TF_THREADS, sm, st>>>(p); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
-        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT)
+        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
 #undef KB_CASE
         default: return cudaErrorInvalidValue;
     }

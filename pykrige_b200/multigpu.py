@@ -55,6 +55,9 @@ def prepare_sharded(model, dist=None, src=0, dtype="float64"):
         dt = _cabi.DTYPES[dtype if dtype in _cabi.DTYPES else str(np.dtype(dtype))]
         h.set_coordinates(getattr(model, "coordinates_type", "euclidean") == "geographic")
         h.set_pseudo_inverse(bool(getattr(model, "pseudo_inv", False)))
+        if mid == model.TABLE_MODEL_ID:      # 'custom' callable: every rank tabulates it itself (no broadcast)
+            dmax = model._table_dmax()
+            h.set_variogram_table(model._variogram_table(dmax), dmax)
         h.describe_problem(model._ndim, dt, x, y, z, v, center, Mt, mid, vp, model.exact_values, model.eps,
                            n_rl=n_rl, drift_data=cols if cols else None)
         model._kb_key = None
@@ -72,6 +75,9 @@ def execute_grid_sharded(model, axes, dist=None, dtype="float64"):
     """Krige this rank's contiguous slice of the flattened grid. Returns (z, ss, first, count) with host
     arrays of the slice; concatenating the slices in rank order reproduces the single-GPU result bit
     for bit (per-point arithmetic does not depend on the sharding)."""
+    if model._device_model()[0] == model.TABLE_MODEL_ID:
+        nd = model._ndim                     # the tabulated range must cover the prediction grid (same on every rank)
+        model._table_dmax([float(np.min(a)) for a in axes[:nd]], [float(np.max(a)) for a in axes[:nd]])
     h = prepare_sharded(model, dist, dtype=dtype)
     gx, gy = axes[0], axes[1]
     gz = axes[2] if len(axes) > 2 else None

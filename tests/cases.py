@@ -201,6 +201,8 @@ def make_model(module_ns, case, inp, reference=False):
     xyz, val = inp["data"], inp["values"]
     kw = dict(variogram_model=case["model"], variogram_parameters=list(case["params"]),
               exact_values=case["exact_values"])
+    if case.get("custom"):
+        kw["variogram_function"] = CUSTOM_VARIOGRAMS[case["custom"]][0]
     kw.update(case["ctor"])
     if case["cls"] in ("UK", "UK3D"):
         kw["drift_terms"] = list(case["drift_terms"])
@@ -345,6 +347,43 @@ SCENARIOS.append(_sc("s3d_uk_fit_linear_rl_masked", "UK3D", "sample3d", "masked"
                      ctor=dict(variogram_model="linear", drift_terms=["regional_linear"]), stats=True))
 SCENARIOS.append(_sc("s3d_ok_fit_power_points", "OK3D", "sample3d", "points", ctor=dict(variogram_model="power"),
                      stats=True))
+
+
+# ---- variogram_model='custom' (ok.py:224-253; tests/test_core.py:1837-1911): user callables f(params, d).
+# Callables cannot live in fixtures, so they are named here; reference outputs: tests/golden/ref_custom.npz.
+CUSTOM_VARIOGRAMS = {
+    # the reference's own test function (tests/test_core.py:1840-1841)
+    "log10": (lambda m, d: m[0] * np.log10(d + m[1]) + m[2], [1.0, 1.0, 1.0]),
+    "log10_short": (lambda m, d: m[0] * np.log10(d + m[1]) + m[2], [0.5, 0.05, 1.0]),
+    # nested structure: exponential + spherical + nugget
+    "nested": (lambda m, d: m[0] * (1.0 - np.exp(-d / m[1])) + m[2] * np.where(
+        d <= m[3], 1.5 * d / m[3] - 0.5 * (d / m[3]) ** 3, 1.0) + m[4], [0.6, 50.0, 0.4, 700.0, 0.02]),
+    "sqrt": (lambda m, d: m[0] * np.sqrt(d) + m[1], [0.05, 0.1]),
+    "cubic": (lambda m, d: m[0] * np.where(d < m[1], 7 * (d / m[1]) ** 2 - 8.75 * (d / m[1]) ** 3 + 3.5 * (d / m[1]) ** 5
+                                           - 0.75 * (d / m[1]) ** 7, 1.0) + m[2], [1.0, 450.0, 0.05]),
+}
+
+
+def _cu(name, cls, n, m, seed, fn, **kw):
+    c = _c(name, cls, n, m, seed, "linear", params=list(CUSTOM_VARIOGRAMS[fn][1]), **kw)
+    c["model"] = "custom"
+    c["custom"] = fn
+    return c
+
+
+CUSTOM_CASES = [
+    _cu("custom_ok2d_log10", "OK", 150, 200, 8001, "log10"),
+    _cu("custom_ok2d_log10_short_nonexact", "OK", 120, 150, 8002, "log10_short", exact_values=False),
+    _cu("custom_ok2d_nested_grid_aniso", "OK", 200, 0, 8003, "nested", style="grid", grid=(21, 16, 1),
+        ctor=dict(anisotropy_scaling=1.7, anisotropy_angle=25.0)),
+    _cu("custom_uk2d_sqrt_rl", "UK", 140, 160, 8004, "sqrt", drift_terms=["regional_linear"]),
+    _cu("custom_ok3d_cubic", "OK3D", 160, 150, 8005, "cubic"),
+    _cu("custom_uk3d_nested_rl_masked", "UK3D", 120, 0, 8006, "nested", style="masked", grid=(9, 8, 5),
+        drift_terms=["regional_linear"]),
+    _cu("custom_knn2d_log10_k12", "OK", 400, 200, 8007, "log10", k=12, ref_backend="loop"),
+    _cu("custom_geo_sqrt", "OK", 150, 120, 8008, "sqrt", geographic=True, box=(60.0, 45.0, 1.0),
+        ctor=dict(coordinates_type="geographic")),
+]
 
 
 def scenario_inputs(sc, validation_data):

@@ -32,6 +32,12 @@ def ref_pinv():
 
 
 @pytest.fixture(scope="session")
+def ref_custom():
+    """Reference outputs for variogram_model='custom' callables (make_golden.py custom)."""
+    return np.load(os.path.join(GOLDEN, "ref_custom.npz"))
+
+
+@pytest.fixture(scope="session")
 def ref_scenarios():
     """Reference outputs of the whole-chain scenarios (make_golden.py scenarios)."""
     return np.load(os.path.join(GOLDEN, "ref_scenarios.npz"))

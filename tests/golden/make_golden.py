@@ -12,6 +12,7 @@ Writes
   tests/golden/ref_pinv.npz : (z, sigmasq) of the reference with pseudo_inv=True (redundant data points).
   tests/golden/ref_scenarios.npz : fitted parameters, lags, (z, sigmasq) and statistics of the reference for the
       whole-chain scenarios (no variogram parameters given) on the reference's own small fixtures.
+  tests/golden/ref_custom.npz : (z, sigmasq) of the reference for variogram_model='custom' callables.
   tests/golden/ref_ctor.npz : lags/semivariance of core._initialize_variogram_model and delta/sigma/epsilon
       of core._find_statistics for the constructor-side cases of tests/cases.py.
 The O(N^4) constructor statistics of OK3D/UK/UK3D are patched out; nothing else of the
@@ -91,6 +92,20 @@ def ref_pinv():
     np.savez_compressed(os.path.join(HERE, "ref_pinv.npz"), **out)
 
 
+def ref_custom():
+    """(z, sigmasq) of the reference for variogram_model='custom' callables (tests/cases.py CUSTOM_CASES)."""
+    out = {}
+    for case in cases.CUSTOM_CASES:
+        inp = cases.build_inputs(case)
+        model = cases.make_model(pykrige, case, inp, reference=True)
+        z, ss = cases.run_model(model, case, inp, case["ref_backend"])
+        out[case["name"] + "/z"] = np.asarray(np.ma.getdata(z), dtype=np.float64)
+        out[case["name"] + "/ss"] = np.asarray(np.ma.getdata(ss), dtype=np.float64)
+        out[case["name"] + "/fp"] = np.array([inp["data"].sum(), inp["values"].sum()])
+        print("%-36s z[%s] mean=%.6f ss mean=%.6f" % (case["name"], z.shape, float(np.mean(z)), float(np.mean(ss))))
+    np.savez_compressed(os.path.join(HERE, "ref_custom.npz"), **out)
+
+
 def ref_scenarios():
     """Whole-chain scenarios (fitted variograms) of tests/cases.py SCENARIOS -> ref_scenarios.npz."""
     gold = np.load(os.path.join(HERE, "reference_goldens.npz"))
@@ -149,7 +164,7 @@ def ref_ctor():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios"]
+    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios", "custom"]
     if "goldens" in which:
         reference_goldens()
     if "cases" in which:
@@ -160,3 +175,5 @@ if __name__ == "__main__":
         ref_pinv()
     if "scenarios" in which:
         ref_scenarios()
+    if "custom" in which:
+        ref_custom()

@@ -201,12 +201,26 @@ def test_edge_sizes(pk):
     assert_allclose(ss, so, rtol=1e-10)
 
 
-def test_custom_variogram_not_on_device(pk):
-    xyz, val = cases.synth_data(3, 30, 2)
-    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="custom", variogram_parameters=[1.0, 0.1],
-                            variogram_function=lambda m, d: m[0] * d + m[1])
-    with pytest.raises(NotImplementedError):
-        ok.execute("points", [1.0], [2.0], backend="cuda")
+def test_custom_variogram_runs_on_device(pk):
+    """A 'custom' callable (which the reference's native backend refuses, variogram_models.pyx:20-21) is
+    tabulated by the host and interpolated on the device; a linear callable must agree with the built-in
+    linear model, also far outside the data (the tabulated range follows the prediction points)."""
+    xyz, val = cases.synth_data(3, 300, 2)
+    fn = lambda m, d: m[0] * d + m[1]
+    oc = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="custom", variogram_parameters=[0.004, 0.05],
+                            variogram_function=fn)
+    ob = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="linear", variogram_parameters=[0.004, 0.05])
+    pts = cases.synth_points(3, 200, 2, xyz)
+    far = np.array([[5000.0, -3000.0], [-20000.0, 40000.0]])
+    for P in (pts, far, pts):                               # growing, then re-used tabulated range
+        zc, sc = oc.execute("points", P[:, 0], P[:, 1], backend="cuda")
+        zb, sb = ob.execute("points", P[:, 0], P[:, 1], backend="cuda")
+        assert_parity(zc, zb, 1e-8, "custom linear z")
+        assert_parity(sc, sb, 1e-8, "custom linear ss")
+    with pytest.raises(ValueError):                         # not finite at d = 0
+        bad = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="custom", variogram_parameters=[1.0],
+                                 variogram_function=lambda m, d: m[0] * np.log(d))
+        bad.execute("points", [1.0], [2.0], backend="cuda")
 
 
 def test_intermediates_match_scipy(pk):
@@ -676,3 +690,36 @@ def test_full_size_properties_cfg5(pk):
     z2, ss2 = ok2.execute("points", pts[:, 0], pts[:, 1], backend="cuda", n_closest_points=64)
     assert_allclose(z2, 0.5 * z + 4.0, rtol=1e-9)
     assert_allclose(ss2, ss, rtol=1e-12, atol=1e-14)
+
+
+# ---- variogram_model='custom' on the device (KB200_VG_TABLE) ------------------------------------------------
+CUSTOM_GLOBAL = [c for c in cases.CUSTOM_CASES]
+
+
+@pytest.mark.parametrize("case", CUSTOM_GLOBAL, ids=[c["name"] for c in CUSTOM_GLOBAL])
+def test_custom_variogram_cases_match_reference(pk, case, ref_custom):
+    """User callables f(params, d) (ok.py:224-253) against the imported reference run with the same callable:
+    global OK/UK 2-D/3-D, anisotropy, masked, non-exact, moving window, geographic."""
+    inp, z, ss = _run(pk, case)
+    zr, sr = ref_custom[case["name"] + "/z"], ref_custom[case["name"] + "/ss"]
+    assert z.shape == zr.shape
+    if case["style"] == "masked":
+        keep = ~np.ma.getmaskarray(z)
+        z, ss, zr, sr = np.ma.getdata(z)[keep], np.ma.getdata(ss)[keep], zr[keep], sr[keep]
+    assert_parity(np.ravel(z), np.ravel(zr), R64, "custom z")
+    assert_parity(np.ravel(ss), np.ravel(sr), R64, "custom ss")
+
+
+def test_custom_variogram_other_dtypes(pk, ref_custom):
+    """The tabulated model also feeds the tcgen05 kernels (float32 3xTF32, float64x INT8 slices)."""
+    case = cases.CUSTOM_CASES[0]
+    inp = cases.build_inputs(case)
+    m = cases.make_model(pk, case, inp)
+    P = inp["points"]
+    zr, sr = ref_custom[case["name"] + "/z"], ref_custom[case["name"] + "/ss"]
+    z, ss = m.execute("points", P[:, 0], P[:, 1], backend="cuda", dtype="float64x")
+    assert_parity(z, zr, R64, "custom float64x z")
+    assert_parity(ss, sr, R64, "custom float64x ss")
+    z, ss = m.execute("points", P[:, 0], P[:, 1], backend="cuda", dtype="float32")
+    assert_parity(z, zr, 1e-2, "custom float32 z")
+    assert_parity(ss, sr, 1e-2, "custom float32 ss")
