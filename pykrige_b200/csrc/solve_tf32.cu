@@ -114,7 +114,8 @@ __device__ __forceinline__ float tf_cov_rhs(const VgParams& v, double dd) {
     else if (MODEL == KB200_VG_EXPONENTIAL) g = p0 * (1.0f - expf(-d / (p1 / 3.0f))) + p2;
     else if (MODEL == KB200_VG_SPHERICAL) {
         if (d <= p1) { float q = d / p1; g = p0 * (1.5f * q - 0.5f * q * q * q) + p2; } else g = p0 + p2;
-    } else { float q = d / (p1 / 3.0f); g = p0 * (1.0f - (1.0f - q) * expf(-q)) + p2; }
+    } else if (MODEL == KB200_VG_TABLE) g = (float)kb_gamma<KB200_VG_TABLE>(v, dd);     // tabulated callable (fp64 table)
+    else { float q = d / (p1 / 3.0f); g = p0 * (1.0f - (1.0f - q) * expf(-q)) + p2; }
     return c0 - g;
 }
 
