@@ -929,7 +929,11 @@ extern "C" int kb200_experimental_variogram(kb200_handle h, int dim, int64_t n,
     cudaSetDevice(h->device);
     cudaStream_t st = h->stream;
     const int nn = (int)n, kdim = h->geo ? KB_GEO : dim;
-    const int grid = kbk_ev_grid(nn, 2 * h->num_sms);
+    // persistent CTAs: as many per SM as the (private-bin) shared memory allows, up to 8 — the pair loop is a
+    // chain of shared-memory read-modify-writes and square roots, so it needs warps to hide latency
+    const size_t ev_sm = kbk_ev_smem(nlags, nlags <= kbk_ev_priv_max_lags() ? 1 : 0) + 1024;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / ev_sm));
+    const int grid = kbk_ev_grid(nn, per_sm * h->num_sms);
     // workspace: x | y | z | v | edges | bmin | bmax | part | out
     const size_t o_edges = 4 * (size_t)nn, o_bmin = o_edges + nlags + 1, o_bmax = o_bmin + grid,
                  o_part = o_bmax + grid, o_out = o_part + (size_t)grid * 3 * nlags, total = o_out + 3 * (size_t)nlags;

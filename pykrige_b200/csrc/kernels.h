@@ -139,6 +139,8 @@ size_t      kbk_knn_smem_per_warp(int k, int chol);
 // variogram.cu: constructor-side kernels (experimental variogram binning, cross-validation residuals)
 cudaError_t kbk_ev_init();
 int         kbk_ev_grid(int n, int num_sms);
+size_t      kbk_ev_smem(int nlags, int priv);
+int         kbk_ev_priv_max_lags();
 cudaError_t kbk_ev_minmax(int dim, int n, const double* x, const double* y, const double* z, int grid,
                           double* bmin, double* bmax, cudaStream_t st);
 cudaError_t kbk_ev_bin(int dim, int n, const double* x, const double* y, const double* z, const double* v,
