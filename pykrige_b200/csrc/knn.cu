@@ -102,7 +102,7 @@ __device__ __forceinline__ void warp_bitonic(double* d2, int* id, const int* __r
 //               re-runs the launch with CHOL = false.
 // CHOL = false: LU with partial pivoting on the full k x k block (dgesv semantics, cok.pyx:165-174).
 template <int DIM, int MODEL, bool CHOL>
-__global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ KnnParams P, int warps_per_cta,
+__global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ KnnParams P, int warps_per_cta,
                                                          int per_warp_doubles) {
     extern __shared__ __align__(16) double ksm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
     double* base = ksm + (size_t)warp * per_warp_doubles;
     double* A = base;                          // k * S  (aliased by the candidate buffers during the search)
     const int kp = CHOL ? ((k + 31) & ~31) : k;      // padded system size of the blocked Cholesky
-    size_t a_doubles = CHOL ? (size_t)(kp / 32) * (kp / 32 + 1) / 2 * (32 * 33) : (size_t)k * S;
+    // blocked Cholesky: off-diagonal blocks 32 x 33, diagonal blocks packed (528) — keep in step with kbk_knn_smem_per_warp
+    size_t a_doubles = CHOL ? (size_t)(kp / 32) * (kp / 32 - 1) / 2 * (32 * 33) + (size_t)(kp / 32) * 528 : (size_t)k * S;
     size_t cand_doubles = KN_CAP + KN_CAP / 2; // d2[CAP] doubles + id[CAP] ints
     size_t off = a_doubles > cand_doubles ? a_doubles : cand_doubles;
     double* rc = base + off;                   // rhs c (becomes C^-1 c)
@@ -247,7 +248,11 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
         // Blocks (bi, bj), bj <= bi, live in shared memory with row stride 33 (conflict-free for lane = row
         // and for lane = column walks). Rows/cols >= k are identity padding with zero right-hand sides.
         const int nbk = (k + 31) >> 5;
-#define KN_BLK(bi, bj) (A + (size_t)((bi) * ((bi) + 1) / 2 + (bj)) * (32 * 33))
+// off-diagonal blocks: 32 x 33 (padded rows); diagonal blocks: packed lower triangle, row r at r(r+1)/2
+// (528 doubles; r(r+1)/2 mod 16 is a permutation of 0..15 within each half-warp, so lane = row walks of one
+// column stay bank-conflict-free). 30 % less shared memory per point = 10 instead of 7 points in flight per SM.
+#define KN_BLK(bi, bj) (A + (size_t)((bi) * ((bi) - 1) / 2) * 1056 + (size_t)(bi) * 528 + (size_t)(bj) * 1056)
+#define KN_TRI(r) ((r) * ((r) + 1) / 2)
         for (int bi = 0; bi < nbk; ++bi)
             for (int bj = 0; bj <= bi; ++bj) {
                 double* blk = KN_BLK(bi, bj);
@@ -261,7 +266,8 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
                         double d = kb_dist<DIM>(nx[i], ny[i], nz[i], nx[j], ny[j], nz[j]);
                         v = vg.c0 - kb_gamma<MODEL>(vg, d);
                     }
-                    blk[li * 33 + lj] = v;
+                    if (bi != bj) blk[li * 33 + lj] = v;
+                    else if (lj <= li) blk[KN_TRI(li) + lj] = v;
                 }
             }
         __syncwarp();
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
             double* Dbb = KN_BLK(b, b);
             double d[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) d[c] = Dbb[lane * 33 + c];
+            for (int c = 0; c < 32; ++c) d[c] = (c <= lane) ? Dbb[KN_TRI(lane) + c] : 0.0;
             double dinv = 1.0;
 #pragma unroll
             for (int pc = 0; pc < 32; ++pc) {
@@ -285,7 +291,7 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
                 for (int c = pc + 1; c < 32; ++c) d[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), d[c]);
             }
 #pragma unroll
-            for (int c = 0; c < 32; ++c) Dbb[lane * 33 + c] = d[c];
+            for (int c = 0; c < 32; ++c) if (c <= lane) Dbb[KN_TRI(lane) + c] = d[c];
             // forward substitution of both right-hand sides for this block (lane r <-> entry b*32 + r)
             double yc = rc[b * 32 + lane], y1 = r1[b * 32 + lane];
 #pragma unroll
@@ -337,7 +343,8 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
                         double acc = 0.0;
 #pragma unroll
                         for (int pc = 0; pc < 32; ++pc) acc = fma(xi[pc], __shfl_sync(0xffffffffu, xj[pc], c), acc);
-                        Aij[lane * 33 + c] -= acc;
+                        if (bj != bi) Aij[lane * 33 + c] -= acc;
+                        else if (c <= lane) Aij[KN_TRI(lane) + c] -= acc;      // diagonal target: packed lower triangle
                     }
                 }
             }
@@ -360,13 +367,13 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
                 }
             }
             const double* Dbb = KN_BLK(b, b);
-            const double dinv = 1.0 / Dbb[lane * 33 + lane];
+            const double dinv = 1.0 / Dbb[KN_TRI(lane) + lane];
 #pragma unroll 4
             for (int pc = 31; pc >= 0; --pc) {
                 const double ip = __shfl_sync(0xffffffffu, dinv, pc);
                 const double xc = __shfl_sync(0xffffffffu, yc, pc) * ip;
                 const double x1 = __shfl_sync(0xffffffffu, y1, pc) * ip;
-                const double lpq = Dbb[pc * 33 + lane];      // L[pc][lane]
+                const double lpq = Dbb[KN_TRI(pc) + lane];   // L[pc][lane] (lane <= pc; unused otherwise, still in range)
                 if (lane == pc) { yc = xc; y1 = x1; }
                 else if (lane < pc) { yc = fma(-lpq, xc, yc); y1 = fma(-lpq, x1, y1); }
             }
@@ -375,6 +382,7 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
             __syncwarp();
         }
 #undef KN_BLK
+#undef KN_TRI
     } else {
     // ---------------- K5: local system ----------------
     // C[i][j] = c0 - gamma(|x_i - x_j|), C[i][i] = c0   (ok.py:641-644 in covariance form)
@@ -479,14 +487,15 @@ __global__ void __launch_bounds__(256) knn_solve_kernel(const __grid_constant__ 
 size_t kbk_knn_smem_per_warp(int k, int chol) {
     size_t S = (size_t)(k | 1);
     size_t kp = chol ? (size_t)((k + 31) & ~31) : (size_t)k;
-    size_t a = chol ? (kp / 32) * (kp / 32 + 1) / 2 * (32 * 33) : (size_t)k * S, c = KN_CAP + KN_CAP / 2;
+    size_t nb = kp / 32;
+    size_t a = chol ? nb * (nb - 1) / 2 * (32 * 33) + nb * 528 : (size_t)k * S, c = KN_CAP + KN_CAP / 2;
     return ((a > c ? a : c) + 7 * kp + 2) * sizeof(double);
 }
 
 template <int DIM, bool CHOL>
 static cudaError_t knn_launch_dim(const KnnParams& p, cudaStream_t st) {
     size_t per = kbk_knn_smem_per_warp(p.k, CHOL ? 1 : 0);
-    int wpc = (int)std::min<size_t>(8, (220 * 1024) / per);       // as many points in flight per SM as fit
+    int wpc = (int)std::min<size_t>(10, (220 * 1024) / per);      // as many points in flight per SM as fit (<= 320 threads)
     if (wpc < 1) return cudaErrorInvalidValue;
     size_t smem = per * wpc;
     unsigned grid = (unsigned)((p.m + wpc - 1) / wpc);
