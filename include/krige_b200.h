@@ -89,7 +89,9 @@ int  kb200_version(void);
  *  center[dim]    anisotropy centre (XCENTER, YCENTER[, ZCENTER])                 ok.py:278-279
  *  aniso[dim*dim] row-major matrix Mt = stretch @ rot of core._adjust_for_anisotropy  core.py:148-189
  *                 (adjusted = Mt @ (p - center) + center); identity when isotropic
- *  model          KB200_VG_*,  vparams: the reference's *stored* parameter list (psill form)
+ *  model          KB200_VG_*,  vparams: the reference's *stored* parameter list (psill form);
+ *                 KB200_VG_TABLE: no parameters (vparams may be NULL, n_vparams = 0), the table set by
+ *                 kb200_set_variogram_table is used
  *  exact_values   ok.py:671-672 semantics;  eps: |d| <= eps counts as an exact hit (ok.py:177)
  *  n_rl           0, or dim: regional-linear drift columns built on device from the adjusted coordinates
  *                 (uk.py:877-883, uk3d.py:708-717)
