@@ -201,3 +201,35 @@ def test_fitted_variogram_matches_reference(sc, ref_scenarios, ref_goldens):
     assert_allclose(m.semivariance, ref_scenarios[sc["name"] + "/semi"], rtol=1e-10)
     pr = ref_scenarios[sc["name"] + "/params"]
     assert_allclose(m.variogram_model_parameters, pr, rtol=1e-6, atol=1e-7 * np.abs(pr).max())
+
+
+# ---- 'custom' callables: host-side tabulation helpers (the device interpolation is in the GPU tests) ----
+def test_custom_variogram_table_helpers():
+    xyz, val = cases.synth_data(3, 60, 2)
+    fn = lambda m, d: m[0] * np.log10(d + m[1]) + m[2]
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="custom", variogram_parameters=[1.0, 1.0, 1.0],
+                            variogram_function=fn, anisotropy_scaling=2.0, anisotropy_angle=30.0)
+    mid, vp = ok._device_model()
+    assert mid == ok.TABLE_MODEL_ID == 6 and vp == []
+    d0 = ok._table_dmax()
+    # covers every data-data distance in the ADJUSTED frame with head-room
+    A = np.column_stack((ok.X_ADJUSTED, ok.Y_ADJUSTED))
+    span = np.sqrt(((A[:, None, :] - A[None, :, :]) ** 2).sum(-1)).max()
+    assert d0 >= 2.0 * span
+    assert ok._table_dmax() == d0                                   # stable
+    d1 = ok._table_dmax([-5000.0, -5000.0], [9000.0, 9000.0])       # far prediction window: grows
+    assert d1 > d0 and ok._table_dmax([0.0, 0.0], [10.0, 10.0]) == d1   # and never shrinks
+    g = ok._variogram_table(d1)
+    n = ok.TABLE_NODES
+    assert g.shape == (n,) and g[0] == fn([1.0, 1.0, 1.0], 0.0)
+    assert_allclose(g[-1], fn([1.0, 1.0, 1.0], d1), rtol=1e-14)
+    i = n // 3
+    assert_allclose(g[i], fn([1.0, 1.0, 1.0], d1 * (i / (n - 1)) ** 2), rtol=1e-14)   # sqrt-spaced nodes
+    assert ok._variogram_table(d1) is g                              # cached per (callable, parameters, dmax)
+    bad = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="custom", variogram_parameters=[1.0],
+                             variogram_function=lambda m, d: m[0] * np.log(d))
+    with pytest.raises(ValueError):
+        bad._variogram_table(100.0)
+    # built-in models keep their closed forms
+    lin = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="linear", variogram_parameters=[0.01, 0.1])
+    assert lin._device_model() == (0, [0.01, 0.1])
