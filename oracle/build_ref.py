@@ -10,7 +10,7 @@ restatement and the CUDA path against the reference's compiled code, and by benc
 Outputs go only into oracle/_ref/ (git-ignored, NOT gpurun-ignored: the .so files travel to the GPU box,
 where /root/reference does not exist):
 
-    oracle/_ref/build/*.c                       Cython-generated C (derived files, not committed)
+    oracle/_ref/build/*.c                       Cython-generated C, deleted again after compilation
     oracle/_ref/pykrige/lib/{cok,variogram_models}.<abi>.so
     oracle/_ref/pykrige/__init__.py, lib/__init__.py   empty package markers written by this script
 
@@ -58,6 +58,11 @@ def build(force=False):
                "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION"]
         cmd += ["-I" + i for i in inc] + [c_file, "-o", os.path.join(pdir, m + suffix)]
         subprocess.check_call(cmd)
+        os.remove(c_file)              # the generated C quotes the .pyx lines in comments: keep only the binary
+    try:
+        os.rmdir(bdir)
+    except OSError:
+        pass
     return built()
 
 
