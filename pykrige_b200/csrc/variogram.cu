@@ -228,21 +228,20 @@ cudaError_t kbk_ev_bin(int dim, int n, const double* x, const double* y, const d
 template <int DIM>
 __global__ void stats_dup_kernel(int n, const double* __restrict__ ax, const double* __restrict__ ay,
                                  const double* __restrict__ az, int* __restrict__ dup) {
+    // blockIdx.x: 256 rows i; blockIdx.y: one 256-column chunk of the candidates j < i (dup[] starts at 0)
     __shared__ double sx[256], sy[256], sz[256];
     const int i = blockIdx.x * 256 + threadIdx.x;
+    const int j0 = blockIdx.y * 256;
+    if (j0 > blockIdx.x * 256 + 255) return;            // chunk entirely above the diagonal (block-uniform)
     const double xi = i < n ? ax[i] : 0.0, yi = i < n ? ay[i] : 0.0, zi = i < n ? az[i] : 0.0;
+    const int j = j0 + threadIdx.x;
+    sx[threadIdx.x] = j < n ? ax[j] : 0.0; sy[threadIdx.x] = j < n ? ay[j] : 0.0; sz[threadIdx.x] = j < n ? az[j] : 0.0;
+    __syncthreads();
     int hit = 0;
-    const int jmax = min(n, blockIdx.x * 256 + 256);
-    for (int j0 = 0; j0 < jmax; j0 += 256) {
-        __syncthreads();
-        const int j = j0 + threadIdx.x;
-        sx[threadIdx.x] = j < n ? ax[j] : 0.0; sy[threadIdx.x] = j < n ? ay[j] : 0.0; sz[threadIdx.x] = j < n ? az[j] : 0.0;
-        __syncthreads();
-        const int je = min(256, min(n, i) - j0);
-        for (int q = 0; q < je; ++q)
-            if (fabs(kb_dist<DIM>(xi, yi, zi, sx[q], sy[q], sz[q])) <= 1e-10) hit = 1;
-    }
-    if (i < n) dup[i] = hit;
+    const int je = min(256, min(n, i) - j0);
+    for (int q = 0; q < je; ++q)
+        if (fabs(kb_dist<DIM>(xi, yi, zi, sx[q], sy[q], sz[q])) <= 1e-10) hit = 1;
+    if (i < n && hit) atomicOr(&dup[i], 1);
 }
 
 __global__ void __launch_bounds__(1024) stats_kernel(int n, const double* __restrict__ L, int ld,
@@ -279,11 +278,14 @@ __global__ void __launch_bounds__(1024) stats_kernel(int n, const double* __rest
 cudaError_t kbk_statistics(int dim, int n, const double* ax, const double* ay, const double* az,
                            const double* L, int ld, const double* u, const double* zeta, int* dup,
                            double* delta, double* sigma, cudaStream_t st) {
-    const int g = (n + 255) / 256;
+    const int gb = (n + 255) / 256;
+    const dim3 g(gb, gb);
+    cudaError_t e = cudaMemsetAsync(dup, 0, (size_t)n * sizeof(int), st);
+    if (e != cudaSuccess) return e;
     if (dim == KB_GEO) stats_dup_kernel<KB_GEO><<<g, 256, 0, st>>>(n, ax, ay, az, dup);
     else if (dim == 3) stats_dup_kernel<3><<<g, 256, 0, st>>>(n, ax, ay, az, dup);
     else stats_dup_kernel<2><<<g, 256, 0, st>>>(n, ax, ay, az, dup);
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     stats_kernel<<<1, 1024, 0, st>>>(n, L, ld, u, zeta, dup, delta, sigma);
     return cudaGetLastError();
