@@ -233,3 +233,29 @@ def test_custom_variogram_table_helpers():
     # built-in models keep their closed forms
     lin = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="linear", variogram_parameters=[0.01, 0.1])
     assert lin._device_model() == (0, [0.01, 0.1])
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/krige_b200.h has a ctypes binding with the same number of parameters and
+    compatible kinds (pointer / integer / double) — ABI drift between the header and pykrige_b200/_cabi.py
+    would otherwise only show up as memory corruption on the GPU box."""
+    lib = _cabi.load_library()
+    text = open(os.path.join(ROOT, "include", "krige_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\n\s*(?:int64_t|int|void\s*\*|const char\s*\*|void)\s*\*?\s*(kb200_\w+)\s*\(([^;]*?)\)\s*;", text)
+    assert len(protos) >= 25
+    for name, params in protos:
+        fn = getattr(lib, name)
+        plist = [p.strip() for p in params.replace("\n", " ").split(",") if p.strip() and p.strip() != "void"]
+        if fn.argtypes is None:
+            assert name in ("kb200_version",), name
+            continue
+        assert len(fn.argtypes) == len(plist), (name, len(fn.argtypes), plist)
+        for ct, decl in zip(fn.argtypes, plist):
+            is_ptr = "*" in decl or "kb200_handle" in decl
+            if is_ptr:
+                assert ct in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(ct, ctypes._Pointer), (name, decl, ct)
+            elif decl.startswith("double"):
+                assert ct is ctypes.c_double, (name, decl, ct)
+            else:
+                assert ct in (ctypes.c_int, ctypes.c_int64), (name, decl, ct)
