@@ -58,8 +58,11 @@ extern "C" {
 /* ---- arithmetic of the big contraction ---------------------------------- */
 #define KB200_F64 0
 #define KB200_F32 1   /* factorisation stays fp64; contraction in 3xTF32 on tcgen05 (fp32-class accuracy) */
-#define KB200_F64X 2  /* fp64-class contraction on the INT8 tensor cores: error-free 6x7-bit slicing, exact int32
-                         accumulation (tcgen05 kind::i8), fp64 recombination; agrees with KB200_F64 to ~1e-10 */
+#define KB200_F64X 2  /* fp64-class contraction on the INT8 tensor cores: error-free slicing into 6 signed slices (41 bits),
+                         exact int32 accumulation (tcgen05 kind::i8), exact int64 recombination; agrees with KB200_F64
+                         to ~1e-10 */
+#define KB200_F64X5 3 /* the same with 5 slices (34 bits, 15 instead of 21 MMAs per k-step) */
+#define KB200_F64X4 4 /* the same with 4 slices (27 bits, 10 MMAs per k-step): between float32 and float64 */
 
 /* ---- coordinates (ok.py:292-318) -------------------------------------------- */
 #define KB200_EUCLIDEAN  0
@@ -82,7 +85,7 @@ int  kb200_version(void);
  * (ok.py:626-648,663; uk.py:861-920,935).
  *
  *  dim            2 or 3
- *  dtype          KB200_F64 (DMMA) / KB200_F32 (tcgen05 3xTF32) / KB200_F64X (tcgen05 INT8 slices, fp64-class)
+ *  dtype          KB200_F64 (DMMA) / KB200_F32 (tcgen05 3xTF32) / KB200_F64X, KB200_F64X5, KB200_F64X4 (tcgen05 INT8 slices)
  *  n              number of data points
  *  x,y,z          host, length n, ORIGINAL (un-adjusted) coordinates; z may be NULL when dim==2
  *  values         host, length n (self.Z / self.VALUES)
@@ -111,7 +114,8 @@ int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
 /*
  * Krige explicit points (style='points', and 'masked' after compaction).
  *   px,py,pz   host, length m, ORIGINAL coordinates (anisotropy is applied on device, ok.py:880-885)
- *   drift_pts  host, column-major m x n_hd values of the host-supplied drift terms at the points (or NULL)
+ *   drift_pts  host, column-major m x (n_hd - n_dev) values of the host-supplied drift terms at the points (or NULL);
+ *              the first n_dev drift terms are evaluated on the device when kb200_set_device_drift described them
  *   z_out, ss_out  host, length m  (zvalues, sigmasq of ok.py:680-681)
  */
 int kb200_execute_points(kb200_handle h, int64_t m,
@@ -196,6 +200,73 @@ int kb200_describe_problem(kb200_handle h, int dim, int dtype, int64_t n,
                            int exact_values, double eps,
                            int n_rl, int n_hd, const double* drift_data);
 int kb200_blob_commit(kb200_handle h);
+
+/*
+ * Drift terms evaluated at the prediction points ON THE DEVICE (universal kriging, 2-D): the point-logarithmic
+ * terms -strength * log(distance to the well), log(0) -> -100 (uk.py:884-896, 955-966) and the external-Z term
+ * sampled from a raster with the reference's bilinear rule incl. its on-node / on-line cases (uk.py:512-628,
+ * 967-971). They are the FIRST n_wells + (raster ? 1 : 0) of the n_hd drift columns of every following
+ * kb200_set_problem / kb200_describe_problem on this handle (the reference's column order, uk.py:884-900); their
+ * values at the DATA points still arrive in drift_data, their values at the prediction points are no longer part
+ * of drift_pts. n_wells = 0 and ext_nx = ext_ny = 0 switch the feature off.
+ *   wells      host, [n_wells][3]: well x, y in the ADJUSTED frame (uk.py:458-467) and strength
+ *   ext_x/y    host raster axes (length ext_nx / ext_ny), ext_z host raster [ext_ny][ext_nx]; sampled at the
+ *              ORIGINAL prediction coordinates; the caller checks that the raster covers the prediction domain
+ *              (uk.py:545-551 raises ValueError). Arrays are copied.
+ */
+int kb200_set_device_drift(kb200_handle h, int n_wells, const double* wells,
+                           int64_t ext_nx, int64_t ext_ny, const double* ext_x, const double* ext_y,
+                           const double* ext_z);
+
+/*
+ * Single-process multi-GPU: a group of handles on n_gpus devices of this box (devices = NULL:
+ * 0 .. n_gpus-1) behind ONE call from ONE host thread — what execute(..., backend='cuda', n_gpus=G) binds.
+ * kb200_group_set_problem: device 0 assembles and factors, the factor blob is copied to the peers over NVLink
+ * (cudaMemcpyPeerAsync), no other transfer. kb200_group_execute_*: the work list is cut into n_gpus contiguous
+ * blocks of the reference's flattened point order (ok.py:864-866); every device kriges its block and writes it
+ * into the caller's z_out / ss_out at its offset, so the result equals the single-GPU result bit for bit.
+ * Arguments as in the single-handle calls. Configuration that precedes a problem description
+ * (kb200_set_coordinates, kb200_set_pseudo_inverse, kb200_set_variogram_table, kb200_set_device_drift) is applied
+ * per member through kb200_group_member(). Errors: the code of the first failing member;
+ * kb200_group_last_error names the device.
+ */
+typedef struct kb200_group_ctx* kb200_group;
+int  kb200_group_create(kb200_group* out, int n_gpus, const int* devices);
+void kb200_group_destroy(kb200_group g);
+const char* kb200_group_last_error(kb200_group g);
+int  kb200_group_size(kb200_group g);
+kb200_handle kb200_group_member(kb200_group g, int i);       /* borrowed; destroyed with the group */
+int kb200_group_set_problem(kb200_group g, int dim, int dtype, int64_t n,
+                            const double* x, const double* y, const double* z,
+                            const double* values,
+                            const double* center, const double* aniso,
+                            int model, const double* vparams, int n_vparams,
+                            int exact_values, double eps,
+                            int n_rl, int n_hd, const double* drift_data);
+int kb200_group_set_problem_knn(kb200_group g, int dim, int64_t n,
+                                const double* x, const double* y, const double* z,
+                                const double* values,
+                                const double* center, const double* aniso,
+                                int model, const double* vparams, int n_vparams,
+                                int exact_values, double eps);
+int kb200_group_execute_points(kb200_group g, int64_t m,
+                               const double* px, const double* py, const double* pz,
+                               const double* drift_pts,
+                               double* z_out, double* ss_out);
+int kb200_group_execute_grid(kb200_group g,
+                             int64_t nx, int64_t ny, int64_t nz,
+                             const double* gx, const double* gy, const double* gz,
+                             const double* drift_pts,
+                             int64_t first, int64_t count,
+                             double* z_out, double* ss_out);
+int kb200_group_execute_knn_points(kb200_group g, int k, int64_t m,
+                                   const double* px, const double* py, const double* pz,
+                                   double* z_out, double* ss_out);
+int kb200_group_execute_knn_grid(kb200_group g, int k,
+                                 int64_t nx, int64_t ny, int64_t nz,
+                                 const double* gx, const double* gy, const double* gz,
+                                 int64_t first, int64_t count,
+                                 double* z_out, double* ss_out);
 
 /* Select the coordinate type of the NEXT kb200_set_problem / kb200_set_problem_knn / kb200_describe_problem
  * call (default KB200_EUCLIDEAN). Geographic mode requires dim == 2 and no drift terms; anisotropy is ignored,

@@ -251,36 +251,50 @@ def krige(data_xyz, values, model, plist_stored, points, *, scaling=None, angle=
     return exec_vector(a, P, Q, np.asarray(values, float), model, plist_stored, exact_values, pcols, pseudo_inv)
 
 
-def krige_chunked(data_xyz, values, model, plist_stored, points, chunk=20000, **kw):
-    """Same as krige() for the global path but inverts once and streams the points in chunks, so
-    large M never materialises M x N (SURVEY F3/F7). Used by bench.py's CPU baseline."""
-    data_xyz = np.asarray(data_xyz, dtype=np.float64)
-    points = np.asarray(points, dtype=np.float64)
-    dim = data_xyz.shape[1]
-    center = (data_xyz.max(axis=0) + data_xyz.min(axis=0)) / 2.0
-    scaling = kw.get("scaling") or [1.0] * (dim - 1)
-    angle = kw.get("angle") or [0.0] * (2 * dim - 3)
-    exact = kw.get("exact_values", True)
-    P = adjust_for_anisotropy(data_xyz, center, scaling, angle)
-    dcols = [P[:, c] for c in range(dim)] if kw.get("regional_linear") else []
-    a = kriging_matrix(P, model, plist_stored, dcols)
-    a_inv = scipy.linalg.inv(a)
-    n, K = P.shape[0], len(dcols)
-    vals = np.asarray(values, float)
-    z = np.empty(points.shape[0])
-    ss = np.empty(points.shape[0])
-    for s in range(0, points.shape[0], chunk):
-        Q = adjust_for_anisotropy(points[s:s + chunk], center, scaling, angle)
-        bd = cdist(Q, P, "euclidean")
+class PreparedKriging:
+    """The reference's global path with the set-up (matrix + scipy.linalg.inv, ok.py:626-648,663) done once and
+    the inverse x RHS step (ok.py:665-681) applied to any number of point slabs — what one execute() call does,
+    cut so that M x N never materialises. Used by krige_chunked and by bench.py's CPU arm."""
+
+    def __init__(self, data_xyz, values, model, plist_stored, *, scaling=None, angle=None, regional_linear=False,
+                 exact_values=True):
+        data_xyz = np.asarray(data_xyz, dtype=np.float64)
+        self.dim = data_xyz.shape[1]
+        self.center = (data_xyz.max(axis=0) + data_xyz.min(axis=0)) / 2.0
+        self.scaling = scaling or [1.0] * (self.dim - 1)
+        self.angle = angle or [0.0] * (2 * self.dim - 3)
+        self.exact = exact_values
+        self.model, self.m = model, plist_stored
+        self.P = adjust_for_anisotropy(data_xyz, self.center, self.scaling, self.angle)
+        dcols = [self.P[:, c] for c in range(self.dim)] if regional_linear else []
+        self.K = len(dcols)
+        self.vals = np.asarray(values, float)
+        self.a_inv = scipy.linalg.inv(kriging_matrix(self.P, model, plist_stored, dcols))
+
+    def krige(self, points):
+        n, K = self.P.shape[0], self.K
+        Q = adjust_for_anisotropy(np.asarray(points, dtype=np.float64), self.center, self.scaling, self.angle)
+        bd = cdist(Q, self.P, "euclidean")
         b = np.ones((Q.shape[0], n + K + 1))
-        b[:, :n] = -variogram(model, plist_stored, bd)
-        if exact:
+        b[:, :n] = -variogram(self.model, self.m, bd)
+        if self.exact:
             b[:, :n][np.absolute(bd) <= EPS] = 0.0
         for c in range(K):
             b[:, n + c] = Q[:, c]
-        x = a_inv @ b.T
-        z[s:s + chunk] = x[:n, :].T @ vals
-        ss[s:s + chunk] = -np.einsum("ij,ji->i", b, x)
+        x = self.a_inv @ b.T
+        return x[:n, :].T @ self.vals, -np.einsum("ij,ji->i", b, x)
+
+
+def krige_chunked(data_xyz, values, model, plist_stored, points, chunk=20000, **kw):
+    """Same as krige() for the global path but inverts once and streams the points in chunks, so
+    large M never materialises M x N (SURVEY F3/F7). Used by bench.py's CPU baseline."""
+    points = np.asarray(points, dtype=np.float64)
+    pk = PreparedKriging(data_xyz, values, model, plist_stored, scaling=kw.get("scaling"), angle=kw.get("angle"),
+                         regional_linear=bool(kw.get("regional_linear")), exact_values=kw.get("exact_values", True))
+    z = np.empty(points.shape[0])
+    ss = np.empty(points.shape[0])
+    for s in range(0, points.shape[0], chunk):
+        z[s:s + chunk], ss[s:s + chunk] = pk.krige(points[s:s + chunk])
     return z, ss
 
 

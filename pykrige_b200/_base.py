@@ -257,13 +257,36 @@ class KrigeBase:
         """(n_rl, [host drift data columns])"""
         return 0, []
 
-    def _cuda_handle(self):
+    def _cuda_handle(self, n_gpus=None):
+        """The C-ABI executor of this model: one kb200 handle (default) or, for n_gpus > 1, a kb200_group of
+        handles on devices 0..n_gpus-1 driven by this host thread."""
+        if n_gpus is not None and int(n_gpus) > 1:
+            g = getattr(self, "_kb_group", None)
+            if g is None or g.size != int(n_gpus):
+                if g is not None:
+                    g.close()
+                g = _cabi.Group(int(n_gpus))
+                self._kb_group = g
+                self._kb_gkey = None
+            return g
         h = getattr(self, "_kb_handle", None)
         if h is None:
             h = _cabi.Handle()
             self._kb_handle = h
             self._kb_key = None
         return h
+
+    def _content_digest(self):
+        """Cheap content hash of everything the device problem is built from (coordinates, values, host drift
+        columns), so that in-place edits of the data arrays invalidate the cached factorisation."""
+        import hashlib
+        x, y, z, v, center, Mt = self._data_arrays()
+        n_rl, cols = self._drift_spec()
+        hsh = hashlib.blake2b(digest_size=16)
+        for a in (x, y, z, v) + tuple(cols):
+            if a is not None:
+                hsh.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+        return hsh.hexdigest()
 
     def _problem_signature(self, dtype, knn):
         x, y, z, v, center, Mt = self._data_arrays()
@@ -274,23 +297,37 @@ class KrigeBase:
                 np.ravel(np.asarray(self.variogram_model_parameters, dtype=float)))
         return (dtype, knn, mid, tuple(vp), bool(self.exact_values), tuple(np.ravel(Mt)), tuple(center),
                 n_rl, len(cols), x.size, getattr(self, "coordinates_type", "euclidean"),
-                bool(getattr(self, "pseudo_inv", False)))
+                bool(getattr(self, "pseudo_inv", False)), self._device_drift_signature(), self._content_digest())
 
-    def _ensure_problem(self, dtype="float64", knn=False):
+    def _device_drift_signature(self):
+        return ()
+
+    def _configure_device_drift(self, h):
+        """Hook for drift terms evaluated on the device (UniversalKriging: point_log, external_Z)."""
+        h.set_device_drift(None, None)
+
+    def _ensure_problem(self, dtype="float64", knn=False, n_gpus=None):
         name = dtype if isinstance(dtype, str) and dtype in _cabi.DTYPES else str(np.dtype(dtype))
         dt = _cabi.DTYPES.get(name)
         if dt is None:
-            raise ValueError("dtype must be 'float64', 'float32' or 'float64x'")
-        h = self._cuda_handle()
+            raise ValueError("dtype must be one of %s" % ", ".join(repr(k) for k in _cabi.DTYPES))
+        h = self._cuda_handle(n_gpus)
+        grouped = isinstance(h, _cabi.Group)
         if self._device_model()[0] == self.TABLE_MODEL_ID:
             self._table_dmax()                  # fixes the tabulated range before it enters the signature
         key = self._problem_signature(dt, knn)
-        if self._kb_key == key:
+        if (self._kb_gkey if grouped else self._kb_key) == key:
             return h
         x, y, z, v, center, Mt = self._data_arrays()
         mid, vp = self._device_model()
         n_rl, cols = self._drift_spec()
-        self._kb_key = None
+        if grouped:
+            self._kb_gkey = None
+        else:
+            self._kb_key = None
+        if knn and bool(getattr(self, "pseudo_inv", False)):
+            warnings.warn("pseudo_inv is ignored by the moving window (n_closest_points), as in the reference "
+                          "(ok.py:753 always calls scipy.linalg.solve).", UserWarning)
         h.set_coordinates(getattr(self, "coordinates_type", "euclidean") == "geographic")
         h.set_pseudo_inverse(bool(getattr(self, "pseudo_inv", False)) and not knn)
         if mid == self.TABLE_MODEL_ID:
@@ -299,59 +336,170 @@ class KrigeBase:
         if knn:
             h.set_problem_knn(self._ndim, x, y, z, v, center, Mt, mid, vp, self.exact_values, self.eps)
         else:
+            self._configure_device_drift(h)
             h.set_problem(self._ndim, dt, x, y, z, v, center, Mt, mid, vp, self.exact_values, self.eps,
                           n_rl=n_rl, drift_data=cols if cols else None)
-        self._kb_key = key
+        if grouped:
+            self._kb_gkey = key
+        else:
+            self._kb_key = key
         return h
 
-    def _run_cuda(self, style, axes, mask, n_closest_points=None, drift_at=None, dtype="float64"):
+    # ---- execute(): argument handling shared by the four classes ---------------------------------
+    _MASK_DIM_MSG = {2: "Mask is not two-dimensional.", 3: "Mask is not three-dimensional."}
+    _POINTS_MSG = {
+        2: "xpoints and ypoints must have same dimensions when treated as listing discrete points.",
+        3: "xpoints, ypoints, and zpoints must have same dimensions when treated as listing discrete points.",
+    }
+
+    def _prepare_points(self, style, coords, mask):
+        """style / mask / point-list validation of execute() (ok.py:834-874, uk.py:1169-1215, ok3d.py:833-876,
+        uk3d.py:981-1024), once for 2-D and 3-D. coords = (xpoints, ypoints[, zpoints]).
+        Returns (axes: list of 1-D float64 arrays, sizes (nx, ny[, nz]), flat_mask or None); the mask is
+        returned in the reference's flattened order (x fastest; 3-D: (z, y, x))."""
+        nd = self._ndim
+        if style != "grid" and style != "masked" and style != "points":
+            raise ValueError("style argument must be 'grid', 'points', or 'masked'")
+        axes = [np.atleast_1d(np.squeeze(np.array(c, copy=True))) for c in coords]
+        sizes = tuple(a.size for a in axes)
+        flat_mask = None
+        if style == "masked":
+            if mask is None:
+                raise IOError("Must specify boolean masking array when style is 'masked'.")
+            if mask.ndim != nd:
+                raise ValueError(self._MASK_DIM_MSG[nd])
+            want = sizes[::-1]                        # (ny, nx) / (nz, ny, nx)
+            if tuple(mask.shape) != want:
+                if tuple(mask.shape) == sizes:        # given as (nx, ny[, nz]): transpose (ok.py:855-859)
+                    mask = mask.T if nd == 2 else mask.swapaxes(0, 2)
+                else:
+                    raise ValueError("Mask dimensions do not match specified grid dimensions.")
+            flat_mask = np.asarray(mask, dtype=bool).flatten()
+        elif style == "points":
+            bad = (sizes[0] != sizes[1]) if nd == 2 else (sizes[0] != sizes[1] and sizes[1] != sizes[2])
+            if bad:
+                raise ValueError(self._POINTS_MSG[nd])
+        return [a.astype(np.float64) for a in axes], sizes, flat_mask
+
+    def _specified_drift_grids(self, style, specified_drift_arrays, sizes, npoints, cls_name):
+        """'specified' drift arrays at the prediction points: validation of uk.py:1217-1274 / uk3d.py:1040-1098.
+        Returns the list of arrays in the reference's orientation ((ny, nx) / (nz, ny, nx) or (n,))."""
+        nd = self._ndim
+        if specified_drift_arrays is None:
+            specified_drift_arrays = []
+        grids = []
+        if self.specified_drift:
+            if len(specified_drift_arrays) == 0:
+                raise ValueError("Must provide drift values for kriging points when using 'specified' drift capability.")
+            if type(specified_drift_arrays) is not list:
+                raise TypeError("Arrays for specified drift terms must be encapsulated in a list.")
+            want = sizes[::-1]
+            for spec in specified_drift_arrays:
+                if style in ["grid", "masked"]:
+                    if spec.ndim < nd:
+                        raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
+                    elif tuple(spec.shape[:nd]) != want:
+                        if tuple(spec.shape[:nd]) == sizes:
+                            grids.append(np.squeeze(spec.T if nd == 2 else spec.swapaxes(0, 2)))
+                        else:
+                            raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
+                    else:
+                        grids.append(np.squeeze(spec))
+                elif style == "points":
+                    if spec.ndim != 1:
+                        raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
+                    elif spec.shape[0] != npoints:
+                        raise ValueError("Number of supplied drift values in array do not match specified number of kriging points.")
+                    else:
+                        grids.append(np.squeeze(spec))
+            if len(grids) != len(self.specified_drift_data_arrays):
+                raise ValueError("Inconsistent number of specified drift terms supplied.")
+        elif len(specified_drift_arrays) != 0:
+            warnings.warn(
+                "Provided specified drift values, but 'specified' drift was not initialized during "
+                "instantiation of %s class." % cls_name, RuntimeWarning,
+            )
+        return grids
+
+    @staticmethod
+    def _shape_output(style, z, ss, sizes, flat_mask):
+        """Masked wrap + reshape of execute() (ok.py:1012-1020, ok3d.py:924-932)."""
+        if style == "masked":
+            z = np.ma.array(z, mask=flat_mask)
+            ss = np.ma.array(ss, mask=flat_mask)
+        if style in ["masked", "grid"]:
+            z = z.reshape(sizes[::-1])
+            ss = ss.reshape(sizes[::-1])
+        return z, ss
+
+    # ---- the device run: plan (what to compute) -> run (one contiguous block of it) -> scatter ----
+    def _plan(self, style, axes, mask, drift_at=None):
+        """What one execute() computes, as a flat work list that can be cut into contiguous blocks (one per
+        GPU): kind 'grid' (points generated on the device from the axes, 0 bytes/point of input) or 'points'
+        (explicit coordinates; 'masked' keeps only the unmasked cells, host-supplied drift forces a list)."""
+        nd = self._ndim
+        if style == "points":
+            pts = [np.ascontiguousarray(a, dtype=np.float64) for a in axes]
+            return {"kind": "points", "pts": pts, "idx": None, "npt": pts[0].size, "count": pts[0].size,
+                    "scatter": False}
+        sizes = [a.size for a in axes[:nd]]
+        npt = int(np.prod(sizes))
+        if mask is None and drift_at is None:
+            return {"kind": "grid", "axes": axes, "npt": npt, "count": npt, "scatter": False}
+        idx = np.flatnonzero(~mask) if mask is not None else np.arange(npt)
+        nx, ny = sizes[0], sizes[1]
+        pts = [np.asarray(axes[0], dtype=np.float64)[idx % nx], np.asarray(axes[1], dtype=np.float64)[(idx // nx) % ny]]
+        if nd == 3:
+            pts.append(np.asarray(axes[2], dtype=np.float64)[idx // (nx * ny)])
+        return {"kind": "points", "pts": pts, "idx": idx, "npt": npt, "count": idx.size, "scatter": mask is not None}
+
+    def _run_block(self, h, plan, first, count, n_closest_points=None, drift_at=None):
+        """Krige items [first, first+count) of the plan's work list on handle (or device group) `h`."""
+        nd = self._ndim
+        knn = n_closest_points is not None
+        if count <= 0:
+            return np.zeros(0), np.zeros(0)
+        if plan["kind"] == "grid":
+            ax = plan["axes"]
+            gz = ax[2] if nd == 3 else None
+            if knn:
+                return h.execute_knn_grid(n_closest_points, ax[0], ax[1], gz, first, count)
+            return h.execute_grid(ax[0], ax[1], gz, None, first, count)
+        sl = slice(first, first + count)
+        pts = [p[sl] for p in plan["pts"]]
+        idx = plan["idx"][sl] if plan["idx"] is not None else None
+        if idx is None and (first != 0 or count != plan["count"]):
+            idx = np.arange(first, first + count)      # 'points' style: position in the caller's arrays
+        dv = drift_at(pts, idx) if drift_at is not None else None
+        if knn:
+            return h.execute_knn_points(n_closest_points, pts[0], pts[1], pts[2] if nd == 3 else None)
+        return h.execute_points(pts[0], pts[1], pts[2] if nd == 3 else None, dv)
+
+    @staticmethod
+    def _scatter(plan, z, ss):
+        if not plan["scatter"]:
+            return z, ss
+        zf = np.zeros(plan["npt"])
+        sf = np.zeros(plan["npt"])
+        zf[plan["idx"]] = z
+        sf[plan["idx"]] = ss
+        return zf, sf
+
+    def _run_cuda(self, style, axes, mask, n_closest_points=None, drift_at=None, dtype="float64", n_gpus=None):
         """axes: list of 1-D coordinate arrays [x, y(, z)] (grid axes or point lists, original coords).
-        mask: flattened bool mask (True = skip) or None.  drift_at: callable(pts list) -> [n_hd, m]
-        host-supplied drift values at the given points, or None.
+        mask: flattened bool mask (True = skip) or None.  drift_at: callable(pts list, idx) -> [n_hd, m]
+        host-supplied drift values at the given points, or None.  n_gpus: None/1 = this handle's device;
+        G > 1 = single-process multi-GPU (one host thread, kb200_group_*: device 0 factors, peer copies of the
+        factor blob, contiguous blocks of the work list, results gathered in the reference's order).
         Returns flat (z, ss) of length npt in the reference's flattened order."""
         knn = n_closest_points is not None
         nd = self._ndim
         if self._device_model()[0] == self.TABLE_MODEL_ID and all(np.size(a) for a in axes[:nd]):
             self._table_dmax([float(np.min(a)) for a in axes[:nd]], [float(np.max(a)) for a in axes[:nd]])
-        h = self._ensure_problem(dtype, knn)
-        if style == "points":
-            pts = [np.ascontiguousarray(a, dtype=np.float64) for a in axes]
-            dv = drift_at(pts, None) if drift_at is not None else None
-            if knn:
-                return h.execute_knn_points(n_closest_points, pts[0], pts[1], pts[2] if nd == 3 else None)
-            return h.execute_points(pts[0], pts[1], pts[2] if nd == 3 else None, dv)
-        # grid / masked
-        gx, gy = axes[0], axes[1]
-        gz = axes[2] if nd == 3 else None
-        nx, ny = gx.size, gy.size
-        nz = gz.size if nd == 3 else 1
-        npt = nx * ny * nz
-        need_points = (mask is not None) or (drift_at is not None)
-        if not need_points:
-            if knn:
-                return h.execute_knn_grid(n_closest_points, gx, gy, gz)
-            return h.execute_grid(gx, gy, gz)
-        idx = np.flatnonzero(~mask) if mask is not None else np.arange(npt)
-        ix = idx % nx
-        iy = (idx // nx) % ny
-        pts = [np.asarray(gx, dtype=np.float64)[ix], np.asarray(gy, dtype=np.float64)[iy]]
-        if nd == 3:
-            pts.append(np.asarray(gz, dtype=np.float64)[idx // (nx * ny)])
-        dv = drift_at(pts, idx) if drift_at is not None else None
-        if idx.size:
-            if knn:
-                zc, sc = h.execute_knn_points(n_closest_points, pts[0], pts[1], pts[2] if nd == 3 else None)
-            else:
-                zc, sc = h.execute_points(pts[0], pts[1], pts[2] if nd == 3 else None, dv)
-        else:
-            zc = sc = np.zeros(0)
-        if mask is None:
-            return zc, sc
-        z = np.zeros(npt)
-        ss = np.zeros(npt)
-        z[idx] = zc
-        ss[idx] = sc
-        return z, ss
+        h = self._ensure_problem(dtype, knn, n_gpus=n_gpus)
+        plan = self._plan(style, axes, mask, drift_at)
+        z, ss = self._run_block(h, plan, 0, plan["count"], n_closest_points, drift_at)
+        return self._scatter(plan, z, ss)
 
     @staticmethod
     def _check_backend(backend, what):

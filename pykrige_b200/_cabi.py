@@ -21,8 +21,11 @@ KB200_ESTATE = -6
 
 KB200_F64 = 0
 KB200_F32 = 1
-KB200_F64X = 2   # fp64-class contraction on the INT8 tensor cores (exact slice products)
-DTYPES = {"float64": KB200_F64, "float32": KB200_F32, "float64x": KB200_F64X}
+KB200_F64X = 2   # fp64-class contraction on the INT8 tensor cores (exact slice products), 6 slices = 41 bits
+KB200_F64X5 = 3  # 5 slices = 34 bits
+KB200_F64X4 = 4  # 4 slices = 27 bits
+DTYPES = {"float64": KB200_F64, "float32": KB200_F32, "float64x": KB200_F64X, "float64x5": KB200_F64X5,
+          "float64x4": KB200_F64X4}
 MAX_DRIFT = 15
 
 # every symbol include/krige_b200.h declares (checked by tests/test_cabi.py)
@@ -35,7 +38,10 @@ EXPORTS = [
     "kb200_blob_bytes", "kb200_blob_ptr", "kb200_describe_problem", "kb200_blob_commit",
     "kb200_set_coordinates", "kb200_set_stream", "kb200_last_timings", "kb200_reset_counters", "kb200_debug_fetch",
     "kb200_experimental_variogram", "kb200_statistics", "kb200_set_pseudo_inverse",
-    "kb200_set_variogram_table",
+    "kb200_set_variogram_table", "kb200_set_device_drift",
+    "kb200_group_create", "kb200_group_destroy", "kb200_group_last_error", "kb200_group_size", "kb200_group_member",
+    "kb200_group_set_problem", "kb200_group_set_problem_knn", "kb200_group_execute_points",
+    "kb200_group_execute_grid", "kb200_group_execute_knn_points", "kb200_group_execute_knn_grid",
 ]
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -96,6 +102,21 @@ def load_library():
     lib.kb200_statistics.argtypes = [h, dp, dp]
     lib.kb200_set_pseudo_inverse.argtypes = [h, i32]
     lib.kb200_set_variogram_table.argtypes = [h, i64, ctypes.c_double, dp]
+    lib.kb200_set_device_drift.argtypes = [h, i32, dp, i64, i64, dp, dp, dp]
+    lib.kb200_group_create.argtypes = [ctypes.POINTER(h), i32, ctypes.POINTER(i32)]
+    lib.kb200_group_destroy.argtypes = [h]
+    lib.kb200_group_destroy.restype = None
+    lib.kb200_group_last_error.argtypes = [h]
+    lib.kb200_group_last_error.restype = ctypes.c_char_p
+    lib.kb200_group_size.argtypes = [h]
+    lib.kb200_group_member.argtypes = [h, i32]
+    lib.kb200_group_member.restype = ctypes.c_void_p
+    lib.kb200_group_set_problem.argtypes = prob
+    lib.kb200_group_set_problem_knn.argtypes = lib.kb200_set_problem_knn.argtypes
+    lib.kb200_group_execute_points.argtypes = lib.kb200_execute_points.argtypes
+    lib.kb200_group_execute_grid.argtypes = grid
+    lib.kb200_group_execute_knn_points.argtypes = lib.kb200_execute_knn_points.argtypes
+    lib.kb200_group_execute_knn_grid.argtypes = kgrid
     _lib = lib
     return lib
 
@@ -144,6 +165,18 @@ class Handle:
     """Owns one kb200_handle. Error codes are mapped to the exception types the reference
     raises at the same places."""
 
+    _PREFIX = "kb200_"
+    _owned = True
+
+    @classmethod
+    def _borrowed(cls, lib, raw):
+        """A view of a handle owned by someone else (a group member): never destroyed from here."""
+        self = cls.__new__(cls)
+        self.lib = lib
+        self._h = ctypes.c_void_p(raw)
+        self._owned = False
+        return self
+
     def __init__(self, device=-1):
         self.lib = load_library()
         self._h = ctypes.c_void_p()
@@ -156,8 +189,16 @@ class Handle:
 
     def close(self):
         if getattr(self, "_h", None):
-            self.lib.kb200_destroy(self._h)
+            if self._owned:
+                self.lib.kb200_destroy(self._h)
             self._h = None
+
+    def _fn(self, name):
+        return getattr(self.lib, self._PREFIX + name)
+
+    def _errmsg(self):
+        msg = self.lib.kb200_last_error(self._h)
+        return msg.decode() if msg else ""
 
     def __del__(self):
         try:
@@ -168,8 +209,7 @@ class Handle:
     def _check(self, rc, knn=False):
         if rc == KB200_OK:
             return
-        msg = self.lib.kb200_last_error(self._h)
-        msg = msg.decode() if msg else ""
+        msg = self._errmsg()
         if rc == KB200_EBADARG:
             raise ValueError(msg)
         if rc == KB200_EUNSUPPORTED:
@@ -206,7 +246,7 @@ class Handle:
                     n_rl=0, drift_data=None):
         args, keep = self._problem_args(dim, dtype, x, y, z, values, center, aniso, model, vparams,
                                         exact_values, eps, n_rl, drift_data)
-        self._check(self.lib.kb200_set_problem(*args))
+        self._check(self._fn("set_problem")(*args))
 
     def describe_problem(self, dim, dtype, x, y, z, values, center, aniso, model, vparams, exact_values, eps,
                          n_rl=0, drift_data=None):
@@ -220,7 +260,7 @@ class Handle:
         center = _f64(center)
         aniso = _f64(np.asarray(aniso).reshape(-1))
         vparams = _f64(vparams)
-        self._check(self.lib.kb200_set_problem_knn(
+        self._check(self._fn("set_problem_knn")(
             self._h, int(dim), int(x.size), _ptr(x), _ptr(y), _ptr(z), _ptr(values), _ptr(center), _ptr(aniso),
             int(model), _ptr(vparams), int(vparams.size), int(bool(exact_values)), float(eps)))
 
@@ -231,7 +271,7 @@ class Handle:
         z = np.empty(m, dtype=np.float64)
         ss = np.empty(m, dtype=np.float64)
         dpts = _f64(drift_pts)
-        self._check(self.lib.kb200_execute_points(self._h, m, _ptr(px), _ptr(py), _ptr(pz), _ptr(dpts),
+        self._check(self._fn("execute_points")(self._h, m, _ptr(px), _ptr(py), _ptr(pz), _ptr(dpts),
                                                   _ptr(z), _ptr(ss)))
         return z, ss
 
@@ -243,7 +283,7 @@ class Handle:
         z = np.empty(count, dtype=np.float64)
         ss = np.empty(count, dtype=np.float64)
         dpts = _f64(drift_pts)
-        self._check(self.lib.kb200_execute_grid(self._h, nx, ny, nz, _ptr(gx), _ptr(gy), _ptr(gz), _ptr(dpts),
+        self._check(self._fn("execute_grid")(self._h, nx, ny, nz, _ptr(gx), _ptr(gy), _ptr(gz), _ptr(dpts),
                                                 int(first), int(count), _ptr(z), _ptr(ss)))
         return z, ss
 
@@ -252,7 +292,7 @@ class Handle:
         m = px.size
         z = np.empty(m, dtype=np.float64)
         ss = np.empty(m, dtype=np.float64)
-        self._check(self.lib.kb200_execute_knn_points(self._h, int(k), m, _ptr(px), _ptr(py), _ptr(pz),
+        self._check(self._fn("execute_knn_points")(self._h, int(k), m, _ptr(px), _ptr(py), _ptr(pz),
                                                       _ptr(z), _ptr(ss)), knn=True)
         return z, ss
 
@@ -263,7 +303,7 @@ class Handle:
             count = nx * ny * nz - first
         z = np.empty(count, dtype=np.float64)
         ss = np.empty(count, dtype=np.float64)
-        self._check(self.lib.kb200_execute_knn_grid(self._h, int(k), nx, ny, nz, _ptr(gx), _ptr(gy), _ptr(gz),
+        self._check(self._fn("execute_knn_grid")(self._h, int(k), nx, ny, nz, _ptr(gx), _ptr(gy), _ptr(gz),
                                                     int(first), int(count), _ptr(z), _ptr(ss)), knn=True)
         return z, ss
 
@@ -309,6 +349,20 @@ class Handle:
     def set_pseudo_inverse(self, enable):
         self._check(self.lib.kb200_set_pseudo_inverse(self._h, 1 if enable else 0))
 
+    def set_device_drift(self, wells, ext):
+        """Drift terms the solve kernels evaluate at the prediction points themselves (kb200_set_device_drift):
+        wells = [n_wells, 3] (adjusted x, adjusted y, strength) or None; ext = (axis_x, axis_y, raster[ny, nx])
+        or None."""
+        w = _f64(np.asarray(wells, dtype=np.float64).reshape(-1, 3)) if wells is not None and len(wells) else None
+        if ext is not None:
+            ex, ey, ez = _f64(np.ravel(ext[0])), _f64(np.ravel(ext[1])), _f64(ext[2])
+            if ez.shape != (ey.size, ex.size):
+                raise ValueError("external drift raster must be shaped (len(y), len(x))")
+            args = (ex.size, ey.size, _ptr(ex), _ptr(ey), _ptr(ez))
+        else:
+            args = (0, 0, None, None, None)
+        self._check(self.lib.kb200_set_device_drift(self._h, 0 if w is None else w.shape[0], _ptr(w), *args))
+
     def experimental_variogram(self, X, values, nlags, geographic=False):
         """Device twin of the pdist binning (core.py:432-505): X = (n, 2|3) ADJUSTED coordinates (or
         lon/lat when geographic). Returns (counts, lag_sum, semi_sum, dmin, dmax)."""
@@ -338,3 +392,70 @@ class Handle:
         if got < 0:
             self._check(int(got))
         return out[:got]
+
+
+class Group(Handle):
+    """kb200_group: n_gpus handles behind one call from one host thread (single-process multi-GPU). Same
+    execute / set_problem methods as Handle; configuration calls fan out to the members."""
+
+    _PREFIX = "kb200_group_"
+
+    def __init__(self, n_gpus, devices=None):
+        self.lib = load_library()
+        self._h = ctypes.c_void_p()
+        dev = None
+        if devices is not None:
+            dev = (ctypes.c_int * int(n_gpus))(*[int(d) for d in devices])
+        rc = self.lib.kb200_group_create(ctypes.byref(self._h), int(n_gpus), dev)
+        if rc != KB200_OK:
+            self._h = None
+            if rc == KB200_EBADARG:
+                raise ValueError("n_gpus=%d: this box does not have that many CUDA devices" % int(n_gpus))
+            raise KrigeB200Error("kb200_group_create failed (code %d): no usable CUDA device" % rc)
+        self.size = int(self.lib.kb200_group_size(self._h))
+        self.members = [Handle._borrowed(self.lib, self.lib.kb200_group_member(self._h, i)) for i in range(self.size)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for m in self.members:
+                m._h = None
+            self.lib.kb200_group_destroy(self._h)
+            self._h = None
+
+    def _errmsg(self):
+        msg = self.lib.kb200_group_last_error(self._h)
+        return msg.decode() if msg else ""
+
+    def describe_problem(self, *a, **k):
+        raise NotImplementedError("a group factors on its first device and copies the blob itself")
+
+    # configuration: per member
+    def set_coordinates(self, geographic):
+        for m in self.members:
+            m.set_coordinates(geographic)
+
+    def set_pseudo_inverse(self, enable):
+        for m in self.members:
+            m.set_pseudo_inverse(enable)
+
+    def set_variogram_table(self, nodes, dmax):
+        for m in self.members:
+            m.set_variogram_table(nodes, dmax)
+
+    def set_device_drift(self, wells, ext):
+        for m in self.members:
+            m.set_device_drift(wells, ext)
+
+    # instrumentation / constructor-side helpers: the factoring member
+    def timings(self):
+        return self.members[0].timings()
+
+    def reset_counters(self):
+        for m in self.members:
+            m.reset_counters()
+
+    def statistics(self, n):
+        return self.members[0].statistics(n)
+
+    def blob(self):
+        return self.members[0].blob()

@@ -142,23 +142,31 @@ def _experimental_variogram(X, y, nlags, block=2048, coordinates_type="euclidean
     n = X.shape[0]
     if coordinates_type == "geographic" and X.shape[1] != 2:
         raise ValueError("Geographic coordinate type only supported for 2D datasets.")
-    if device is True or (device == "auto" and n >= 2 and _device_available()):
+    small = n * (n - 1) // 2 <= 20_000_000 and coordinates_type == "euclidean"
+    # "auto": the pdist route below reproduces the reference's lags bit for bit (same summation order), which the
+    # least-squares fit needs; it is cheap up to ~6300 points. Beyond that only the device can hold the pair pass.
+    if device is True or (device == "auto" and n >= 2 and not small and _device_available()):
         from . import _cabi
         cnt, sd, sg, _, _ = _cabi.aux_handle().experimental_variogram(
             X, y, nlags, geographic=(coordinates_type == "geographic"))
         keep = cnt > 0
         return sd[keep] / cnt[keep], sg[keep] / cnt[keep]
-    if n * (n - 1) // 2 <= 20_000_000 and coordinates_type == "euclidean":
+    if small:
         d = pdist(X, metric="euclidean")
         g = 0.5 * pdist(y[:, None], metric="sqeuclidean")
         dmax, dmin = np.amax(d), np.amin(d)
         dd = (dmax - dmin) / nlags
         edges = np.array([dmin + k * dd for k in range(nlags)] + [dmax + 0.001])
-        which = np.searchsorted(edges, d, side="right") - 1
-        ok = (which >= 0) & (which < nlags)
-        cnt = np.bincount(which[ok], minlength=nlags)
-        sd = np.bincount(which[ok], weights=d[ok], minlength=nlags)
-        sg = np.bincount(which[ok], weights=g[ok], minlength=nlags)
+        # per-bin np.mean over the selected pairs, exactly the reference's expression (core.py:493-505): the same
+        # pairwise summation order, so that the least-squares fit (which amplifies 1e-14 differences of the lags
+        # to ~1e-4 in the fitted parameters) starts from bit-identical inputs
+        lags, semi = [], []
+        for k in range(nlags):
+            sel = (d >= edges[k]) & (d < edges[k + 1])
+            if np.any(sel):
+                lags.append(np.mean(d[sel]))
+                semi.append(np.mean(g[sel]))
+        return np.array(lags), np.array(semi)
     else:
         dmin, dmax = np.inf, 0.0
         for s in range(0, n, block):

@@ -8,10 +8,12 @@
 #include <cstdio>
 #include <cmath>
 #include <algorithm>
+#include <thread>
 #include "kernels.h"
 
-#define KB_VERSION 1001
-#define KB_CHUNK (128 * 1024)        // prediction points per solve launch (partials stay L2-sized)
+#define KB_VERSION 2000
+static const int64_t KB_STAGE_PTS = 1 << 20;   // prediction points per staged output chunk (2 x 8 MB through pinned memory)
+static const int64_t KB_STAGE_MIN = 1 << 18;   // below this the outputs go straight to the caller's buffers
 
 struct Src {
     bool grid; int64_t nx, ny, nz;
@@ -43,6 +45,7 @@ struct kb200_ctx {
     // description
     bool described = false, ready = false, knn_ready = false;
     bool factor_live = false;  // L (wC) and the forward solves (wF) of the ready problem are still in the workspace
+    int slices = 0;           // int8-slice dtypes: number of slices (6 / 5 / 4), else 0
     int gform = 0;            // 1: general (indefinite) fallback, tiles hold the symmetric inverse
     int geo = 0;              // 1: coordinates_type='geographic' for the next problem description
     int pinv = 0;             // 1: pseudo_inv=True for the next problem description (global path only)
@@ -64,6 +67,14 @@ struct kb200_ctx {
     // execute workspace
     DevBuf wPart, wAux, wPts, wOut, wAxes, wDrift, wScratch;
     int num_sms = 148;
+    // device-evaluated drift terms (kb200_set_device_drift): configuration + the count used by the described problem
+    DeviceDrift dd{};
+    DevBuf wWells, wExt;
+    int n_dev = 0;
+    // pinned staging of the outputs (two chunks in flight) and the stream that drains them
+    void* pin[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t evk[2] = {}, evc[2] = {};
     // knn workspace
     DevBuf kSorted, kCells;
     DevBuf wVario;            // constructor-side helpers (experimental variogram, statistics)
@@ -116,7 +127,14 @@ extern "C" void kb200_destroy(kb200_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->blob, &h->wC, &h->wW, &h->wT, &h->wF, &h->wRaw, &h->wFlag, &h->wPart, &h->wAux,
-                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->wScratch, &h->kSorted, &h->kCells, &h->wVario, &h->wTab}) b->release();
+                      &h->wPts, &h->wOut, &h->wAxes, &h->wDrift, &h->wScratch, &h->kSorted, &h->kCells, &h->wVario, &h->wTab,
+                      &h->wWells, &h->wExt}) b->release();
+    for (int i = 0; i < 2; ++i) {
+        if (h->pin[i]) cudaFreeHost(h->pin[i]);
+        if (h->evk[i]) cudaEventDestroy(h->evk[i]);
+        if (h->evc[i]) cudaEventDestroy(h->evc[i]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -218,8 +236,8 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     if (dim != 2 && dim != 3) return fail(h, KB200_EBADARG, "dim must be 2 or 3");
     if (h->geo && dim != 2) return fail(h, KB200_EBADARG, "geographic coordinates are two-dimensional (lon, lat)");
     if (h->geo && (n_rl || n_hd)) return fail(h, KB200_EUNSUPPORTED, "universal kriging has no geographic mode (uk.py:337)");
-    if (dtype != KB200_F64 && dtype != KB200_F32 && dtype != KB200_F64X)
-        return fail(h, KB200_EBADARG, "dtype must be KB200_F64, KB200_F32 or KB200_F64X");
+    if (dtype < KB200_F64 || dtype > KB200_F64X4)
+        return fail(h, KB200_EBADARG, "dtype must be KB200_F64, KB200_F32, KB200_F64X, KB200_F64X5 or KB200_F64X4");
     if (n < 1 || (!knn_only && n > (int64_t)(KB_MAXRB - 1) * KB_BM) || n > (1LL << 30)) return fail(h, KB200_EBADARG, "n out of range");
     if (!x || !y || (dim == 3 && !z) || !values || !center || !aniso || (!vparams && model != KB200_VG_TABLE))
         return fail(h, KB200_EBADARG, "null input array");
@@ -234,6 +252,11 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     if (n_hd < 0 || n_rl + n_hd > KB200_MAX_DRIFT) return fail(h, KB200_EBADARG, "too many drift terms");
     if (n_hd > 0 && !drift_data) return fail(h, KB200_EBADARG, "drift_data is null");
     if (knn_only && (n_rl || n_hd)) return fail(h, KB200_EUNSUPPORTED, "moving window supports ordinary kriging only");
+    const int n_dev = h->dd.n_wells + h->dd.ext;
+    if (n_dev > n_hd) return fail(h, KB200_EBADARG, "device drift terms (kb200_set_device_drift) exceed the n_hd described drift columns");
+    if (n_dev && dim != 2) return fail(h, KB200_EUNSUPPORTED, "point_log / external_Z drift terms are two-dimensional (uk.py)");
+    h->n_dev = n_dev;
+    h->slices = dtype == KB200_F64X ? 6 : dtype == KB200_F64X5 ? 5 : dtype == KB200_F64X4 ? 4 : 0;
 
     const int user_dim = dim;
     h->dim = h->geo ? KB_GEO : dim; h->dtype = dtype; h->n = (int)n; h->n_rl = n_rl; h->n_hd = n_hd;
@@ -327,10 +350,10 @@ static int describe(kb200_ctx* h, bool knn_only, int dim, int dtype, int64_t n,
     h->off_ay = o; o += align_up((size_t)h->n_pad * 8, 256);
     h->off_az = o; o += align_up((size_t)h->n_pad * 8, 256);
     h->off_tiles = o;
-    if (dtype == KB200_F64X) {
-        o += (size_t)kbk_i8_total_tiles((int)n, h->na, nullptr) * kbk_i8_tile_bytes();
+    if (h->slices) {
+        o += (size_t)kbk_i8_total_tiles(h->slices, (int)n, h->na, nullptr) * kbk_i8_tile_bytes(h->slices);
         o = align_up(o, 256);
-        h->off_rowscale = o; o += align_up((size_t)kbk_i8_rows((int)n, h->na) * sizeof(double), 256);
+        h->off_rowscale = o; o += align_up((size_t)kbk_i8_rows(h->slices, (int)n, h->na) * sizeof(double), 256);
     } else {
         o += (size_t)off * KB_BM * KB_BK * esz;
     }
@@ -460,7 +483,7 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
         // partial pivoting + quadratic-form solve. fp64 only.
         if (h->dtype != KB200_F64) {
             h->launches += launches;
-            return fail(h, KB200_EUNSUPPORTED, "dtype=float32 needs a positive definite covariance form "
+            return fail(h, KB200_EUNSUPPORTED, "dtype float32 / float64x need a positive definite covariance form "
                         "(the variogram is not valid in this dimension); use float64");
         }
         h->vg.c0 = c0_first;
@@ -492,15 +515,15 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
                    Fz, Hz, Uz, consts, flag, st, &launches));
     if (h->dtype == KB200_F32) {
         CU(h, kbk_pack_tf32(h->wW.as<double>(), ld, nn, np, h->na, Uz, h->pm, blob + h->off_tiles, st));
-    } else if (h->dtype == KB200_F64X) {
-        const int nrb8 = kbk_i8_nrb(nn, h->na);
+    } else if (h->slices) {
+        const int nrb8 = kbk_i8_nrb(h->slices, nn, h->na);
         std::vector<long long> toff(nrb8 + 1);
-        kbk_i8_total_tiles(nn, h->na, toff.data());
+        kbk_i8_total_tiles(h->slices, nn, h->na, toff.data());
         // workspace (T1 scratch is free now): tile offsets | row exponents
         long long* d_toff = reinterpret_cast<long long*>(h->wT.as<char>());
         int* d_rowexp = reinterpret_cast<int*>(h->wT.as<char>() + align_up((size_t)(nrb8 + 1) * sizeof(long long), 256));   // kbk_i8_rows ints
         CU(h, cudaMemcpyAsync(d_toff, toff.data(), (size_t)(nrb8 + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-        CU(h, kbk_pack_i8(h->wW.as<double>(), ld, nn, np, h->na, Uz, d_rowexp,
+        CU(h, kbk_pack_i8(h->slices, h->wW.as<double>(), ld, nn, np, h->na, Uz, d_rowexp,
                           reinterpret_cast<double*>(blob + h->off_rowscale), d_toff, blob + h->off_tiles, st));
         CU(h, cudaStreamSynchronize(st));      // toff is a host temporary
         ++launches;
@@ -527,7 +550,45 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
     return KB200_OK;
 }
 
+// ---- device-evaluated drift terms -----------------------------------------------------------------------
+extern "C" int kb200_set_device_drift(kb200_handle h, int n_wells, const double* wells,
+                                      int64_t ext_nx, int64_t ext_ny, const double* ext_x, const double* ext_y,
+                                      const double* ext_z) {
+    if (!h) return KB200_EBADARG;
+    if (n_wells < 0 || n_wells > KB200_MAX_DRIFT || (n_wells > 0 && !wells))
+        return fail(h, KB200_EBADARG, "device drift: bad point_log description");
+    const bool ext = ext_nx > 0 || ext_ny > 0;
+    if (ext && (ext_nx < 1 || ext_ny < 1 || ext_nx > (1 << 30) || ext_ny > (1 << 30) || !ext_x || !ext_y || !ext_z))
+        return fail(h, KB200_EBADARG, "device drift: bad external_Z raster description");
+    h->described = false; h->ready = false; h->factor_live = false;
+    cudaSetDevice(h->device);
+    h->dd = DeviceDrift{};
+    if (n_wells) {
+        CU(h, h->wWells.reserve((size_t)3 * n_wells * 8));
+        CU(h, cudaMemcpyAsync(h->wWells.p, wells, (size_t)3 * n_wells * 8, cudaMemcpyHostToDevice, h->stream));
+        h->dd.n_wells = n_wells; h->dd.wells = h->wWells.as<double>();
+    }
+    if (ext) {
+        const size_t nx = (size_t)ext_nx, ny = (size_t)ext_ny;
+        CU(h, h->wExt.reserve((nx + ny + nx * ny) * 8));
+        double* d = h->wExt.as<double>();
+        CU(h, cudaMemcpyAsync(d, ext_x, nx * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(d + nx, ext_y, ny * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(d + nx + ny, ext_z, nx * ny * 8, cudaMemcpyHostToDevice, h->stream));
+        bool sorted = true;
+        for (size_t i = 1; i < nx && sorted; ++i) sorted = ext_x[i] >= ext_x[i - 1];
+        for (size_t i = 1; i < ny && sorted; ++i) sorted = ext_y[i] >= ext_y[i - 1];
+        h->dd.ext = 1; h->dd.ext_nx = (int)ext_nx; h->dd.ext_ny = (int)ext_ny; h->dd.ext_sorted = sorted ? 1 : 0;
+        h->dd.ext_x = d; h->dd.ext_y = d + nx; h->dd.ext_z = d + nx + ny;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));     // the caller's arrays may go away
+    return KB200_OK;
+}
+
 // ---- execute --------------------------------------------------------------
+// One persistent launch of the solve kernel of the handle's dtype over points [s.first, s.first + s.count).
+// NOTE: one kernel for every point count: the summation order per point must not depend on how the points are
+// sharded or chunked (concatenated shards == single call, bit for bit).
 static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     cudaStream_t st = h->stream;
     char* blob = h->blob.as<char>();
@@ -535,67 +596,90 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     ps.grid = s.grid ? 1 : 0;
     ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
     ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
-    const bool f32 = h->dtype == KB200_F32 || h->dtype == KB200_F64X;   // tcgen05 kernels (128-point tiles)
-    const bool i8 = h->dtype == KB200_F64X;
-    // NOTE: one kernel for every point count: the summation order per point must not depend on how the
-    // points are sharded (concatenated shards == single call, bit for bit).
-    if (f32 || !kbk_solve_use_v1()) {
-        // K3 v3 (fp64 DMMA) / tcgen05 TF32 kernel: one persistent launch for the whole slice
-        const int tp = i8 ? kbk_solve_i8_tile_points() : (f32 ? kbk_solve_tf32_tile_points() : KB_TN);
-        long long ntiles = (s.count + tp - 1) / tp;
-        int grid = (int)std::min<long long>(ntiles, h->num_sms);
-        CU(h, h->wScratch.reserve(i8 ? kbk_solve_i8_scratch_bytes(h->n, grid) : f32 ? kbk_solve_tf32_scratch_bytes(h->n, grid)
-                                      : kbk_solve_pt_scratch_doubles(h->n, grid) * sizeof(double)));
-        SolvePtParams pp{};
-        pp.vg = h->vg; pp.an = h->an; ps.first = s.first; pp.ps = ps;
-        pp.n = h->n; pp.na = h->na; pp.nrb = h->nrb; pp.n_rl = h->n_rl; pp.n_hd = h->n_hd;
-        pp.ax = reinterpret_cast<double*>(blob + h->off_ax);
-        pp.ay = reinterpret_cast<double*>(blob + h->off_ay);
-        pp.az = reinterpret_cast<double*>(blob + h->off_az);
-        pp.tiles = blob + h->off_tiles; pp.pm = h->pm; pp.ds = h->ds;
-        pp.consts = reinterpret_cast<double*>(blob + h->off_consts);
-        pp.drift_pts = s.d_drift; pp.drift_stride = s.drift_stride; pp.drift_first = s.drift_first;
-        pp.m = s.count; pp.scratch = h->wScratch.as<double>(); pp.gform = h->gform;
-        pp.z_out = d_z; pp.ss_out = d_ss;
-        CU(h, cudaEventRecord(h->ev[7], st));
-        pp.rowscale = reinterpret_cast<const double*>(blob + h->off_rowscale);
-        if (i8) CU(h, kbk_solve_i8(h->dim, pp, grid, st));
-        else if (f32) CU(h, kbk_solve_tf32(h->dim, pp, grid, st));
-        else CU(h, kbk_solve_pt(h->dim, pp, grid, st));
+    const bool i8 = h->slices != 0;
+    const bool f32 = h->dtype == KB200_F32;
+    const int tp = i8 ? kbk_solve_i8_tile_points() : (f32 ? kbk_solve_tf32_tile_points() : KB_TN);
+    long long ntiles = (s.count + tp - 1) / tp;
+    int grid = (int)std::min<long long>(ntiles, h->num_sms);
+    CU(h, h->wScratch.reserve(i8 ? kbk_solve_i8_scratch_bytes(h->slices, h->n, grid) : f32 ? kbk_solve_tf32_scratch_bytes(h->n, grid)
+                                  : kbk_solve_pt_scratch_doubles(h->n, grid) * sizeof(double)));
+    SolvePtParams pp{};
+    pp.vg = h->vg; pp.an = h->an; ps.first = s.first; pp.ps = ps;
+    pp.n = h->n; pp.na = h->na; pp.nrb = h->nrb; pp.n_rl = h->n_rl; pp.n_hd = h->n_hd;
+    pp.ax = reinterpret_cast<double*>(blob + h->off_ax);
+    pp.ay = reinterpret_cast<double*>(blob + h->off_ay);
+    pp.az = reinterpret_cast<double*>(blob + h->off_az);
+    pp.tiles = blob + h->off_tiles; pp.pm = h->pm; pp.ds = h->ds;
+    pp.consts = reinterpret_cast<double*>(blob + h->off_consts);
+    pp.dd = h->dd; pp.n_dev = h->n_dev;
+    pp.drift_pts = s.d_drift; pp.drift_stride = s.drift_stride; pp.drift_first = s.drift_first;
+    pp.m = s.count; pp.scratch = h->wScratch.as<double>(); pp.gform = h->gform;
+    pp.z_out = d_z; pp.ss_out = d_ss;
+    pp.rowscale = reinterpret_cast<const double*>(blob + h->off_rowscale);
+    if (i8) CU(h, kbk_solve_i8(h->slices, h->dim, pp, grid, st));
+    else if (f32) CU(h, kbk_solve_tf32(h->dim, pp, grid, st));
+    else CU(h, kbk_solve_pt(h->dim, pp, grid, st));
+    h->launches += 1; h->solve_launches += 1;
+    return KB200_OK;
+}
+
+static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss, int chol);
+
+// Launch `total` points in chunks and bring (z, ss) to the caller's HOST buffers. Large outputs travel through two
+// pinned staging buffers on a second stream while the next chunk computes; the host drains a buffer into the
+// caller's (pageable) memory while the GPU works. launch(o, m, d_z, d_ss) enqueues points [o, o+m) of the call.
+template <class Launch>
+static int run_to_host(kb200_ctx* h, int64_t total, double* z_out, double* ss_out, Launch launch) {
+    cudaStream_t st = h->stream;
+    CU(h, h->wOut.reserve((size_t)2 * total * 8));
+    double* dz = h->wOut.as<double>();
+    double* dss = dz + total;
+    CU(h, cudaEventRecord(h->ev[7], st));
+    if (total < KB_STAGE_MIN) {
+        int rc = launch((int64_t)0, total, dz, dss); if (rc) return rc;
         CU(h, cudaEventRecord(h->ev[8], st));
-        h->launches += 1; h->solve_launches += 1;
+        CU(h, cudaMemcpyAsync(z_out, dz, total * 8, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(ss_out, dss, total * 8, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaEventRecord(h->ev[11], st));
+        CU(h, cudaStreamSynchronize(st));
+        h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
         return KB200_OK;
     }
-    if (h->gform) return fail(h, KB200_EUNSUPPORTED, "KB200_SOLVE_V1 does not implement the general fallback");
-    const int64_t chunk = KB_CHUNK;
-    int64_t cmax = std::min<int64_t>(chunk, (int64_t)align_up((size_t)s.count, KB_TN));
-    CU(h, h->wPart.reserve((size_t)h->nrb * cmax * sizeof(double)));
-    CU(h, h->wAux.reserve((size_t)h->na * cmax * sizeof(double)));
-    SolveParams sp{};
-    sp.vg = h->vg; sp.an = h->an;
-    sp.n = h->n; sp.n_pad = h->n_pad; sp.na = h->na; sp.nrb = h->nrb;
-    sp.ax = reinterpret_cast<double*>(blob + h->off_ax);
-    sp.ay = reinterpret_cast<double*>(blob + h->off_ay);
-    sp.az = reinterpret_cast<double*>(blob + h->off_az);
-    sp.tiles = blob + h->off_tiles; sp.pm = h->pm;
-    sp.partial = h->wPart.as<double>(); sp.auxout = h->wAux.as<double>();
-    FinalizeParams fp{};
-    fp.vg = h->vg; fp.an = h->an; fp.dim = h->dim; fp.n_rl = h->n_rl; fp.n_hd = h->n_hd; fp.nrb = h->nrb;
-    fp.ds = h->ds; fp.consts = reinterpret_cast<double*>(blob + h->off_consts);
-    fp.drift_pts = s.d_drift; fp.drift_stride = s.drift_stride;
-    fp.partial = sp.partial; fp.auxout = sp.auxout;
-    CU(h, cudaEventRecord(h->ev[7], st));
-    for (int64_t o = 0; o < s.count; o += chunk) {
-        int64_t m = std::min(chunk, s.count - o);
-        ps.first = s.first + o;
-        sp.ps = ps; sp.m = m; sp.mpad = (long long)align_up((size_t)m, KB_TN);
-        CU(h, kbk_solve(h->dim, h->dtype, sp, st));
-        fp.ps = ps; fp.m = m; fp.mpad = sp.mpad; fp.drift_first = s.drift_first + o;
-        fp.z_out = d_z + o; fp.ss_out = d_ss + o;
-        CU(h, kbk_finalize(fp, st));
-        h->launches += 2; h->solve_launches += 1;
+    if (!h->copy_stream) {
+        CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(h, cudaHostAlloc(&h->pin[i], (size_t)2 * KB_STAGE_PTS * 8, cudaHostAllocDefault));
+            CU(h, cudaEventCreateWithFlags(&h->evk[i], cudaEventDisableTiming));
+            CU(h, cudaEventCreate(&h->evc[i]));
+        }
     }
-    CU(h, cudaEventRecord(h->ev[8], st));
+    const int64_t nch = (total + KB_STAGE_PTS - 1) / KB_STAGE_PTS;
+    auto chunk_len = [&](int64_t c) { return std::min<int64_t>(KB_STAGE_PTS, total - c * KB_STAGE_PTS); };
+    auto drain = [&](int64_t c) -> int {          // staged chunk c -> the caller's buffers
+        const int b = (int)(c & 1);
+        CU(h, cudaEventSynchronize(h->evc[b]));
+        const double* p = reinterpret_cast<const double*>(h->pin[b]);
+        const int64_t m = chunk_len(c);
+        std::memcpy(z_out + c * KB_STAGE_PTS, p, (size_t)m * 8);
+        std::memcpy(ss_out + c * KB_STAGE_PTS, p + KB_STAGE_PTS, (size_t)m * 8);
+        return KB200_OK;
+    };
+    for (int64_t c = 0; c < nch; ++c) {
+        const int b = (int)(c & 1);
+        const int64_t o = c * KB_STAGE_PTS, m = chunk_len(c);
+        int rc = launch(o, m, dz + o, dss + o); if (rc) return rc;
+        CU(h, cudaEventRecord(h->evk[b], st));
+        if (c == nch - 1) CU(h, cudaEventRecord(h->ev[8], st));
+        if (c >= 2) { rc = drain(c - 2); if (rc) return rc; }
+        double* p = reinterpret_cast<double*>(h->pin[b]);
+        CU(h, cudaStreamWaitEvent(h->copy_stream, h->evk[b], 0));
+        CU(h, cudaMemcpyAsync(p, dz + o, (size_t)m * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(h, cudaMemcpyAsync(p + KB_STAGE_PTS, dss + o, (size_t)m * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(h, cudaEventRecord(h->evc[b], h->copy_stream));
+    }
+    for (int64_t c = std::max<int64_t>(0, nch - 2); c < nch; ++c) { int rc = drain(c); if (rc) return rc; }
+    CU(h, cudaStreamSynchronize(st));
+    h->tm[7] += ev_ms(h->ev[8], h->evc[(nch - 1) & 1]);
     return KB200_OK;
 }
 
@@ -605,6 +689,7 @@ static int check_ready(kb200_ctx* h) {
     cudaSetDevice(h->device);
     return KB200_OK;
 }
+static int n_host_drift(const kb200_ctx* h) { return h->n_hd - h->n_dev; }
 
 extern "C" int kb200_execute_points_dev(kb200_handle h, int64_t m,
                                         const double* d_px, const double* d_py, const double* d_pz,
@@ -612,11 +697,20 @@ extern "C" int kb200_execute_points_dev(kb200_handle h, int64_t m,
     int rc = check_ready(h); if (rc) return rc;
     if (m <= 0) return KB200_OK;
     if (!d_px || !d_py || (h->dim == 3 && !d_pz) || !d_z || !d_ss) return fail(h, KB200_EBADARG, "null pointer");
-    if (h->n_hd && !d_drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
+    if (n_host_drift(h) && !d_drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
     Src s{false, 0, 0, 0, d_px, d_py, d_pz, 0, m, d_drift_pts, m, 0};
+    CU(h, cudaEventRecord(h->ev[7], h->stream));
     rc = run_solve(h, s, d_z, d_ss); if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev[8], h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
+    return KB200_OK;
+}
+
+static int check_grid(kb200_ctx* h, int64_t nx, int64_t ny, int64_t nz, int64_t first, int64_t count) {
+    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
+        return fail(h, KB200_EBADARG, "bad grid slice");
+    if (h->dim != 3 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
     return KB200_OK;
 }
 
@@ -625,15 +719,55 @@ extern "C" int kb200_execute_grid_dev(kb200_handle h, int64_t nx, int64_t ny, in
                                       const double* d_drift_pts, int64_t first, int64_t count,
                                       double* d_z, double* d_ss) {
     int rc = check_ready(h); if (rc) return rc;
-    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
-        return fail(h, KB200_EBADARG, "bad grid slice");
+    rc = check_grid(h, nx, ny, nz, first, count); if (rc) return rc;
     if (count == 0) return KB200_OK;
     if (!d_gx || !d_gy || (h->dim == 3 && !d_gz) || !d_z || !d_ss) return fail(h, KB200_EBADARG, "null pointer");
-    if (h->dim != 3 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
-    if (h->n_hd && !d_drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
+    if (n_host_drift(h) && !d_drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
     Src s{true, nx, ny, nz, d_gx, d_gy, d_gz, first, count, d_drift_pts, count, 0};
+    CU(h, cudaEventRecord(h->ev[7], h->stream));
     rc = run_solve(h, s, d_z, d_ss); if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev[8], h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
+    return KB200_OK;
+}
+
+// host drift columns [n_host][stride] -> device columns [n_host][m] holding items [off, off + m) of each column
+static int upload_drift(kb200_ctx* h, const double* drift_pts, int64_t stride, int64_t off, int64_t m, const double** dd) {
+    *dd = nullptr;
+    const int nh = n_host_drift(h);
+    if (!nh) return KB200_OK;
+    CU(h, h->wDrift.reserve((size_t)nh * m * 8));
+    for (int c = 0; c < nh; ++c)
+        CU(h, cudaMemcpyAsync(h->wDrift.as<double>() + (size_t)c * m, drift_pts + (size_t)c * stride + off, (size_t)m * 8,
+                              cudaMemcpyHostToDevice, h->stream));
+    *dd = h->wDrift.as<double>();
+    return KB200_OK;
+}
+
+// points [off, off + m) of the caller's arrays (drift columns have `stride` items each)
+static int exec_points_impl(kb200_ctx* h, int64_t off, int64_t m, const double* px, const double* py, const double* pz,
+                            const double* drift_pts, int64_t stride, double* z_out, double* ss_out) {
+    int rc = check_ready(h); if (rc) return rc;
+    if (m <= 0) return KB200_OK;
+    if (!px || !py || (h->dim == 3 && !pz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
+    if (n_host_drift(h) && !drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
+    cudaStream_t st = h->stream;
+    CU(h, h->wPts.reserve((size_t)3 * m * 8));
+    double* dp = h->wPts.as<double>();
+    CU(h, cudaEventRecord(h->ev[9], st));
+    CU(h, cudaMemcpyAsync(dp, px + off, m * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(dp + m, py + off, m * 8, cudaMemcpyHostToDevice, st));
+    if (h->dim == 3) CU(h, cudaMemcpyAsync(dp + 2 * m, pz + off, m * 8, cudaMemcpyHostToDevice, st));
+    const double* dd = nullptr;
+    rc = upload_drift(h, drift_pts, stride, off, m, &dd); if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev[10], st));
+    rc = run_to_host(h, m, z_out + off, ss_out + off, [&](int64_t o, int64_t c, double* dz, double* dss) {
+        Src s{false, 0, 0, 0, dp, dp + m, dp + 2 * m, o, c, dd, m, o};
+        return run_solve(h, s, dz, dss);
+    });
+    if (rc) return rc;
+    h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
     h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
     return KB200_OK;
 }
@@ -641,35 +775,39 @@ extern "C" int kb200_execute_grid_dev(kb200_handle h, int64_t nx, int64_t ny, in
 extern "C" int kb200_execute_points(kb200_handle h, int64_t m,
                                     const double* px, const double* py, const double* pz,
                                     const double* drift_pts, double* z_out, double* ss_out) {
+    if (!h) return KB200_EBADARG;
+    return exec_points_impl(h, 0, m, px, py, pz, drift_pts, m, z_out, ss_out);
+}
+
+// grid points [first, first + count); drift columns cover the caller's slice [cfirst, cfirst + ccount) and
+// z_out / ss_out are indexed relative to cfirst
+static int exec_grid_impl(kb200_ctx* h, int64_t nx, int64_t ny, int64_t nz,
+                          const double* gx, const double* gy, const double* gz,
+                          const double* drift_pts, int64_t cfirst, int64_t ccount, int64_t first, int64_t count,
+                          double* z_out, double* ss_out) {
     int rc = check_ready(h); if (rc) return rc;
-    if (m <= 0) return KB200_OK;
-    if (!px || !py || (h->dim == 3 && !pz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
-    if (h->n_hd && !drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
+    rc = check_grid(h, nx, ny, nz, first, count); if (rc) return rc;
+    if (count == 0) return KB200_OK;
+    if (!gx || !gy || (h->dim == 3 && !gz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
+    if (n_host_drift(h) && !drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
     cudaStream_t st = h->stream;
-    CU(h, h->wPts.reserve((size_t)3 * m * 8));
-    CU(h, h->wOut.reserve((size_t)2 * m * 8));
-    double* dp = h->wPts.as<double>();
-    double* dout = h->wOut.as<double>();
+    CU(h, h->wAxes.reserve((size_t)(nx + ny + nz) * 8));
+    double* da = h->wAxes.as<double>();
     CU(h, cudaEventRecord(h->ev[9], st));
-    CU(h, cudaMemcpyAsync(dp, px, m * 8, cudaMemcpyHostToDevice, st));
-    CU(h, cudaMemcpyAsync(dp + m, py, m * 8, cudaMemcpyHostToDevice, st));
-    if (h->dim == 3) CU(h, cudaMemcpyAsync(dp + 2 * m, pz, m * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(da, gx, nx * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(da + nx, gy, ny * 8, cudaMemcpyHostToDevice, st));
+    if (h->dim == 3) CU(h, cudaMemcpyAsync(da + nx + ny, gz, nz * 8, cudaMemcpyHostToDevice, st));
     const double* dd = nullptr;
-    if (h->n_hd) {
-        CU(h, h->wDrift.reserve((size_t)h->n_hd * m * 8));
-        CU(h, cudaMemcpyAsync(h->wDrift.p, drift_pts, (size_t)h->n_hd * m * 8, cudaMemcpyHostToDevice, st));
-        dd = h->wDrift.as<double>();
-    }
+    rc = upload_drift(h, drift_pts, ccount, first - cfirst, count, &dd); if (rc) return rc;
     CU(h, cudaEventRecord(h->ev[10], st));
-    Src s{false, 0, 0, 0, dp, dp + m, dp + 2 * m, 0, m, dd, m, 0};
-    rc = run_solve(h, s, dout, dout + m); if (rc) return rc;
-    CU(h, cudaMemcpyAsync(z_out, dout, m * 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaMemcpyAsync(ss_out, dout + m, m * 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaEventRecord(h->ev[11], st));
-    CU(h, cudaStreamSynchronize(st));
+    rc = run_to_host(h, count, z_out + (first - cfirst), ss_out + (first - cfirst),
+                     [&](int64_t o, int64_t c, double* dz, double* dss) {
+        Src s{true, nx, ny, nz, da, da + nx, da + nx + ny, first + o, c, dd, count, o};
+        return run_solve(h, s, dz, dss);
+    });
+    if (rc) return rc;
     h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
     h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
-    h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
     return KB200_OK;
 }
 
@@ -677,39 +815,8 @@ extern "C" int kb200_execute_grid(kb200_handle h, int64_t nx, int64_t ny, int64_
                                   const double* gx, const double* gy, const double* gz,
                                   const double* drift_pts, int64_t first, int64_t count,
                                   double* z_out, double* ss_out) {
-    int rc = check_ready(h); if (rc) return rc;
-    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
-        return fail(h, KB200_EBADARG, "bad grid slice");
-    if (count == 0) return KB200_OK;
-    if (!gx || !gy || (h->dim == 3 && !gz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
-    if (h->dim != 3 && nz != 1) return fail(h, KB200_EBADARG, "nz must be 1 for 2-D");
-    if (h->n_hd && !drift_pts) return fail(h, KB200_EBADARG, "drift values at the points are required");
-    cudaStream_t st = h->stream;
-    CU(h, h->wAxes.reserve((size_t)(nx + ny + nz) * 8));
-    CU(h, h->wOut.reserve((size_t)2 * count * 8));
-    double* da = h->wAxes.as<double>();
-    double* dout = h->wOut.as<double>();
-    CU(h, cudaEventRecord(h->ev[9], st));
-    CU(h, cudaMemcpyAsync(da, gx, nx * 8, cudaMemcpyHostToDevice, st));
-    CU(h, cudaMemcpyAsync(da + nx, gy, ny * 8, cudaMemcpyHostToDevice, st));
-    if (h->dim == 3) CU(h, cudaMemcpyAsync(da + nx + ny, gz, nz * 8, cudaMemcpyHostToDevice, st));
-    const double* dd = nullptr;
-    if (h->n_hd) {   // drift_pts: column-major [n_hd][count], values for this slice
-        CU(h, h->wDrift.reserve((size_t)h->n_hd * count * 8));
-        CU(h, cudaMemcpyAsync(h->wDrift.p, drift_pts, (size_t)h->n_hd * count * 8, cudaMemcpyHostToDevice, st));
-        dd = h->wDrift.as<double>();
-    }
-    CU(h, cudaEventRecord(h->ev[10], st));
-    Src s{true, nx, ny, nz, da, da + nx, da + nx + ny, first, count, dd, count, 0};
-    rc = run_solve(h, s, dout, dout + count); if (rc) return rc;
-    CU(h, cudaMemcpyAsync(z_out, dout, count * 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaMemcpyAsync(ss_out, dout + count, count * 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaEventRecord(h->ev[11], st));
-    CU(h, cudaStreamSynchronize(st));
-    h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
-    h->tm[4] += ev_ms(h->ev[7], h->ev[8]);
-    h->tm[7] += ev_ms(h->ev[8], h->ev[11]);
-    return KB200_OK;
+    if (!h) return KB200_EBADARG;
+    return exec_grid_impl(h, nx, ny, nz, gx, gy, gz, drift_pts, first, count, first, count, z_out, ss_out);
 }
 
 // ---- moving window ----------------------------------------------------------
@@ -786,13 +893,10 @@ extern "C" int kb200_set_problem_knn(kb200_handle h, int dim, int64_t n,
     return KB200_OK;
 }
 
+
+// ---- moving window: execute ---------------------------------------------------------------------------------
 static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss, int chol) {
-    if (k < 2) return fail(h, KB200_EBADARG, "n_closest_points has to be at least two!");
-    if (k > h->n) return fail(h, KB200_EBADARG, "n_closest_points exceeds the number of data points");
-    if (kbk_knn_smem_per_warp(k, 0) > 200 * 1024) return fail(h, KB200_EUNSUPPORTED, "n_closest_points too large for the shared-memory local solver");
     cudaStream_t st = h->stream;
-    int* flag = h->wFlag.as<int>();
-    CU(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
     KnnParams kp = h->kp;
     kp.vg = h->vg; kp.an = h->an; kp.k = k;
     {   // radius (in cells) of the ball expected to hold k points at the mean density
@@ -807,110 +911,281 @@ static int run_knn(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss,
     ps.grid = s.grid ? 1 : 0;
     ps.px = s.a; ps.py = s.b; ps.pz = s.c; ps.gx = s.a; ps.gy = s.b; ps.gz = s.c;
     ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz; ps.first = s.first;
-    kp.ps = ps; kp.m = s.count; kp.z_out = d_z; kp.ss_out = d_ss; kp.flag = flag;
-    CU(h, cudaEventRecord(h->ev[7], st));
+    kp.ps = ps; kp.m = s.count; kp.z_out = d_z; kp.ss_out = d_ss; kp.flag = h->wFlag.as<int>();
     CU(h, kbk_knn_solve(kp, chol, st));
-    CU(h, cudaEventRecord(h->ev[8], st));
     h->launches += 1; h->solve_launches += 1;
     return KB200_OK;
 }
 
-// run the moving window, wait for it and handle the solver flag: 2 = a local covariance block was
-// not positive definite (variogram not valid in this dimension) -> repeat with the pivoted-LU solver
-// (dgesv semantics); 1 = exactly singular local system -> ValueError('Singular matrix').
-static int run_knn_checked(kb200_ctx* h, int k, const Src& s, double* d_z, double* d_ss) {
-    int rc = run_knn(h, k, s, d_z, d_ss, 1);
-    if (rc) return rc;
-    int hflag = 0;
-    CU(h, cudaMemcpyAsync(&hflag, h->wFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    h->tm[9] += ev_ms(h->ev[7], h->ev[8]);
-    if (hflag == 2) {
-        rc = run_knn(h, k, s, d_z, d_ss, 0);
-        if (rc) return rc;
-        CU(h, cudaMemcpyAsync(&hflag, h->wFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CU(h, cudaStreamSynchronize(h->stream));
-        h->tm[9] += ev_ms(h->ev[7], h->ev[8]);
-    }
-    if (hflag) return fail(h, KB200_ESINGULAR, "Singular matrix");
-    return KB200_OK;
-}
-
-static int check_knn_ready(kb200_ctx* h) {
+static int check_knn(kb200_ctx* h, int k) {
     if (!h) return KB200_EBADARG;
     if (!h->knn_ready) return fail(h, KB200_ESTATE, "call kb200_set_problem_knn first");
     cudaSetDevice(h->device);
+    if (k < 2) return fail(h, KB200_EBADARG, "n_closest_points has to be at least two!");
+    if (k > h->n) return fail(h, KB200_EBADARG, "n_closest_points exceeds the number of data points");
+    if (kbk_knn_smem_per_warp(k, 0) > 200 * 1024) return fail(h, KB200_EUNSUPPORTED, "n_closest_points too large for the shared-memory local solver");
+    return KB200_OK;
+}
+
+// Run the moving window to HOST buffers and handle the solver flag: 2 = a local covariance block was not positive
+// definite (variogram not valid in this dimension) -> repeat with the pivoted-LU solver (dgesv semantics);
+// 1 = exactly singular local system -> ValueError('Singular matrix') (cok.pyx:176-179).
+template <class MakeSrc>
+static int knn_to_host(kb200_ctx* h, int k, int64_t total, double* z_out, double* ss_out, MakeSrc make_src) {
+    int* flag = h->wFlag.as<int>();
+    for (int chol = 1; chol >= 0; --chol) {
+        CU(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+        int rc = run_to_host(h, total, z_out, ss_out, [&](int64_t o, int64_t c, double* dz, double* dss) {
+            return run_knn(h, k, make_src(o, c), dz, dss, chol);
+        });
+        if (rc) return rc;
+        int hflag = 0;
+        CU(h, cudaMemcpy(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost));
+        h->tm[9] += ev_ms(h->ev[7], h->ev[8]);
+        if (hflag == 0) return KB200_OK;
+        if (hflag != 2 || chol == 0) return fail(h, KB200_ESINGULAR, "Singular matrix");
+    }
     return KB200_OK;
 }
 
 extern "C" int kb200_execute_knn_grid_dev(kb200_handle h, int k, int64_t nx, int64_t ny, int64_t nz,
                                           const double* d_gx, const double* d_gy, const double* d_gz,
                                           int64_t first, int64_t count, double* d_z, double* d_ss) {
-    int rc = check_knn_ready(h); if (rc) return rc;
-    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
-        return fail(h, KB200_EBADARG, "bad grid slice");
+    int rc = check_knn(h, k); if (rc) return rc;
+    rc = check_grid(h, nx, ny, nz, first, count); if (rc) return rc;
     if (count == 0) return KB200_OK;
     if (!d_gx || !d_gy || (h->dim == 3 && !d_gz) || !d_z || !d_ss) return fail(h, KB200_EBADARG, "null pointer");
     Src s{true, nx, ny, nz, d_gx, d_gy, d_gz, first, count, nullptr, 0, 0};
-    return run_knn_checked(h, k, s, d_z, d_ss);
+    int* flag = h->wFlag.as<int>();
+    for (int chol = 1; chol >= 0; --chol) {
+        CU(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+        CU(h, cudaEventRecord(h->ev[7], h->stream));
+        rc = run_knn(h, k, s, d_z, d_ss, chol); if (rc) return rc;
+        CU(h, cudaEventRecord(h->ev[8], h->stream));
+        int hflag = 0;
+        CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->tm[9] += ev_ms(h->ev[7], h->ev[8]);
+        if (hflag == 0) return KB200_OK;
+        if (hflag != 2 || chol == 0) return fail(h, KB200_ESINGULAR, "Singular matrix");
+    }
+    return KB200_OK;
 }
 
-extern "C" int kb200_execute_knn_grid(kb200_handle h, int k, int64_t nx, int64_t ny, int64_t nz,
-                                      const double* gx, const double* gy, const double* gz,
-                                      int64_t first, int64_t count, double* z_out, double* ss_out) {
-    int rc = check_knn_ready(h); if (rc) return rc;
-    if (nx < 1 || ny < 1 || nz < 1 || first < 0 || count < 0 || first + count > nx * ny * nz)
-        return fail(h, KB200_EBADARG, "bad grid slice");
+static int exec_knn_grid_impl(kb200_ctx* h, int k, int64_t nx, int64_t ny, int64_t nz,
+                              const double* gx, const double* gy, const double* gz,
+                              int64_t cfirst, int64_t first, int64_t count, double* z_out, double* ss_out) {
+    int rc = check_knn(h, k); if (rc) return rc;
+    rc = check_grid(h, nx, ny, nz, first, count); if (rc) return rc;
     if (count == 0) return KB200_OK;
     if (!gx || !gy || (h->dim == 3 && !gz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
     cudaStream_t st = h->stream;
     CU(h, h->wAxes.reserve((size_t)(nx + ny + nz) * 8));
-    CU(h, h->wOut.reserve((size_t)2 * count * 8));
     double* da = h->wAxes.as<double>();
-    double* dout = h->wOut.as<double>();
     CU(h, cudaEventRecord(h->ev[9], st));
     CU(h, cudaMemcpyAsync(da, gx, nx * 8, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemcpyAsync(da + nx, gy, ny * 8, cudaMemcpyHostToDevice, st));
     if (h->dim == 3) CU(h, cudaMemcpyAsync(da + nx + ny, gz, nz * 8, cudaMemcpyHostToDevice, st));
     CU(h, cudaEventRecord(h->ev[10], st));
-    Src s{true, nx, ny, nz, da, da + nx, da + nx + ny, first, count, nullptr, 0, 0};
-    rc = run_knn_checked(h, k, s, dout, dout + count); if (rc) return rc;
-    CU(h, cudaEventRecord(h->ev[12], st));
-    CU(h, cudaMemcpyAsync(z_out, dout, count * 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaMemcpyAsync(ss_out, dout + count, count * 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaEventRecord(h->ev[11], st));
-    CU(h, cudaStreamSynchronize(st));
+    rc = knn_to_host(h, k, count, z_out + (first - cfirst), ss_out + (first - cfirst), [&](int64_t o, int64_t c) {
+        return Src{true, nx, ny, nz, da, da + nx, da + nx + ny, first + o, c, nullptr, 0, 0};
+    });
+    if (rc) return rc;
     h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
-    h->tm[7] += ev_ms(h->ev[12], h->ev[11]);
+    return KB200_OK;
+}
+
+extern "C" int kb200_execute_knn_grid(kb200_handle h, int k, int64_t nx, int64_t ny, int64_t nz,
+                                      const double* gx, const double* gy, const double* gz,
+                                      int64_t first, int64_t count, double* z_out, double* ss_out) {
+    if (!h) return KB200_EBADARG;
+    return exec_knn_grid_impl(h, k, nx, ny, nz, gx, gy, gz, first, first, count, z_out, ss_out);
+}
+
+static int exec_knn_points_impl(kb200_ctx* h, int k, int64_t off, int64_t m,
+                                const double* px, const double* py, const double* pz, double* z_out, double* ss_out) {
+    int rc = check_knn(h, k); if (rc) return rc;
+    if (m <= 0) return KB200_OK;
+    if (!px || !py || (h->dim == 3 && !pz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
+    cudaStream_t st = h->stream;
+    CU(h, h->wPts.reserve((size_t)3 * m * 8));
+    double* dp = h->wPts.as<double>();
+    CU(h, cudaEventRecord(h->ev[9], st));
+    CU(h, cudaMemcpyAsync(dp, px + off, m * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(dp + m, py + off, m * 8, cudaMemcpyHostToDevice, st));
+    if (h->dim == 3) CU(h, cudaMemcpyAsync(dp + 2 * m, pz + off, m * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaEventRecord(h->ev[10], st));
+    rc = knn_to_host(h, k, m, z_out + off, ss_out + off, [&](int64_t o, int64_t c) {
+        return Src{false, 0, 0, 0, dp, dp + m, dp + 2 * m, o, c, nullptr, 0, 0};
+    });
+    if (rc) return rc;
+    h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
     return KB200_OK;
 }
 
 extern "C" int kb200_execute_knn_points(kb200_handle h, int k, int64_t m,
                                         const double* px, const double* py, const double* pz,
                                         double* z_out, double* ss_out) {
-    int rc = check_knn_ready(h); if (rc) return rc;
-    if (m <= 0) return KB200_OK;
-    if (!px || !py || (h->dim == 3 && !pz) || !z_out || !ss_out) return fail(h, KB200_EBADARG, "null pointer");
-    cudaStream_t st = h->stream;
-    CU(h, h->wPts.reserve((size_t)3 * m * 8));
-    CU(h, h->wOut.reserve((size_t)2 * m * 8));
-    double* dp = h->wPts.as<double>();
-    double* dout = h->wOut.as<double>();
-    CU(h, cudaEventRecord(h->ev[9], st));
-    CU(h, cudaMemcpyAsync(dp, px, m * 8, cudaMemcpyHostToDevice, st));
-    CU(h, cudaMemcpyAsync(dp + m, py, m * 8, cudaMemcpyHostToDevice, st));
-    if (h->dim == 3) CU(h, cudaMemcpyAsync(dp + 2 * m, pz, m * 8, cudaMemcpyHostToDevice, st));
-    CU(h, cudaEventRecord(h->ev[10], st));
-    Src s{false, 0, 0, 0, dp, dp + m, dp + 2 * m, 0, m, nullptr, 0, 0};
-    rc = run_knn_checked(h, k, s, dout, dout + m); if (rc) return rc;
-    CU(h, cudaEventRecord(h->ev[12], st));
-    CU(h, cudaMemcpyAsync(z_out, dout, m * 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaMemcpyAsync(ss_out, dout + m, m * 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaEventRecord(h->ev[11], st));
-    CU(h, cudaStreamSynchronize(st));
-    h->tm[6] += ev_ms(h->ev[9], h->ev[10]);
-    h->tm[7] += ev_ms(h->ev[12], h->ev[11]);
+    if (!h) return KB200_EBADARG;
+    return exec_knn_points_impl(h, k, 0, m, px, py, pz, z_out, ss_out);
+}
+
+// ---- single-process multi-GPU: a group of handles driven by one caller thread --------------------------------
+// the caller makes ONE call from one host thread; inside, one worker thread per device runs
+// the per-device call on that device's handle (CUDA work of different devices overlaps, and so do the host-side
+// drains of the staged outputs). Device 0 factors; the factor blob goes to the peers by cudaMemcpyPeerAsync over
+// NVLink (the single transfer of the path); prediction points are cut into contiguous blocks in the reference's
+// flattened order (ok.py:864-866), so the gathered result equals the single-GPU result bit for bit.
+struct kb200_group_ctx {
+    std::vector<kb200_ctx*> m;
+    bool peers = false;
+    std::string err;
+};
+
+static int gfail(kb200_group_ctx* g, int code, const std::string& msg) { if (g) g->err = msg; return code; }
+
+template <class F>
+static int group_parallel(kb200_group_ctx* g, F f) {
+    const int G = (int)g->m.size();
+    std::vector<int> rc(G, KB200_OK);
+    std::vector<std::thread> th;
+    th.reserve(G);
+    for (int i = 1; i < G; ++i) th.emplace_back([&, i]() { rc[i] = f(i); });
+    rc[0] = f(0);
+    for (auto& t : th) t.join();
+    for (int i = 0; i < G; ++i)
+        if (rc[i] != KB200_OK) return gfail(g, rc[i], "device " + std::to_string(g->m[i]->device) + ": " + g->m[i]->err);
     return KB200_OK;
+}
+
+static void shard_block(int64_t count, int rank, int world, int64_t* first, int64_t* n) {
+    const int64_t base = count / world, rem = count % world;
+    *first = rank * base + std::min<int64_t>(rank, rem);
+    *n = base + (rank < rem ? 1 : 0);
+}
+
+extern "C" int kb200_group_create(kb200_group* out, int n_gpus, const int* devices) {
+    if (!out) return KB200_EBADARG;
+    *out = nullptr;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) return KB200_ECUDA;
+    if (n_gpus < 1 || n_gpus > cnt) return KB200_EBADARG;
+    kb200_group_ctx* g = new kb200_group_ctx();
+    for (int i = 0; i < n_gpus; ++i) {
+        kb200_handle h = nullptr;
+        int rc = kb200_create(&h, devices ? devices[i] : i);
+        if (rc != KB200_OK) { for (auto* m : g->m) kb200_destroy(m); delete g; return rc; }
+        g->m.push_back(h);
+    }
+    *out = g;
+    return KB200_OK;
+}
+
+extern "C" void kb200_group_destroy(kb200_group g) {
+    if (!g) return;
+    for (auto* m : g->m) kb200_destroy(m);
+    delete g;
+}
+
+extern "C" const char* kb200_group_last_error(kb200_group g) { return g ? g->err.c_str() : "null group"; }
+extern "C" int kb200_group_size(kb200_group g) { return g ? (int)g->m.size() : 0; }
+extern "C" kb200_handle kb200_group_member(kb200_group g, int i) {
+    return (g && i >= 0 && i < (int)g->m.size()) ? g->m[i] : nullptr;
+}
+
+extern "C" int kb200_group_set_problem(kb200_group g, int dim, int dtype, int64_t n,
+                                       const double* x, const double* y, const double* z, const double* values,
+                                       const double* center, const double* aniso,
+                                       int model, const double* vparams, int n_vparams,
+                                       int exact_values, double eps, int n_rl, int n_hd, const double* drift_data) {
+    if (!g || g->m.empty()) return KB200_EBADARG;
+    // member 0 assembles + factors while the peers describe the problem (allocating their blobs)
+    int rc = group_parallel(g, [&](int i) {
+        if (i == 0) return kb200_set_problem(g->m[0], dim, dtype, n, x, y, z, values, center, aniso, model, vparams,
+                                             n_vparams, exact_values, eps, n_rl, n_hd, drift_data);
+        return kb200_describe_problem(g->m[i], dim, dtype, n, x, y, z, values, center, aniso, model, vparams,
+                                      n_vparams, exact_values, eps, n_rl, n_hd, drift_data);
+    });
+    if (rc) return rc;
+    const int G = (int)g->m.size();
+    kb200_ctx* h0 = g->m[0];
+    if (G > 1 && !g->peers) {
+        for (int i = 1; i < G; ++i) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, g->m[i]->device, h0->device);
+            if (can) { cudaSetDevice(g->m[i]->device); cudaDeviceEnablePeerAccess(h0->device, 0); cudaGetLastError(); }
+        }
+        g->peers = true;
+    }
+    cudaSetDevice(h0->device);
+    for (int i = 1; i < G; ++i) {
+        if (g->m[i]->blob_bytes != h0->blob_bytes) return gfail(g, KB200_ESTATE, "group: blob size mismatch");
+        cudaError_t e = cudaMemcpyPeerAsync(g->m[i]->blob.p, g->m[i]->device, h0->blob.p, h0->device, h0->blob_bytes, h0->stream);
+        if (e != cudaSuccess) return gfail(g, KB200_ECUDA, std::string("cudaMemcpyPeerAsync: ") + cudaGetErrorString(e));
+    }
+    if (cudaStreamSynchronize(h0->stream) != cudaSuccess) return gfail(g, KB200_ECUDA, "group: blob copy failed");
+    for (int i = 1; i < G; ++i) {
+        rc = kb200_blob_commit(g->m[i]);
+        if (rc) return gfail(g, rc, g->m[i]->err);
+    }
+    return KB200_OK;
+}
+
+extern "C" int kb200_group_set_problem_knn(kb200_group g, int dim, int64_t n,
+                                           const double* x, const double* y, const double* z, const double* values,
+                                           const double* center, const double* aniso,
+                                           int model, const double* vparams, int n_vparams, int exact_values, double eps) {
+    if (!g || g->m.empty()) return KB200_EBADARG;
+    // every device builds its own cell grid from the coordinates (1.6-2.4 MB of input; nothing to broadcast)
+    return group_parallel(g, [&](int i) {
+        return kb200_set_problem_knn(g->m[i], dim, n, x, y, z, values, center, aniso, model, vparams, n_vparams,
+                                     exact_values, eps);
+    });
+}
+
+extern "C" int kb200_group_execute_grid(kb200_group g, int64_t nx, int64_t ny, int64_t nz,
+                                        const double* gx, const double* gy, const double* gz,
+                                        const double* drift_pts, int64_t first, int64_t count,
+                                        double* z_out, double* ss_out) {
+    if (!g || g->m.empty()) return KB200_EBADARG;
+    const int G = (int)g->m.size();
+    return group_parallel(g, [&](int i) {
+        int64_t f, c; shard_block(count, i, G, &f, &c);
+        return exec_grid_impl(g->m[i], nx, ny, nz, gx, gy, gz, drift_pts, first, count, first + f, c, z_out, ss_out);
+    });
+}
+
+extern "C" int kb200_group_execute_points(kb200_group g, int64_t m,
+                                          const double* px, const double* py, const double* pz,
+                                          const double* drift_pts, double* z_out, double* ss_out) {
+    if (!g || g->m.empty()) return KB200_EBADARG;
+    const int G = (int)g->m.size();
+    return group_parallel(g, [&](int i) {
+        int64_t f, c; shard_block(m, i, G, &f, &c);
+        return exec_points_impl(g->m[i], f, c, px, py, pz, drift_pts, m, z_out, ss_out);
+    });
+}
+
+extern "C" int kb200_group_execute_knn_grid(kb200_group g, int k, int64_t nx, int64_t ny, int64_t nz,
+                                            const double* gx, const double* gy, const double* gz,
+                                            int64_t first, int64_t count, double* z_out, double* ss_out) {
+    if (!g || g->m.empty()) return KB200_EBADARG;
+    const int G = (int)g->m.size();
+    return group_parallel(g, [&](int i) {
+        int64_t f, c; shard_block(count, i, G, &f, &c);
+        return exec_knn_grid_impl(g->m[i], k, nx, ny, nz, gx, gy, gz, first, first + f, c, z_out, ss_out);
+    });
+}
+
+extern "C" int kb200_group_execute_knn_points(kb200_group g, int k, int64_t m,
+                                              const double* px, const double* py, const double* pz,
+                                              double* z_out, double* ss_out) {
+    if (!g || g->m.empty()) return KB200_EBADARG;
+    const int G = (int)g->m.size();
+    return group_parallel(g, [&](int i) {
+        int64_t f, c; shard_block(m, i, G, &f, &c);
+        return exec_knn_points_impl(g->m[i], k, f, c, px, py, pz, z_out, ss_out);
+    });
 }
 
 // ---- debug taps (tests only) ------------------------------------------------

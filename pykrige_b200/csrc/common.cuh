@@ -149,9 +149,9 @@ struct PointSource {
 };
 
 template <int DIM>
-__device__ __forceinline__ void kb_load_point(const PointSource& ps, const Aniso& an, long long p,
-                                              double& x, double& y, double& z) {
-    double rx, ry, rz = 0.0;
+__device__ __forceinline__ void kb_load_point_raw(const PointSource& ps, long long p,
+                                                  double& rx, double& ry, double& rz) {
+    rz = 0.0;
     long long q = p + ps.first;
     if (ps.grid) {
         long long ix = q % ps.nx;
@@ -165,6 +165,13 @@ __device__ __forceinline__ void kb_load_point(const PointSource& ps, const Aniso
         ry = ps.py[q];
         if (DIM == 3) rz = ps.pz[q];
     }
+}
+
+template <int DIM>
+__device__ __forceinline__ void kb_load_point(const PointSource& ps, const Aniso& an, long long p,
+                                              double& x, double& y, double& z) {
+    double rx, ry, rz;
+    kb_load_point_raw<DIM>(ps, p, rx, ry, rz);
     kb_adjust<DIM>(an, rx, ry, rz, x, y, z);
 }
 

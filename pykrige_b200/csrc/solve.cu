@@ -1,5 +1,4 @@
-// solve.cu — K3: the per-grid-point hot kernel of the global kriging path, and the
-// tiny per-point finalize.
+// solve.cu — K3: the per-grid-point hot kernel of the global kriging path (fp64 DMMA), finalize fused.
 //
 // Reference semantics (ok.py:665-681, uk.py:942-1007): for every prediction point j
 //     b_j = [-gamma(|p_j - x_k|) (0 on an exact hit) ; drift(p_j) ; 1],  x_j = A^-1 b_j,
@@ -13,15 +12,10 @@
 //   solve_kernel_pt   (K3 v3, the product path) persistent CTAs, one CTA = 64 points x all rows of W, RHS column
 //                     block generated once per tile, W/RHS tiles streamed by cp.async.bulk + mbarrier, fused
 //                     finalize. See the comment above the kernel.
-//   solve_kernel_f64 + finalize_kernel (K3 v1) CTA = (row block x point tile), RHS regenerated per row block;
-//                     kept behind KB200_SOLVE_V1=1 for A/B profiling only.
 // The tcgen05 variants live in solve_tf32.cu (dtype float32) and solve_i8.cu (dtype float64x).
 #include "common.cuh"
 #include "kernels.h"
 #include <cstdlib>
-
-#define SV_STAGES 3
-#define SV_THREADS 256
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -50,146 +44,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template <int DIM, int MODEL>
-__global__ void __launch_bounds__(SV_THREADS, 1) solve_kernel_f64(const __grid_constant__ SolveParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* Ts = reinterpret_cast<double*>(smem_raw);                   // SV_STAGES * BM*BK
-    double* Bs = Ts + SV_STAGES * KB_BM * KB_BK;                        // SV_STAGES * BK*TN
-    double* red = Bs + SV_STAGES * KB_BK * KB_TN;                       // 8 * 64
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + 8 * KB_TN);      // SV_STAGES
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int jt = blockIdx.x;
-    const int I = P.nrb - 1 - (int)blockIdx.y;          // heavy row blocks first
-    const int nkt = P.pm.ktiles[I];
-    const double* gt = reinterpret_cast<const double*>(P.tiles) + (size_t)P.pm.tile_off[I] * (KB_BM * KB_BK);
-    constexpr uint32_t TILE_BYTES = KB_BM * KB_BK * sizeof(double);
-
-    // the prediction point this thread generates RHS entries for
-    const long long pj = (long long)jt * KB_TN + warp * 8 + (lane >> 2);
-    const bool pvalid = pj < P.m;
-    double px = 0.0, py = 0.0, pz = 0.0;
-    if (pvalid) kb_load_point<DIM>(P.ps, P.an, pj, px, py, pz);
-
-    if (tid == 0) {
-        for (int s = 0; s < SV_STAGES; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    }
-    __syncthreads();
-
-    // which k tiles this warp's 32 rows need: W rows are lower-triangular, dual rows are dense
-    const int r0w = I * KB_BM + warp * 32;
-    int warp_kmax;
-    if (r0w + 31 >= P.n && r0w < P.n + P.na) warp_kmax = 0x7fffffff;
-    else if (r0w >= P.n + P.na) warp_kmax = -1;
-    else warp_kmax = r0w + 31;
-
-    auto issue_load = [&](int t) {
-        int s = t % SV_STAGES;
-        mbar_expect_tx(&full[s], TILE_BYTES);
-        bulk_g2s(Ts + (size_t)s * KB_BM * KB_BK, gt + (size_t)t * KB_BM * KB_BK, TILE_BYTES, &full[s]);
-    };
-    auto gen_rhs = [&](int t) {
-        double* bs = Bs + (size_t)(t % SV_STAGES) * KB_BK * KB_TN;
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-            int k = t * KB_BK + 4 * s4 + (lane & 3);
-            double v = 0.0;
-            if (pvalid && k < P.n) {
-                double d = kb_dist<DIM>(P.ax[k], P.ay[k], KB_HASZ(DIM) ? P.az[k] : 0.0, px, py, pz);
-                v = kb_cov_rhs<MODEL>(P.vg, d);
-            }
-            bs[(s4 * 8 + warp) * 32 + lane] = v;
-        }
-    };
-
-    double acc[4][8][2];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
-
-    for (int t = 0; t < SV_STAGES - 1 && t < nkt; ++t) {
-        if (tid == 0) issue_load(t);
-        gen_rhs(t);
-    }
-    for (int it = 0; it < nkt; ++it) {
-        const int s = it % SV_STAGES;
-        mbar_wait(&full[s], (uint32_t)((it / SV_STAGES) & 1));
-        __syncthreads();      // everyone is done with tile it-1 (its stage is refilled below); RHS tile `it` is visible
-        const int tn = it + SV_STAGES - 1;
-        if (tn < nkt) {
-            if (tid == 0) issue_load(tn);
-            gen_rhs(tn);
-        }
-        if (it * KB_BK <= warp_kmax) {
-            const double* ts = Ts + (size_t)s * KB_BM * KB_BK;
-            const double* bs = Bs + (size_t)s * KB_BK * KB_TN;
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                double fa[4], fb[8];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) fa[mt] = ts[(k4 * 32 + warp * 4 + mt) * 32 + lane];
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) fb[nt] = bs[(k4 * 8 + nt) * 32 + lane];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 8; ++nt)
-                        kb_dmma(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fb[nt]);
-            }
-        }
-    }
-
-    // epilogue: W rows -> sum of squares per point; dual rows -> direct output
-    double qs[8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { qs[nt][0] = 0.0; qs[nt][1] = 0.0; }
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-        const int r = r0w + mt * 8 + (lane >> 2);
-        if (r < P.n) {
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                qs[nt][0] += acc[mt][nt][0] * acc[mt][nt][0];
-                qs[nt][1] += acc[mt][nt][1] * acc[mt][nt][1];
-            }
-        } else if (r < P.n + P.na) {
-            double* ao = P.auxout + (size_t)(r - P.n) * P.mpad + (size_t)jt * KB_TN + 2 * (lane & 3);
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                ao[nt * 8] = acc[mt][nt][0];
-                ao[nt * 8 + 1] = acc[mt][nt][1];
-            }
-        }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            double v = qs[nt][i];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            qs[nt][i] = v;
-        }
-    if ((lane >> 2) == 0) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            red[warp * KB_TN + nt * 8 + 2 * lane] = qs[nt][0];
-            red[warp * KB_TN + nt * 8 + 2 * lane + 1] = qs[nt][1];
-        }
-    }
-    __syncthreads();
-    if (tid < KB_TN) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[w * KB_TN + tid];     // fixed order: deterministic
-        P.partial[(size_t)I * P.mpad + (size_t)jt * KB_TN + tid] = v;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -230,7 +84,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
     double* scratch = P.scratch + (size_t)blockIdx.x * nk * (KB_BK * KB_TN);
     const double* gt = reinterpret_cast<const double*>(P.tiles);
     const long long ntiles = (P.m + KB_TN - 1) / KB_TN;
-    const int K = P.n_rl + P.n_hd, K1 = K + 1;
 
     if (tid == 0) {
         for (int s = 0; s < PT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
@@ -410,106 +263,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                 double q = 0.0;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) q += qred[w * KB_TN + tid];     // fixed order: deterministic
-                double r[KB200_MAX_DRIFT + 1];
-                double f[KB200_MAX_DRIFT + 1];
-                if (P.n_rl > 0) {
-                    double x, y, z;
-                    kb_load_point<DIM>(P.ps, P.an, pj, x, y, z);
-                    f[0] = (x - P.ds.shift[0]) * P.ds.scale[0];
-                    f[1] = (y - P.ds.shift[1]) * P.ds.scale[1];
-                    if (DIM == 3) f[2] = (z - P.ds.shift[2]) * P.ds.scale[2];
-                }
-                for (int c = 0; c < P.n_hd; ++c) {
-                    double v = P.drift_pts[(size_t)c * P.drift_stride + P.drift_first + pj];
-                    f[P.n_rl + c] = (v - P.ds.shift[P.n_rl + c]) * P.ds.scale[P.n_rl + c];
-                }
-                f[K] = 1.0;
-                const double zc = auxs[K1 * KB_TN + tid];
-                const double* Sinv = P.consts;
-                const double* phi = P.consts + K1 * K1;
-                if (P.gform == 2) {
-                    // pseudo-inverse form (pinv.cu): b = [c; f], sigma^2 = -b^T A^+ b, z = w1.c + w2.f with
-                    // q = c^T G11 c, aux rows = G21 c, consts = G22 | w2
-                    double acc = q, zz = zc;
-                    for (int a = 0; a < K1; ++a) {
-                        double gf = 0.0;
-                        for (int b = 0; b < K1; ++b) gf += Sinv[a * K1 + b] * f[b];
-                        acc += f[a] * (2.0 * auxs[a * KB_TN + tid] + gf);
-                        zz += phi[a] * f[a];
-                    }
-                    P.ss_out[pj] = -acc;
-                    P.z_out[pj] = zz;
-                } else {
-                for (int a = 0; a < K1; ++a) r[a] = auxs[a * KB_TN + tid] - f[a];
-                double rmu = 0.0, muphi = 0.0;
-                for (int a = 0; a < K1; ++a) {
-                    double mu = 0.0;
-                    for (int b = 0; b < K1; ++b) mu += Sinv[a * K1 + b] * r[b];
-                    rmu += r[a] * mu;
-                    muphi += mu * phi[a];
-                }
-                P.ss_out[pj] = P.vg.c0 - q + rmu;
-                P.z_out[pj] = zc - muphi;
-                }
+                kb_finalize_point<DIM, double>(P, pj, q, auxs + tid, KB_TN);
             }
         }
         __syncthreads();      // qred / auxs / scratch are re-used by the next tile
     }
 }
 
-// Per-point finalize (deterministic reduction over row blocks + the (K+1)x(K+1) drift solve).
-template <int DIM>
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams P) {
-    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.m) return;
-    double q = 0.0;
-    for (int I = 0; I < P.nrb; ++I) q += P.partial[(size_t)I * P.mpad + p];
-    const int K = P.n_rl + P.n_hd, K1 = K + 1;
-    double r[KB200_MAX_DRIFT + 1];
-    double f[KB200_MAX_DRIFT + 1];
-    if (P.n_rl > 0) {
-        double x, y, z;
-        kb_load_point<DIM>(P.ps, P.an, p, x, y, z);
-        f[0] = (x - P.ds.shift[0]) * P.ds.scale[0];
-        f[1] = (y - P.ds.shift[1]) * P.ds.scale[1];
-        if (DIM == 3) f[2] = (z - P.ds.shift[2]) * P.ds.scale[2];
-    }
-    for (int c = 0; c < P.n_hd; ++c) {
-        double v = P.drift_pts[(size_t)c * P.drift_stride + P.drift_first + p];
-        f[P.n_rl + c] = (v - P.ds.shift[P.n_rl + c]) * P.ds.scale[P.n_rl + c];
-    }
-    f[K] = 1.0;
-    for (int a = 0; a < K1; ++a) r[a] = P.auxout[(size_t)a * P.mpad + p] - f[a];
-    const double zc = P.auxout[(size_t)K1 * P.mpad + p];
-    const double* Sinv = P.consts;
-    const double* phi = P.consts + K1 * K1;
-    double rmu = 0.0, muphi = 0.0;
-    for (int a = 0; a < K1; ++a) {
-        double mu = 0.0;
-        for (int b = 0; b < K1; ++b) mu += Sinv[a * K1 + b] * r[b];
-        rmu += r[a] * mu;
-        muphi += mu * phi[a];
-    }
-    P.ss_out[p] = P.vg.c0 - q + rmu;
-    P.z_out[p] = zc - muphi;
-}
-
-size_t kbk_solve_smem(int dtype) {
-    (void)dtype;
-    return (size_t)SV_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
-           SV_STAGES * sizeof(uint64_t) + 64;
-}
-// A/B switch for profiling only: KB200_SOLVE_V1=1 selects the non-specialised kernel.
-static bool use_v1() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("KB200_SOLVE_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
 static size_t solve_smem_pt() {
     return (size_t)PT_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
            KB_MAXAUX * KB_TN * sizeof(double) + 2 * PT_STAGES * sizeof(uint64_t) + 64;
 }
-bool kbk_solve_use_v1() { return use_v1(); }
 size_t kbk_solve_pt_scratch_doubles(int n, int grid) {
     return (size_t)grid * ((n + KB_BK - 1) / KB_BK) * (KB_BK * KB_TN);
 }
@@ -517,10 +281,8 @@ size_t kbk_solve_pt_scratch_doubles(int n, int grid) {
 
 template <int DIM, int MODEL>
 static cudaError_t solve_set_attr() {
-    KB_CUDA_OK(cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)solve_smem_pt()));
-    return cudaFuncSetAttribute(solve_kernel_f64<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)kbk_solve_smem(KB200_F64));
+    return cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)solve_smem_pt());
 }
 
 cudaError_t kbk_solve_init() {
@@ -529,26 +291,6 @@ cudaError_t kbk_solve_init() {
     KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT) KB_ATTR(KB200_VG_TABLE)
 #undef KB_ATTR
     return cudaSuccess;
-}
-
-template <int DIM>
-static cudaError_t solve_dim(int dtype, const SolveParams& p, cudaStream_t st) {
-    if (dtype != KB200_F64) return cudaErrorNotSupported;
-    dim3 grid((unsigned)(p.mpad / KB_TN), (unsigned)p.nrb);
-    size_t sm = kbk_solve_smem(dtype);
-    switch (p.vg.model) {
-#define KB_CASE(M) case M: solve_kernel_f64<DIM, M><<<grid, SV_THREADS, sm, st>>>(p); break;
-        KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
-        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
-#undef KB_CASE
-        default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
-}
-
-cudaError_t kbk_solve(int dim, int dtype, const SolveParams& p, cudaStream_t st) {
-    if (dim == KB_GEO) return solve_dim<KB_GEO>(dtype, p, st);
-    return dim == 2 ? solve_dim<2>(dtype, p, st) : solve_dim<3>(dtype, p, st);
 }
 
 template <int DIM>
@@ -569,10 +311,3 @@ cudaError_t kbk_solve_pt(int dim, const SolvePtParams& p, int grid, cudaStream_t
     return dim == 2 ? solve_pt_dim<2>(p, grid, st) : solve_pt_dim<3>(p, grid, st);
 }
 
-cudaError_t kbk_finalize(const FinalizeParams& p, cudaStream_t st) {
-    unsigned g = (unsigned)((p.m + 255) / 256);
-    if (p.dim == 2) finalize_kernel<2><<<g, 256, 0, st>>>(p);
-    else if (p.dim == 3) finalize_kernel<3><<<g, 256, 0, st>>>(p);
-    else finalize_kernel<KB_GEO><<<g, 256, 0, st>>>(p);
-    return cudaGetLastError();
-}

@@ -1,33 +1,40 @@
-// solve_i8.cu — K3 for dtype = KB200_F64X: fp64-class accuracy of q_j = ||W c_j||^2 on the
-// INT8 path of the 5th-generation tensor cores (tcgen05.mma kind::i8, exact int32 accumulation in TMEM).
+// solve_i8.cu — K3 for dtype = KB200_F64X / F64X5 / F64X4: fp64-class accuracy of q_j = ||W c_j||^2
+// on the INT8 path of the 5th-generation tensor cores (tcgen05.mma kind::i8, exact int32 accumulation in TMEM).
 //
 // Error-free slicing (the "Ozaki scheme"): every row of W and every RHS column is scaled by a power of two
-// into (-1, 1) and cut into S = 6 signed slices of 6+7+7+7+7+7 = 41 bits,
+// into (-1, 1) and cut into S signed slices of 6+7+...+7 bits (S = 6: 41 bits, 5: 34 bits, 4: 27 bits),
 //      x = 2^e * sum_s slice_s * 2^(-6-7s),   |slice_s| <= 64,
 // so that  W_rk c_k = 2^(ew_r + ec_j) * sum_{s,t} w_s c_t 2^(-12-7(s+t)).  All slice products with the
 // same d = s + t are summed EXACTLY in one int32 TMEM accumulator (|sum| <= n * (d+1) * 64^2 < 2^31 for
-// n <= 32512); pairs with d >= S are dropped (relative 2^-48 per term). The six accumulators are combined
-// in fp64 in the epilogue. The result agrees with the fp64 DMMA kernel to ~1e-10 (tests), at several
-// times its rate; dtype='float64' keeps the DMMA kernel as the default.
+// n <= 32512); pairs with d >= S are dropped (relative 2^-(7S+6) per term). The S accumulators are combined
+// exactly in int64 in the epilogue and converted to fp64 once. S = 6 agrees with the fp64 DMMA kernel to ~1e-10
+// (tests) at several times its rate; fewer slices trade bits for MMAs (S(S+1)/2 per k-stage: 21 / 15 / 10) and
+// operand bytes; dtype='float64' keeps the DMMA kernel as the default.
 //
-// Orientation as in solve_tf32.cu: D[point][W row], M = 128 points (TMEM lanes), N = 80 W rows per row
-// block (as many as the six accumulators leave room for in TMEM: the RHS slices are re-read once per row block), K = 32 per MMA; operands in the canonical no-swizzle K-major UMMA layout (8-row x 16-byte core
-// matrices, k-chunks 128 B apart, 8-row groups 256 B apart), one stage = 32 k = one MMA k-step,
-// 21 MMAs per stage (all slice pairs with s + t <= 5).
+// Orientation as in solve_tf32.cu: D[point][W row], M = 128 points (TMEM lanes), N = BN W rows per row block
+// with S * BN <= 512 TMEM columns (BN = 80 / 96 / 128: the RHS slices are re-read once per row block, so fewer
+// slices also mean fewer re-reads), K = 32 per MMA; operands in the canonical no-swizzle K-major UMMA layout
+// (8-row x 16-byte core matrices, k-chunks 128 B apart, 8-row groups 256 B apart), one stage = 32 k = one MMA
+// k-step. The variogram model is a run-time switch here (phase G is < 10 % of the kernel), so that the slice
+// count and the dimension are the only template parameters.
 #include "common.cuh"
 #include "kernels.h"
 
-#define I8_S 6
-#define I8_STAGES 5
 #define I8_THREADS 256
 #define I8_TM 128
-#define I8_BN 80                               // 6 accumulators x 80 columns = 480 of the 512 TMEM columns
 #define I8_BK 32
-#define I8_W_SLICE (I8_BN * I8_BK)            // 2 KB
 #define I8_C_SLICE (I8_TM * I8_BK)            // 4 KB
-#define I8_W_BYTES (I8_S * I8_W_SLICE)        // 12 KB
-#define I8_C_BYTES (I8_S * I8_C_SLICE)        // 24 KB
-#define I8_STAGE_BYTES (I8_W_BYTES + I8_C_BYTES)
+
+template <int S> struct I8Cfg {
+    static constexpr int BN = (S == 6) ? 80 : (S == 5) ? 96 : 128;     // S * BN <= 512 TMEM columns, BN % 16 == 0
+    static constexpr int STAGES = (S == 4) ? 6 : 5;
+    static constexpr int W_SLICE = BN * I8_BK;
+    static constexpr int W_BYTES = S * W_SLICE;
+    static constexpr int C_BYTES = S * I8_C_SLICE;
+    static constexpr int STAGE_BYTES = W_BYTES + C_BYTES;
+    // D = S32 (bits 4-5 = 2), A = B = signed 8 bit (bits 7-9, 10-12 = 1), K-major, N = BN, M = 128
+    static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(I8_TM >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t i8_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void i8_mbar_init(uint64_t* bar, int count) {
@@ -59,24 +66,23 @@ __device__ __forceinline__ uint64_t i8_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
            (1ull << 46);
 }
-// D = S32 (bits 4-5 = 2), A = B = signed 8 bit (bits 7-9, 10-12 = 1), K-major, N = 64, M = 128
-#define I8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_TM >> 4) << 24))
-__device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(I8_IDESC), "r"(accumulate) : "memory");
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void i8_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
                  :: "r"(i8_smem_u32(bar)) : "memory");
 }
 
-// six signed slices of y = x * 2^-e (|y| < 1): x = 2^e * sum_s out[s] * 2^(-6-7s) + O(2^(e-42))
-__device__ __forceinline__ void i8_slice(double x, int e, signed char (&out)[I8_S]) {
+// S signed slices of y = x * 2^-e (|y| < 1): x = 2^e * sum_s out[s] * 2^(-6-7s) + O(2^(e-7S))
+template <int S>
+__device__ __forceinline__ void i8_slice(double x, int e, signed char (&out)[S]) {
     double t = scalbn(x, 6 - e);           // y * 64
 #pragma unroll
-    for (int s = 0; s < I8_S; ++s) {
+    for (int s = 0; s < S; ++s) {
         double r = rint(t);
         out[s] = (signed char)(int)r;
         t = (t - r) * 128.0;
@@ -85,8 +91,8 @@ __device__ __forceinline__ void i8_slice(double x, int e, signed char (&out)[I8_
 // byte offset of element (r, k) inside one slice tile with `rows` rows (k in [0, 32))
 __device__ __forceinline__ int i8_off(int r, int k) { return (r >> 3) * 256 + (k >> 4) * 128 + (r & 7) * 16 + (k & 15); }
 
-__host__ __device__ __forceinline__ int i8_ktiles(int J, int n, int nk) {
-    return ((J + 1) * I8_BN > n) ? nk : min(nk, ((J + 1) * I8_BN + I8_BK - 1) / I8_BK);
+__host__ __device__ __forceinline__ int i8_ktiles(int J, int n, int nk, int BN) {
+    return ((J + 1) * BN > n) ? nk : min(nk, ((J + 1) * BN + I8_BK - 1) / I8_BK);
 }
 
 // ---- pack ---------------------------------------------------------------------------------------------
@@ -109,50 +115,66 @@ __global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restri
     }
 }
 
-// tile (row block J, k stage t): 6 slices x (64 rows x 32 k) int8 in UMMA layout
+// tile (row block J, k stage t): S slices x (BN rows x 32 k) int8 in UMMA layout
+template <int S>
 __global__ void __launch_bounds__(256) i8_pack_kernel(const double* __restrict__ W, int ld, int n, int n_pad, int na,
                                                        const double* __restrict__ Uz, const int* __restrict__ rowexp,
                                                        int nk, const long long* __restrict__ tile_off,
                                                        signed char* __restrict__ out) {
+    typedef I8Cfg<S> C;
     const int J = blockIdx.y, t = blockIdx.x;
-    if (t >= i8_ktiles(J, n, nk)) return;
-    signed char* o = out + (size_t)(tile_off[J] + t) * I8_W_BYTES;
-    for (int e = threadIdx.x; e < I8_BN * I8_BK; e += 256) {
+    if (t >= i8_ktiles(J, n, nk, C::BN)) return;
+    signed char* o = out + (size_t)(tile_off[J] + t) * C::W_BYTES;
+    for (int e = threadIdx.x; e < C::BN * I8_BK; e += 256) {
         const int rl = e >> 5, kl = e & 31;
-        const int r = J * I8_BN + rl, k = t * I8_BK + kl;
+        const int r = J * C::BN + rl, k = t * I8_BK + kl;
         double v = 0.0;
         if (r < n) { if (k <= r) v = W[(size_t)r * ld + k]; }
         else if (r < n + na) { if (k < n) v = Uz[(size_t)(r - n) * n_pad + k]; }
-        signed char sl[I8_S];
-        i8_slice(v, (r < n + na) ? rowexp[r] : 0, sl);
+        signed char sl[S];
+        i8_slice<S>(v, (r < n + na) ? rowexp[r] : 0, sl);
         const int off = i8_off(rl, kl);
 #pragma unroll
-        for (int s = 0; s < I8_S; ++s) o[s * I8_W_SLICE + off] = sl[s];
+        for (int s = 0; s < S; ++s) o[s * C::W_SLICE + off] = sl[s];
     }
 }
 
-template <int DIM, int MODEL>
+// shifted covariance with the model as a run-time switch (uniform across the grid)
+__device__ __forceinline__ double i8_cov_rhs(const VgParams& v, double d) {
+    switch (v.model) {
+        case KB200_VG_LINEAR: return kb_cov_rhs<KB200_VG_LINEAR>(v, d);
+        case KB200_VG_POWER: return kb_cov_rhs<KB200_VG_POWER>(v, d);
+        case KB200_VG_GAUSSIAN: return kb_cov_rhs<KB200_VG_GAUSSIAN>(v, d);
+        case KB200_VG_EXPONENTIAL: return kb_cov_rhs<KB200_VG_EXPONENTIAL>(v, d);
+        case KB200_VG_SPHERICAL: return kb_cov_rhs<KB200_VG_SPHERICAL>(v, d);
+        case KB200_VG_TABLE: return kb_cov_rhs<KB200_VG_TABLE>(v, d);
+        default: return kb_cov_rhs<KB200_VG_HOLE_EFFECT>(v, d);
+    }
+}
+
+template <int S, int DIM>
 __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_constant__ SolvePtParams P) {
+    typedef I8Cfg<S> C;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* stage_base = smem_raw;                                                    // I8_STAGES * 36 KB
-    double* auxs = reinterpret_cast<double*>(smem_raw + (size_t)I8_STAGES * I8_STAGE_BYTES);  // KB_MAXAUX * 128
+    unsigned char* stage_base = smem_raw;                                                    // STAGES * STAGE_BYTES
+    double* auxs = reinterpret_cast<double*>(smem_raw + (size_t)C::STAGES * C::STAGE_BYTES);  // KB_MAXAUX * 128
     int* pexp = reinterpret_cast<int*>(auxs + KB_MAXAUX * I8_TM);                            // 128 point exponents
-    uint64_t* full = reinterpret_cast<uint64_t*>(pexp + I8_TM);                              // I8_STAGES
-    uint64_t* empty = full + I8_STAGES;
-    uint64_t* tfull = empty + I8_STAGES;                                                     // 1
+    uint64_t* full = reinterpret_cast<uint64_t*>(pexp + I8_TM);                              // STAGES
+    uint64_t* empty = full + C::STAGES;
+    uint64_t* tfull = empty + C::STAGES;                                                     // 1
     uint64_t* tempty = tfull + 1;                                                            // 1
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nk = (P.n + I8_BK - 1) / I8_BK;
-    const int nrb = (P.n + P.na + I8_BN - 1) / I8_BN;
-    unsigned char* scratch = reinterpret_cast<unsigned char*>(P.scratch) + (size_t)blockIdx.x * nk * I8_C_BYTES;
+    const int nrb = (P.n + P.na + C::BN - 1) / C::BN;
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(P.scratch) + (size_t)blockIdx.x * nk * C::C_BYTES;
     const unsigned char* gt = reinterpret_cast<const unsigned char*>(P.tiles);
     const long long ntiles = (P.m + I8_TM - 1) / I8_TM;
-    const int K = P.n_rl + P.n_hd, K1 = K + 1;
+    const int model = P.vg.model;
 
     if (tid == 0) {
-        for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(&full[s], 1); i8_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::STAGES; ++s) { i8_mbar_init(&full[s], 1); i8_mbar_init(&empty[s], 1); }
         i8_mbar_init(tfull, 1); i8_mbar_init(tempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -171,7 +193,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
     uint32_t ga = 0;     // accumulator hand-over counter (row blocks)
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---------------- phase G: RHS column block -> 6 int8 slices per value, UMMA layout ----------------
+        // ---------------- phase G: RHS column block -> S int8 slices per value, UMMA layout ----------------
         {
             const int pl = tid & (I8_TM - 1);
             const int ks = tid >> 7;                       // 0..1
@@ -179,39 +201,39 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
             const bool pvalid = pj < P.m;
             double px = 0.0, py = 0.0, pz = 0.0;
             if (pvalid) kb_load_point<DIM>(P.ps, P.an, pj, px, py, pz);
-            // scale of this point's column: |c| <= c0 for the bounded models (gamma <= sill); for linear / power
-            // a first pass finds the maximum
+            // scale of this point's column: |c| <= c0 for the bounded models (gamma <= sill); for linear / power /
+            // tabulated models a first pass finds the maximum
             int ec;
             {
                 double cmax = fabs(P.vg.c0);
-                if (MODEL == KB200_VG_LINEAR || MODEL == KB200_VG_POWER) {
+                if (model == KB200_VG_LINEAR || model == KB200_VG_POWER || model == KB200_VG_TABLE) {
                     if (pvalid)
                         for (int k = 0; k < P.n; ++k) {
                             double d = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), KB_HASZ(DIM) ? __ldg(P.az + k) : 0.0, px, py, pz);
-                            cmax = fmax(cmax, fabs(kb_cov_rhs<MODEL>(P.vg, d)));
+                            cmax = fmax(cmax, fabs(i8_cov_rhs(P.vg, d)));
                         }
                 }
                 (void)frexp(cmax * 1.0000001, &ec);        // cmax * 2^-ec < 1
             }
             if (ks == 0) pexp[pl] = ec;
             for (int t = ks; t < nk; t += I8_THREADS / I8_TM) {
-                unsigned char* ct = scratch + (size_t)t * I8_C_BYTES;
+                unsigned char* ct = scratch + (size_t)t * C::C_BYTES;
 #pragma unroll 1
                 for (int kc = 0; kc < 2; ++kc) {           // two 16-byte k-chunks per stage
-                    signed char sl[16][I8_S];
+                    signed char sl[16][S];
 #pragma unroll
                     for (int kk = 0; kk < 16; ++kk) {
                         const int k = t * I8_BK + kc * 16 + kk;
                         double c = 0.0;
                         if (pvalid && k < P.n) {
                             double d = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), KB_HASZ(DIM) ? __ldg(P.az + k) : 0.0, px, py, pz);
-                            c = kb_cov_rhs<MODEL>(P.vg, d);
+                            c = i8_cov_rhs(P.vg, d);
                         }
-                        i8_slice(c, ec, sl[kk]);
+                        i8_slice<S>(c, ec, sl[kk]);
                     }
                     const int off = (pl >> 3) * 256 + kc * 128 + (pl & 7) * 16;
 #pragma unroll
-                    for (int s = 0; s < I8_S; ++s) {
+                    for (int s = 0; s < S; ++s) {
                         uint32_t w[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
@@ -232,14 +254,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
                 uint32_t gg = g;
                 long long tau = 0;
                 for (int J = 0; J < nrb; ++J) {
-                    const int kt = i8_ktiles(J, P.n, nk);
+                    const int kt = i8_ktiles(J, P.n, nk, C::BN);
                     for (int t = 0; t < kt; ++t, ++tau, ++gg) {
-                        const int s = gg % I8_STAGES;
-                        i8_mbar_wait(&empty[s], (uint32_t)(((gg / I8_STAGES) & 1) ^ 1));
-                        i8_mbar_expect_tx(&full[s], I8_STAGE_BYTES);
-                        unsigned char* sb = stage_base + (size_t)s * I8_STAGE_BYTES;
-                        i8_bulk_g2s(sb, gt + (size_t)tau * I8_W_BYTES, I8_W_BYTES, &full[s]);
-                        i8_bulk_g2s(sb + I8_W_BYTES, scratch + (size_t)t * I8_C_BYTES, I8_C_BYTES, &full[s]);
+                        const int s = gg % C::STAGES;
+                        i8_mbar_wait(&empty[s], (uint32_t)(((gg / C::STAGES) & 1) ^ 1));
+                        i8_mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                        unsigned char* sb = stage_base + (size_t)s * C::STAGE_BYTES;
+                        i8_bulk_g2s(sb, gt + (size_t)tau * C::W_BYTES, C::W_BYTES, &full[s]);
+                        i8_bulk_g2s(sb + C::W_BYTES, scratch + (size_t)t * C::C_BYTES, C::C_BYTES, &full[s]);
                     }
                 }
             }
@@ -247,23 +269,23 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
             if (lane == 0) {
                 uint32_t gg = g, gb = ga;
                 for (int J = 0; J < nrb; ++J, ++gb) {
-                    const int kt = i8_ktiles(J, P.n, nk);
+                    const int kt = i8_ktiles(J, P.n, nk, C::BN);
                     i8_mbar_wait(tempty, (uint32_t)((gb & 1) ^ 1));
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     for (int t = 0; t < kt; ++t, ++gg) {
-                        const int s = gg % I8_STAGES;
-                        i8_mbar_wait(&full[s], (uint32_t)((gg / I8_STAGES) & 1));
+                        const int s = gg % C::STAGES;
+                        i8_mbar_wait(&full[s], (uint32_t)((gg / C::STAGES) & 1));
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                        const uint32_t wb = i8_smem_u32(stage_base + (size_t)s * I8_STAGE_BYTES);
-                        const uint32_t cb = wb + I8_W_BYTES;
+                        const uint32_t wb = i8_smem_u32(stage_base + (size_t)s * C::STAGE_BYTES);
+                        const uint32_t cb = wb + C::W_BYTES;
 #pragma unroll
-                        for (int d = 0; d < I8_S; ++d) {
+                        for (int d = 0; d < S; ++d) {
 #pragma unroll
                             for (int sw = 0; sw <= d; ++sw) {
                                 const int sc = d - sw;                                     // slice of c
                                 const uint32_t acc = (t == 0 && sw == 0) ? 0u : 1u;
-                                i8_mma(tmem_base + (uint32_t)d * I8_BN, i8_desc(cb + sc * I8_C_SLICE),
-                                       i8_desc(wb + sw * I8_W_SLICE), acc);
+                                i8_mma(tmem_base + (uint32_t)d * C::BN, i8_desc(cb + sc * I8_C_SLICE),
+                                       i8_desc(wb + sw * C::W_SLICE), C::IDESC, acc);
                             }
                         }
                         i8_commit(&empty[s]);
@@ -274,7 +296,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
         } else if (warp >= 4) {
             // epilogue: thread = TMEM lane = prediction point
             const int pl = (warp & 3) * 32 + lane;
-            const double pscale = scalbn(1.0, pexp[pl]);
+            const double pscale = scalbn(1.0, pexp[pl] - 7 * (S - 1));
             double q = 0.0;
             uint32_t gb = ga;
             for (int J = 0; J < nrb; ++J, ++gb) {
@@ -282,30 +304,31 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t t_addr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
 #pragma unroll 1
-                for (int ch = 0; ch < I8_BN / 16; ++ch) {
-                    double v[16];
+                for (int ch = 0; ch < C::BN / 16; ++ch) {
+                    // exact recombination: V = sum_d acc_d * 2^(7 (S-1-d)) fits in int64 (|acc_d| < 2^30, d = 0 has one
+                    // slice pair: < 2^27 * 2^35)
+                    long long V[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0.0;
-#pragma unroll 1
-                    for (int d = I8_S - 1; d >= 0; --d) {       // smallest contributions first
+                    for (int j = 0; j < 16; ++j) V[j] = 0;
+#pragma unroll
+                    for (int d = 0; d < S; ++d) {
                         uint32_t u[16];
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                             : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
                               "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-                            : "r"(t_addr + (uint32_t)d * I8_BN + (uint32_t)ch * 16u));
+                            : "r"(t_addr + (uint32_t)d * C::BN + (uint32_t)ch * 16u));
                         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                        const double sd = scalbn(1.0, -7 * d);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += (double)(int)u[j] * sd;
+                        for (int j = 0; j < 16; ++j) V[j] = V[j] * 128 + (long long)(int)u[j];
                     }
-                    const int r0 = J * I8_BN + ch * 16;
+                    const int r0 = J * C::BN + ch * 16;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int r = r0 + j;
                         if (r < P.n + P.na) {
-                            const double x = v[j] * __ldg(P.rowscale + r) * pscale;
+                            const double x = (double)V[j] * (__ldg(P.rowscale + r) * pscale);
                             if (r < P.n) q += x * x;
                             else auxs[(r - P.n) * I8_TM + pl] = x;
                         }
@@ -317,37 +340,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
             }
             // ---------------- phase F: finalize, thread = point ----------------
             const long long pj = tile * I8_TM + pl;
-            if (pj < P.m) {
-                double r[KB200_MAX_DRIFT + 1];
-                double f[KB200_MAX_DRIFT + 1];
-                if (P.n_rl > 0) {
-                    double x, y, z;
-                    kb_load_point<DIM>(P.ps, P.an, pj, x, y, z);
-                    f[0] = (x - P.ds.shift[0]) * P.ds.scale[0];
-                    f[1] = (y - P.ds.shift[1]) * P.ds.scale[1];
-                    if (DIM == 3) f[2] = (z - P.ds.shift[2]) * P.ds.scale[2];
-                }
-                for (int c = 0; c < P.n_hd; ++c) {
-                    double v = P.drift_pts[(size_t)c * P.drift_stride + P.drift_first + pj];
-                    f[P.n_rl + c] = (v - P.ds.shift[P.n_rl + c]) * P.ds.scale[P.n_rl + c];
-                }
-                f[K] = 1.0;
-                for (int a = 0; a < K1; ++a) r[a] = auxs[a * I8_TM + pl] - f[a];
-                const double zc = auxs[K1 * I8_TM + pl];
-                const double* Sinv = P.consts;
-                const double* phi = P.consts + K1 * K1;
-                double rmu = 0.0, muphi = 0.0;
-                for (int a = 0; a < K1; ++a) {
-                    double mu = 0.0;
-                    for (int b = 0; b < K1; ++b) mu += Sinv[a * K1 + b] * r[b];
-                    rmu += r[a] * mu;
-                    muphi += mu * phi[a];
-                }
-                P.ss_out[pj] = P.vg.c0 - q + rmu;
-                P.z_out[pj] = zc - muphi;
-            }
+            if (pj < P.m) kb_finalize_point<DIM, double>(P, pj, q, auxs + pl, I8_TM);
         }
-        for (int J = 0; J < nrb; ++J) g += (uint32_t)i8_ktiles(J, P.n, nk);
+        for (int J = 0; J < nrb; ++J) g += (uint32_t)i8_ktiles(J, P.n, nk, C::BN);
         ga += (uint32_t)nrb;
         __syncthreads();
     }
@@ -359,59 +354,58 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-static size_t i8_smem() {
-    return (size_t)I8_STAGES * I8_STAGE_BYTES + (size_t)KB_MAXAUX * I8_TM * sizeof(double) + I8_TM * sizeof(int) +
-           (2 * I8_STAGES + 2) * sizeof(uint64_t) + 64;
+template <int S> static size_t i8_smem_s() {
+    return (size_t)I8Cfg<S>::STAGES * I8Cfg<S>::STAGE_BYTES + (size_t)KB_MAXAUX * I8_TM * sizeof(double) + I8_TM * sizeof(int) +
+           (2 * I8Cfg<S>::STAGES + 2) * sizeof(uint64_t) + 64;
 }
-int kbk_i8_nrb(int n, int na) { return (n + na + I8_BN - 1) / I8_BN; }
-int kbk_i8_rows(int n, int na) { return kbk_i8_nrb(n, na) * I8_BN; }
-long long kbk_i8_total_tiles(int n, int na, long long* tile_off /* [nrb+1] or null */) {
-    int nk = (n + I8_BK - 1) / I8_BK, nrb = kbk_i8_nrb(n, na);
+static int i8_bn(int S) { return S == 6 ? I8Cfg<6>::BN : S == 5 ? I8Cfg<5>::BN : I8Cfg<4>::BN; }
+bool kbk_i8_valid_slices(int S) { return S >= 4 && S <= 6; }
+int kbk_i8_nrb(int S, int n, int na) { return (n + na + i8_bn(S) - 1) / i8_bn(S); }
+int kbk_i8_rows(int S, int n, int na) { return kbk_i8_nrb(S, n, na) * i8_bn(S); }
+long long kbk_i8_total_tiles(int S, int n, int na, long long* tile_off /* [nrb+1] or null */) {
+    int nk = (n + I8_BK - 1) / I8_BK, nrb = kbk_i8_nrb(S, n, na);
     long long off = 0;
-    for (int J = 0; J < nrb; ++J) { if (tile_off) tile_off[J] = off; off += i8_ktiles(J, n, nk); }
+    for (int J = 0; J < nrb; ++J) { if (tile_off) tile_off[J] = off; off += i8_ktiles(J, n, nk, i8_bn(S)); }
     if (tile_off) tile_off[nrb] = off;
     return off;
 }
-size_t kbk_i8_tile_bytes() { return I8_W_BYTES; }
-size_t kbk_solve_i8_scratch_bytes(int n, int grid) { return (size_t)grid * ((n + I8_BK - 1) / I8_BK) * I8_C_BYTES; }
+size_t kbk_i8_tile_bytes(int S) { return (size_t)S * i8_bn(S) * I8_BK; }
+size_t kbk_solve_i8_scratch_bytes(int S, int n, int grid) { return (size_t)grid * ((n + I8_BK - 1) / I8_BK) * S * I8_C_SLICE; }
 int kbk_solve_i8_tile_points() { return I8_TM; }
 
-template <int DIM, int MODEL>
+template <int S, int DIM>
 static cudaError_t i8_attr() {
-    return cudaFuncSetAttribute(solve_kernel_i8<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem());
+    return cudaFuncSetAttribute(solve_kernel_i8<S, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem_s<S>());
 }
 cudaError_t kbk_solve_i8_init() {
-#define KB_ATTR(M) KB_CUDA_OK((i8_attr<2, M>())); KB_CUDA_OK((i8_attr<3, M>())); KB_CUDA_OK((i8_attr<KB_GEO, M>()));
-    KB_ATTR(KB200_VG_LINEAR) KB_ATTR(KB200_VG_POWER) KB_ATTR(KB200_VG_GAUSSIAN)
-    KB_ATTR(KB200_VG_EXPONENTIAL) KB_ATTR(KB200_VG_SPHERICAL) KB_ATTR(KB200_VG_HOLE_EFFECT) KB_ATTR(KB200_VG_TABLE)
+#define KB_ATTR(S) KB_CUDA_OK((i8_attr<S, 2>())); KB_CUDA_OK((i8_attr<S, 3>())); KB_CUDA_OK((i8_attr<S, KB_GEO>()));
+    KB_ATTR(4) KB_ATTR(5) KB_ATTR(6)
 #undef KB_ATTR
     return cudaSuccess;
 }
 
-template <int DIM>
-static cudaError_t i8_dim(const SolvePtParams& p, int grid, cudaStream_t st) {
-    size_t sm = i8_smem();
-    switch (p.vg.model) {
-#define KB_CASE(M) case M: solve_kernel_i8<DIM, M><<<grid, I8_THREADS, sm, st>>>(p); break;
-        KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
-        KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
-#undef KB_CASE
-        default: return cudaErrorInvalidValue;
-    }
+template <int S>
+static cudaError_t i8_launch(int dim, const SolvePtParams& p, int grid, cudaStream_t st) {
+    const size_t sm = i8_smem_s<S>();
+    if (dim == KB_GEO) solve_kernel_i8<S, KB_GEO><<<grid, I8_THREADS, sm, st>>>(p);
+    else if (dim == 2) solve_kernel_i8<S, 2><<<grid, I8_THREADS, sm, st>>>(p);
+    else solve_kernel_i8<S, 3><<<grid, I8_THREADS, sm, st>>>(p);
     return cudaGetLastError();
 }
-cudaError_t kbk_solve_i8(int dim, const SolvePtParams& p, int grid, cudaStream_t st) {
-    if (dim == KB_GEO) return i8_dim<KB_GEO>(p, grid, st);
-    return dim == 2 ? i8_dim<2>(p, grid, st) : i8_dim<3>(p, grid, st);
+cudaError_t kbk_solve_i8(int S, int dim, const SolvePtParams& p, int grid, cudaStream_t st) {
+    if (p.vg.model < KB200_VG_LINEAR || p.vg.model > KB200_VG_TABLE) return cudaErrorInvalidValue;
+    return S == 6 ? i8_launch<6>(dim, p, grid, st) : S == 5 ? i8_launch<5>(dim, p, grid, st) : i8_launch<4>(dim, p, grid, st);
 }
 
 // W (+ dual rows) -> row scales + int8 slice tiles. tile_off_dev: device copy of the per-row-block tile offsets.
-cudaError_t kbk_pack_i8(const double* W, int ld, int n, int n_pad, int na, const double* Uz,
+cudaError_t kbk_pack_i8(int S, const double* W, int ld, int n, int n_pad, int na, const double* Uz,
                         int* rowexp, double* rowscale, const long long* tile_off_dev, void* out, cudaStream_t st) {
-    int nrb = kbk_i8_nrb(n, na), nk = (n + I8_BK - 1) / I8_BK;
-    int nrows = nrb * I8_BN;
+    int nrb = kbk_i8_nrb(S, n, na), nk = (n + I8_BK - 1) / I8_BK;
+    int nrows = nrb * i8_bn(S);
     i8_rowscale_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(W, ld, n, n_pad, na, Uz, nrows, rowexp, rowscale);
     dim3 grid(nk, nrb);
-    i8_pack_kernel<<<grid, 256, 0, st>>>(W, ld, n, n_pad, na, Uz, rowexp, nk, tile_off_dev, (signed char*)out);
+    if (S == 6) i8_pack_kernel<6><<<grid, 256, 0, st>>>(W, ld, n, n_pad, na, Uz, rowexp, nk, tile_off_dev, (signed char*)out);
+    else if (S == 5) i8_pack_kernel<5><<<grid, 256, 0, st>>>(W, ld, n, n_pad, na, Uz, rowexp, nk, tile_off_dev, (signed char*)out);
+    else i8_pack_kernel<4><<<grid, 256, 0, st>>>(W, ld, n, n_pad, na, Uz, rowexp, nk, tile_off_dev, (signed char*)out);
     return cudaGetLastError();
 }

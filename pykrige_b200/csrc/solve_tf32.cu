@@ -135,7 +135,6 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
     unsigned char* scratch = reinterpret_cast<unsigned char*>(P.scratch) + (size_t)blockIdx.x * nk * TF_C_BYTES;
     const unsigned char* gt = reinterpret_cast<const unsigned char*>(P.tiles);
     const long long ntiles = (P.m + TF_TM - 1) / TF_TM;
-    const int K = P.n_rl + P.n_hd, K1 = K + 1;
 
     if (tid == 0) {
         for (int s = 0; s < TF_STAGES; ++s) { tf_mbar_init(&full[s], 1); tf_mbar_init(&empty[s], 1); }
@@ -281,35 +280,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
             }
             // ---------------- phase F: finalize, thread = point ----------------
             const long long pj = tile * TF_TM + pl;
-            if (pj < P.m) {
-                double r[KB200_MAX_DRIFT + 1];
-                double f[KB200_MAX_DRIFT + 1];
-                if (P.n_rl > 0) {
-                    double x, y, z;
-                    kb_load_point<DIM>(P.ps, P.an, pj, x, y, z);
-                    f[0] = (x - P.ds.shift[0]) * P.ds.scale[0];
-                    f[1] = (y - P.ds.shift[1]) * P.ds.scale[1];
-                    if (DIM == 3) f[2] = (z - P.ds.shift[2]) * P.ds.scale[2];
-                }
-                for (int c = 0; c < P.n_hd; ++c) {
-                    double v = P.drift_pts[(size_t)c * P.drift_stride + P.drift_first + pj];
-                    f[P.n_rl + c] = (v - P.ds.shift[P.n_rl + c]) * P.ds.scale[P.n_rl + c];
-                }
-                f[K] = 1.0;
-                for (int a = 0; a < K1; ++a) r[a] = (double)auxs[a * TF_TM + pl] - f[a];
-                const double zc = (double)auxs[K1 * TF_TM + pl];
-                const double* Sinv = P.consts;
-                const double* phi = P.consts + K1 * K1;
-                double rmu = 0.0, muphi = 0.0;
-                for (int a = 0; a < K1; ++a) {
-                    double mu = 0.0;
-                    for (int b = 0; b < K1; ++b) mu += Sinv[a * K1 + b] * r[b];
-                    rmu += r[a] * mu;
-                    muphi += mu * phi[a];
-                }
-                P.ss_out[pj] = P.vg.c0 - q + rmu;
-                P.z_out[pj] = zc - muphi;
-            }
+            if (pj < P.m) kb_finalize_point<DIM, float>(P, pj, q, auxs + pl, TF_TM);
         }
         // every role advances the ring counters by the same amounts
         for (int I = 0; I < P.nrb; ++I) g += (uint32_t)P.pm.ktiles[I];

@@ -200,11 +200,13 @@ class OrdinaryKriging(KrigeBase):
         Mt = core.anisotropy_matrix(2, [self.anisotropy_scaling], [self.anisotropy_angle])
         return self.X_ORIG, self.Y_ORIG, None, self.Z, [self.XCENTER, self.YCENTER], Mt
 
-    def execute(self, style, xpoints, ypoints, mask=None, backend="cuda", n_closest_points=None, dtype="float64"):
+    def execute(self, style, xpoints, ypoints, mask=None, backend="cuda", n_closest_points=None, dtype="float64",
+                n_gpus=None):
         """Calculates a kriged grid and the associated variance (ok.py:760-1020).
 
         ``backend='cuda'`` is the only backend of this package. ``style``, ``mask`` and
         ``n_closest_points`` behave as in the reference, including the exception types.
+        ``n_gpus=G`` shards the prediction points over G GPUs of this box from this one host thread.
         Returns ``(zvalues, sigmasq)`` shaped ``(ny, nx)`` for 'grid'/'masked' (masked arrays
         for 'masked') or ``(n,)`` for 'points'.
         """
@@ -214,37 +216,8 @@ class OrdinaryKriging(KrigeBase):
             raise ValueError("style argument must be 'grid', 'points', or 'masked'")
         if n_closest_points is not None and n_closest_points <= 1:
             raise ValueError("n_closest_points has to be at least two!")
-
-        xpts = np.atleast_1d(np.squeeze(np.array(xpoints, copy=True)))
-        ypts = np.atleast_1d(np.squeeze(np.array(ypoints, copy=True)))
-        nx = xpts.size
-        ny = ypts.size
-        flat_mask = None
-        if style in ["grid", "masked"]:
-            if style == "masked":
-                if mask is None:
-                    raise IOError("Must specify boolean masking array when style is 'masked'.")
-                if mask.shape[0] != ny or mask.shape[1] != nx:
-                    if mask.shape[0] == nx and mask.shape[1] == ny:
-                        mask = mask.T
-                    else:
-                        raise ValueError("Mask dimensions do not match specified grid dimensions.")
-                flat_mask = np.asarray(mask, dtype=bool).flatten()
-        elif style == "points":
-            if xpts.size != ypts.size:
-                raise ValueError(
-                    "xpoints and ypoints must have same dimensions when treated as listing discrete points."
-                )
+        axes, sizes, flat_mask = self._prepare_points(style, (xpoints, ypoints), mask)
         self._check_backend(backend, "2D ordinary kriging")
-
-        zvalues, sigmasq = self._run_cuda(
-            style, [xpts.astype(np.float64), ypts.astype(np.float64)], flat_mask,
-            n_closest_points=n_closest_points, dtype=dtype,
-        )
-        if style == "masked":
-            zvalues = np.ma.array(zvalues, mask=flat_mask)
-            sigmasq = np.ma.array(sigmasq, mask=flat_mask)
-        if style in ["masked", "grid"]:
-            zvalues = zvalues.reshape((ny, nx))
-            sigmasq = sigmasq.reshape((ny, nx))
-        return zvalues, sigmasq
+        zvalues, sigmasq = self._run_cuda(style, axes, flat_mask, n_closest_points=n_closest_points, dtype=dtype,
+                                          n_gpus=n_gpus)
+        return self._shape_output(style, zvalues, sigmasq, sizes, flat_mask)

@@ -138,34 +138,6 @@ class _Krige3DMixin:
         return (self.X_ORIG, self.Y_ORIG, self.Z_ORIG, self.VALUES,
                 [self.XCENTER, self.YCENTER, self.ZCENTER], Mt)
 
-    def _prep_points_3d(self, style, xpoints, ypoints, zpoints, mask):
-        """Input validation of execute (ok3d.py:833-876): returns (xpts, ypts, zpts, nx, ny, nz, flat_mask)."""
-        if style != "grid" and style != "masked" and style != "points":
-            raise ValueError("style argument must be 'grid', 'points', or 'masked'")
-        xpts = np.atleast_1d(np.squeeze(np.array(xpoints, copy=True)))
-        ypts = np.atleast_1d(np.squeeze(np.array(ypoints, copy=True)))
-        zpts = np.atleast_1d(np.squeeze(np.array(zpoints, copy=True)))
-        nx, ny, nz = xpts.size, ypts.size, zpts.size
-        flat_mask = None
-        if style in ["grid", "masked"]:
-            if style == "masked":
-                if mask is None:
-                    raise IOError("Must specify boolean masking array when style is 'masked'.")
-                if mask.ndim != 3:
-                    raise ValueError("Mask is not three-dimensional.")
-                if mask.shape[0] != nz or mask.shape[1] != ny or mask.shape[2] != nx:
-                    if mask.shape[0] == nx and mask.shape[2] == nz and mask.shape[1] == ny:
-                        mask = mask.swapaxes(0, 2)
-                    else:
-                        raise ValueError("Mask dimensions do not match specified grid dimensions.")
-                flat_mask = np.asarray(mask, dtype=bool).flatten()
-        elif style == "points":
-            if xpts.size != ypts.size and ypts.size != zpts.size:
-                raise ValueError(
-                    "xpoints, ypoints, and zpoints must have same dimensions when treated as listing discrete points."
-                )
-        return (xpts.astype(np.float64), ypts.astype(np.float64), zpts.astype(np.float64), nx, ny, nz, flat_mask)
-
 
 class OrdinaryKriging3D(_Krige3DMixin, KrigeBase):
     """Three-dimensional ordinary kriging; arguments as in the reference docstring (ok3d.py:37-196)."""
@@ -198,21 +170,15 @@ class OrdinaryKriging3D(_Krige3DMixin, KrigeBase):
                              pseudo_inv, pseudo_inv_type)
 
     def execute(self, style, xpoints, ypoints, zpoints, mask=None, backend="cuda", n_closest_points=None,
-                dtype="float64"):
+                dtype="float64", n_gpus=None):
         """Calculates a kriged 3-D grid and the associated variance (ok3d.py:735-932); ``backend='cuda'``.
         Output shape (nz, ny, nx) for 'grid'/'masked', (n,) for 'points'."""
         if self.verbose:
             print("Executing Ordinary Kriging...\n")
-        xpts, ypts, zpts, nx, ny, nz, flat_mask = self._prep_points_3d(style, xpoints, ypoints, zpoints, mask)
+        axes, sizes, flat_mask = self._prepare_points(style, (xpoints, ypoints, zpoints), mask)
         if n_closest_points is not None and n_closest_points <= 1:
             raise ValueError("n_closest_points has to be at least two!")
         self._check_backend(backend, "3D ordinary kriging")
-        kvalues, sigmasq = self._run_cuda(style, [xpts, ypts, zpts], flat_mask,
-                                          n_closest_points=n_closest_points, dtype=dtype)
-        if style == "masked":
-            kvalues = np.ma.array(kvalues, mask=flat_mask)
-            sigmasq = np.ma.array(sigmasq, mask=flat_mask)
-        if style in ["masked", "grid"]:
-            kvalues = kvalues.reshape((nz, ny, nx))
-            sigmasq = sigmasq.reshape((nz, ny, nx))
-        return kvalues, sigmasq
+        kvalues, sigmasq = self._run_cuda(style, axes, flat_mask, n_closest_points=n_closest_points, dtype=dtype,
+                                          n_gpus=n_gpus)
+        return self._shape_output(style, kvalues, sigmasq, sizes, flat_mask)

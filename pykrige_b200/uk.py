@@ -303,104 +303,58 @@ class UniversalKriging(KrigeBase):
                 cols.append(np.asarray(func(self.X_ADJUSTED, self.Y_ADJUSTED), dtype=float))
         return (2 if self.regional_linear_drift else 0), cols
 
-    def _problem_signature(self, dtype, knn):
-        sig = super()._problem_signature(dtype, knn)
-        _, cols = self._drift_spec()
-        return sig + tuple(float(np.sum(c)) for c in cols)
+    def _device_drift_signature(self):
+        """point_log wells and the external-Z raster are evaluated at the prediction points by the solve
+        kernels themselves (kb200_set_device_drift); their content is part of the problem key."""
+        import hashlib
+        hsh = hashlib.blake2b(digest_size=16)
+        if self.point_log_drift:
+            hsh.update(np.ascontiguousarray(self.point_log_array, dtype=np.float64).tobytes())
+        if self.external_Z_drift:
+            for a in (self.external_Z_array_x, self.external_Z_array_y, self.external_Z_array):
+                hsh.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+        return (bool(self.point_log_drift), bool(self.external_Z_drift), hsh.hexdigest())
+
+    def _configure_device_drift(self, h):
+        wells = self.point_log_array if self.point_log_drift else None
+        ext = ((self.external_Z_array_x, self.external_Z_array_y, self.external_Z_array)
+               if self.external_Z_drift else None)
+        h.set_device_drift(wells, ext)
 
     def execute(self, style, xpoints, ypoints, mask=None, backend="cuda", specified_drift_arrays=None,
-                dtype="float64"):
-        """Calculates a kriged grid and the associated variance (uk.py:1090-1328); ``backend='cuda'``."""
+                dtype="float64", n_gpus=None):
+        """Calculates a kriged grid and the associated variance (uk.py:1090-1328); ``backend='cuda'``.
+        point_log and external_Z drift terms are evaluated at the prediction points on the device
+        (uk.py:955-971, bilinear sampler uk.py:512-628); 'specified' and 'functional' terms are host
+        arrays / host callables by definition and are shipped as columns."""
         if self.verbose:
             print("Executing Universal Kriging...\n")
-        if style != "grid" and style != "masked" and style != "points":
-            raise ValueError("style argument must be 'grid', 'points', or 'masked'")
-        xpts = np.atleast_1d(np.squeeze(np.array(xpoints, copy=True)))
-        ypts = np.atleast_1d(np.squeeze(np.array(ypoints, copy=True)))
-        nx = xpts.size
-        ny = ypts.size
-        flat_mask = None
-        if style in ["grid", "masked"]:
-            if style == "masked":
-                if mask is None:
-                    raise IOError("Must specify boolean masking array when style is 'masked'.")
-                if mask.shape[0] != ny or mask.shape[1] != nx:
-                    if mask.shape[0] == nx and mask.shape[1] == ny:
-                        mask = mask.T
-                    else:
-                        raise ValueError("Mask dimensions do not match specified grid dimensions.")
-                flat_mask = np.asarray(mask, dtype=bool).flatten()
-        elif style == "points":
-            if xpts.size != ypts.size:
-                raise ValueError("xpoints and ypoints must have same dimensions when treated as listing discrete points.")
-
-        # specified-drift validation (uk.py:1217-1274)
-        if specified_drift_arrays is None:
-            specified_drift_arrays = []
-        spec_drift_grids = []
-        if self.specified_drift:
-            if len(specified_drift_arrays) == 0:
-                raise ValueError("Must provide drift values for kriging points when using 'specified' drift capability.")
-            if type(specified_drift_arrays) is not list:
-                raise TypeError("Arrays for specified drift terms must be encapsulated in a list.")
-            for spec in specified_drift_arrays:
-                if style in ["grid", "masked"]:
-                    if spec.ndim < 2:
-                        raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
-                    elif spec.shape[0] != ny or spec.shape[1] != nx:
-                        if spec.shape[0] == nx and spec.shape[1] == ny:
-                            spec_drift_grids.append(np.squeeze(spec.T))
-                        else:
-                            raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
-                    else:
-                        spec_drift_grids.append(np.squeeze(spec))
-                elif style == "points":
-                    if spec.ndim != 1:
-                        raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
-                    elif spec.shape[0] != xpts.size:
-                        raise ValueError("Number of supplied drift values in array do not match specified number of kriging points.")
-                    else:
-                        spec_drift_grids.append(np.squeeze(spec))
-            if len(spec_drift_grids) != len(self.specified_drift_data_arrays):
-                raise ValueError("Inconsistent number of specified drift terms supplied.")
-        else:
-            if len(specified_drift_arrays) != 0:
-                warnings.warn(
-                    "Provided specified drift values, but 'specified' drift was not initialized during "
-                    "instantiation of UniversalKriging class.", RuntimeWarning,
-                )
+        axes, sizes, flat_mask = self._prepare_points(style, (xpoints, ypoints), mask)
+        xpts, ypts = axes
+        spec_drift_grids = self._specified_drift_grids(style, specified_drift_arrays, sizes, xpts.size,
+                                                       "UniversalKriging")
         self._check_backend(backend, "2D universal kriging")
+        if self.external_Z_drift and xpts.size and ypts.size:
+            ax, ay = self.external_Z_array_x, self.external_Z_array_y      # domain check of uk.py:545-551
+            if (np.amax(xpts) > np.amax(ax) or np.amin(xpts) < np.amin(ax)
+                    or np.amax(ypts) > np.amax(ay) or np.amin(ypts) < np.amin(ay)):
+                raise ValueError("External drift array does not cover specified kriging domain.")
 
-        host_terms = self.point_log_drift or self.external_Z_drift or self.specified_drift or self.functional_drift
         drift_at = None
-        if host_terms:
+        if self.specified_drift or self.functional_drift:
             def drift_at(pts, idx):
-                xo, yo = pts[0], pts[1]
-                xa, ya = _adjust_for_anisotropy(
-                    np.vstack((xo, yo)).T, [self.XCENTER, self.YCENTER],
-                    [self.anisotropy_scaling], [self.anisotropy_angle]).T
                 cols = []
-                if self.point_log_drift:
-                    for w in range(self.point_log_array.shape[0]):
-                        cols.append(self._point_log_column(w, xa, ya))
-                if self.external_Z_drift:
-                    cols.append(self._calculate_data_point_zscalars(xo, yo))
                 if self.specified_drift:
                     for g in spec_drift_grids:
                         flat = np.asarray(g, dtype=float).flatten()
                         cols.append(flat if idx is None else flat[idx])
                 if self.functional_drift:
+                    xa, ya = _adjust_for_anisotropy(
+                        np.vstack((pts[0], pts[1])).T, [self.XCENTER, self.YCENTER],
+                        [self.anisotropy_scaling], [self.anisotropy_angle]).T
                     for func in self.functional_drift_terms:
                         cols.append(np.asarray(func(xa, ya), dtype=float) * np.ones(xa.shape))
                 return np.ascontiguousarray(np.vstack(cols), dtype=np.float64)
 
-        zvalues, sigmasq = self._run_cuda(
-            style, [xpts.astype(np.float64), ypts.astype(np.float64)], flat_mask, drift_at=drift_at, dtype=dtype,
-        )
-        if style == "masked":
-            zvalues = np.ma.array(zvalues, mask=flat_mask)
-            sigmasq = np.ma.array(sigmasq, mask=flat_mask)
-        if style in ["masked", "grid"]:
-            zvalues = zvalues.reshape((ny, nx))
-            sigmasq = sigmasq.reshape((ny, nx))
-        return zvalues, sigmasq
+        zvalues, sigmasq = self._run_cuda(style, axes, flat_mask, drift_at=drift_at, dtype=dtype, n_gpus=n_gpus)
+        return self._shape_output(style, zvalues, sigmasq, sizes, flat_mask)

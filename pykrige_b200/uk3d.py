@@ -91,78 +91,33 @@ class UniversalKriging3D(_Krige3DMixin, KrigeBase):
                 cols.append(np.asarray(func(self.X_ADJUSTED, self.Y_ADJUSTED, self.Z_ADJUSTED), dtype=float))
         return (3 if self.regional_linear_drift else 0), cols
 
-    def _problem_signature(self, dtype, knn):
-        sig = super()._problem_signature(dtype, knn)
-        _, cols = self._drift_spec()
-        return sig + tuple(float(np.sum(c)) for c in cols)
-
     def execute(self, style, xpoints, ypoints, zpoints, mask=None, backend="cuda", specified_drift_arrays=None,
-                dtype="float64"):
+                dtype="float64", n_gpus=None):
         """Calculates a kriged 3-D grid and the associated variance (uk3d.py:877-1146); ``backend='cuda'``."""
         if self.verbose:
             print("Executing Universal Kriging...\n")
-        xpts, ypts, zpts, nx, ny, nz, flat_mask = self._prep_points_3d(style, xpoints, ypoints, zpoints, mask)
-
-        # specified-drift validation (uk3d.py:1040-1098)
-        if specified_drift_arrays is None:
-            specified_drift_arrays = []
-        spec_drift_grids = []
-        if self.specified_drift:
-            if len(specified_drift_arrays) == 0:
-                raise ValueError("Must provide drift values for kriging points when using 'specified' drift capability.")
-            if type(specified_drift_arrays) is not list:
-                raise TypeError("Arrays for specified drift terms must be encapsulated in a list.")
-            for spec in specified_drift_arrays:
-                if style in ["grid", "masked"]:
-                    if spec.ndim < 3:
-                        raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
-                    elif spec.shape[0] != nz or spec.shape[1] != ny or spec.shape[2] != nx:
-                        if spec.shape[0] == nx and spec.shape[2] == nz and spec.shape[1] == ny:
-                            spec_drift_grids.append(np.squeeze(spec.swapaxes(0, 2)))
-                        else:
-                            raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
-                    else:
-                        spec_drift_grids.append(np.squeeze(spec))
-                elif style == "points":
-                    if spec.ndim != 1:
-                        raise ValueError("Dimensions of drift values array do not match specified grid dimensions.")
-                    elif spec.shape[0] != xpts.size:
-                        raise ValueError("Number of supplied drift values in array do not match specified number of kriging points.")
-                    else:
-                        spec_drift_grids.append(np.squeeze(spec))
-            if len(spec_drift_grids) != len(self.specified_drift_data_arrays):
-                raise ValueError("Inconsistent number of specified drift terms supplied.")
-        else:
-            if len(specified_drift_arrays) != 0:
-                warnings.warn(
-                    "Provided specified drift values, but 'specified' drift was not initialized during "
-                    "instantiation of UniversalKriging3D class.", RuntimeWarning,
-                )
+        axes, sizes, flat_mask = self._prepare_points(style, (xpoints, ypoints, zpoints), mask)
+        spec_drift_grids = self._specified_drift_grids(style, specified_drift_arrays, sizes, axes[0].size,
+                                                       "UniversalKriging3D")
         self._check_backend(backend, "3D universal kriging")
 
         drift_at = None
         if self.specified_drift or self.functional_drift:
             def drift_at(pts, idx):
-                xa, ya, za = _adjust_for_anisotropy(
-                    np.vstack((pts[0], pts[1], pts[2])).T,
-                    [self.XCENTER, self.YCENTER, self.ZCENTER],
-                    [self.anisotropy_scaling_y, self.anisotropy_scaling_z],
-                    [self.anisotropy_angle_x, self.anisotropy_angle_y, self.anisotropy_angle_z]).T
                 cols = []
                 if self.specified_drift:
                     for g in spec_drift_grids:
                         flat = np.asarray(g, dtype=float).flatten()
                         cols.append(flat if idx is None else flat[idx])
                 if self.functional_drift:
+                    xa, ya, za = _adjust_for_anisotropy(
+                        np.vstack((pts[0], pts[1], pts[2])).T,
+                        [self.XCENTER, self.YCENTER, self.ZCENTER],
+                        [self.anisotropy_scaling_y, self.anisotropy_scaling_z],
+                        [self.anisotropy_angle_x, self.anisotropy_angle_y, self.anisotropy_angle_z]).T
                     for func in self.functional_drift_terms:
                         cols.append(np.asarray(func(xa, ya, za), dtype=float) * np.ones(xa.shape))
                 return np.ascontiguousarray(np.vstack(cols), dtype=np.float64)
 
-        kvalues, sigmasq = self._run_cuda(style, [xpts, ypts, zpts], flat_mask, drift_at=drift_at, dtype=dtype)
-        if style == "masked":
-            kvalues = np.ma.array(kvalues, mask=flat_mask)
-            sigmasq = np.ma.array(sigmasq, mask=flat_mask)
-        if style in ["masked", "grid"]:
-            kvalues = kvalues.reshape((nz, ny, nx))
-            sigmasq = sigmasq.reshape((nz, ny, nx))
-        return kvalues, sigmasq
+        kvalues, sigmasq = self._run_cuda(style, axes, flat_mask, drift_at=drift_at, dtype=dtype, n_gpus=n_gpus)
+        return self._shape_output(style, kvalues, sigmasq, sizes, flat_mask)

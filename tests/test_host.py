@@ -242,8 +242,9 @@ def test_ctypes_signatures_match_the_header():
     lib = _cabi.load_library()
     text = open(os.path.join(ROOT, "include", "krige_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    protos = re.findall(r"\n\s*(?:int64_t|int|void\s*\*|const char\s*\*|void)\s*\*?\s*(kb200_\w+)\s*\(([^;]*?)\)\s*;", text)
-    assert len(protos) >= 25
+    protos = re.findall(r"\n\s*(?:int64_t|int|void\s*\*|const char\s*\*|void|kb200_handle)\s*\*?\s*(kb200_\w+)\s*\(([^;]*?)\)\s*;", text)
+    assert len(protos) >= 37
+    assert sorted(n for n, _ in protos) == sorted(_cabi.EXPORTS)
     for name, params in protos:
         fn = getattr(lib, name)
         plist = [p.strip() for p in params.replace("\n", " ").split(",") if p.strip() and p.strip() != "void"]
@@ -252,7 +253,7 @@ def test_ctypes_signatures_match_the_header():
             continue
         assert len(fn.argtypes) == len(plist), (name, len(fn.argtypes), plist)
         for ct, decl in zip(fn.argtypes, plist):
-            is_ptr = "*" in decl or "kb200_handle" in decl
+            is_ptr = "*" in decl or "kb200_handle" in decl or "kb200_group" in decl
             if is_ptr:
                 assert ct in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(ct, ctypes._Pointer), (name, decl, ct)
             elif decl.startswith("double"):

@@ -84,6 +84,110 @@ def test_kt3d_3d_golden(pk, ref_goldens):
     assert_allclose(ss, g["answer3d"][:, 1].reshape(10, 10, 10), rtol=1e-3, atol=1e-8)
 
 
+def test_meuk_external_drift_golden(pk, ref_goldens):
+    """tests/test_core.py:1479-1507 through backend='cuda': universal kriging with the external-Z drift sampled
+    from the DEM raster (test3_dem.asc) against the MEUK answer grid (test3_answer.asc), at the reference's own
+    tolerance. The raster is sampled at the prediction points on the device (kb200_set_device_drift)."""
+    g = ref_goldens
+    d = g["data"]
+    uk = pk.UniversalKriging(d[:, 0], d[:, 1], d[:, 2], variogram_model="spherical",
+                             variogram_parameters=[500.0, 3000.0, 0.0], anisotropy_scaling=1.0, anisotropy_angle=0.0,
+                             drift_terms=["external_Z"], external_drift=g["dem"], external_drift_x=g["dem_x"],
+                             external_drift_y=g["dem_y"])
+    z, ss = uk.execute("grid", g["ext_gridx"], g["ext_gridy"], backend="cuda")
+    assert z.shape == g["ext_answer"].shape
+    assert_allclose(z, g["ext_answer"], rtol=1e-5, atol=1e-8)
+    # a raster that does not cover the prediction domain is refused like uk.py:545-551
+    with pytest.raises(ValueError):
+        uk.execute("grid", g["ext_gridx"] + 1.0e6, g["ext_gridy"], backend="cuda")
+
+
+def test_ucla_uk_single_point(pk):
+    """tests/test_core.py:856-895 (lecture notes by N. Christou, UCLA): universal kriging of one point, and an
+    exact hit on a data point."""
+    data = np.array([[61.0, 139.0, 477.0], [63.0, 140.0, 696.0], [64.0, 129.0, 227.0], [68.0, 128.0, 646.0],
+                     [71.0, 140.0, 606.0], [73.0, 141.0, 791.0], [75.0, 128.0, 783.0]])
+    uk = pk.UniversalKriging(data[:, 0], data[:, 1], data[:, 2], variogram_model="exponential",
+                             variogram_parameters=[10.0, 9.99, 0.0], drift_terms=["regional_linear"])
+    z, ss = uk.execute("points", np.array([65.0]), np.array([137.0]), backend="cuda")
+    assert z[0] == pytest.approx(567.54, rel=0.1)
+    assert ss[0] == pytest.approx(9.044, rel=0.1)
+    z, ss = uk.execute("points", np.array([61.0]), np.array([139.0]), backend="cuda")
+    assert z[0] == pytest.approx(477.0, rel=1e-3)
+    assert abs(ss[0]) < 1e-3
+
+
+def test_device_drift_equals_host_columns(pk):
+    """point_log and external_Z evaluated at the prediction points BY THE KERNEL (kb200_set_device_drift) against
+    the same terms evaluated by host numpy and shipped as 'specified' columns — two independent routes to the
+    same system (uk.py:884-900 column order). Covers grid / points / masked styles, float32 and float64x, an
+    on-node / on-line query of the bilinear sampler and a raster with a DESCENDING axis (the reference's
+    first->= / last-<= node rule then brackets with nodes 0 and n-1)."""
+    xyz, val = cases.synth_data(777, 400, 2)
+    ex, ey = np.linspace(-100.0, 1100.0, 49), np.linspace(-50.0, 1050.0, 37)
+    EX, EY = np.meshgrid(ex, ey)
+    raster = 30.0 + 0.02 * EX - 0.01 * EY + 5.0 * np.sin(EX / 170.0) * np.cos(EY / 230.0)
+    wells = np.array([[250.0, 300.0, 1.5], [700.0, 650.0, -0.8]])
+    kw = dict(variogram_model="exponential", variogram_parameters=[1.0, 300.0, 0.05])
+    for flip in (False, True):
+        ry, rz = (ey[::-1].copy(), raster[::-1].copy()) if flip else (ey, raster)
+        uk = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, drift_terms=["regional_linear", "point_log", "external_Z"],
+                                 point_drift=wells, external_drift=rz, external_drift_x=ex, external_drift_y=ry,
+                                 anisotropy_scaling=1.7, anisotropy_angle=25.0, **kw)
+        # host twin: the same columns as 'specified' drift
+        cols_d = [uk._point_log_column(w, uk.X_ADJUSTED, uk.Y_ADJUSTED) for w in range(2)] + [np.asarray(uk.z_scalars)]
+        us = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, drift_terms=["regional_linear", "specified"],
+                                 specified_drift=cols_d, anisotropy_scaling=1.7, anisotropy_angle=25.0, **kw)
+
+        def host_cols(px, py):
+            from pykrige_b200.core import _adjust_for_anisotropy
+            xa, ya = _adjust_for_anisotropy(np.vstack((px, py)).T, [uk.XCENTER, uk.YCENTER], [1.7], [25.0]).T
+            return [uk._point_log_column(w, xa, ya) for w in range(2)] + [uk._calculate_data_point_zscalars(px, py)]
+
+        gx, gy = np.linspace(0.0, 1000.0, 41), np.linspace(0.0, 1000.0, 29)       # hits raster nodes and lines
+        GX, GY = np.meshgrid(gx, gy)
+        spec = [c.reshape(GX.shape) for c in host_cols(GX.ravel(), GY.ravel())]
+        for dt, R in (("float64", 1e-9), ("float64x", 1e-7), ("float32", 1e-2)):
+            zd, sd = uk.execute("grid", gx, gy, backend="cuda", dtype=dt)
+            zh, sh = us.execute("grid", gx, gy, backend="cuda", specified_drift_arrays=spec, dtype=dt)
+            assert_parity(zd, zh, R, "device drift grid z %s flip=%s" % (dt, flip))
+            assert_parity(sd, sh, R, "device drift grid ss %s flip=%s" % (dt, flip))
+        rng = np.random.default_rng(3)
+        px = np.concatenate([rng.uniform(0, 1000, 500), [ex[7], ex[9], 333.3, wells[0, 0]]])
+        py = np.concatenate([rng.uniform(0, 1000, 500), [ey[5], 444.4, ey[11], wells[0, 1]]])   # node, lines, a well
+        zd, sd = uk.execute("points", px, py, backend="cuda")
+        zh, sh = us.execute("points", px, py, backend="cuda", specified_drift_arrays=host_cols(px, py))
+        assert_parity(zd, zh, 1e-9, "device drift points z flip=%s" % flip)
+        assert_parity(sd, sh, 1e-9, "device drift points ss flip=%s" % flip)
+        mask = rng.uniform(size=GX.shape) < 0.4
+        zd, sd = uk.execute("masked", gx, gy, mask=mask, backend="cuda")
+        zh, sh = us.execute("masked", gx, gy, mask=mask, backend="cuda", specified_drift_arrays=spec)
+        assert np.array_equal(np.ma.getmaskarray(zd), mask)
+        assert_parity(np.ma.getdata(zd)[~mask], np.ma.getdata(zh)[~mask], 1e-9, "device drift masked z")
+        assert_parity(np.ma.getdata(sd)[~mask], np.ma.getdata(sh)[~mask], 1e-9, "device drift masked ss")
+
+
+def test_large_outputs_are_staged_in_chunks(pk):
+    """> 2^20 prediction points travel back through the pinned two-buffer pipeline in several launches; the
+    result must equal the same points kriged in small direct calls, bit for bit (global and moving window)."""
+    xyz, val = cases.synth_data(12, 300, 2)
+    ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="spherical", variogram_parameters=[1.0, 400.0, 0.05])
+    gx, gy = np.linspace(0, 1000, 1500), np.linspace(0, 1000, 1700)            # 2.55e6 points: 3 staged chunks
+    z, ss = ok.execute("grid", gx, gy, backend="cuda")
+    h = ok._ensure_problem()
+    for first in (0, (1 << 20) - 100, 2 * (1 << 20) - 50, z.size - 1000):
+        za, sa = h.execute_grid(gx, gy, None, None, first, 1000)
+        assert np.array_equal(za, z.ravel()[first:first + 1000]) and np.array_equal(sa, ss.ravel()[first:first + 1000])
+    zk, sk = ok.execute("grid", gx, gy, backend="cuda", n_closest_points=8)
+    hk = ok._ensure_problem("float64", knn=True)
+    for first in (0, (1 << 20) - 100, z.size - 1000):
+        za, sa = hk.execute_knn_grid(8, gx, gy, None, first, 1000)
+        assert np.array_equal(za, zk.ravel()[first:first + 1000]) and np.array_equal(sa, sk.ravel()[first:first + 1000])
+    px, py = np.tile(gx, 900), np.repeat(gy[:900], gx.size)                    # 1.35e6 explicit points
+    zp, sp = ok.execute("points", px, py, backend="cuda")
+    assert np.array_equal(zp, z.ravel()[:zp.size]) and np.array_equal(sp, ss.ravel()[:sp.size])
+
+
 def test_ok3d_equals_ok2d_on_a_plane(pk, ref_goldens):
     """tests/test_core.py:1914-1956: 3-D kriging with z == 0 reproduces the 2-D KT3D_H2O answer."""
     g = ref_goldens
@@ -131,16 +235,21 @@ def test_full_size_properties_cfg2(pk):
     zb, sb = h.execute_grid(gx, gy, None, None, 3000, 5000)
     assert np.array_equal(np.concatenate([za, zb]), z.ravel())
     assert np.array_equal(np.concatenate([sa, sb]), ss.ravel())
-    # oracle on a subsample of 256 grid points + 16 exact hits
+    # oracle (5001^2 inverse, the reference's formulation) on 4096 grid points + 16 exact hits
     rng = np.random.default_rng(5)
-    pick = rng.choice(z.size, 256, replace=False)
+    pick = rng.choice(z.size, 4096, replace=False)
     G = ko.grid_points([gx, gy])
     pts = np.vstack([G[pick], xyz[:16]])
-    zo, so = ko.krige(xyz, val, "exponential", ko.stored_parameters("exponential", params), pts)
+    zo, so = ko.krige_chunked(xyz, val, "exponential", ko.stored_parameters("exponential", params), pts)
     zc, sc = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
     assert_parity(zc, zo, R64, "cfg2 z")
     assert_parity(sc, so, R64, "cfg2 ss")
-    assert_allclose(z.ravel()[pick], zc[:256], rtol=1e-12)
+    assert_allclose(z.ravel()[pick], zc[:4096], rtol=1e-12)
+    # the tensor-core arithmetics against the ORACLE (not against the fp64 CUDA path)
+    for dt, R in (("float64x", R64), ("float64x5", R64), ("float64x4", R64), ("float32", 1e-2)):
+        zt, st = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda", dtype=dt)
+        assert_parity(zt, zo, R, "cfg2 %s z vs oracle" % dt)
+        assert_parity(st, so, R, "cfg2 %s ss vs oracle" % dt)
 
 
 def test_indefinite_variogram_takes_general_path(pk, ref_cases):
@@ -633,15 +742,14 @@ def test_full_size_properties_cfg3(pk):
     zp, sp = ok.execute("points", G[:, 0], G[:, 1], G[:, 2], backend="cuda")
     assert_allclose(zg, zp, rtol=1e-12)
     assert_allclose(sg, sp, rtol=1e-10, atol=1e-13)
-    sub = np.r_[0:48, 4096:4112]
-    zo, so = ko.krige(xyz, val, "gaussian", ko.stored_parameters("gaussian", params), pts[sub])
-    assert_parity(z[sub], zo, R64, "cfg3 z")
-    assert_parity(ss[sub], so, R64, "cfg3 ss")
+    zo, so = ko.krige_chunked(xyz, val, "gaussian", ko.stored_parameters("gaussian", params), pts)   # 4096 + 16
+    assert_parity(z, zo, R64, "cfg3 z")
+    assert_parity(ss, so, R64, "cfg3 ss")
 
 
 def test_full_size_properties_cfg4(pk):
-    """Config 4 (UK regional_linear, N=10000, exponential, fp32 device math): float32 vs float64 device paths
-    within the fp32 tolerance, float64 vs the oracle (10003^2 inverse) on a subsample, drift reproduction
+    """Config 4 (UK regional_linear, N=10000, exponential, fp32 device math): float32 and float64 device paths
+    vs the oracle (10003^2 inverse) on 4096 + 16 points at their tolerances, drift reproduction
     (a field that IS a linear trend is returned exactly with zero-mean residual structure)."""
     from oracle import krige_oracle as ko
     xyz, val = cases.synth_data(1004, 10000, 2)
@@ -652,13 +760,12 @@ def test_full_size_properties_cfg4(pk):
     pts = np.vstack([rng.uniform(0, 1000, (4096, 2)), xyz[:16]])
     z64, s64 = uk.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
     z32, s32 = uk.execute("points", pts[:, 0], pts[:, 1], backend="cuda", dtype="float32")
-    assert_parity(z32, z64, 1e-2, "cfg4 fp32 z")
-    assert_parity(s32, s64, 1e-2, "cfg4 fp32 ss")
-    sub = np.r_[0:32, 4096:4112]
-    zo, so = ko.krige(xyz, val, "exponential", ko.stored_parameters("exponential", params), pts[sub],
-                      regional_linear=True)
-    assert_parity(z64[sub], zo, R64, "cfg4 z")
-    assert_parity(s64[sub], so, R64, "cfg4 ss")
+    zo, so = ko.krige_chunked(xyz, val, "exponential", ko.stored_parameters("exponential", params), pts,
+                              regional_linear=True)                       # 10003^2 inverse, 4096 + 16 points
+    assert_parity(z64, zo, R64, "cfg4 z")
+    assert_parity(s64, so, R64, "cfg4 ss")
+    assert_parity(z32, zo, 1e-2, "cfg4 fp32 z vs oracle")
+    assert_parity(s32, so, 1e-2, "cfg4 fp32 ss vs oracle")
     trend = 3.0 + 0.01 * xyz[:, 0] - 0.02 * xyz[:, 1]
     ut = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], trend, variogram_model="exponential", variogram_parameters=params,
                              drift_terms=["regional_linear"])
