@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 #include <thread>
 #include "kernels.h"
@@ -75,6 +76,9 @@ struct kb200_ctx {
     void* pin[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t evk[2] = {}, evc[2] = {};
+    // look-ahead Cholesky: high-priority side stream for the panel chain + ordering events
+    cudaStream_t hi_stream = nullptr;
+    std::vector<cudaEvent_t> fev;
     // knn workspace
     DevBuf kSorted, kCells;
     DevBuf wVario;            // constructor-side helpers (experimental variogram, statistics)
@@ -135,6 +139,8 @@ extern "C" void kb200_destroy(kb200_handle h) {
         if (h->evc[i]) cudaEventDestroy(h->evc[i]);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
+    for (auto& e : h->fev) cudaEventDestroy(e);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -451,11 +457,26 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
             t_asm += ev_ms(h->ev[2], h->ev[3]);
             break;
         }
-        CU(h, kbk_cholesky(h->wC.as<double>(), h->wW.as<double>(), ld, np, flag, 3.6e-15 * h->vg.c0, st, &launches));
+        {
+            if (!h->hi_stream) {
+                int lo = 0, hi = 0;
+                CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CU(h, cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, hi));
+            }
+            const size_t need = 2 * (size_t)((np / 64 + 3) / 4) + 1;
+            while (h->fev.size() < need) {
+                cudaEvent_t e;
+                CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->fev.push_back(e);
+            }
+        }
+        CU(h, kbk_cholesky(h->wC.as<double>(), h->wW.as<double>(), h->wT.as<double>(), ld, np, flag, 3.6e-15 * h->vg.c0, st, h->hi_stream,
+                           h->fev.data(), (int)h->fev.size(), &launches));
         CU(h, cudaEventRecord(h->ev[4], st));
         CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
         t_asm += ev_ms(h->ev[2], h->ev[3]); t_chol += ev_ms(h->ev[3], h->ev[4]);
+        if (hflag != 0 && std::getenv("KB200_DEBUG")) std::fprintf(stderr, "[kb200] cholesky flag %d (attempt %d, c0 %g)\n", hflag, attempt, h->vg.c0);
         if (hflag == 0) break;
         h->vg.c0 *= 2.0;
     }

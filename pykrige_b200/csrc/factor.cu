@@ -168,110 +168,222 @@ __device__ __forceinline__ void gemm_tile_store(const double (&acc)[4][4][2], do
 }
 
 // ---------------------------------------------------------------------------
-// K2a.1  potf2 of one 64x64 diagonal block (one CTA, 256 threads). Writes L_kk into C (strict upper part
-// of the block zeroed). A pivot at or below dtol (16 eps c0: the rounding noise of c0 - sum l^2, so exactly
-// redundant points are caught like scipy's exact zero pivot) sets *flag = 1 + global column index. The inverse of the
-// block (needed only by the triangular inverse, K2b) is computed later for all blocks at once
-// (diag_inv_kernel), off the critical path of the factorisation.
-__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ C, int ld, int kb, int* __restrict__ flag, double dtol) {
-    __shared__ double a[64][65];
-    const int tid = threadIdx.x;
-    double* Cb = C + (size_t)kb * 64 * ld + kb * 64;
-    for (int e = tid; e < 64 * 64; e += 256) {
-        int r = e >> 6, c = e & 63;
-        a[r][c] = (c <= r) ? Cb[(size_t)r * ld + c] : 0.0;
-    }
-    __syncthreads();
-    const int ur = tid >> 2, uc = tid & 3;          // update mapping: row offset, column phase
-    for (int j = 0; j < 64; ++j) {
-        if (tid == 0) {
-            double d = a[j][j];
-            if (!(d > dtol)) { if (*flag == 0) *flag = 1 + kb * 64 + j; d = 1.0; }   // dtol: rounding noise of the diagonal
-            a[j][j] = sqrt(d);
+// K2a.1  fused panel step of the blocked Cholesky (one launch per 64-column step; replaces the potf2 / trsm /
+// thin-update launch triple of round 1). Block column kb of the outer panel that starts at block ob:
+//   every CTA   D = C[kb][kb] - A_d A_d^T   (A_d = C[kb rows][ob*64 .. kb*64): the updates of the earlier steps of
+//               this outer panel, applied left-looking),  L = chol(D),  Winv = L^-1     -- redundantly, in shared memory:
+//               the 64^3/3 flops are nothing, the point is that no CTA waits for another one;
+//   CTA 0       writes Winv into the diagonal block of W (the starting point of the triangular inverse K2b), L into a
+//               STAGING tile (the other CTAs of this launch may still be reading D from C: the diagonal blocks of C are
+//               overwritten by diag_writeback_kernel after the factorisation), and reports a non-positive pivot;
+//   CTA b >= 1  its 64-row slab X = C[slab][kb] - A_s A_d^T, then X <- X Winv^T (= X L^-T) on the DMMA pipe.
+// potf2 and the triangular inverse are blocked by 16 inside the 64x64 tile: the 16x16 diagonal blocks are done by
+// one warp without block-wide barriers, everything else is small dense updates by all 256 threads (12 + 6 barriers
+// instead of 256). A pivot at or below dtol (16 eps c0: the rounding noise of c0 - sum l^2, so exactly redundant
+// points are caught like scipy's exact zero pivot) sets *flag = 1 + global column index.
+#define PN_LD 65
+#define PN_SMEM ((3 * 64 * PN_LD + 64) * sizeof(double))
+
+// acc(8 rows of this warp x 64 cols) (+)= sign * A[r][k] * B[c][k], k in [0, 64): A, B row-major [64][PN_LD] in smem
+__device__ __forceinline__ void pn_mma_nt(double (&acc)[8][2], const double* A, const double* B, int warp, int lane, int kend) {
+#pragma unroll 4
+    for (int k4 = 0; k4 < kend; k4 += 4) {
+        const double fa = A[(warp * 8 + (lane >> 2)) * PN_LD + k4 + (lane & 3)];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const double fb = B[(nt * 8 + (lane >> 2)) * PN_LD + k4 + (lane & 3)];
+            kb_dmma(acc[nt][0], acc[nt][1], fa, fb);
         }
-        __syncthreads();
-        const double dj = a[j][j];
-        if (tid > j && tid < 64) a[tid][j] /= dj;
-        __syncthreads();
-        // trailing update of the lower triangle: a[i][k] -= a[i][j]*a[k][j], j < k <= i
-        const int i = j + 1 + ur;
-        if (i < 64) {
-            const double lij = a[i][j];
-            for (int k = j + 1 + uc; k <= i; k += 4) a[i][k] -= lij * a[k][j];
-        }
-        __syncthreads();
-    }
-    for (int e = tid; e < 64 * 64; e += 256) {
-        int r = e >> 6, c = e & 63;
-        Cb[(size_t)r * ld + c] = a[r][c];     // upper part is 0
     }
 }
 
-// inverse of every 64x64 diagonal block of L into the diagonal blocks of W (one CTA per block).
-// Four threads (same warp) share column c of X = L^-1 and split the dot product over k; row i of every
-// column is finished before row i+1 starts.
-__global__ void __launch_bounds__(256) diag_inv_kernel(const double* __restrict__ C, double* __restrict__ W, int ld) {
-    extern __shared__ double dsm[];
-    double (*a)[65] = reinterpret_cast<double (*)[65]>(dsm);
-    double (*x)[65] = reinterpret_cast<double (*)[65]>(dsm + 64 * 65);
-    const int tid = threadIdx.x, kb = blockIdx.x;
-    const double* Cb = C + (size_t)kb * 64 * ld + kb * 64;
-    double* Wb = W + (size_t)kb * 64 * ld + kb * 64;
-    for (int e = tid; e < 64 * 64; e += 256) {
-        int r = e >> 6, c = e & 63;
-        a[r][c] = (c <= r) ? Cb[(size_t)r * ld + c] : 0.0;
-        x[r][c] = 0.0;
+// the same restricted to the column tiles nt <= warp (lower block triangle of a symmetric product)
+__device__ __forceinline__ void pn_mma_nt_lower(double (&acc)[8][2], const double* A, const double* B, int warp, int lane) {
+#pragma unroll 4
+    for (int k4 = 0; k4 < 64; k4 += 4) {
+        const double fa = A[(warp * 8 + (lane >> 2)) * PN_LD + k4 + (lane & 3)];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            if (nt <= warp) {
+                const double fb = B[(nt * 8 + (lane >> 2)) * PN_LD + k4 + (lane & 3)];
+                kb_dmma(acc[nt][0], acc[nt][1], fa, fb);
+            }
+        }
     }
-    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) panel_kernel(double* __restrict__ C, double* __restrict__ W, double* __restrict__ Lstage,
+                                                     int ld, int kb, int ob, int* __restrict__ flag, double dtol) {
+    extern __shared__ double pn_sm[];
+    double* a = pn_sm;                       // D -> L
+    double* b1 = pn_sm + 64 * PN_LD;         // chunk of A_d, later Winv
+    double* b2 = pn_sm + 2 * 64 * PN_LD;     // chunk of A_s, later the slab X
+    double* dnv = pn_sm + 3 * 64 * PN_LD;    // 1 / L[j][j]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool owner = blockIdx.x == 0;
+    const size_t drow = (size_t)kb * 64;
+    const size_t srow = owner ? drow : (size_t)(kb + blockIdx.x) * 64;        // slab rows (CTA 0: the diagonal block itself)
+    // fragment ownership of the 64x64 results: warp -> rows 8w..8w+7, lane -> row (lane>>2), cols nt*8 + 2*(lane&3) + {0,1}
+    double accD[8][2], accX[8][2];
     {
-        const int c = tid >> 2, part = tid & 3;
-        if (part == 0) x[c][c] = 1.0 / a[c][c];
-        __syncwarp();
-        for (int i = 1; i < 64; ++i) {
-            double sacc = 0.0;
-            if (i > c)
-                for (int k = c + part; k < i; k += 4) sacc += a[i][k] * x[k][c];
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-            if (i > c && part == 0) x[i][c] = -sacc / a[i][i];
-            __syncwarp();
+        const double* Dg = C + (drow + warp * 8 + (lane >> 2)) * ld + drow;
+        const double* Xg = C + (srow + warp * 8 + (lane >> 2)) * ld + drow;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * (lane & 3);
+            const double2 d = *reinterpret_cast<const double2*>(Dg + c);
+            accD[nt][0] = -d.x; accD[nt][1] = -d.y;          // accumulate the NEGATIVE: acc = A A^T - D
+            if (!owner) {
+                const double2 x = *reinterpret_cast<const double2*>(Xg + c);
+                accX[nt][0] = -x.x; accX[nt][1] = -x.y;
+            } else { accX[nt][0] = 0.0; accX[nt][1] = 0.0; }
+        }
+    }
+    for (int pc = ob; pc < kb; ++pc) {                       // pending 64-column chunks of this outer panel
+        __syncthreads();
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            const double2 vd = *reinterpret_cast<const double2*>(C + (drow + r) * ld + (size_t)pc * 64 + c);
+            b1[r * PN_LD + c] = vd.x; b1[r * PN_LD + c + 1] = vd.y;
+            if (!owner) {
+                const double2 vs = *reinterpret_cast<const double2*>(C + (srow + r) * ld + (size_t)pc * 64 + c);
+                b2[r * PN_LD + c] = vs.x; b2[r * PN_LD + c + 1] = vs.y;
+            }
+        }
+        __syncthreads();
+        pn_mma_nt_lower(accD, b1, b1, warp, lane);           // only the tiles on/below the diagonal of D are used
+        if (!owner) pn_mma_nt(accX, b2, b1, warp, lane, 64);
+    }
+    __syncthreads();
+    {   // D (updated, lower part) -> a ; slab X -> b2
+        const int r = warp * 8 + (lane >> 2);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * (lane & 3);
+            a[r * PN_LD + c] = -accD[nt][0]; a[r * PN_LD + c + 1] = -accD[nt][1];
+            b2[r * PN_LD + c] = -accX[nt][0]; b2[r * PN_LD + c + 1] = -accX[nt][1];
         }
     }
     __syncthreads();
-    for (int e = tid; e < 64 * 64; e += 256) {
-        int r = e >> 6, c = e & 63;
-        Wb[(size_t)r * ld + c] = x[r][c];
+    // ---- potf2 of a (lower triangle), blocked by 16 ----
+    for (int jb = 0; jb < 4; ++jb) {
+        const int j0 = jb * 16;
+        if (warp == 0) {                                     // 16x16 diagonal block in registers: lane & 15 = row, shuffles
+            const int r = lane & 15;                         // (both half-warps compute the same thing)
+            double d[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) d[c] = (c <= r) ? a[(j0 + r) * PN_LD + j0 + c] : 0.0;
+            double dinv = 1.0;
+#pragma unroll
+            for (int pc = 0; pc < 16; ++pc) {
+                double piv = __shfl_sync(0xffffffffu, d[pc], pc, 16);
+                if (!(piv > dtol)) { if (owner && lane == 0 && *flag == 0) *flag = 1 + kb * 64 + j0 + pc; piv = 1.0; }
+                const double inv = rsqrt(piv);
+                const double l = d[pc] * inv;                // lane pc: sqrt(piv); lanes below: L[r][pc]
+                d[pc] = (r == pc) ? piv * inv : l;
+                if (r == pc) dinv = inv;
+#pragma unroll
+                for (int c = pc + 1; c < 16; ++c) d[c] = fma(-l, __shfl_sync(0xffffffffu, l, c, 16), d[c]);
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) if (c <= r) a[(j0 + r) * PN_LD + j0 + c] = d[c];
+                dnv[j0 + r] = dinv;
+            }
+        }
+        __syncthreads();
+        const int below = 64 - j0 - 16;                      // rows under the diagonal block
+        if (below > 0) {
+            if (tid < below) {                               // X <- X L16^-T: one thread per row, 16-step substitution
+                double* xr = a + (j0 + 16 + tid) * PN_LD + j0;
+                double x[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) x[c] = xr[c];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    double sacc = x[c];
+#pragma unroll
+                    for (int j = 0; j < c; ++j) sacc = fma(-x[j], a[(j0 + c) * PN_LD + j0 + j], sacc);
+                    x[c] = sacc * dnv[j0 + c];
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) xr[c] = x[c];
+            }
+            __syncthreads();
+            for (int i = warp; i < below; i += 8) {          // rank-16 update of the trailing lower triangle: warp = row
+                const double* pi = a + (j0 + 16 + i) * PN_LD + j0;
+                for (int k = lane; k <= i; k += 32) {
+                    const double* pk = a + (j0 + 16 + k) * PN_LD + j0;
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sacc = fma(pi[j], pk[j], sacc);
+                    a[(j0 + 16 + i) * PN_LD + j0 + 16 + k] -= sacc;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- Winv = L^-1 into b1, blocked by 16 ----
+    for (int e = tid; e < 64 * 64; e += 256) b1[(e >> 6) * PN_LD + (e & 63)] = 0.0;
+    __syncthreads();
+    if (tid < 64) {                                          // the four 16x16 diagonal inverses: thread = (block, column)
+        const int blk = tid >> 4, c = tid & 15, o = blk * 16;
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) if (k >= c) sacc -= a[(o + i) * PN_LD + o + k] * x[k];
+            x[i] = (i >= c) ? sacc * dnv[o + i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) b1[(o + i) * PN_LD + o + c] = x[i];
+    }
+    __syncthreads();
+    for (int ib = 1; ib < 4; ++ib) {                         // block row ib: X_ij = -X_ii (sum_{k=j}^{ib-1} L_ik X_kj), j < ib
+        // T_ij goes (transposed) into the strict upper triangle of `a`, which nothing reads: rows < ib*16, columns >= ib*16
+        for (int e = tid; e < 16 * 16 * ib; e += 256) {
+            const int j = e >> 8, r = (e >> 4) & 15, c = e & 15;          // block column j, element (r, c)
+            double sacc = 0.0;
+            for (int k = j * 16; k < ib * 16; ++k) sacc += a[(ib * 16 + r) * PN_LD + k] * b1[k * PN_LD + j * 16 + c];
+            a[(j * 16 + c) * PN_LD + ib * 16 + r] = sacc;
+        }
+        __syncthreads();
+        for (int e = tid; e < 16 * 16 * ib; e += 256) {
+            const int j = e >> 8, r = (e >> 4) & 15, c = e & 15;
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sacc += b1[(ib * 16 + r) * PN_LD + ib * 16 + k] * a[(j * 16 + c) * PN_LD + ib * 16 + k];
+            b1[(ib * 16 + r) * PN_LD + j * 16 + c] = -sacc;
+        }
+        __syncthreads();
+    }
+    if (owner) {
+        for (int e = tid; e < 64 * 64; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            Lstage[(size_t)kb * 4096 + e] = (c <= r) ? a[r * PN_LD + c] : 0.0;
+            W[(drow + r) * ld + drow + c] = b1[r * PN_LD + c];
+        }
+        return;
+    }
+    // ---- slab: X <- X Winv^T  (out[i][c] = sum_{j <= c} X[i][j] Winv[c][j]) ----
+    double acc[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+    pn_mma_nt(acc, b2, b1, warp, lane, 64);
+    {
+        double* Xg = C + (srow + warp * 8 + (lane >> 2)) * ld + drow;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<double2*>(Xg + nt * 8 + 2 * (lane & 3)) = make_double2(acc[nt][0], acc[nt][1]);
     }
 }
 
-// K2a.2  panel solve: rows below the diagonal block:  X <- X * L_kk^-T  (in place) by forward
-// substitution against L_kk itself: x[c] = (x[c] - sum_{j<c} x[j] L[c][j]) / L[c][c].  One thread per row,
-// the row lives in registers; L_kk is broadcast from shared memory.
-__global__ void __launch_bounds__(128) trsm_panel_kernel(double* __restrict__ C, int ld, int kb, int n_pad) {
-    __shared__ double l[64][65];
-    const int tid = threadIdx.x;
-    const double* Lb = C + (size_t)kb * 64 * ld + kb * 64;
-    for (int e = tid; e < 64 * 64; e += 128) {
-        int r = e >> 6, c = e & 63;
-        l[r][c] = Lb[(size_t)r * ld + c];
-    }
-    __syncthreads();
-    const int row = (kb + 1) * 64 + blockIdx.x * 128 + tid;
-    if (row >= n_pad) return;
-    double* xr = C + (size_t)row * ld + kb * 64;
-    double x[64];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) x[c] = xr[c];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) {
-        double s0 = x[c], s1 = 0.0;
-#pragma unroll
-        for (int j = 0; j + 1 < c; j += 2) { s0 -= x[j] * l[c][j]; s1 -= x[j + 1] * l[c][j + 1]; }
-        if (c & 1) s0 -= x[c - 1] * l[c][c - 1];
-        x[c] = (s0 + s1) / l[c][c];
-    }
-#pragma unroll
-    for (int c = 0; c < 64; ++c) xr[c] = x[c];
+// staged diagonal factors -> the diagonal blocks of C (after the last panel step; one CTA per block)
+__global__ void __launch_bounds__(256) diag_writeback_kernel(double* __restrict__ C, const double* __restrict__ Lstage, int ld) {
+    const size_t drow = (size_t)blockIdx.x * 64;
+    for (int e = threadIdx.x; e < 4096; e += 256)
+        C[(drow + (e >> 6)) * ld + drow + (e & 63)] = Lstage[(size_t)blockIdx.x * 4096 + e];
 }
 
 // K2a.3  rank-(64*pkw) update:  C[it][jt] -= P_it P_jt^T  with  P_x = C[x-rows][pk0*64 .. (pk0+pkw)*64),
@@ -377,27 +489,51 @@ __global__ void __launch_bounds__(256) dual_h_kernel(const double* __restrict__ 
     }
 }
 
-// Uz[k][c] = sum_{i>=k} W[i][k] Hz[i][c]   (block: 32 columns x 8 row slices)
-__global__ void __launch_bounds__(256) dual_u_kernel(const double* __restrict__ W, int ld, int n, int n_pad, int na,
-                                                      const double* __restrict__ Hz, double* __restrict__ Uz) {
-    __shared__ double red[8][32];
-    int kx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    int k = blockIdx.x * 32 + kx;
-    int kfirst = blockIdx.x * 32;
-    for (int c = 0; c < na; ++c) {
-        double s = 0.0;
-        if (k < n)
-            for (int i = kfirst + ty; i < n; i += 8)
-                if (i >= k) s += W[(size_t)i * ld + k] * Hz[(size_t)c * n_pad + i];
-        red[ty][kx] = s;
-        __syncthreads();
-        if (ty == 0) {
-            double v = 0.0;
+// Uz[k][c] = sum_{i>=k} W[i][k] Hz[i][c]   (block: 32 columns x 32 row slices; W is read ONCE for all na columns,
+// four independent row loads in flight per thread: the kernel is a memory-bound pass over the lower triangle)
+__global__ void __launch_bounds__(1024) dual_u_kernel(const double* __restrict__ W, int ld, int n, int n_pad, int na,
+                                                       const double* __restrict__ Hz, double* __restrict__ Uz) {
+    __shared__ double red[32][33];
+    const int kx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + kx;
+    const int kfirst = blockIdx.x * 32;
+    double acc[KB_MAXAUX];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v += red[q][kx];
-            if (k < n_pad) Uz[(size_t)c * n_pad + k] = (k < n) ? v : 0.0;
+    for (int c = 0; c < KB_MAXAUX; ++c) acc[c] = 0.0;
+    if (k < n) {
+        int i = kfirst + ty;
+        for (; i + 96 < n; i += 128) {
+            double w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int ii = i + 32 * u; w[u] = (ii >= k) ? W[(size_t)ii * ld + k] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ii = i + 32 * u;
+#pragma unroll
+                for (int c = 0; c < KB_MAXAUX; ++c) if (c < na) acc[c] = fma(w[u], Hz[(size_t)c * n_pad + ii], acc[c]);
+            }
         }
-        __syncthreads();
+        for (; i < n; i += 32) {
+            if (i >= k) {
+                const double w = W[(size_t)i * ld + k];
+#pragma unroll
+                for (int c = 0; c < KB_MAXAUX; ++c) if (c < na) acc[c] = fma(w, Hz[(size_t)c * n_pad + i], acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < KB_MAXAUX; ++c) {
+        if (c < na) {                                   // na is uniform: every thread takes the same branches
+            red[ty][kx] = acc[c];
+            __syncthreads();
+            if (ty == 0) {
+                double v = 0.0;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v += red[q][kx];
+                if (k < n_pad) Uz[(size_t)c * n_pad + k] = (k < n) ? v : 0.0;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -504,38 +640,57 @@ cudaError_t kbk_assemble(int dim, const VgParams& vg, int n, int n_pad, int ld,
     return launch_assemble_dim<KB_GEO>(vg, n, n_pad, ld, ax, ay, az, C, st);
 }
 
-#define KB_SM66 (2 * 64 * 65 * sizeof(double))
 cudaError_t kbk_factor_init() {
-    return cudaFuncSetAttribute(diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SM66);
+    return cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PN_SMEM);
 }
 
-// Blocked right-looking Cholesky + diagonal-block inverses (into W's diagonal blocks).
-cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, double dtol, cudaStream_t st, int* launches) {
+// Blocked right-looking Cholesky with one level of look-ahead. Outer panels of OW = 4 block columns (256 columns):
+//   panel(ob)   four fused panel steps (left-looking inside the outer panel)            -> side stream `hi`
+//   T_look(ob)  update of the NEXT outer panel's columns with this panel (k = 256)        -> side stream `hi`
+//   T_rest(ob)  update of everything to the right of the next panel (k = 256): the bulk
+//               of the flops, one pass over the trailing matrix per 256 factored columns  -> main stream `st`
+// panel(ob+1) and T_look(ob) depend only on T_look / T_rest of earlier panels, so the latency-bound panel chain runs on
+// the high-priority stream `hi` UNDER the DMMA-bound trailing update of the previous panel. Events (ev[0..2*nob)) order
+// the read-modify-write passes over shared regions:
+//   T_look(ob) after T_rest(ob-1);  T_rest(ob) after panel(ob).
+// The diagonal-block inverses land in W's diagonal blocks (input of kbk_trtri).
+cudaError_t kbk_cholesky(double* C, double* W, double* Lstage, int ld, int n_pad, int* flag, double dtol, cudaStream_t st,
+                         cudaStream_t hi, cudaEvent_t* ev, int n_ev, int* launches) {
     const int nb = n_pad / 64;
-    const int OW = 4;                                   // outer panel = 4 x 64 columns
-    for (int ob = 0; ob < nb; ob += OW) {
+    const int OW = 4;
+    const int nob = (nb + OW - 1) / OW;
+    if (2 * nob + 1 > n_ev) return cudaErrorInvalidValue;
+    cudaEvent_t* evP = ev;               // panel(ob) complete            (recorded on hi)
+    cudaEvent_t* evR = ev + nob;         // T_rest(ob) complete           (recorded on st)
+    KB_CUDA_OK(cudaEventRecord(ev[2 * nob], st));                 // everything before (assemble) precedes the panel chain
+    KB_CUDA_OK(cudaStreamWaitEvent(hi, ev[2 * nob], 0));
+    for (int ob = 0, o = 0; ob < nb; ob += OW, ++o) {
         const int oe = ob + OW < nb ? ob + OW : nb;     // end of the outer panel (tile units)
         for (int kb = ob; kb < oe; ++kb) {
-            potf2_kernel<<<1, 256, 0, st>>>(C, ld, kb, flag, dtol);
+            panel_kernel<<<nb - kb, 256, PN_SMEM, hi>>>(C, W, Lstage, ld, kb, ob, flag, dtol);
             ++*launches;
-            const int below = nb - kb - 1;
-            if (below > 0) {
-                trsm_panel_kernel<<<(below * 64 + 127) / 128, 128, 0, st>>>(C, ld, kb, n_pad);
-                ++*launches;
-            }
-            if (kb + 1 < oe) {                          // thin update of the rest of the outer panel
-                dim3 g(nb - (kb + 1), oe - (kb + 1));
-                syrk_kernel<<<g, 128, 0, st>>>(C, ld, kb, 1, kb + 1, nb);
-                ++*launches;
-            }
         }
-        if (oe < nb) {                                  // one trailing update per outer panel
-            dim3 g(nb - oe, nb - oe);
-            syrk_kernel<<<g, 128, 0, st>>>(C, ld, ob, oe - ob, oe, nb);
-            ++*launches;
+        KB_CUDA_OK(cudaEventRecord(evP[o], hi));
+        if (oe < nb) {
+            const int le = oe + OW < nb ? oe + OW : nb; // end of the look-ahead columns
+            if (o > 0) KB_CUDA_OK(cudaStreamWaitEvent(hi, evR[o - 1], 0));
+            {
+                dim3 g(nb - oe, le - oe);
+                syrk_kernel<<<g, 128, 0, hi>>>(C, ld, ob, oe - ob, oe, nb);
+                ++*launches;
+            }
+            KB_CUDA_OK(cudaStreamWaitEvent(st, evP[o], 0));
+            if (le < nb) {
+                dim3 g(nb - le, nb - le);
+                syrk_kernel<<<g, 128, 0, st>>>(C, ld, ob, oe - ob, le, nb);
+                ++*launches;
+            }
+            KB_CUDA_OK(cudaEventRecord(evR[o], st));
+        } else {
+            KB_CUDA_OK(cudaStreamWaitEvent(st, evP[o], 0));      // join: the main stream continues after the last panel
         }
     }
-    diag_inv_kernel<<<nb, 256, KB_SM66, st>>>(C, W, ld);
+    diag_writeback_kernel<<<nb, 256, 0, st>>>(C, Lstage, ld);
     ++*launches;
     return cudaGetLastError();
 }
@@ -558,7 +713,7 @@ cudaError_t kbk_dual(const double* W, int ld, int n, int n_pad, int n_rl, int n_
     int K1 = n_rl + n_hd + 1, na = K1 + 1;
     build_fz_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, n_rl, n_hd, ax, ay, az, ds, hd, values, Fz);
     dual_h_kernel<<<(n + 7) / 8, 256, 0, st>>>(W, ld, n, n_pad, na, Fz, Hz);
-    dual_u_kernel<<<(n_pad + 31) / 32, 256, 0, st>>>(W, ld, n, n_pad, na, Hz, Uz);
+    dual_u_kernel<<<(n_pad + 31) / 32, 1024, 0, st>>>(W, ld, n, n_pad, na, Hz, Uz);
     dual_small_kernel<<<1, 256, 0, st>>>(n, n_pad, K1, Fz, Uz, consts, flag);
     *launches += 4;
     return cudaGetLastError();

@@ -153,7 +153,9 @@ cudaError_t kbk_adjust_data(int dim, const Aniso& an, int n, const double* x, co
                             double* ax, double* ay, double* az, cudaStream_t st);
 cudaError_t kbk_assemble(int dim, const VgParams& vg, int n, int n_pad, int ld,
                          const double* ax, const double* ay, const double* az, double* C, cudaStream_t st);
-cudaError_t kbk_cholesky(double* C, double* W, int ld, int n_pad, int* flag, double dtol, cudaStream_t st, int* launches);
+cudaError_t kbk_cholesky(double* C, double* W, double* Lstage, int ld, int n_pad, int* flag, double dtol, cudaStream_t st,
+                         cudaStream_t hi, cudaEvent_t* ev, int n_ev, int* launches);   // Lstage: (n_pad/64) x 4096 doubles of scratch;
+                                                                                       // hi: high-priority side stream; ev: >= 2*ceil(n_pad/256)+1 events
 cudaError_t kbk_trtri(const double* L, double* W, double* T1, int ld, int n_pad, cudaStream_t st, int* launches);
 cudaError_t kbk_dual(const double* W, int ld, int n, int n_pad, int n_rl, int n_hd,
                      const double* ax, const double* ay, const double* az, const DriftScale& ds,

@@ -113,9 +113,10 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
     const int S = k | 1;                       // odd row stride: conflict-free column walks
     double* base = ksm + (size_t)warp * per_warp_doubles;
     double* A = base;                          // k * S  (aliased by the candidate buffers during the search)
-    const int kp = CHOL ? ((k + 31) & ~31) : k;      // padded system size of the blocked Cholesky
-    // blocked Cholesky: off-diagonal blocks 32 x 33, diagonal blocks packed (528) — keep in step with kbk_knn_smem_per_warp
-    size_t a_doubles = CHOL ? (size_t)(kp / 32) * (kp / 32 - 1) / 2 * (32 * 33) + (size_t)(kp / 32) * 528 : (size_t)k * S;
+    const int kp = CHOL ? ((k + 7) & ~7) : k;        // padded system size of the tiled Cholesky
+    // tiled Cholesky: nt (nt + 1) / 2 lower tiles + nt augmented tiles + 1 tile for the diagonal inverse, 64 doubles each
+    // — keep in step with kbk_knn_smem_per_warp
+    size_t a_doubles = CHOL ? ((size_t)(kp / 8) * (kp / 8 + 1) / 2 + kp / 8 + 1) * 64 : (size_t)k * S;
     size_t cand_doubles = KN_CAP + KN_CAP / 2; // d2[CAP] doubles + id[CAP] ints
     size_t off = a_doubles > cand_doubles ? a_doubles : cand_doubles;
     double* rc = base + off;                   // rhs c (becomes C^-1 c)
@@ -241,111 +242,117 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
     __syncwarp();                                      // candidates consumed: A may be overwritten now
 
     if (CHOL) {
-        // ---------------- K5 (Cholesky): 32x32 blocks, factorised in REGISTERS with warp shuffles ----------------
-        // lane r owns row r of the active block (32 doubles); L[c][q] of another row comes by __shfl_sync.
-        // One shuffle + one DFMA per multiply-add, no predicates or address arithmetic in the inner loops
-        // (the packed shared-memory update this replaces issued ~14 instructions per useful FMA).
-        // Blocks (bi, bj), bj <= bi, live in shared memory with row stride 33 (conflict-free for lane = row
-        // and for lane = column walks). Rows/cols >= k are identity padding with zero right-hand sides.
-        const int nbk = (k + 31) >> 5;
-// off-diagonal blocks: 32 x 33 (padded rows); diagonal blocks: packed lower triangle, row r at r(r+1)/2
-// (528 doubles; r(r+1)/2 mod 16 is a permutation of 0..15 within each half-warp, so lane = row walks of one
-// column stay bank-conflict-free). 30 % less shared memory per point = 10 instead of 7 points in flight per SM.
-#define KN_BLK(bi, bj) (A + (size_t)((bi) * ((bi) - 1) / 2) * 1056 + (size_t)(bi) * 528 + (size_t)(bj) * 1056)
-#define KN_TRI(r) ((r) * ((r) + 1) / 2)
-        for (int bi = 0; bi < nbk; ++bi)
-            for (int bj = 0; bj <= bi; ++bj) {
-                double* blk = KN_BLK(bi, bj);
-#pragma unroll 4
-                for (int e = lane; e < 1024; e += 32) {
-                    const int li = e >> 5, lj = e & 31;
-                    const int i = bi * 32 + li, j = bj * 32 + lj;
+        // ---------------- K5 (Cholesky): augmented 8x8-tiled factorisation on the fp64 tensor pipe ----------------
+        // The k x k block C = c0 - gamma (identity-padded to kp = 8 * nt) is stored as lower-triangular 8x8 tiles in
+        // MMA-operand order: element (r, q) of a tile at (q >> 2) * 32 + r * 4 + (q & 3), so that the A/B fragment of
+        // mma.m8n8k4 (lane <-> (r = lane >> 2, q = 4 k4 + (lane & 3))) is one conflict-free LDS.64 at k4 * 32 + lane and
+        // the C fragment one LDS.128. Three extra rows [c ; 1 ; Z] form an augmented tile row: after the right-looking
+        // factorisation they hold y_c = L^-1 c, y_1 = L^-1 1, y_Z = L^-1 Z, and the bordered system of ok.py:738-756
+        // follows from dot products alone (no back substitution):
+        //     mu = (y_1.y_c - 1) / (y_1.y_1),  z = y_c.y_Z - mu y_1.y_Z,  sigma^2 = c0 - (y_c.y_c - mu y_1.y_c) - mu.
+        // Per 8-column step: potf2 + inverse of the diagonal tile in registers (warp shuffles inside groups of 8 lanes),
+        // panel tiles X <- X Winv^T and trailing tiles C_ij -= L_ip L_jp^T as DMMAs (2 per tile).
+        const int nt = kp >> 3;                       // tile rows of the covariance block; tile row nt = the augmented rows
+#define KN_T(i, j) (A + ((size_t)(i) * ((i) + 1) / 2 + (j)) * 64)
+        double* Wt = A + ((size_t)nt * (nt + 1) / 2 + nt) * 64;          // inverse of the current diagonal tile
+        const int fr = lane >> 2, fq = lane & 3;
+        // assembly: lane <-> (row fr, columns fq and 4 + fq) of every tile
+        for (int ti = 0; ti < nt; ++ti) {
+            const int i = ti * 8 + fr;
+            const double xi = nx[i], yi = ny[i], zi = nz[i];
+            for (int tj = 0; tj <= ti; ++tj) {
+                double* T = KN_T(ti, tj);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int j = tj * 8 + half * 4 + fq;
                     double v = 0.0;
                     if (i == j) v = (i < k) ? vg.c0 : 1.0;
                     else if (j < i && i < k) {
-                        double d = kb_dist<DIM>(nx[i], ny[i], nz[i], nx[j], ny[j], nz[j]);
+                        double d = kb_dist<DIM>(xi, yi, zi, nx[j], ny[j], nz[j]);
                         v = vg.c0 - kb_gamma<MODEL>(vg, d);
                     }
-                    if (bi != bj) blk[li * 33 + lj] = v;
-                    else if (lj <= li) blk[KN_TRI(li) + lj] = v;
+                    T[half * 32 + lane] = v;
                 }
             }
+        }
+        for (int tj = 0; tj < nt; ++tj) {             // augmented rows: 0 = c, 1 = ones, 2 = Z (rows 3..7 zero)
+            double* T = KN_T(nt, tj);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int t = tj * 8 + half * 4 + fq;
+                double v = 0.0;
+                if (fr == 0) v = rc[t];
+                else if (fr == 1) v = (t < k) ? 1.0 : 0.0;
+                else if (fr == 2) v = nv[t];
+                T[half * 32 + lane] = v;
+            }
+        }
         __syncwarp();
         bool notpd = false;
         const double ptol = 3.6e-15 * vg.c0;       // 16 eps: exact duplicates (nugget 0) give a pivot of +-1 ulp, not 0
-        for (int b = 0; b < nbk; ++b) {
-            double* Dbb = KN_BLK(b, b);
-            double d[32];
+        const int gr = lane & 7, gg = lane >> 3;   // potf2: row within the tile, redundant group
+        for (int ps = 0; ps < nt; ++ps) {
+            // ---- diagonal tile: L_pp (rows in registers) and Winv = L_pp^-1 ----
+            {
+                const double* T = KN_T(ps, ps);
+                double d[8];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) d[c] = (c <= lane) ? Dbb[KN_TRI(lane) + c] : 0.0;
-            double dinv = 1.0;
+                for (int q = 0; q < 8; ++q) d[q] = T[(q >> 2) * 32 + gr * 4 + (q & 3)];
+                double dinv = 1.0;
 #pragma unroll
-            for (int pc = 0; pc < 32; ++pc) {
-                const double piv = __shfl_sync(0xffffffffu, d[pc], pc);
-                if (!(piv > ptol)) notpd = true;        // at or below the rounding noise of c0 - sum l^2: not PD
-                const double inv = 1.0 / sqrt(piv);
-                const double l = d[pc] * inv;             // lane pc: sqrt(piv); lanes below: L[r][pc]
-                d[pc] = l;
-                if (lane == pc) dinv = inv;
+                for (int pc = 0; pc < 8; ++pc) {
+                    const double piv = __shfl_sync(0xffffffffu, d[pc], pc, 8);
+                    if (!(piv > ptol)) notpd = true;    // at or below the rounding noise of c0 - sum l^2: not PD
+                    const double inv = rsqrt(piv);
+                    const double l = d[pc] * inv;       // lane pc: sqrt(piv); lanes below: L[r][pc]
+                    d[pc] = l;
+                    if (gr == pc) dinv = inv;
 #pragma unroll
-                for (int c = pc + 1; c < 32; ++c) d[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), d[c]);
-            }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) if (c <= lane) Dbb[KN_TRI(lane) + c] = d[c];
-            // forward substitution of both right-hand sides for this block (lane r <-> entry b*32 + r)
-            double yc = rc[b * 32 + lane], y1 = r1[b * 32 + lane];
-#pragma unroll
-            for (int pc = 0; pc < 32; ++pc) {
-                const double ip = __shfl_sync(0xffffffffu, dinv, pc);
-                const double tc = __shfl_sync(0xffffffffu, yc, pc) * ip;
-                const double t1 = __shfl_sync(0xffffffffu, y1, pc) * ip;
-                if (lane == pc) { yc = tc; y1 = t1; }
-                else if (lane > pc) { yc = fma(-d[pc], tc, yc); y1 = fma(-d[pc], t1, y1); }
-            }
-            rc[b * 32 + lane] = yc; r1[b * 32 + lane] = y1;
-            // panel: X = A(bi, b) L_bb^-T for the blocks below, and their right-hand side update
-            for (int bi = b + 1; bi < nbk; ++bi) {
-                double* Bib = KN_BLK(bi, b);
-                double x[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) x[c] = Bib[lane * 33 + c];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-#pragma unroll
-                    for (int q = 0; q < c; ++q) x[c] = fma(-x[q], __shfl_sync(0xffffffffu, d[q], c), x[c]);
-                    x[c] *= __shfl_sync(0xffffffffu, dinv, c);
+                    for (int c = pc + 1; c < 8; ++c) d[c] = fma(-l, __shfl_sync(0xffffffffu, l, c, 8), d[c]);
                 }
-                double tc = 0.0, t1 = 0.0;
+                // column gr of the inverse: x[i] = Winv[i][gr]
+                double x[8];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    Bib[lane * 33 + c] = x[c];
-                    tc = fma(x[c], __shfl_sync(0xffffffffu, yc, c), tc);
-                    t1 = fma(x[c], __shfl_sync(0xffffffffu, y1, c), t1);
+                for (int i = 0; i < 8; ++i) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < i; ++q) sacc = fma(__shfl_sync(0xffffffffu, d[q], i, 8), x[q], sacc);
+                    const double di = __shfl_sync(0xffffffffu, dinv, i, 8);
+                    x[i] = (i < gr) ? 0.0 : ((i == gr) ? dinv : -sacc * di);
                 }
-                rc[bi * 32 + lane] -= tc;
-                r1[bi * 32 + lane] -= t1;
+                // group gg writes rows 2 gg and 2 gg + 1 of Winv (operand order)
+                const double v0 = gg == 0 ? x[0] : (gg == 1 ? x[2] : (gg == 2 ? x[4] : x[6]));
+                const double v1 = gg == 0 ? x[1] : (gg == 1 ? x[3] : (gg == 2 ? x[5] : x[7]));
+                Wt[(gr >> 2) * 32 + (2 * gg) * 4 + (gr & 3)] = v0;
+                Wt[(gr >> 2) * 32 + (2 * gg + 1) * 4 + (gr & 3)] = v1;
             }
             __syncwarp();
-            // trailing update: A(bi, bj) -= L(bi, b) L(bj, b)^T
-            for (int bi = b + 1; bi < nbk; ++bi) {
-                const double* Lib = KN_BLK(bi, b);
-                double xi[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) xi[c] = Lib[lane * 33 + c];
-                for (int bj = b + 1; bj <= bi; ++bj) {
-                    const double* Ljb = KN_BLK(bj, b);
-                    double* Aij = KN_BLK(bi, bj);
-                    double xj[32];
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) xj[c] = Ljb[lane * 33 + c];
-#pragma unroll 4
-                    for (int c = 0; c < 32; ++c) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int pc = 0; pc < 32; ++pc) acc = fma(xi[pc], __shfl_sync(0xffffffffu, xj[pc], c), acc);
-                        if (bj != bi) Aij[lane * 33 + c] -= acc;
-                        else if (c <= lane) Aij[KN_TRI(lane) + c] -= acc;      // diagonal target: packed lower triangle
-                    }
+            // ---- panel: X(i, p) <- X Winv^T for the tile rows below (incl. the augmented row) ----
+            {
+                const double wb0 = Wt[lane], wb1 = Wt[32 + lane];
+                for (int i = ps + 1; i <= nt; ++i) {
+                    double* T = KN_T(i, ps);
+                    const double a0 = T[lane], a1 = T[32 + lane];
+                    double c0 = 0.0, c1 = 0.0;
+                    kb_dmma(c0, c1, a0, wb0);
+                    kb_dmma(c0, c1, a1, wb1);
+                    __syncwarp();                   // every lane has read its operands before the tile is overwritten
+                    *reinterpret_cast<double2*>(T + (fq >> 1) * 32 + fr * 4 + 2 * (fq & 1)) = make_double2(c0, c1);
+                }
+            }
+            __syncwarp();
+            // ---- trailing update: C(i, j) -= L(i, p) L(j, p)^T,  p < j <= i  (augmented row: j < nt) ----
+            for (int i = ps + 1; i <= nt; ++i) {
+                const double* Li = KN_T(i, ps);
+                const double a0 = -Li[lane], a1 = -Li[32 + lane];
+                const int jend = i < nt ? i : nt - 1;
+                for (int j = ps + 1; j <= jend; ++j) {
+                    const double* Lj = KN_T(j, ps);
+                    double2* Cp = reinterpret_cast<double2*>(KN_T(i, j) + (fq >> 1) * 32 + fr * 4 + 2 * (fq & 1));
+                    double2 c = *Cp;
+                    kb_dmma(c.x, c.y, a0, Lj[lane]);
+                    kb_dmma(c.x, c.y, a1, Lj[32 + lane]);
+                    *Cp = c;
                 }
             }
             __syncwarp();
@@ -354,35 +361,26 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
             if (lane == 0) { atomicMax(P.flag, 2); P.z_out[p] = 0.0; P.ss_out[p] = 0.0; }
             return;
         }
-        // backward substitution L^T x = y, block by block from the bottom
-        for (int b = nbk - 1; b >= 0; --b) {
-            double yc = rc[b * 32 + lane], y1 = r1[b * 32 + lane];
-            for (int bi = b + 1; bi < nbk; ++bi) {          // minus L(bi, b)^T x_bi : lane c walks column c
-                const double* Lib = KN_BLK(bi, b);
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const double lrc = Lib[r * 33 + lane];
-                    yc = fma(-lrc, rc[bi * 32 + r], yc);
-                    y1 = fma(-lrc, r1[bi * 32 + r], y1);
-                }
-            }
-            const double* Dbb = KN_BLK(b, b);
-            const double dinv = 1.0 / Dbb[KN_TRI(lane) + lane];
-#pragma unroll 4
-            for (int pc = 31; pc >= 0; --pc) {
-                const double ip = __shfl_sync(0xffffffffu, dinv, pc);
-                const double xc = __shfl_sync(0xffffffffu, yc, pc) * ip;
-                const double x1 = __shfl_sync(0xffffffffu, y1, pc) * ip;
-                const double lpq = Dbb[KN_TRI(pc) + lane];   // L[pc][lane] (lane <= pc; unused otherwise, still in range)
-                if (lane == pc) { yc = xc; y1 = x1; }
-                else if (lane < pc) { yc = fma(-lpq, xc, yc); y1 = fma(-lpq, x1, y1); }
-            }
-            __syncwarp();
-            rc[b * 32 + lane] = yc; r1[b * 32 + lane] = y1;
-            __syncwarp();
+        // ---- bordered-system identities from the augmented rows ----
+        double s11 = 0.0, s1c = 0.0, scc = 0.0, s1z = 0.0, scz = 0.0;
+        for (int t = lane; t < kp; t += 32) {
+            const double* T = KN_T(nt, t >> 3) + ((t & 7) >> 2) * 32 + (t & 3);
+            const double yc = T[0], y1 = T[4], yz = T[8];
+            s11 = fma(y1, y1, s11); s1c = fma(y1, yc, s1c); scc = fma(yc, yc, scc);
+            s1z = fma(y1, yz, s1z); scz = fma(yc, yz, scz);
         }
-#undef KN_BLK
-#undef KN_TRI
+        for (int o = 16; o > 0; o >>= 1) {
+            s11 += __shfl_xor_sync(0xffffffffu, s11, o); s1c += __shfl_xor_sync(0xffffffffu, s1c, o);
+            scc += __shfl_xor_sync(0xffffffffu, scc, o); s1z += __shfl_xor_sync(0xffffffffu, s1z, o);
+            scz += __shfl_xor_sync(0xffffffffu, scz, o);
+        }
+        if (lane == 0) {
+            const double mu = (s1c - 1.0) / s11;
+            P.z_out[p] = scz - mu * s1z;                       // ok.py:755
+            P.ss_out[p] = vg.c0 - (scc - mu * s1c) - mu;       // ok.py:756 (= -x.b) in covariance form
+        }
+        return;
+#undef KN_T
     } else {
     // ---------------- K5: local system ----------------
     // C[i][j] = c0 - gamma(|x_i - x_j|), C[i][i] = c0   (ok.py:641-644 in covariance form)
@@ -486,9 +484,9 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
 // ---- host side -------------------------------------------------------------
 size_t kbk_knn_smem_per_warp(int k, int chol) {
     size_t S = (size_t)(k | 1);
-    size_t kp = chol ? (size_t)((k + 31) & ~31) : (size_t)k;
-    size_t nb = kp / 32;
-    size_t a = chol ? nb * (nb - 1) / 2 * (32 * 33) + nb * 528 : (size_t)k * S, c = KN_CAP + KN_CAP / 2;
+    size_t kp = chol ? (size_t)((k + 7) & ~7) : (size_t)k;
+    size_t nt = kp / 8;
+    size_t a = chol ? (nt * (nt + 1) / 2 + nt + 1) * 64 : (size_t)k * S, c = KN_CAP + KN_CAP / 2;
     return ((a > c ? a : c) + 7 * kp + 2) * sizeof(double);
 }
 

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
         if (warp == 0) {
             if (lane == 0) {
                 uint32_t g = git;
+                const uint64_t pol_w = kb_policy_evict_last(), pol_c = kb_policy_evict_first();
                 long long tau = 0;                   // W tiles are stored contiguously in (I, t) order
                 for (int I = 0; I < P.nrb; ++I) {
                     const int kt = P.pm.ktiles[I];
@@ -143,10 +144,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                         const int s = g % PT_STAGES;
                         mbar_wait(&empty[s], (uint32_t)(((g / PT_STAGES) & 1) ^ 1));
                         mbar_expect_tx(&full[s], PT_STAGE_BYTES);
-                        bulk_g2s(Ts + (size_t)s * KB_BM * KB_BK, gt + (size_t)tau * (KB_BM * KB_BK),
-                                 KB_BM * KB_BK * 8, &full[s]);
-                        bulk_g2s(Bs + (size_t)s * KB_BK * KB_TN, scratch + (size_t)t * (KB_BK * KB_TN),
-                                 KB_BK * KB_TN * 8, &full[s]);
+                        kb_bulk_g2s_hint(Ts + (size_t)s * KB_BM * KB_BK, gt + (size_t)tau * (KB_BM * KB_BK),
+                                         KB_BM * KB_BK * 8, &full[s], pol_w);
+                        kb_bulk_g2s_hint(Bs + (size_t)s * KB_BK * KB_TN, scratch + (size_t)t * (KB_BK * KB_TN),
+                                         KB_BK * KB_TN * 8, &full[s], pol_c);
                     }
                 }
             }

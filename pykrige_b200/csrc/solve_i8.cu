@@ -20,7 +20,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#define I8_THREADS 256
+#define I8_THREADS 512
+#define I8_GEN_THREADS 256                 // warps 8..15: two generator threads per prediction point
 #define I8_TM 128
 #define I8_BK 32
 #define I8_C_SLICE (I8_TM * I8_BK)            // 4 KB
@@ -77,15 +78,41 @@ __device__ __forceinline__ void i8_commit(uint64_t* bar) {
                  :: "r"(i8_smem_u32(bar)) : "memory");
 }
 
-// S signed slices of y = x * 2^-e (|y| < 1): x = 2^e * sum_s out[s] * 2^(-6-7s) + O(2^(e-7S))
+// S signed 7-bit digits of y = x * 2^-e (|y| < 1): x = 2^e * sum_s out[s] * 2^(-6-7s) + O(2^(e-7S)), out[s] in [-64, 64].
+// One fp64 multiply + one round-to-nearest conversion to a 6+7(S-1)-bit integer, then balanced base-128 digits with
+// integer ops (the digit loop used to be 4 fp64 instructions per slice on the pipe the RHS generators are bound by).
 template <int S>
 __device__ __forceinline__ void i8_slice(double x, int e, signed char (&out)[S]) {
-    double t = scalbn(x, 6 - e);           // y * 64
+    long long v = __double2ll_rn(scalbn(x, 6 + 7 * (S - 1) - e));      // |v| <= 2^(6+7(S-1))
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        double r = rint(t);
-        out[s] = (signed char)(int)r;
-        t = (t - r) * 128.0;
+    for (int s = S - 1; s >= 1; --s) {
+        const int d = (int)((v + 64) & 127) - 64;                        // balanced digit in [-64, 63]
+        out[s] = (signed char)d;
+        v = (v - d) >> 7;                                                // exact: v - d is a multiple of 128
+    }
+    out[0] = (signed char)v;                                             // |v| <= 64
+}
+// the same with the scale 2^(6+7(S-1)-e) precomputed by the caller (one per prediction point)
+template <int S>
+__device__ __forceinline__ void i8_slice_scaled(double x, double scale, signed char (&out)[S]) {
+    if (S <= 4) {                                                        // 27 bits + sign: 32-bit integer digits
+        int v = __double2int_rn(x * scale);
+#pragma unroll
+        for (int s = S - 1; s >= 1; --s) {
+            const int d = ((v + 64) & 127) - 64;
+            out[s] = (signed char)d;
+            v = (v - d) >> 7;
+        }
+        out[0] = (signed char)v;
+    } else {
+        long long v = __double2ll_rn(x * scale);
+#pragma unroll
+        for (int s = S - 1; s >= 1; --s) {
+            const int d = (int)((v + 64) & 127) - 64;
+            out[s] = (signed char)d;
+            v = (v - d) >> 7;
+        }
+        out[0] = (signed char)v;
     }
 }
 // byte offset of element (r, k) inside one slice tile with `rows` rows (k in [0, 32))
@@ -152,23 +179,32 @@ __device__ __forceinline__ double i8_cov_rhs(const VgParams& v, double d) {
     }
 }
 
+// Warp roles (512 threads): warp 0 lane 0 = bulk-copy producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (thread = TMEM lane = prediction point), warps 8-15 = RHS generators (two threads per point,
+// alternating k-stages: the fp64 sqrt/exp chains are latency-bound, eight warps keep the pipe fed).
+// The generators work one point tile AHEAD of the tensor pipe: they evaluate and slice the RHS column block of
+// tile i+1 into the other half of the double-buffered scratch ring while the MMAs of tile i run (the fp64 pipe
+// and the tensor pipe do not compete); gfull / gempty mbarriers hand the buffers over.
 template <int S, int DIM>
 __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_constant__ SolvePtParams P) {
     typedef I8Cfg<S> C;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* stage_base = smem_raw;                                                    // STAGES * STAGE_BYTES
     double* auxs = reinterpret_cast<double*>(smem_raw + (size_t)C::STAGES * C::STAGE_BYTES);  // KB_MAXAUX * 128
-    int* pexp = reinterpret_cast<int*>(auxs + KB_MAXAUX * I8_TM);                            // 128 point exponents
-    uint64_t* full = reinterpret_cast<uint64_t*>(pexp + I8_TM);                              // STAGES
+    int* pexp = reinterpret_cast<int*>(auxs + KB_MAXAUX * I8_TM);                            // 2 x 128 point exponents
+    uint64_t* full = reinterpret_cast<uint64_t*>(pexp + 2 * I8_TM);                          // STAGES
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;                                                     // 1
     uint64_t* tempty = tfull + 1;                                                            // 1
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty + 1);
+    uint64_t* gfull = tempty + 1;                                                            // 2
+    uint64_t* gempty = gfull + 2;                                                            // 2
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(gempty + 2);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nk = (P.n + I8_BK - 1) / I8_BK;
     const int nrb = (P.n + P.na + C::BN - 1) / C::BN;
-    unsigned char* scratch = reinterpret_cast<unsigned char*>(P.scratch) + (size_t)blockIdx.x * nk * C::C_BYTES;
+    const size_t sbuf = (size_t)nk * C::C_BYTES;                                             // one RHS column block
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(P.scratch) + (size_t)blockIdx.x * 2 * sbuf;
     const unsigned char* gt = reinterpret_cast<const unsigned char*>(P.tiles);
     const long long ntiles = (P.m + I8_TM - 1) / I8_TM;
     const int model = P.vg.model;
@@ -176,6 +212,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) { i8_mbar_init(&full[s], 1); i8_mbar_init(&empty[s], 1); }
         i8_mbar_init(tfull, 1); i8_mbar_init(tempty, 4);
+        for (int b = 0; b < 2; ++b) { i8_mbar_init(&gfull[b], I8_GEN_THREADS); i8_mbar_init(&gempty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
@@ -189,14 +226,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_base_smem;
 
-    uint32_t g = 0;      // smem stage ring counter
-    uint32_t ga = 0;     // accumulator hand-over counter (row blocks)
-
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---------------- phase G: RHS column block -> S int8 slices per value, UMMA layout ----------------
-        {
-            const int pl = tid & (I8_TM - 1);
-            const int ks = tid >> 7;                       // 0..1
+    if (warp >= 8) {
+        // ---------------- generators: RHS column block -> S int8 slices per value, UMMA layout ----------------
+        const int pl = (tid - 8 * 32) & (I8_TM - 1);       // 0..127: point within the tile
+        const int ks = (tid - 8 * 32) >> 7;                // 0..1: k-stage parity handled by this thread
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = (int)(it & 1);
+            i8_mbar_wait(&gempty[b], ((it >> 1) & 1) ^ 1);         // the tile that used this buffer is finished
+            unsigned char* sc = scratch + (size_t)b * sbuf;
             const long long pj = tile * I8_TM + pl;
             const bool pvalid = pj < P.m;
             double px = 0.0, py = 0.0, pz = 0.0;
@@ -215,9 +253,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
                 }
                 (void)frexp(cmax * 1.0000001, &ec);        // cmax * 2^-ec < 1
             }
-            if (ks == 0) pexp[pl] = ec;
-            for (int t = ks; t < nk; t += I8_THREADS / I8_TM) {
-                unsigned char* ct = scratch + (size_t)t * C::C_BYTES;
+            if (ks == 0) pexp[b * I8_TM + pl] = ec;
+            const double cscale = scalbn(1.0, 6 + 7 * (S - 1) - ec);
+            for (int t = ks; t < nk; t += I8_GEN_THREADS / I8_TM) {
+                unsigned char* ct = sc + (size_t)t * C::C_BYTES;
 #pragma unroll 1
                 for (int kc = 0; kc < 2; ++kc) {           // two 16-byte k-chunks per stage
                     signed char sl[16][S];
@@ -229,7 +268,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
                             double d = kb_dist<DIM>(__ldg(P.ax + k), __ldg(P.ay + k), KB_HASZ(DIM) ? __ldg(P.az + k) : 0.0, px, py, pz);
                             c = i8_cov_rhs(P.vg, d);
                         }
-                        i8_slice<S>(c, ec, sl[kk]);
+                        i8_slice_scaled<S>(c, cscale, sl[kk]);
                     }
                     const int off = (pl >> 3) * 256 + kc * 128 + (pl & 7) * 16;
 #pragma unroll
@@ -243,15 +282,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
                     }
                 }
             }
+            // generic-proxy global writes -> read by the async proxy (bulk copies) of this CTA
             __threadfence();
             asm volatile("fence.proxy.async.global;\n" ::: "memory");
+            i8_mbar_arrive(&gfull[b]);
         }
-        __syncthreads();
-
-        // ---------------- phase M ----------------
-        if (warp == 0) {
-            if (lane == 0) {
-                uint32_t gg = g;
+    } else if (warp == 0) {
+        // ---------------- producer: W tiles + RHS tiles -> smem ring ----------------
+        if (lane == 0) {
+            const uint64_t pol_w = kb_policy_evict_last(), pol_c = kb_policy_evict_first();
+            uint32_t gg = 0, it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int b = (int)(it & 1);
+                const unsigned char* sc = scratch + (size_t)b * sbuf;
+                i8_mbar_wait(&gfull[b], (it >> 1) & 1);
                 long long tau = 0;
                 for (int J = 0; J < nrb; ++J) {
                     const int kt = i8_ktiles(J, P.n, nk, C::BN);
@@ -260,14 +304,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
                         i8_mbar_wait(&empty[s], (uint32_t)(((gg / C::STAGES) & 1) ^ 1));
                         i8_mbar_expect_tx(&full[s], C::STAGE_BYTES);
                         unsigned char* sb = stage_base + (size_t)s * C::STAGE_BYTES;
-                        i8_bulk_g2s(sb, gt + (size_t)tau * C::W_BYTES, C::W_BYTES, &full[s]);
-                        i8_bulk_g2s(sb + C::W_BYTES, scratch + (size_t)t * C::C_BYTES, C::C_BYTES, &full[s]);
+                        kb_bulk_g2s_hint(sb, gt + (size_t)tau * C::W_BYTES, C::W_BYTES, &full[s], pol_w);
+                        kb_bulk_g2s_hint(sb + C::W_BYTES, sc + (size_t)t * C::C_BYTES, C::C_BYTES, &full[s], pol_c);
                     }
                 }
             }
-        } else if (warp == 1) {
-            if (lane == 0) {
-                uint32_t gg = g, gb = ga;
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            uint32_t gg = 0, gb = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int J = 0; J < nrb; ++J, ++gb) {
                     const int kt = i8_ktiles(J, P.n, nk, C::BN);
                     i8_mbar_wait(tempty, (uint32_t)((gb & 1) ^ 1));
@@ -293,16 +340,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
                     i8_commit(tfull);
                 }
             }
-        } else if (warp >= 4) {
-            // epilogue: thread = TMEM lane = prediction point
-            const int pl = (warp & 3) * 32 + lane;
-            const double pscale = scalbn(1.0, pexp[pl] - 7 * (S - 1));
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue: thread = TMEM lane = prediction point ----------------
+        const int pl = (warp & 3) * 32 + lane;
+        const uint32_t t_addr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+        uint32_t gb = 0, it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = (int)(it & 1);
+            i8_mbar_wait(&gfull[b], (it >> 1) & 1);            // acquire the generators' pexp[b]
+            const double pscale = scalbn(1.0, pexp[b * I8_TM + pl] - 7 * (S - 1));
             double q = 0.0;
-            uint32_t gb = ga;
             for (int J = 0; J < nrb; ++J, ++gb) {
                 i8_mbar_wait(tfull, (uint32_t)(gb & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t t_addr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
 #pragma unroll 1
                 for (int ch = 0; ch < C::BN / 16; ++ch) {
                     // exact recombination: V = sum_d acc_d * 2^(7 (S-1-d)) fits in int64 (|acc_d| < 2^30, d = 0 has one
@@ -341,10 +392,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
             // ---------------- phase F: finalize, thread = point ----------------
             const long long pj = tile * I8_TM + pl;
             if (pj < P.m) kb_finalize_point<DIM, double>(P, pj, q, auxs + pl, I8_TM);
+            __syncwarp();
+            if (lane == 0) i8_mbar_arrive(&gempty[b]);       // scratch half b and pexp[b] may be rewritten
         }
-        for (int J = 0; J < nrb; ++J) g += (uint32_t)i8_ktiles(J, P.n, nk, C::BN);
-        ga += (uint32_t)nrb;
-        __syncthreads();
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -355,8 +405,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) solve_kernel_i8(const __grid_co
 
 // ---- host side ---------------------------------------------------------------------------------------
 template <int S> static size_t i8_smem_s() {
-    return (size_t)I8Cfg<S>::STAGES * I8Cfg<S>::STAGE_BYTES + (size_t)KB_MAXAUX * I8_TM * sizeof(double) + I8_TM * sizeof(int) +
-           (2 * I8Cfg<S>::STAGES + 2) * sizeof(uint64_t) + 64;
+    return (size_t)I8Cfg<S>::STAGES * I8Cfg<S>::STAGE_BYTES + (size_t)KB_MAXAUX * I8_TM * sizeof(double) + 2 * I8_TM * sizeof(int) +
+           (2 * I8Cfg<S>::STAGES + 6) * sizeof(uint64_t) + 64;
 }
 static int i8_bn(int S) { return S == 6 ? I8Cfg<6>::BN : S == 5 ? I8Cfg<5>::BN : I8Cfg<4>::BN; }
 bool kbk_i8_valid_slices(int S) { return S >= 4 && S <= 6; }
@@ -370,7 +420,7 @@ long long kbk_i8_total_tiles(int S, int n, int na, long long* tile_off /* [nrb+1
     return off;
 }
 size_t kbk_i8_tile_bytes(int S) { return (size_t)S * i8_bn(S) * I8_BK; }
-size_t kbk_solve_i8_scratch_bytes(int S, int n, int grid) { return (size_t)grid * ((n + I8_BK - 1) / I8_BK) * S * I8_C_SLICE; }
+size_t kbk_solve_i8_scratch_bytes(int S, int n, int grid) { return (size_t)grid * 2 * ((n + I8_BK - 1) / I8_BK) * S * I8_C_SLICE; }   // double-buffered
 int kbk_solve_i8_tile_points() { return I8_TM; }
 
 template <int S, int DIM>

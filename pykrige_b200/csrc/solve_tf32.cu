@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
             if (lane == 0) {
                 uint32_t gg = g;
                 long long tau = 0;
+                const uint64_t pol_w = kb_policy_evict_last(), pol_c = kb_policy_evict_first();
                 for (int I = 0; I < P.nrb; ++I) {
                     const int kt = P.pm.ktiles[I];
                     for (int t = 0; t < kt; ++t, ++tau, ++gg) {
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
                         tf_mbar_wait(&empty[s], (uint32_t)(((gg / TF_STAGES) & 1) ^ 1));
                         tf_mbar_expect_tx(&full[s], TF_STAGE_BYTES);
                         unsigned char* sb = stage_base + (size_t)s * TF_STAGE_BYTES;
-                        tf_bulk_g2s(sb, gt + (size_t)tau * TF_W_BYTES, TF_W_BYTES, &full[s]);
-                        tf_bulk_g2s(sb + TF_W_BYTES, scratch + (size_t)t * TF_C_BYTES, TF_C_BYTES, &full[s]);
+                        kb_bulk_g2s_hint(sb, gt + (size_t)tau * TF_W_BYTES, TF_W_BYTES, &full[s], pol_w);
+                        kb_bulk_g2s_hint(sb + TF_W_BYTES, scratch + (size_t)t * TF_C_BYTES, TF_C_BYTES, &full[s], pol_c);
                     }
                 }
             }

@@ -260,3 +260,44 @@ def test_ctypes_signatures_match_the_header():
                 assert ct is ctypes.c_double, (name, decl, ct)
             else:
                 assert ct in (ctypes.c_int, ctypes.c_int64), (name, decl, ct)
+
+
+def test_gstools_route_on_the_host():
+    """ok.py:224-239 / ok3d.py:248-262 with a stand-in gstools package (tests/gstools_stub.py): a CovModel becomes a
+    'custom' model whose callable is model.pykrige_vario, the anisotropy comes from the model, the dimension and
+    version checks of compat_gstools.py:21-37 raise as in the reference."""
+    import gstools_stub
+    from pykrige_b200.compat_gstools import GSToolsException
+    xyz, val = cases.synth_data(5, 40, 2)
+    try:
+        gstools_stub.install("1.5.2")
+        m = gstools_stub.CovModel(dim=2, var=2.0, len_scale=150.0, nugget=0.1, anis=0.5, angle=20.0)
+        ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, m)
+        assert ok.variogram_model == "custom" and ok.model is m
+        assert ok.variogram_model_parameters == []
+        assert ok.anisotropy_scaling == m.pykrige_anis and ok.anisotropy_angle == m.pykrige_angle
+        d = np.linspace(0.0, 500.0, 7)
+        assert_allclose(ok.variogram_function(ok.variogram_model_parameters, d), m.variogram(d), rtol=0, atol=0)
+        assert ok._device_model() == (ok.TABLE_MODEL_ID, [])           # tabulated on the device
+        uk = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, m, drift_terms=["regional_linear"])
+        assert uk.variogram_model == "custom"
+        with pytest.raises(ValueError):                                 # 3-D model on a 2-D class
+            pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, gstools_stub.CovModel(dim=3))
+        with pytest.raises(ValueError):                                 # latlon model needs geographic coordinates
+            pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, gstools_stub.CovModel(dim=2, latlon=True))
+        x3, v3 = cases.synth_data(6, 30, 3)
+        with pytest.raises(ValueError):                                 # 2-D model on a 3-D class
+            pk.OrdinaryKriging3D(x3[:, 0], x3[:, 1], x3[:, 2], v3, gstools_stub.CovModel(dim=2))
+        k3 = pk.OrdinaryKriging3D(x3[:, 0], x3[:, 1], x3[:, 2], v3, gstools_stub.CovModel(dim=3, anis=0.5))
+        assert k3.anisotropy_scaling_y == 2.0 and k3.variogram_model == "custom"
+        gstools_stub.install("1.2.0")
+        with pytest.raises(GSToolsException):
+            pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, m)
+        gstools_stub.install("1.3.0")
+        with pytest.raises(GSToolsException):                           # latlon needs >= 1.4
+            pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, gstools_stub.CovModel(dim=2, latlon=True),
+                               coordinates_type="geographic")
+    finally:
+        gstools_stub.uninstall()
+    with pytest.raises(GSToolsException):                               # gstools absent
+        pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, m)

@@ -830,3 +830,36 @@ def test_custom_variogram_other_dtypes(pk, ref_custom):
     z, ss = m.execute("points", P[:, 0], P[:, 1], backend="cuda", dtype="float32")
     assert_parity(z, zr, 1e-2, "custom float32 z")
     assert_parity(ss, sr, 1e-2, "custom float32 ss")
+
+
+def test_gstools_model_through_cuda(pk):
+    """The GSTools route (ok.py:224-239) end to end on the device with the stand-in package of tests/gstools_stub.py:
+    the CovModel's pykrige_vario is tabulated (KB200_VG_TABLE) and the result agrees with the oracle run with the
+    same callable and the model's anisotropy; global path, moving window and 3-D."""
+    import gstools_stub
+    from oracle import krige_oracle as ko
+    xyz, val = cases.synth_data(88, 500, 2)
+    pts = cases.synth_points(88, 400, 2, xyz)
+    try:
+        gstools_stub.install()
+        m = gstools_stub.CovModel(dim=2, var=1.2, len_scale=120.0, nugget=0.05, anis=0.6, angle=35.0)
+        ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, m)
+        z, ss = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
+        zo, so = ko.krige(xyz, val, m.pykrige_vario, [], pts, scaling=[m.pykrige_anis], angle=[m.pykrige_angle])
+        assert_parity(z, zo, R64, "gstools z")
+        assert_parity(ss, so, R64, "gstools ss")
+        zk, sk = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda", n_closest_points=12)
+        zo, so = ko.krige(xyz, val, m.pykrige_vario, [], pts, scaling=[m.pykrige_anis], angle=[m.pykrige_angle],
+                          n_closest_points=12)
+        assert_parity(zk, zo, R64, "gstools knn z")
+        assert_parity(sk, so, R64, "gstools knn ss")
+        x3, v3 = cases.synth_data(89, 300, 3)
+        p3 = cases.synth_points(89, 200, 3, x3)
+        m3 = gstools_stub.CovModel(dim=3, var=1.0, len_scale=200.0, nugget=0.02)
+        k3 = pk.OrdinaryKriging3D(x3[:, 0], x3[:, 1], x3[:, 2], v3, m3)
+        z, ss = k3.execute("points", p3[:, 0], p3[:, 1], p3[:, 2], backend="cuda")
+        zo, so = ko.krige(x3, v3, m3.pykrige_vario, [], p3)
+        assert_parity(z, zo, R64, "gstools 3d z")
+        assert_parity(ss, so, R64, "gstools 3d ss")
+    finally:
+        gstools_stub.uninstall()
