@@ -21,6 +21,8 @@
 struct VgParams {
     int model;
     double p0, p1, p2;   // stored (psill-form) parameters, variogram_models.py:25-81
+    double inv_a;        // host-computed reciprocal of the model's distance scale: 1/(range/3) (exponential, hole-effect),
+                         // 1/(4 range/7)^2 (gaussian), 1/range (spherical): one fp64 division less per evaluation
     double c0;           // covariance shift: cov(d) = c0 - gamma(d)
     double eps;          // exact-hit cutoff, ok.py:177
     int exact;           // ok.py:671-672
@@ -85,13 +87,12 @@ __device__ __forceinline__ double kb_gamma(const VgParams& v, double d) {
     } else if (MODEL == KB200_VG_POWER) {
         return v.p0 * pow(d, v.p1) + v.p2;                            // scale*d^exponent + nugget
     } else if (MODEL == KB200_VG_GAUSSIAN) {
-        double r = v.p1 * (4.0 / 7.0);
-        return v.p0 * (1.0 - exp(-(d * d) / (r * r))) + v.p2;
+        return v.p0 * (1.0 - exp(-(d * d) * v.inv_a)) + v.p2;
     } else if (MODEL == KB200_VG_EXPONENTIAL) {
-        return v.p0 * (1.0 - exp(-d / (v.p1 / 3.0))) + v.p2;
+        return v.p0 * (1.0 - exp(-d * v.inv_a)) + v.p2;
     } else if (MODEL == KB200_VG_SPHERICAL) {
         if (d <= v.p1) {
-            double q = d / v.p1;
+            double q = d * v.inv_a;
             return v.p0 * (1.5 * q - 0.5 * q * q * q) + v.p2;
         }
         return v.p0 + v.p2;
@@ -106,7 +107,7 @@ __device__ __forceinline__ double kb_gamma(const VgParams& v, double d) {
         return (2.0 * t3 - 3.0 * t2 + 1.0) * a.x + (t3 - 2.0 * t2 + t) * a.y
              + (3.0 * t2 - 2.0 * t3) * b.x + (t3 - t2) * b.y;
     } else {  // hole-effect
-        double q = d / (v.p1 / 3.0);
+        double q = d * v.inv_a;
         return v.p0 * (1.0 - (1.0 - q) * exp(-q)) + v.p2;
     }
 }

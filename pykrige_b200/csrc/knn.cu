@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #define KN_CAP 512          // candidate buffer (per warp)
+#define KN_SELECT_DOUBLES 272   // selection scratch: 256 histogram ints + 256 slot ints + 32 boundary ints
 
 __global__ void knn_count_kernel(int dim, int n, const double* __restrict__ ax, const double* __restrict__ ay,
                                  const double* __restrict__ az, KnnParams kp, int* __restrict__ cell_of,
@@ -66,6 +67,27 @@ __global__ void knn_scatter_kernel(int n, const int* __restrict__ cell_of, const
     int c = cell_of[i];
     int pos = start[c] + atomicAdd(&cursor[c], 1);
     sx[pos] = ax[i]; sy[pos] = ay[i]; sz[pos] = az[i]; sv[pos] = val[i]; sorig[pos] = i;
+}
+
+// The counting-sort scatter leaves the points of a cell in the order the atomics happened to run; one thread per
+// cell re-orders its run by original index (cells hold ~2 points: insertion sort), so that the candidate walk -
+// and with it the order of the neighbours in the local system - is the same on every launch and every device.
+__global__ void knn_cellsort_kernel(int ncells, const int* __restrict__ start, double* __restrict__ sx,
+                                    double* __restrict__ sy, double* __restrict__ sz, double* __restrict__ sv,
+                                    int* __restrict__ sorig) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int b = start[c], e = start[c + 1];
+    for (int i = b + 1; i < e; ++i) {
+        const int oi = sorig[i];
+        const double x = sx[i], y = sy[i], z = sz[i], v = sv[i];
+        int j = i - 1;
+        while (j >= b && sorig[j] > oi) {
+            sorig[j + 1] = sorig[j]; sx[j + 1] = sx[j]; sy[j + 1] = sy[j]; sz[j + 1] = sz[j]; sv[j + 1] = sv[j];
+            --j;
+        }
+        sorig[j + 1] = oi; sx[j + 1] = x; sy[j + 1] = y; sz[j + 1] = z; sv[j + 1] = v;
+    }
 }
 
 // ---- warp helpers -----------------------------------------------------------
@@ -117,7 +139,7 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
     // tiled Cholesky: nt (nt + 1) / 2 lower tiles + nt augmented tiles + 1 tile for the diagonal inverse, 64 doubles each
     // — keep in step with kbk_knn_smem_per_warp
     size_t a_doubles = CHOL ? ((size_t)(kp / 8) * (kp / 8 + 1) / 2 + kp / 8 + 1) * 64 : (size_t)k * S;
-    size_t cand_doubles = KN_CAP + KN_CAP / 2; // d2[CAP] doubles + id[CAP] ints
+    size_t cand_doubles = KN_CAP + KN_CAP / 2 + KN_SELECT_DOUBLES;   // d2[CAP] doubles + id[CAP] ints + selection scratch
     size_t off = a_doubles > cand_doubles ? a_doubles : cand_doubles;
     double* rc = base + off;                   // rhs c (becomes C^-1 c)
     double* r1 = rc + kp;                      // rhs 1 (becomes C^-1 1)
@@ -217,12 +239,119 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
         if (inside >= k) break;
         r += (r < 2) ? 1 : (r >> 1);                   // not enough inside the inscribed sphere: larger block, start over
     }
-    compact(k);                                        // ascending distance, first k are the neighbours
+    // ---- the k nearest of the cnt candidates, WITHOUT sorting them ----
+    // d^2 of points scattered in the plane/space is close to uniform in area/volume, so 256 linear buckets over
+    // [0, max d^2] put ~1 candidate into the bucket that holds the k-th smallest: everything in lower buckets is
+    // selected, the boundary bucket is ranked exactly by (d^2, original index) - the rule of the sort it replaces.
+    // The neighbours keep the order of the candidate walk (cells are ordered by original index: deterministic).
+    // A boundary bucket with more than 32 entries (lattices, duplicates) falls back to the full sort.
+    double dk2;                                        // d^2 of the k-th neighbour
+    {
+        int* hist = reinterpret_cast<int*>(base + KN_CAP + KN_CAP / 2);   // 256 ints behind the candidate buffers
+        int* sel = hist + 256;                         // k (<= 256) selected candidate slots, then the boundary list (32)
+        double dmax = 0.0;
+        for (int t = lane; t < cnt; t += 32) dmax = fmax(dmax, cd2[t]);
+        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        const double bs = dmax > 0.0 ? 255.999 / dmax : 0.0;
+        for (int t = lane; t < 256; t += 32) hist[t] = 0;
+        __syncwarp();
+        for (int t = lane; t < cnt; t += 32) atomicAdd(&hist[(int)(cd2[t] * bs)], 1);
+        __syncwarp();
+        // bucket of the k-th smallest: lane owns buckets 8 lane .. 8 lane + 7
+        int hloc[8], run = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { hloc[q] = hist[lane * 8 + q]; run += hloc[q]; }
+        int incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        int before = incl - run;                       // candidates in the buckets of lower lanes
+        int bstar = -1, below = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (bstar < 0 && before + hloc[q] >= k && before < k) { bstar = lane * 8 + q; below = before; }
+            before += hloc[q];
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, bstar >= 0);
+        const int src = __ffs(who) - 1;                // exactly one lane found it (cnt >= k)
+        bstar = __shfl_sync(0xffffffffu, bstar, src);
+        below = __shfl_sync(0xffffffffu, below, src);
+        const int nbound = hist[bstar];                // entries of the boundary bucket
+        const int need = k - below;                    // how many of them are neighbours
+        if (nbound > 32 || cnt < k) {
+            compact(k);                                // degenerate distribution: exact full sort (ascending)
+            dk2 = cd2[k - 1];
+        } else {
+            // pass 1: the boundary candidates into a list; pass 2 ranks them; pass 3 compacts the selection in walk order
+            int nb_seen = 0;
+            for (int t0 = 0; t0 < cnt; t0 += 32) {
+                const int t = t0 + lane;
+                const bool isb = t < cnt && (int)(cd2[t] * bs) == bstar;
+                const unsigned m = __ballot_sync(0xffffffffu, isb);
+                if (isb) sel[k + nb_seen + __popc(m & ((1u << lane) - 1u))] = t;
+                nb_seen += __popc(m);
+            }
+            __syncwarp();
+            // lane j < nbound: rank of boundary candidate j by (d^2, original index)
+            bool take = false;
+            double myd = 0.0; int myo = 0, myt = -1;
+            if (lane < nbound) { myt = sel[k + lane]; myd = cd2[myt]; myo = P.sorig[cid[myt]]; }
+            int rank = 0;
+            for (int j = 0; j < nbound; ++j) {
+                const double dj = __shfl_sync(0xffffffffu, myd, j);
+                const int oj = __shfl_sync(0xffffffffu, myo, j);
+                if (lane < nbound && j != lane && cand_less(dj, oj, myd, myo)) ++rank;
+            }
+            take = lane < nbound && rank < need;
+            // threshold = the largest selected boundary d^2 (or the largest d^2 below the bucket when need == 0)
+            double thr = take ? myd : -1.0;
+            for (int o = 16; o > 0; o >>= 1) thr = fmax(thr, __shfl_xor_sync(0xffffffffu, thr, o));
+            // mark the taken boundary candidates in the hist area (reuse: 1 flag per candidate slot is too large, so a
+            // 32-bit mask over the boundary list positions is broadcast instead)
+            const unsigned takemask = __ballot_sync(0xffffffffu, take);
+            int nsel = 0;
+            double dmaxsel = thr;
+            for (int t0 = 0; t0 < cnt; t0 += 32) {
+                const int t = t0 + lane;
+                bool pick = false;
+                if (t < cnt) {
+                    const int b = (int)(cd2[t] * bs);
+                    if (b < bstar) { pick = true; dmaxsel = fmax(dmaxsel, cd2[t]); }
+                    else if (b == bstar) {
+                        for (int j = 0; j < nbound; ++j) if (((takemask >> j) & 1u) && sel[k + j] == t) pick = true;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, pick);
+                if (pick) sel[nsel + __popc(m & ((1u << lane) - 1u))] = t;
+                nsel += __popc(m);
+            }
+            for (int o = 16; o > 0; o >>= 1) dmaxsel = fmax(dmaxsel, __shfl_xor_sync(0xffffffffu, dmaxsel, o));
+            dk2 = dmaxsel;
+            __syncwarp();
+            // gather the selection to the front of the candidate arrays (slots are increasing: reads of slot s >= t
+            // happen before writes of slot t only if staged through registers)
+            for (int c0 = 0; c0 < k; c0 += 128) {      // 128 slots per round: reads of a round never see its own writes
+                double gd[4]; int gi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = c0 + lane + 32 * u;
+                    if (t < k) { const int sidx = sel[t]; gd[u] = cd2[sidx]; gi[u] = cid[sidx]; }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = c0 + lane + 32 * u;
+                    if (t < k) { cd2[t] = gd[u]; cid[t] = gi[u]; }
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+        }
+    }
     // neighbours -> per-warp arrays (these live outside the region the candidate buffers alias)
     VgParams vg = P.vg;
     if (MODEL == KB200_VG_LINEAR || MODEL == KB200_VG_POWER || MODEL == KB200_VG_TABLE) {
         // unbounded (or unknown: tabulated) models: local shift c0 = gamma(2 d_k) >= gamma of any neighbour pair
-        double dk = sqrt(cd2[k - 1]);
+        double dk = sqrt(dk2);
         if (DIM == KB_GEO) dk = 2.0 * asin(fmin(1.0, 0.5 * dk)) * 57.29577951308232;   // chord -> degrees
         double g = kb_gamma<MODEL>(vg, 2.0 * dk);
         vg.c0 = g > 0.0 ? g : 1.0;
@@ -486,7 +615,7 @@ size_t kbk_knn_smem_per_warp(int k, int chol) {
     size_t S = (size_t)(k | 1);
     size_t kp = chol ? (size_t)((k + 7) & ~7) : (size_t)k;
     size_t nt = kp / 8;
-    size_t a = chol ? (nt * (nt + 1) / 2 + nt + 1) * 64 : (size_t)k * S, c = KN_CAP + KN_CAP / 2;
+    size_t a = chol ? (nt * (nt + 1) / 2 + nt + 1) * 64 : (size_t)k * S, c = KN_CAP + KN_CAP / 2 + KN_SELECT_DOUBLES;
     return ((a > c ? a : c) + 7 * kp + 2) * sizeof(double);
 }
 
@@ -528,7 +657,8 @@ cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, co
     knn_scan_kernel<<<1, 1024, 0, st>>>(ncells, cursor, cell_start);
     KB_CUDA_OK(cudaMemsetAsync(cursor, 0, (size_t)(ncells + 1) * sizeof(int), st));
     knn_scatter_kernel<<<g, 256, 0, st>>>(n, cell_of, cell_start, cursor, ax, ay, az, values, sx, sy, sz, sv, sorig);
-    *launches += 3;
+    knn_cellsort_kernel<<<(ncells + 255) / 256, 256, 0, st>>>(ncells, cell_start, sx, sy, sz, sv, sorig);
+    *launches += 4;
     kp.ax = sx; kp.ay = sy; kp.az = sz; kp.values = sv; kp.sorig = sorig; kp.cell_start = cell_start;
     return cudaGetLastError();
 }
