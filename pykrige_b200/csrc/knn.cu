@@ -385,23 +385,30 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
 #define KN_T(i, j) (A + ((size_t)(i) * ((i) + 1) / 2 + (j)) * 64)
         double* Wt = A + ((size_t)nt * (nt + 1) / 2 + nt) * 64;          // inverse of the current diagonal tile
         const int fr = lane >> 2, fq = lane & 3;
-        // assembly: lane <-> (row fr, columns fq and 4 + fq) of every tile
+        // assembly: lane <-> (row fr, columns fq and 4 + fq) of every tile; two tiles (four independent sqrt/exp chains)
+        // per iteration: the evaluation is latency-bound with 8 warps per SM
         for (int ti = 0; ti < nt; ++ti) {
             const int i = ti * 8 + fr;
             const double xi = nx[i], yi = ny[i], zi = nz[i];
-            for (int tj = 0; tj <= ti; ++tj) {
-                double* T = KN_T(ti, tj);
+            for (int tj = 0; tj <= ti; tj += 2) {
+                double v[4];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int j = tj * 8 + half * 4 + fq;
-                    double v = 0.0;
-                    if (i == j) v = (i < k) ? vg.c0 : 1.0;
-                    else if (j < i && i < k) {
-                        double d = kb_dist<DIM>(xi, yi, zi, nx[j], ny[j], nz[j]);
-                        v = vg.c0 - kb_gamma<MODEL>(vg, d);
+                for (int u = 0; u < 4; ++u) {
+                    const int tjj = tj + (u >> 1);
+                    const int j = tjj * 8 + (u & 1) * 4 + fq;
+                    double val = 0.0;
+                    if (tjj <= ti) {
+                        if (i == j) val = (i < k) ? vg.c0 : 1.0;
+                        else if (j < i && i < k) {
+                            double d = kb_dist<DIM>(xi, yi, zi, nx[j], ny[j], nz[j]);
+                            val = vg.c0 - kb_gamma<MODEL>(vg, d);
+                        }
                     }
-                    T[half * 32 + lane] = v;
+                    v[u] = val;
                 }
+                double* T = KN_T(ti, tj);
+                T[lane] = v[0]; T[32 + lane] = v[1];
+                if (tj + 1 <= ti) { T[64 + lane] = v[2]; T[96 + lane] = v[3]; }     // tile (ti, tj + 1) follows (ti, tj)
             }
         }
         for (int tj = 0; tj < nt; ++tj) {             // augmented rows: 0 = c, 1 = ones, 2 = Z (rows 3..7 zero)
@@ -471,13 +478,29 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
             }
             __syncwarp();
             // ---- trailing update: C(i, j) -= L(i, p) L(j, p)^T,  p < j <= i  (augmented row: j < nt) ----
+            // two column tiles per iteration: independent accumulator chains hide the DMMA / LDS latency
             for (int i = ps + 1; i <= nt; ++i) {
                 const double* Li = KN_T(i, ps);
                 const double a0 = -Li[lane], a1 = -Li[32 + lane];
                 const int jend = i < nt ? i : nt - 1;
-                for (int j = ps + 1; j <= jend; ++j) {
+                const int coff = (fq >> 1) * 32 + fr * 4 + 2 * (fq & 1);
+                int j = ps + 1;
+                for (; j + 1 <= jend; j += 2) {
+                    const double* Lj0 = KN_T(j, ps);
+                    const double* Lj1 = KN_T(j + 1, ps);
+                    double2* Cp0 = reinterpret_cast<double2*>(KN_T(i, j) + coff);
+                    double2* Cp1 = reinterpret_cast<double2*>(KN_T(i, j + 1) + coff);
+                    double2 ca = *Cp0, cb = *Cp1;
+                    const double b00 = Lj0[lane], b01 = Lj0[32 + lane], b10 = Lj1[lane], b11 = Lj1[32 + lane];
+                    kb_dmma(ca.x, ca.y, a0, b00);
+                    kb_dmma(cb.x, cb.y, a0, b10);
+                    kb_dmma(ca.x, ca.y, a1, b01);
+                    kb_dmma(cb.x, cb.y, a1, b11);
+                    *Cp0 = ca; *Cp1 = cb;
+                }
+                if (j <= jend) {
                     const double* Lj = KN_T(j, ps);
-                    double2* Cp = reinterpret_cast<double2*>(KN_T(i, j) + (fq >> 1) * 32 + fr * 4 + 2 * (fq & 1));
+                    double2* Cp = reinterpret_cast<double2*>(KN_T(i, j) + coff);
                     double2 c = *Cp;
                     kb_dmma(c.x, c.y, a0, Lj[lane]);
                     kb_dmma(c.x, c.y, a1, Lj[32 + lane]);

@@ -181,7 +181,8 @@ __device__ __forceinline__ double i8_cov_rhs(const VgParams& v, double d) {
 
 // Warp roles (512 threads): warp 0 lane 0 = bulk-copy producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (thread = TMEM lane = prediction point), warps 8-15 = RHS generators (two threads per point,
-// alternating k-stages: the fp64 sqrt/exp chains are latency-bound, eight warps keep the pipe fed).
+// alternating k-stages: the fp64 sqrt/exp chains are latency-bound, eight warps keep the pipe fed; twelve gave +2 % at
+// S = 4 and -8 % at S = 6 through register spills).
 // The generators work one point tile AHEAD of the tensor pipe: they evaluate and slice the RHS column block of
 // tile i+1 into the other half of the double-buffered scratch ring while the MMAs of tile i run (the fp64 pipe
 // and the tensor pipe do not compete); gfull / gempty mbarriers hand the buffers over.

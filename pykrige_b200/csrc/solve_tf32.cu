@@ -19,7 +19,8 @@
 #include "kernels.h"
 
 #define TF_STAGES 4
-#define TF_THREADS 256
+#define TF_THREADS 512
+#define TF_GEN_THREADS 256              // warps 8..15: two generator threads per prediction point
 #define TF_TM 128                  // points per CTA tile (UMMA M)
 #define TF_BN KB_BM                // W rows per row block (UMMA N) = 256
 #define TF_BK KB_BK                // k per stage = 16
@@ -128,17 +129,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
     uint64_t* empty = full + TF_STAGES;                                              // TF_STAGES
     uint64_t* tfull = empty + TF_STAGES;                                             // 2
     uint64_t* tempty = tfull + 2;                                                    // 2
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* gfull = tempty + 2;                                                    // 2
+    uint64_t* gempty = gfull + 2;                                                    // 2
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(gempty + 2);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nk = (P.n + TF_BK - 1) / TF_BK;
-    unsigned char* scratch = reinterpret_cast<unsigned char*>(P.scratch) + (size_t)blockIdx.x * nk * TF_C_BYTES;
+    const size_t sbuf = (size_t)nk * TF_C_BYTES;                                     // one RHS column block
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(P.scratch) + (size_t)blockIdx.x * 2 * sbuf;
     const unsigned char* gt = reinterpret_cast<const unsigned char*>(P.tiles);
     const long long ntiles = (P.m + TF_TM - 1) / TF_TM;
 
     if (tid == 0) {
         for (int s = 0; s < TF_STAGES; ++s) { tf_mbar_init(&full[s], 1); tf_mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { tf_mbar_init(&tfull[b], 1); tf_mbar_init(&tempty[b], 4); }
+        for (int b = 0; b < 2; ++b) { tf_mbar_init(&gfull[b], TF_GEN_THREADS); tf_mbar_init(&gempty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
@@ -152,20 +157,24 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_base_smem;
 
-    uint32_t g = 0;      // smem stage ring counter
-    uint32_t ga = 0;     // accumulator ring counter (row blocks)
-
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---------------- phase G: RHS column block of the 128 points, TF32 hi/lo, UMMA layout ------------
-        {
-            const int pl = tid & (TF_TM - 1);
-            const int ks = tid >> 7;                       // 0..1
+    // Warp roles (512 threads): warp 0 lane 0 = bulk-copy producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM allocator,
+    // warps 4-7 = epilogue, warps 8-15 = RHS generators working ONE POINT TILE AHEAD of the tensor pipe into the other
+    // half of a double-buffered scratch ring (gfull / gempty mbarriers), as in solve_i8.cu.
+    if (warp >= 8) {
+        const int gt_ = tid - 8 * 32;
+        const int pl = gt_ & (TF_TM - 1);
+        const int ks = gt_ >> 7;                           // 0..1
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = (int)(it & 1);
+            tf_mbar_wait(&gempty[b], ((it >> 1) & 1) ^ 1);
+            unsigned char* sc = scratch + (size_t)b * sbuf;
             const long long pj = tile * TF_TM + pl;
             const bool pvalid = pj < P.m;
             double px = 0.0, py = 0.0, pz = 0.0;
             if (pvalid) kb_load_point<DIM>(P.ps, P.an, pj, px, py, pz);
-            for (int t = ks; t < nk; t += TF_THREADS / TF_TM) {
-                float* ct = reinterpret_cast<float*>(scratch + (size_t)t * TF_C_BYTES);
+            for (int t = ks; t < nk; t += TF_GEN_THREADS / TF_TM) {
+                float* ct = reinterpret_cast<float*>(sc + (size_t)t * TF_C_BYTES);
 #pragma unroll
                 for (int kc = 0; kc < 4; ++kc) {
                     float hi[4], lo[4];
@@ -188,15 +197,17 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
             }
             __threadfence();
             asm volatile("fence.proxy.async.global;\n" ::: "memory");
+            tf_mbar_arrive(&gfull[b]);
         }
-        __syncthreads();
-
-        // ---------------- phase M ----------------
-        if (warp == 0) {
-            if (lane == 0) {
-                uint32_t gg = g;
+    } else if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol_w = kb_policy_evict_last(), pol_c = kb_policy_evict_first();
+            uint32_t gg = 0, it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int b = (int)(it & 1);
+                const unsigned char* sc = scratch + (size_t)b * sbuf;
+                tf_mbar_wait(&gfull[b], (it >> 1) & 1);
                 long long tau = 0;
-                const uint64_t pol_w = kb_policy_evict_last(), pol_c = kb_policy_evict_first();
                 for (int I = 0; I < P.nrb; ++I) {
                     const int kt = P.pm.ktiles[I];
                     for (int t = 0; t < kt; ++t, ++tau, ++gg) {
@@ -205,13 +216,15 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
                         tf_mbar_expect_tx(&full[s], TF_STAGE_BYTES);
                         unsigned char* sb = stage_base + (size_t)s * TF_STAGE_BYTES;
                         kb_bulk_g2s_hint(sb, gt + (size_t)tau * TF_W_BYTES, TF_W_BYTES, &full[s], pol_w);
-                        kb_bulk_g2s_hint(sb + TF_W_BYTES, scratch + (size_t)t * TF_C_BYTES, TF_C_BYTES, &full[s], pol_c);
+                        kb_bulk_g2s_hint(sb + TF_W_BYTES, sc + (size_t)t * TF_C_BYTES, TF_C_BYTES, &full[s], pol_c);
                     }
                 }
             }
-        } else if (warp == 1) {
-            if (lane == 0) {
-                uint32_t gg = g, gb = ga;
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t gg = 0, gb = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int I = 0; I < P.nrb; ++I, ++gb) {
                     const int kt = P.pm.ktiles[I];
                     const int buf = gb & 1;
@@ -238,11 +251,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
                     tf_commit(&tfull[buf]);                // accumulator of row block I complete
                 }
             }
-        } else if (warp >= 4) {
-            // epilogue: thread = TMEM lane = prediction point
-            const int pl = (warp & 3) * 32 + lane;
+        }
+    } else if (warp >= 4) {
+        // epilogue: thread = TMEM lane = prediction point
+        const int pl = (warp & 3) * 32 + lane;
+        uint32_t gb = 0, it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             double q = 0.0;
-            uint32_t gb = ga;
             for (int I = 0; I < P.nrb; ++I, ++gb) {
                 const int buf = gb & 1;
                 tf_mbar_wait(&tfull[buf], (uint32_t)((gb >> 1) & 1));
@@ -282,11 +297,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
             // ---------------- phase F: finalize, thread = point ----------------
             const long long pj = tile * TF_TM + pl;
             if (pj < P.m) kb_finalize_point<DIM, float>(P, pj, q, auxs + pl, TF_TM);
+            __syncwarp();
+            if (lane == 0) tf_mbar_arrive(&gempty[(int)(it & 1)]);      // this tile's scratch half may be rewritten
         }
-        // every role advances the ring counters by the same amounts
-        for (int I = 0; I < P.nrb; ++I) g += (uint32_t)P.pm.ktiles[I];
-        ga += (uint32_t)P.nrb;
-        __syncthreads();      // scratch and auxs are re-used by the next tile
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -298,11 +311,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) solve_kernel_tf32(const __grid_
 // ---- host side ---------------------------------------------------------------------------------------
 static size_t tf32_smem() {
     return (size_t)TF_STAGES * TF_STAGE_BYTES + (size_t)KB_MAXAUX * TF_TM * sizeof(float) +
-           (2 * TF_STAGES + 4) * sizeof(uint64_t) + 64;
+           (2 * TF_STAGES + 8) * sizeof(uint64_t) + 64;
 }
 
 size_t kbk_solve_tf32_scratch_bytes(int n, int grid) {
-    return (size_t)grid * ((n + TF_BK - 1) / TF_BK) * TF_C_BYTES;
+    return (size_t)grid * 2 * ((n + TF_BK - 1) / TF_BK) * TF_C_BYTES;      // double-buffered
 }
 int kbk_solve_tf32_tile_points() { return TF_TM; }
 
