@@ -69,21 +69,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
 
-template <int DIM, int MODEL>
+// NT = n-tiles (of 8 points) per point tile: 8 (64 points) is the default; 6 (48 points) is chosen by the host when it saves a
+// whole round of the persistent loop (few tiles per SM: multi-GPU strong scaling). The per-point arithmetic does not depend on NT.
+template <int DIM, int MODEL, int NT>
 __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_constant__ SolvePtParams P) {
+    constexpr int TN = NT * 8;                                          // points per tile
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Ts = reinterpret_cast<double*>(smem_raw);                   // PT_STAGES * BM*BK
     double* Bs = Ts + PT_STAGES * KB_BM * KB_BK;                        // PT_STAGES * BK*TN
-    double* qred = Bs + PT_STAGES * KB_BK * KB_TN;                      // 8 * 64
-    double* auxs = qred + 8 * KB_TN;                                    // KB_MAXAUX * 64
-    uint64_t* full = reinterpret_cast<uint64_t*>(auxs + KB_MAXAUX * KB_TN);   // PT_STAGES
+    double* qred = Bs + PT_STAGES * KB_BK * TN;                      // 8 * 64
+    double* auxs = qred + 8 * TN;                                    // KB_MAXAUX * 64
+    uint64_t* full = reinterpret_cast<uint64_t*>(auxs + KB_MAXAUX * TN);   // PT_STAGES
     uint64_t* empty = full + PT_STAGES;                                 // PT_STAGES
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nk = (P.n + KB_BK - 1) / KB_BK;                           // k tiles of a full column block
-    double* scratch = P.scratch + (size_t)blockIdx.x * nk * (KB_BK * KB_TN);
+    double* scratch = P.scratch + (size_t)blockIdx.x * nk * (KB_BK * TN);
     const double* gt = reinterpret_cast<const double*>(P.tiles);
-    const long long ntiles = (P.m + KB_TN - 1) / KB_TN;
+    const long long ntiles = (P.m + TN - 1) / TN;
 
     if (tid == 0) {
         for (int s = 0; s < PT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
@@ -98,14 +101,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---------------- phase G: RHS column block of this tile, once ----------------
         {
-            const int pl = tid & 63;                 // point within the tile
-            const int ks = tid >> 6;                 // 0..5: k-tile slice
-            const long long pj = tile * KB_TN + pl;
+            const int pl = tid % TN;                 // point within the tile
+            const int ks = tid / TN;                 // k-tile slice (6 slices at 64 points, 8 at 48)
+            const long long pj = tile * TN + pl;
             const bool pvalid = pj < P.m;
             double px = 0.0, py = 0.0, pz = 0.0;
             if (pvalid) kb_load_point<DIM>(P.ps, P.an, pj, px, py, pz);
-            for (int t = ks; t < nk; t += PT_THREADS / 64) {
-                double* bt = scratch + (size_t)t * (KB_BK * KB_TN);
+            for (int t = ks; t < nk; t += PT_THREADS / TN) {
+                double* bt = scratch + (size_t)t * (KB_BK * TN);
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     double v[4];
@@ -120,8 +123,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                         }
                         v[kk] = val;
                     }
-                    // fragment order ((k4*8 + n/8)*32 + (n%8)*4 + k%4): 4 consecutive k = 32 contiguous bytes
-                    double2* dst = reinterpret_cast<double2*>(bt + (k4 * 8 + (pl >> 3)) * 32 + (pl & 7) * 4);
+                    // fragment order ((k4*NT + n/8)*32 + (n%8)*4 + k%4): 4 consecutive k = 32 contiguous bytes
+                    double2* dst = reinterpret_cast<double2*>(bt + (k4 * NT + (pl >> 3)) * 32 + (pl & 7) * 4);
                     dst[0] = make_double2(v[0], v[1]);
                     dst[1] = make_double2(v[2], v[3]);
                 }
@@ -143,19 +146,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                     for (int t = 0; t < kt; ++t, ++tau, ++g) {
                         const int s = g % PT_STAGES;
                         mbar_wait(&empty[s], (uint32_t)(((g / PT_STAGES) & 1) ^ 1));
-                        mbar_expect_tx(&full[s], PT_STAGE_BYTES);
+                        mbar_expect_tx(&full[s], (KB_BM * KB_BK + KB_BK * TN) * 8);
                         kb_bulk_g2s_hint(Ts + (size_t)s * KB_BM * KB_BK, gt + (size_t)tau * (KB_BM * KB_BK),
                                          KB_BM * KB_BK * 8, &full[s], pol_w);
-                        kb_bulk_g2s_hint(Bs + (size_t)s * KB_BK * KB_TN, scratch + (size_t)t * (KB_BK * KB_TN),
-                                         KB_BK * KB_TN * 8, &full[s], pol_c);
+                        kb_bulk_g2s_hint(Bs + (size_t)s * KB_BK * TN, scratch + (size_t)t * (KB_BK * TN),
+                                         KB_BK * TN * 8, &full[s], pol_c);
                     }
                 }
             }
         } else if (warp >= 4) {
             uint32_t g = git;
-            double qs[8][2];
+            double qs[NT][2];
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) { qs[nt][0] = 0.0; qs[nt][1] = 0.0; }
+            for (int nt = 0; nt < NT; ++nt) { qs[nt][0] = 0.0; qs[nt][1] = 0.0; }
             for (int I = 0; I < P.nrb; ++I) {
                 const int kt = P.pm.ktiles[I];
                 // this warp owns the m-tiles cw, cw+8, cw+16, cw+24 of the 256-row block (8 rows each):
@@ -170,11 +173,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                     else if (r0 >= P.n + P.na) kmax[q] = -1;
                     else kmax[q] = r0 + 7;
                 }
-                double acc[4][8][2];
+                double acc[4][NT][2];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+                    for (int b = 0; b < NT; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
                 for (int t = 0; t < kt; ++t, ++g) {
                     const int s = g % PT_STAGES;
                     // every consumer waits for every stage (also the ones it skips) so that no warp can lap
@@ -183,18 +186,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                     const int k0 = t * KB_BK;
                     if (k0 <= kmax[3] || k0 <= kmax[2] || k0 <= kmax[1] || k0 <= kmax[0]) {
                         const double* ts = Ts + (size_t)s * KB_BM * KB_BK;
-                        const double* bs = Bs + (size_t)s * KB_BK * KB_TN;
+                        const double* bs = Bs + (size_t)s * KB_BK * TN;
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
-                            double fb[8];
+                            double fb[NT];
 #pragma unroll
-                            for (int nt = 0; nt < 8; ++nt) fb[nt] = bs[(k4 * 8 + nt) * 32 + lane];
+                            for (int nt = 0; nt < NT; ++nt) fb[nt] = bs[(k4 * NT + nt) * 32 + lane];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 if (k0 <= kmax[q]) {
                                     const double fa = ts[(k4 * 32 + cw + 8 * q) * 32 + lane];
 #pragma unroll
-                                    for (int nt = 0; nt < 8; ++nt)
+                                    for (int nt = 0; nt < NT; ++nt)
                                         kb_dmma(acc[q][nt][0], acc[q][nt][1], fa, fb[nt]);
                                 }
                             }
@@ -210,25 +213,25 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                     if (r < P.n) {
                         if (!P.gform) {
 #pragma unroll
-                            for (int nt = 0; nt < 8; ++nt) {
+                            for (int nt = 0; nt < NT; ++nt) {
                                 qs[nt][0] += acc[mt][nt][0] * acc[mt][nt][0];
                                 qs[nt][1] += acc[mt][nt][1] * acc[mt][nt][1];
                             }
                         } else {
                             // quadratic form c^T G c: multiply row r of T c by c[r] (read back from the
                             // scratch ring: tile r/16, fragment order)
-                            const double* bt = scratch + (size_t)(r >> 4) * (KB_BK * KB_TN) + ((r & 15) >> 2) * 256 + (r & 3);
+                            const double* bt = scratch + (size_t)(r >> 4) * (KB_BK * TN) + ((r & 15) >> 2) * (NT * 32) + (r & 3);
 #pragma unroll
-                            for (int nt = 0; nt < 8; ++nt) {
+                            for (int nt = 0; nt < NT; ++nt) {
                                 const int c0i = nt * 8 + 2 * (lane & 3);
                                 qs[nt][0] += acc[mt][nt][0] * bt[(c0i >> 3) * 32 + (c0i & 7) * 4];
                                 qs[nt][1] += acc[mt][nt][1] * bt[((c0i + 1) >> 3) * 32 + ((c0i + 1) & 7) * 4];
                             }
                         }
                     } else if (r < P.n + P.na) {
-                        double* ao = auxs + (r - P.n) * KB_TN + 2 * (lane & 3);
+                        double* ao = auxs + (r - P.n) * TN + 2 * (lane & 3);
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) {
+                        for (int nt = 0; nt < NT; ++nt) {
                             ao[nt * 8] = acc[mt][nt][0];
                             ao[nt * 8 + 1] = acc[mt][nt][1];
                         }
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                 }
             }
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     double v = qs[nt][i];
@@ -247,9 +250,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
                 }
             if ((lane >> 2) == 0) {
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    qred[cw * KB_TN + nt * 8 + 2 * lane] = qs[nt][0];
-                    qred[cw * KB_TN + nt * 8 + 2 * lane + 1] = qs[nt][1];
+                for (int nt = 0; nt < NT; ++nt) {
+                    qred[cw * TN + nt * 8 + 2 * lane] = qs[nt][0];
+                    qred[cw * TN + nt * 8 + 2 * lane + 1] = qs[nt][1];
                 }
             }
         }
@@ -258,20 +261,20 @@ __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_co
         __syncthreads();
 
         // ---------------- phase F: per-point finalize ----------------
-        if (tid < KB_TN) {
-            const long long pj = tile * KB_TN + tid;
+        if (tid < TN) {
+            const long long pj = tile * TN + tid;
             if (pj < P.m) {
                 double q = 0.0;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) q += qred[w * KB_TN + tid];     // fixed order: deterministic
-                kb_finalize_point<DIM, double>(P, pj, q, auxs + tid, KB_TN);
+                for (int w = 0; w < 8; ++w) q += qred[w * TN + tid];     // fixed order: deterministic
+                kb_finalize_point<DIM, double>(P, pj, q, auxs + tid, TN);
             }
         }
         __syncthreads();      // qred / auxs / scratch are re-used by the next tile
     }
 }
 
-static size_t solve_smem_pt() {
+static size_t solve_smem_pt() {     // sized for the 64-point tile (the 48-point variant needs less)
     return (size_t)PT_STAGES * (KB_BM * KB_BK + KB_BK * KB_TN) * sizeof(double) + 8 * KB_TN * sizeof(double) +
            KB_MAXAUX * KB_TN * sizeof(double) + 2 * PT_STAGES * sizeof(uint64_t) + 64;
 }
@@ -282,7 +285,9 @@ size_t kbk_solve_pt_scratch_doubles(int n, int grid) {
 
 template <int DIM, int MODEL>
 static cudaError_t solve_set_attr() {
-    return cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    KB_CUDA_OK(cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)solve_smem_pt()));
+    return cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)solve_smem_pt());
 }
 
@@ -295,10 +300,11 @@ cudaError_t kbk_solve_init() {
 }
 
 template <int DIM>
-static cudaError_t solve_pt_dim(const SolvePtParams& p, int grid, cudaStream_t st) {
+static cudaError_t solve_pt_dim(const SolvePtParams& p, int grid, int tile_points, cudaStream_t st) {
     size_t sm = solve_smem_pt();
     switch (p.vg.model) {
-#define KB_CASE(M) case M: solve_kernel_pt<DIM, M><<<grid, PT_THREADS, sm, st>>>(p); break;
+#define KB_CASE(M) case M: if (tile_points == 48) solve_kernel_pt<DIM, M, 6><<<grid, PT_THREADS, sm, st>>>(p); \
+                           else solve_kernel_pt<DIM, M, 8><<<grid, PT_THREADS, sm, st>>>(p); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
         KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
 #undef KB_CASE
@@ -307,8 +313,9 @@ static cudaError_t solve_pt_dim(const SolvePtParams& p, int grid, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t kbk_solve_pt(int dim, const SolvePtParams& p, int grid, cudaStream_t st) {
-    if (dim == KB_GEO) return solve_pt_dim<KB_GEO>(p, grid, st);
-    return dim == 2 ? solve_pt_dim<2>(p, grid, st) : solve_pt_dim<3>(p, grid, st);
+cudaError_t kbk_solve_pt(int dim, const SolvePtParams& p, int grid, int tile_points, cudaStream_t st) {
+    if (tile_points != 64 && tile_points != 48) return cudaErrorInvalidValue;
+    if (dim == KB_GEO) return solve_pt_dim<KB_GEO>(p, grid, tile_points, st);
+    return dim == 2 ? solve_pt_dim<2>(p, grid, tile_points, st) : solve_pt_dim<3>(p, grid, tile_points, st);
 }
 

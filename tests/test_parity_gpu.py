@@ -863,3 +863,19 @@ def test_gstools_model_through_cuda(pk):
         assert_parity(ss, so, R64, "gstools 3d ss")
     finally:
         gstools_stub.uninstall()
+
+
+def test_tile_width_is_invisible(pk):
+    """The fp64 solve kernel switches from 64- to 48-point tiles when that saves a whole round of its persistent loop
+    (e.g. 125 000 points on 148 SMs: multi-GPU strong scaling). Per-point arithmetic must not depend on it: a slice
+    kriged with 48-point tiles equals the same points of a call that used 64-point tiles, bit for bit (OK and UK)."""
+    xyz, val = cases.synth_data(77, 600, 2)
+    gx, gy = np.linspace(0, 1000, 500), np.linspace(0, 1000, 500)
+    for m in (pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential", variogram_parameters=[1.0, 300.0, 0.05]),
+              pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="spherical", variogram_parameters=[1.0, 400.0, 0.05],
+                                  drift_terms=["regional_linear"])):
+        z, ss = m.execute("grid", gx, gy, backend="cuda")              # 250 000 points: 64-point tiles
+        h = m._ensure_problem()
+        for first, count in ((0, 125000), (60000, 125000), (125000, 125000), (1000, 9472 * 2 + 100)):
+            za, sa = h.execute_grid(gx, gy, None, None, first, count)   # 125 000 points: 48-point tiles
+            assert np.array_equal(za, z.ravel()[first:first + count]) and np.array_equal(sa, ss.ravel()[first:first + count])
