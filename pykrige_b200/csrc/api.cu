@@ -955,7 +955,7 @@ static int check_knn(kb200_ctx* h, int k) {
     cudaSetDevice(h->device);
     if (k < 2) return fail(h, KB200_EBADARG, "n_closest_points has to be at least two!");
     if (k > h->n) return fail(h, KB200_EBADARG, "n_closest_points exceeds the number of data points");
-    if (kbk_knn_smem_per_warp(k, 0) > 200 * 1024) return fail(h, KB200_EUNSUPPORTED, "n_closest_points too large for the shared-memory local solver");
+    if (kbk_knn_smem_per_warp(k, 0, 1) > 200 * 1024) return fail(h, KB200_EUNSUPPORTED, "n_closest_points too large for the shared-memory local solver");
     return KB200_OK;
 }
 

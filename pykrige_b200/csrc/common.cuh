@@ -78,6 +78,35 @@ __device__ __forceinline__ void kb_adjust(const Aniso& a, double x, double y, do
     }
 }
 
+// exp(x) for x <= 0 (the variogram models only evaluate decaying exponentials): k = rint(x log2 e), r = x - k ln 2
+// (Cody-Waite with the two fdlibm constants), exp(r) by the degree-13 Taylor polynomial on |r| <= ln 2 / 2 (truncation
+// 4e-18; Horner form: a few ulp), scaling by 2^k through the exponent field. About half the instructions of exp():
+// no overflow / NaN / denormal handling (x < -708 returns 0; the arguments are finite distances over a range), and the
+// evaluation is on the critical path of the moving window (2016 per point) and of every RHS generator.
+// exp(0) is exactly 1, so gamma(0) stays exactly the nugget.
+__device__ __forceinline__ double kb_exp_neg(double x) {
+    const double kd = rint(x * 1.4426950408889634);
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kd;                         // in [-1022, 0] for x >= -708
+    const double v = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return x < -708.0 ? 0.0 : v;
+}
+
 // gamma(d) for the six built-in models, variogram_models.py:25-81 (same closed
 // forms; docs/source/variogram_models.rst:8-44), and the tabulated model for custom callables.
 template <int MODEL>
@@ -87,9 +116,9 @@ __device__ __forceinline__ double kb_gamma(const VgParams& v, double d) {
     } else if (MODEL == KB200_VG_POWER) {
         return v.p0 * pow(d, v.p1) + v.p2;                            // scale*d^exponent + nugget
     } else if (MODEL == KB200_VG_GAUSSIAN) {
-        return v.p0 * (1.0 - exp(-(d * d) * v.inv_a)) + v.p2;
+        return v.p0 * (1.0 - kb_exp_neg(-(d * d) * v.inv_a)) + v.p2;
     } else if (MODEL == KB200_VG_EXPONENTIAL) {
-        return v.p0 * (1.0 - exp(-d * v.inv_a)) + v.p2;
+        return v.p0 * (1.0 - kb_exp_neg(-d * v.inv_a)) + v.p2;
     } else if (MODEL == KB200_VG_SPHERICAL) {
         if (d <= v.p1) {
             double q = d * v.inv_a;
@@ -108,7 +137,7 @@ __device__ __forceinline__ double kb_gamma(const VgParams& v, double d) {
              + (3.0 * t2 - 2.0 * t3) * b.x + (t3 - t2) * b.y;
     } else {  // hole-effect
         double q = d * v.inv_a;
-        return v.p0 * (1.0 - (1.0 - q) * exp(-q)) + v.p2;
+        return v.p0 * (1.0 - (1.0 - q) * kb_exp_neg(-q)) + v.p2;
     }
 }
 

@@ -220,7 +220,7 @@ cudaError_t kbk_knn_build(int dim, int n, const double* ax, const double* ay, co
                           KnnParams& kp, double* sx, double* sy, double* sz, double* sv, int* sorig,
                           int* cell_of, int* cell_start, int* cursor, int ncells, cudaStream_t st, int* launches);
 cudaError_t kbk_knn_solve(const KnnParams& p, int chol, cudaStream_t st);
-size_t      kbk_knn_smem_per_warp(int k, int chol);
+size_t      kbk_knn_smem_per_warp(int k, int chol, int hasz);
 
 // variogram.cu: constructor-side kernels (experimental variogram binning, cross-validation residuals)
 cudaError_t kbk_ev_init();

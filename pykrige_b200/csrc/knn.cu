@@ -141,10 +141,17 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
     size_t a_doubles = CHOL ? ((size_t)(kp / 8) * (kp / 8 + 1) / 2 + kp / 8 + 1) * 64 : (size_t)k * S;
     size_t cand_doubles = KN_CAP + KN_CAP / 2 + KN_SELECT_DOUBLES;   // d2[CAP] doubles + id[CAP] ints + selection scratch
     size_t off = a_doubles > cand_doubles ? a_doubles : cand_doubles;
-    double* rc = base + off;                   // rhs c (becomes C^-1 c)
-    double* r1 = rc + kp;                      // rhs 1 (becomes C^-1 1)
-    double* cv = r1 + kp;                      // c kept for sigma^2
-    double* nx = cv + kp; double* ny = nx + kp; double* nz = ny + kp; double* nv = nz + kp;
+    // per-neighbour arrays behind the matrix: the tiled Cholesky needs rc, nx, ny, (nz,) nv only (its right-hand sides
+    // live in the augmented tile row) - one array fewer in 2-D lets a ninth point fit into an SM's shared memory;
+    // the LU path keeps all seven. Keep in step with kbk_knn_smem_per_warp.
+    double* rc = base + off;                   // rhs c (LU: becomes C^-1 c)
+    double* tailp = rc + kp;
+    double* r1 = rc; double* cv = rc;          // LU only: rhs 1 (becomes C^-1 1), c kept for sigma^2
+    if (!CHOL) { r1 = tailp; cv = tailp + kp; tailp += 2 * kp; }
+    double* nx = tailp; double* ny = nx + kp; tailp = ny + kp;
+    double* nz = nx;                           // 2-D: never read (kb_dist<2> ignores z)
+    if (KB_HASZ(DIM)) { nz = tailp; tailp += kp; }
+    double* nv = tailp;
     double* cd2 = base;
     int* cid = reinterpret_cast<int*>(base + KN_CAP);
 
@@ -358,15 +365,19 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
     }
     for (int t = lane; t < k; t += 32) {
         int i = cid[t];
-        nx[t] = P.ax[i]; ny[t] = P.ay[i]; nz[t] = KB_HASZ(DIM) ? P.az[i] : 0.0; nv[t] = P.values[i];
+        nx[t] = P.ax[i]; ny[t] = P.ay[i]; nv[t] = P.values[i];
+        if (KB_HASZ(DIM)) nz[t] = P.az[i];
         // euclidean: the search distance is the kriging distance; geographic: neighbours were ranked by chord
         // length (ok.py:936-960), the kriging distance is the great-circle distance (ok.py:962-969)
         const double dq = DIM == KB_GEO ? kb_dist<DIM>(nx[t], ny[t], nz[t], qx, qy, qz) : sqrt(cd2[t]);
         double c = kb_cov_rhs<MODEL>(vg, dq);
-        rc[t] = c; cv[t] = c; r1[t] = 1.0;
+        rc[t] = c;
+        if (!CHOL) { cv[t] = c; r1[t] = 1.0; }
     }
     for (int t = k + lane; t < kp; t += 32) {          // identity padding of the blocked system
-        nx[t] = 0.0; ny[t] = 0.0; nz[t] = 0.0; nv[t] = 0.0; rc[t] = 0.0; cv[t] = 0.0; r1[t] = 0.0;
+        nx[t] = 0.0; ny[t] = 0.0; nv[t] = 0.0; rc[t] = 0.0;
+        if (KB_HASZ(DIM)) nz[t] = 0.0;
+        if (!CHOL) { cv[t] = 0.0; r1[t] = 0.0; }
     }
     __syncwarp();                                      // candidates consumed: A may be overwritten now
 
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
         // per iteration: the evaluation is latency-bound with 8 warps per SM
         for (int ti = 0; ti < nt; ++ti) {
             const int i = ti * 8 + fr;
-            const double xi = nx[i], yi = ny[i], zi = nz[i];
+            const double xi = nx[i], yi = ny[i], zi = KB_HASZ(DIM) ? nz[i] : 0.0;
             for (int tj = 0; tj <= ti; tj += 2) {
                 double v[4];
 #pragma unroll
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
                     if (tjj <= ti) {
                         if (i == j) val = (i < k) ? vg.c0 : 1.0;
                         else if (j < i && i < k) {
-                            double d = kb_dist<DIM>(xi, yi, zi, nx[j], ny[j], nz[j]);
+                            double d = kb_dist<DIM>(xi, yi, zi, nx[j], ny[j], KB_HASZ(DIM) ? nz[j] : 0.0);
                             val = vg.c0 - kb_gamma<MODEL>(vg, d);
                         }
                     }
@@ -634,18 +645,19 @@ __global__ void __launch_bounds__(320) knn_solve_kernel(const __grid_constant__ 
 }
 
 // ---- host side -------------------------------------------------------------
-size_t kbk_knn_smem_per_warp(int k, int chol) {
+size_t kbk_knn_smem_per_warp(int k, int chol, int hasz) {
     size_t S = (size_t)(k | 1);
     size_t kp = chol ? (size_t)((k + 7) & ~7) : (size_t)k;
     size_t nt = kp / 8;
     size_t a = chol ? (nt * (nt + 1) / 2 + nt + 1) * 64 : (size_t)k * S, c = KN_CAP + KN_CAP / 2 + KN_SELECT_DOUBLES;
-    return ((a > c ? a : c) + 7 * kp + 2) * sizeof(double);
+    const size_t tail = chol ? (hasz ? 5 : 4) : 7;      // rc, nx, ny, (nz,) nv  |  + r1, cv for the LU path
+    return ((a > c ? a : c) + tail * kp + 2) * sizeof(double);
 }
 
 template <int DIM, bool CHOL>
 static cudaError_t knn_launch_dim(const KnnParams& p, cudaStream_t st) {
-    size_t per = kbk_knn_smem_per_warp(p.k, CHOL ? 1 : 0);
-    int wpc = (int)std::min<size_t>(10, (220 * 1024) / per);      // as many points in flight per SM as fit (<= 320 threads)
+    size_t per = kbk_knn_smem_per_warp(p.k, CHOL ? 1 : 0, KB_HASZ(DIM) ? 1 : 0);
+    int wpc = (int)std::min<size_t>(10, (size_t)(226 * 1024) / per);   // as many points in flight per SM as fit (<= 320 threads; 227 KB minus the static 1 KB)
     if (wpc < 1) return cudaErrorInvalidValue;
     size_t smem = per * wpc;
     unsigned grid = (unsigned)((p.m + wpc - 1) / wpc);
