@@ -14,6 +14,8 @@
 
 #define KB_VERSION 2000
 static const int64_t KB_STAGE_PTS = 1 << 20;   // prediction points per staged output chunk (2 x 8 MB through pinned memory)
+#define KB_TILE_COST_32 0.532     // one round of 32-point tiles relative to one round of 64-point tiles (fp64 kernel, N=5000:
+#define KB_TILE_COST_16 0.301     // 7.34 / 3.91 / 2.21 ms per round; scripts/tile_timing.py, profiles/r02/tile_width_timing_run21.log)
 static const int64_t KB_STAGE_MIN = 1 << 18;   // below this the outputs go straight to the caller's buffers
 
 struct Src {
@@ -614,7 +616,9 @@ extern "C" int kb200_set_device_drift(kb200_handle h, int n_wells, const double*
 // One persistent launch of the solve kernel of the handle's dtype over points [s.first, s.first + s.count).
 // NOTE: one kernel for every point count: the summation order per point must not depend on how the points are
 // sharded or chunked (concatenated shards == single call, bit for bit).
-static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
+// One persistent launch of the solve kernel of the handle's dtype over points [s.first, s.first + s.count) with point
+// tiles of `tp` points.
+static int launch_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss, int tp) {
     cudaStream_t st = h->stream;
     char* blob = h->blob.as<char>();
     PointSource ps{};
@@ -623,14 +627,6 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     ps.nx = s.nx; ps.ny = s.ny; ps.nz = s.nz;
     const bool i8 = h->slices != 0;
     const bool f32 = h->dtype == KB200_F32;
-    int tp = i8 ? kbk_solve_i8_tile_points() : (f32 ? kbk_solve_tf32_tile_points() : KB_TN);
-    if (!i8 && !f32) {
-        // fp64 DMMA kernel: 64-point tiles, or 48-point tiles when that saves a whole round of the persistent loop
-        // (125 000 points on 148 SMs: 14 rounds x 64 vs 18 rounds x 48 points = 3.6 % less work on the critical path;
-        // matters for multi-GPU strong scaling, irrelevant at 1e6 points per GPU). Per-point results do not depend on it.
-        auto cost = [&](int t) { long long nt = (s.count + t - 1) / t; return ((nt + h->num_sms - 1) / h->num_sms) * (long long)t; };
-        if (cost(48) * 100 < cost(64) * 98) tp = 48;
-    }
     long long ntiles = (s.count + tp - 1) / tp;
     int grid = (int)std::min<long long>(ntiles, h->num_sms);
     CU(h, h->wScratch.reserve(i8 ? kbk_solve_i8_scratch_bytes(h->slices, h->n, grid) : f32 ? kbk_solve_tf32_scratch_bytes(h->n, grid)
@@ -652,6 +648,43 @@ static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
     else if (f32) CU(h, kbk_solve_tf32(h->dim, pp, grid, st));
     else CU(h, kbk_solve_pt(h->dim, pp, grid, tp, st));
     h->launches += 1; h->solve_launches += 1;
+    return KB200_OK;
+}
+
+// Relative cost of one round of the fp64 kernel with 64 / 32 / 16-point tiles (a tile streams all of W once whatever its
+// width; the DMMA work is proportional to the width). Measured at N=5000 (profiles/r02/tile_width_timing_*.log).
+static double tile_cost(int tp) { return tp == 64 ? 1.0 : (tp == 32 ? KB_TILE_COST_32 : KB_TILE_COST_16); }
+
+// NOTE: the summation order per point does not depend on the tile width, on how the points are sharded or chunked, or on
+// the number of launches (concatenated shards == single call, bit for bit).
+static int run_solve(kb200_ctx* h, const Src& s, double* d_z, double* d_ss) {
+    const bool i8 = h->slices != 0;
+    const bool f32 = h->dtype == KB200_F32;
+    if (i8 || f32) return launch_solve(h, s, d_z, d_ss, i8 ? kbk_solve_i8_tile_points() : kbk_solve_tf32_tile_points());
+    // fp64 DMMA kernel: full rounds of 64-point tiles over all SMs, then the leftover points as ONE more launch whose tile
+    // width minimises rounds x cost: a partial round of 64-point tiles keeps a few SMs busy for a whole tile time
+    const long long S = h->num_sms;
+    if (const char* e = std::getenv("KB200_TILE")) {           // profiling override: one launch, fixed width
+        const int t = std::atoi(e);
+        if (t == 64 || t == 32 || t == 16) return launch_solve(h, s, d_z, d_ss, t);
+    }
+    const long long nt64 = (s.count + KB_TN - 1) / KB_TN;
+    const long long main_pts = std::min<long long>(s.count, (nt64 / S) * S * KB_TN);
+    const long long rem = s.count - main_pts;
+    if (main_pts > 0) {
+        Src m = s; m.count = main_pts;
+        int rc = launch_solve(h, m, d_z, d_ss, KB_TN); if (rc) return rc;
+    }
+    if (rem > 0) {
+        int best = KB_TN; double bc = 1e300;
+        for (int tp : {64, 32, 16}) {
+            const long long nt = (rem + tp - 1) / tp;
+            const double c = (double)((nt + S - 1) / S) * tile_cost(tp);
+            if (c < bc * 0.999) { bc = c; best = tp; }
+        }
+        Src t = s; t.first = s.first + main_pts; t.count = rem; t.drift_first = s.drift_first + main_pts;
+        int rc = launch_solve(h, t, d_z + main_pts, d_ss + main_pts, best); if (rc) return rc;
+    }
     return KB200_OK;
 }
 

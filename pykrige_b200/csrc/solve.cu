@@ -69,8 +69,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// NT = n-tiles (of 8 points) per point tile: 8 (64 points) is the default; 6 (48 points) is chosen by the host when it saves a
-// whole round of the persistent loop (few tiles per SM: multi-GPU strong scaling). The per-point arithmetic does not depend on NT.
+// NT = n-tiles (of 8 points) per point tile: 8 (64 points) is the default. Narrower tiles (NT = 4, 2: 32 / 16 points) are used by
+// the host for the TAIL of a launch: the points left over after the last full round of 64-point tiles would keep only a few of
+// the 148 persistent CTAs busy for a whole tile time (1953 tiles on 148 SMs = 13.2 rounds: 4.9 of 102 ms at 125 000 points per
+// GPU); as narrow tiles they spread over all SMs and a tile costs little more than streaming W once. The per-point arithmetic
+// does not depend on NT (tests/test_parity_gpu.py::test_tile_width_is_invisible).
 template <int DIM, int MODEL, int NT>
 __global__ void __launch_bounds__(PT_THREADS, 1) solve_kernel_pt(const __grid_constant__ SolvePtParams P) {
     constexpr int TN = NT * 8;                                          // points per tile
@@ -287,7 +290,9 @@ template <int DIM, int MODEL>
 static cudaError_t solve_set_attr() {
     KB_CUDA_OK(cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)solve_smem_pt()));
-    return cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    KB_CUDA_OK(cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)solve_smem_pt()));
+    return cudaFuncSetAttribute(solve_kernel_pt<DIM, MODEL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)solve_smem_pt());
 }
 
@@ -303,7 +308,8 @@ template <int DIM>
 static cudaError_t solve_pt_dim(const SolvePtParams& p, int grid, int tile_points, cudaStream_t st) {
     size_t sm = solve_smem_pt();
     switch (p.vg.model) {
-#define KB_CASE(M) case M: if (tile_points == 48) solve_kernel_pt<DIM, M, 6><<<grid, PT_THREADS, sm, st>>>(p); \
+#define KB_CASE(M) case M: if (tile_points == 16) solve_kernel_pt<DIM, M, 2><<<grid, PT_THREADS, sm, st>>>(p); \
+                           else if (tile_points == 32) solve_kernel_pt<DIM, M, 4><<<grid, PT_THREADS, sm, st>>>(p); \
                            else solve_kernel_pt<DIM, M, 8><<<grid, PT_THREADS, sm, st>>>(p); break;
         KB_CASE(KB200_VG_LINEAR) KB_CASE(KB200_VG_POWER) KB_CASE(KB200_VG_GAUSSIAN)
         KB_CASE(KB200_VG_EXPONENTIAL) KB_CASE(KB200_VG_SPHERICAL) KB_CASE(KB200_VG_HOLE_EFFECT) KB_CASE(KB200_VG_TABLE)
@@ -314,7 +320,7 @@ static cudaError_t solve_pt_dim(const SolvePtParams& p, int grid, int tile_point
 }
 
 cudaError_t kbk_solve_pt(int dim, const SolvePtParams& p, int grid, int tile_points, cudaStream_t st) {
-    if (tile_points != 64 && tile_points != 48) return cudaErrorInvalidValue;
+    if (tile_points != 64 && tile_points != 32 && tile_points != 16) return cudaErrorInvalidValue;
     if (dim == KB_GEO) return solve_pt_dim<KB_GEO>(p, grid, tile_points, st);
     return dim == 2 ? solve_pt_dim<2>(p, grid, tile_points, st) : solve_pt_dim<3>(p, grid, tile_points, st);
 }

@@ -186,6 +186,19 @@ def test_large_outputs_are_staged_in_chunks(pk):
     px, py = np.tile(gx, 900), np.repeat(gy[:900], gx.size)                    # 1.35e6 explicit points
     zp, sp = ok.execute("points", px, py, backend="cuda")
     assert np.array_equal(zp, z.ravel()[:zp.size]) and np.array_equal(sp, ss.ravel()[:sp.size])
+    # host-supplied drift columns (functional + specified) travel with their chunk: 1.2e6 points in two staged launches
+    uk = pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="spherical", variogram_parameters=[1.0, 400.0, 0.05],
+                             drift_terms=["regional_linear", "functional", "specified"],
+                             functional_drift=[lambda x, y: np.sin(x / 300.0)], specified_drift=[0.002 * xyz[:, 0] * xyz[:, 1] / 1000.0])
+    gxu, gyu = gx[:1200], gy[:1000]
+    GX, GY = np.meshgrid(gxu, gyu)
+    spec = [0.002 * GX * GY / 1000.0]
+    zu, su = uk.execute("grid", gxu, gyu, backend="cuda", specified_drift_arrays=spec)
+    rng = np.random.default_rng(2)
+    for r0 in (0, 873, 999):                                                     # rows across the chunk boundary at 2^20
+        zr, sr = uk.execute("points", gxu, np.full(gxu.size, gyu[r0]), backend="cuda",
+                            specified_drift_arrays=[spec[0][r0].copy()])
+        assert np.array_equal(zr, zu[r0]) and np.array_equal(sr, su[r0])
 
 
 def test_ok3d_equals_ok2d_on_a_plane(pk, ref_goldens):
@@ -866,16 +879,17 @@ def test_gstools_model_through_cuda(pk):
 
 
 def test_tile_width_is_invisible(pk):
-    """The fp64 solve kernel switches from 64- to 48-point tiles when that saves a whole round of its persistent loop
-    (e.g. 125 000 points on 148 SMs: multi-GPU strong scaling). Per-point arithmetic must not depend on it: a slice
-    kriged with 48-point tiles equals the same points of a call that used 64-point tiles, bit for bit (OK and UK)."""
+    """The fp64 solve kernel kriges the points left over after the last full round of 64-point tiles in a second launch
+    with 32- or 16-point tiles (they spread over all SMs instead of keeping a few busy for a whole tile time: multi-GPU
+    strong scaling). Per-point arithmetic must not depend on the tile width: slices whose tails fall on narrow tiles
+    equal the same points of a call with a different split, bit for bit (OK and UK)."""
     xyz, val = cases.synth_data(77, 600, 2)
     gx, gy = np.linspace(0, 1000, 500), np.linspace(0, 1000, 500)
     for m in (pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="exponential", variogram_parameters=[1.0, 300.0, 0.05]),
               pk.UniversalKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="spherical", variogram_parameters=[1.0, 400.0, 0.05],
                                   drift_terms=["regional_linear"])):
-        z, ss = m.execute("grid", gx, gy, backend="cuda")              # 250 000 points: 64-point tiles
+        z, ss = m.execute("grid", gx, gy, backend="cuda")              # 250 000 points: 26 full rounds + a narrow-tile tail
         h = m._ensure_problem()
         for first, count in ((0, 125000), (60000, 125000), (125000, 125000), (1000, 9472 * 2 + 100)):
-            za, sa = h.execute_grid(gx, gy, None, None, first, count)   # 125 000 points: 48-point tiles
+            za, sa = h.execute_grid(gx, gy, None, None, first, count)   # different full-round / tail split
             assert np.array_equal(za, z.ravel()[first:first + count]) and np.array_equal(sa, ss.ravel()[first:first + count])
