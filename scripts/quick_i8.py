@@ -1,5 +1,5 @@
 """fp64-class int8-slice kernels (dtype='float64x' / 'float64x5' / 'float64x4') vs the fp64 DMMA kernel: agreement
-(and, at N <= 2000, vs the CPU oracle) and solve-kernel rate. Prints one JSON line per problem."""
+and solve-kernel rate. Prints one JSON line per problem."""
 import os, sys, json
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

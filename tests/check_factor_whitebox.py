@@ -1,4 +1,5 @@
-"""White-box check of the blocked Cholesky / triangular inverse against numpy (debug taps of the C ABI)."""
+"""White-box check of the blocked Cholesky / triangular inverse against numpy through the debug taps of the C ABI (a GPU
+tool, not collected by pytest: `python tests/check_factor_whitebox.py`; lives under tests/ because it uses the oracle)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
