@@ -10,9 +10,8 @@ import numpy as np
 
 from . import core
 from ._base import KrigeBase
-from .core import _adjust_for_anisotropy, _make_variogram_parameter_list, _initialize_variogram_model
-
-P_INV_TYPES = ("pinv", "pinvh")
+from ._krige2d import Krige2DMixin, P_INV_TYPES  # noqa: F401
+from .core import _adjust_for_anisotropy
 
 
 def _first_last_index(axis, v):
@@ -26,11 +25,10 @@ def _first_last_index(axis, v):
     return i1, i2
 
 
-class UniversalKriging(KrigeBase):
+class UniversalKriging(Krige2DMixin, KrigeBase):
     """Two-dimensional universal kriging; arguments as in the reference docstring (uk.py:40-205)."""
 
     UNBIAS = True  # the unbiasedness row is always present on the device path (uk.py:208)
-    _ndim = 2
 
     def __init__(
         self,
@@ -57,74 +55,15 @@ class UniversalKriging(KrigeBase):
         pseudo_inv=False,
         pseudo_inv_type="pinv",
     ):
-        self.pseudo_inv = bool(pseudo_inv)
-        self.pseudo_inv_type = str(pseudo_inv_type)
-        if self.pseudo_inv_type not in P_INV_TYPES:
-            raise ValueError("pseudo inv type not valid: " + str(pseudo_inv_type))
         if drift_terms is None:
             drift_terms = []
         if specified_drift is None:
             specified_drift = []
         if functional_drift is None:
             functional_drift = []
-        if not isinstance(exact_values, bool):
-            raise ValueError("exact_values has to be boolean True or False")
-        self.exact_values = exact_values
-        self.coordinates_type = "euclidean"
-
-        def _dim_ok(model):
-            from .compat_gstools import validate_gstools
-
-            validate_gstools(model)
-            if model.field_dim == 3:
-                raise ValueError("GSTools: model dim is not 1 or 2")
-
-        ov = self._select_variogram(variogram_model, variogram_function, _dim_ok)
-        if "gstools" in ov:
-            variogram_parameters = []
-            anisotropy_scaling = ov["gstools"].pykrige_anis
-            anisotropy_angle = ov["gstools"].pykrige_angle
-
-        self.X_ORIG = np.atleast_1d(np.squeeze(np.array(x, copy=True, dtype=np.float64)))
-        self.Y_ORIG = np.atleast_1d(np.squeeze(np.array(y, copy=True, dtype=np.float64)))
-        self.Z = np.atleast_1d(np.squeeze(np.array(z, copy=True, dtype=np.float64)))
-        self.verbose = verbose
-        self.enable_plotting = enable_plotting
-        if self.enable_plotting and self.verbose:
-            print("Plotting Enabled\n")
-
-        self.XCENTER = (np.amax(self.X_ORIG) + np.amin(self.X_ORIG)) / 2.0
-        self.YCENTER = (np.amax(self.Y_ORIG) + np.amin(self.Y_ORIG)) / 2.0
-        self.anisotropy_scaling = anisotropy_scaling
-        self.anisotropy_angle = anisotropy_angle
-        if self.verbose:
-            print("Adjusting data for anisotropy...")
-        self.X_ADJUSTED, self.Y_ADJUSTED = _adjust_for_anisotropy(
-            np.vstack((self.X_ORIG, self.Y_ORIG)).T,
-            [self.XCENTER, self.YCENTER],
-            [self.anisotropy_scaling],
-            [self.anisotropy_angle],
-        ).T
-
-        if self.verbose:
-            print("Initializing variogram model...")
-        vp_temp = _make_variogram_parameter_list(self.variogram_model, variogram_parameters)
-        self.lags, self.semivariance, self.variogram_model_parameters = _initialize_variogram_model(
-            np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T,
-            self.Z,
-            self.variogram_model,
-            vp_temp,
-            self.variogram_function,
-            nlags,
-            weight,
-            "euclidean", lazy=True,
-        )
-        if self.verbose:
-            self._print_variogram()
-        if self.enable_plotting:
-            self.display_variogram_model()
-        # statistics: computed on first access (the reference runs the O(N^4) loop here, uk.py:380)
-        self._stats_state = "lazy"
+        self._init_common_2d(x, y, z, variogram_model, variogram_parameters, variogram_function, nlags, weight,
+                             anisotropy_scaling, anisotropy_angle, verbose, enable_plotting, exact_values, pseudo_inv,
+                             pseudo_inv_type, coordinates_type="euclidean", statistics="lazy")
 
         if self.verbose:
             print("Initializing drift terms...")
@@ -200,9 +139,6 @@ class UniversalKriging(KrigeBase):
         else:
             self.functional_drift = False
 
-    def _stats_inputs(self):
-        return np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T, self.Z
-
     def _calculate_data_point_zscalars(self, x, y, type_="array"):
         """Bilinear sample of the external-Z grid at (x, y) (uk.py:512-628), vectorised; node
         selection, degenerate (on-node / on-line) cases and the domain check follow the reference."""
@@ -234,51 +170,6 @@ class UniversalKriging(KrigeBase):
         if type_ == "scalar":
             return out[0]
         return out.reshape(shape)
-
-    def update_variogram_model(self, variogram_model, variogram_parameters=None, variogram_function=None,
-                               nlags=6, weight=False, anisotropy_scaling=1.0, anisotropy_angle=0.0):
-        """Change the variogram model and/or its parameters (uk.py:630-790)."""
-
-        def _dim_ok(model):
-            from .compat_gstools import validate_gstools
-
-            validate_gstools(model)
-            if model.field_dim == 3:
-                raise ValueError("GSTools: model dim is not 1 or 2")
-
-        ov = self._select_variogram(variogram_model, variogram_function, _dim_ok)
-        if "gstools" in ov:
-            variogram_parameters = []
-            anisotropy_scaling = ov["gstools"].pykrige_anis
-            anisotropy_angle = ov["gstools"].pykrige_angle
-        if anisotropy_scaling != self.anisotropy_scaling or anisotropy_angle != self.anisotropy_angle:
-            if self.verbose:
-                print("Adjusting data for anisotropy...")
-            self.anisotropy_scaling = anisotropy_scaling
-            self.anisotropy_angle = anisotropy_angle
-            self.X_ADJUSTED, self.Y_ADJUSTED = _adjust_for_anisotropy(
-                np.vstack((self.X_ORIG, self.Y_ORIG)).T,
-                [self.XCENTER, self.YCENTER],
-                [self.anisotropy_scaling],
-                [self.anisotropy_angle],
-            ).T
-        if self.verbose:
-            print("Updating variogram mode...")
-        vp_temp = _make_variogram_parameter_list(self.variogram_model, variogram_parameters)
-        self.lags, self.semivariance, self.variogram_model_parameters = _initialize_variogram_model(
-            np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T, self.Z, self.variogram_model, vp_temp,
-            self.variogram_function, nlags, weight, "euclidean", lazy=True,
-        )
-        if self.verbose:
-            self._print_variogram()
-        if self.enable_plotting:
-            self.display_variogram_model()
-        self._stats_state = "lazy"
-
-    # ---- device description -----------------------------------------------------------
-    def _data_arrays(self):
-        Mt = core.anisotropy_matrix(2, [self.anisotropy_scaling], [self.anisotropy_angle])
-        return self.X_ORIG, self.Y_ORIG, None, self.Z, [self.XCENTER, self.YCENTER], Mt
 
     def _point_log_column(self, well, xa, ya):
         """-strength * log(distance to the well), log(0) clamped to -100 (uk.py:885-896, 955-966)."""
