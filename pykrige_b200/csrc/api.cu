@@ -506,7 +506,7 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
         h->gform = 2;
     } else if (hflag != 0) {
         // C is not positive definite: the variogram is not conditionally negative definite in this
-        // dimension (e.g. hole-effect on dense scatter). General fallback: Gauss-Jordan inverse with
+        // dimension (e.g. hole-effect on dense scatter). General fallback: blocked Gauss-Jordan inverse with
         // partial pivoting + quadratic-form solve. fp64 only.
         if (h->dtype != KB200_F64) {
             h->launches += launches;
@@ -517,10 +517,10 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
         CU(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
         CU(h, cudaEventRecord(h->ev[3], st));
         CU(h, kbk_assemble(h->dim, h->vg, nn, np, ld, ax, ay, az, h->wC.as<double>(), st)); ++launches;
-        double* rowbuf = h->wT.as<double>();
-        double* colbuf = rowbuf + np;
-        int* piv = reinterpret_cast<int*>(colbuf + np);
-        CU(h, kbk_general_inverse(h->wC.as<double>(), ld, nn, np, rowbuf, colbuf, piv, flag, 3.6e-15 * h->vg.c0, st, &launches));
+        CU(h, h->wVario.reserve(kbk_general_inverse_workspace_bytes(np)));
+        const char* gj_env = std::getenv("KB200_GJ_SCALAR");     // cross-check switch of the tests: column-at-a-time form
+        CU(h, kbk_general_inverse(h->wC.as<double>(), ld, nn, np, h->wVario.p, flag, 3.6e-15 * h->vg.c0, st, &launches,
+                                  gj_env && gj_env[0] == '1'));
         CU(h, cudaEventRecord(h->ev[4], st));
         CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));

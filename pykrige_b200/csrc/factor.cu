@@ -8,6 +8,8 @@
 // reference's inverse x RHS, ok.py:679-681, to rounding).
 #include "common.cuh"
 #include "kernels.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 // ---------------------------------------------------------------------------
 // adjusted data coordinates (core.py:120-193 applied to the data, ok.py:284-289)
@@ -874,17 +876,269 @@ __global__ void symmetrize_kernel(double* __restrict__ C, int ld, int n_pad) {
     if (j < n_pad && j > i) C[(size_t)i * ld + j] = C[(size_t)j * ld + i];
 }
 
-cudaError_t kbk_general_inverse(double* C, int ld, int n, int n_pad, double* rowbuf, double* colbuf, int* piv,
-                                int* flag, double ptol, cudaStream_t st, int* launches) {
-    // C holds the assembled lower triangle (+ diagonal); build the full matrix, then invert the n x n part
+// ---------------------------------------------------------------------------
+// Blocked form of the same Gauss-Jordan inversion (the default; the column-at-a-time kernels above stay as the route
+// for devices that cannot co-schedule the panel grid, and as the cross-check of tests/test_parity_gpu.py).
+// 64 scalar steps compose into the block exchange of the pivot block K against the rest R (after the row swaps):
+//     A_KK <- A_KK^-1,  A_RK <- -A_RK A_KK^-1,  A_KR <- A_KK^-1 A_KR,  A_RR <- A_RR - A_RK A_KK^-1 A_KR
+// so one 64-column step is
+//   gj_panel_kernel      the 64 scalar steps with partial pivoting restricted to the n_pad x 64 column panel. The rows
+//                        are dealt to the CTAs of ONE cooperative grid, each CTA keeps its rows of the panel in shared
+//                        memory; per step every CTA publishes its best pivot candidate (|value|, row index, the row's 64
+//                        panel entries) and the owner of row k publishes that row, ONE grid barrier, then every CTA
+//                        picks the same winner, swaps and eliminates locally. Double-buffered slots: the barrier of step
+//                        j+1 separates the reads of step j from the writes of step j+2.
+//   gj_swap_copy_kernel  the recorded row swaps on all other columns, then T = A[K rows][other columns] to a buffer
+//   gj_gemm_kernel       A[:, other] = (rows K: 0, else A[:, other]) + Panel * T   -- rank-64 update on the DMMA pipe
+// i.e. 3 launches and 64 grid barriers per 64 columns instead of 128 launches. The padded rows/columns (identity)
+// take part, so every block is full. Same pivot order, same singularity test as the scalar form.
+#define GJ_PLD 65
+#define GJ_MAX_CTAS 256
+
+struct GjWork {
+    double* Tbuf;       // [64][n_pad]
+    double* cand_row;   // [2][GJ_MAX_CTAS][64]
+    double* krow;       // [2][64]
+    double* cand_val;   // [2][GJ_MAX_CTAS]
+    int* cand_idx;      // [2][GJ_MAX_CTAS]
+    int* piv;           // [n_pad]
+    double* rowbuf;     // [n_pad]  (scalar form)
+    double* colbuf;     // [n_pad]
+};
+
+size_t kbk_general_inverse_workspace_bytes(int n_pad) {
+    size_t d = (size_t)64 * n_pad + 2 * GJ_MAX_CTAS * 64 + 128 + 2 * GJ_MAX_CTAS + 2 * (size_t)n_pad;
+    return d * sizeof(double) + (2 * GJ_MAX_CTAS + (size_t)n_pad + 64) * sizeof(int);
+}
+
+static GjWork gj_carve(void* work, int n_pad) {
+    GjWork w;
+    double* d = reinterpret_cast<double*>(work);
+    w.Tbuf = d; d += (size_t)64 * n_pad;
+    w.cand_row = d; d += 2 * GJ_MAX_CTAS * 64;
+    w.krow = d; d += 128;
+    w.cand_val = d; d += 2 * GJ_MAX_CTAS;
+    w.rowbuf = d; d += n_pad;
+    w.colbuf = d; d += n_pad;
+    int* i = reinterpret_cast<int*>(d);
+    w.cand_idx = i; i += 2 * GJ_MAX_CTAS;
+    w.piv = i;
+    return w;
+}
+
+static size_t gj_panel_smem(int rpc) { return ((size_t)rpc * (GJ_PLD + 1) + 3 * 64) * sizeof(double); }
+
+// candidates (|v|, row): larger |v| wins, ties go to the lower row index (the scalar form's order)
+__device__ __forceinline__ bool gj_better(double v, int i, double bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__global__ void __launch_bounds__(256) gj_panel_kernel(double* A, int ld, int n_pad, int k0, int rpc,
+                                                        double* cand_row, double* krow, double* cand_val, int* cand_idx,
+                                                        int* __restrict__ piv, int* flag, double ptol) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double gj_sm[];
+    double* P = gj_sm;                          // [rpc][GJ_PLD]: this CTA's rows of the panel
+    double* colv = P + (size_t)rpc * GJ_PLD;    // [rpc]  column j before the step
+    double* prow = colv + rpc;                  // [64]   pivot row
+    double* kr = prow + 64;                     // [64]   row k before the swap
+    double* rv = kr + 64;                       // [64]   scaled pivot row
+    __shared__ double s_val[8];
+    __shared__ int s_idx[8];
+    __shared__ int s_win[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int row0 = cta * rpc;
+    const int R = max(0, min(rpc, n_pad - row0));
+    for (int e = tid; e < R * 64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        P[r * GJ_PLD + c] = A[(size_t)(row0 + r) * ld + k0 + c];
+    }
+    __syncthreads();
+    for (int j = 0; j < 64; ++j) {
+        const int kk = k0 + j, par = j & 1;
+        // (1) this CTA's candidate among its rows >= kk
+        double best = -1.0; int bi = 0x7fffffff;
+        for (int r = tid; r < R; r += 256) {
+            const int g = row0 + r;
+            if (g >= kk) {
+                const double v = fabs(P[r * GJ_PLD + j]);
+                if (gj_better(v, g, best, bi)) { best = v; bi = g; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (gj_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < 8 ? s_val[lane] : -1.0;
+            bi = lane < 8 ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (gj_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { s_val[0] = best; s_idx[0] = bi; }
+        }
+        __syncthreads();
+        best = s_val[0]; bi = s_idx[0];
+        // (2) publish: candidate (+ its panel row), and row kk by its owner
+        if (tid == 0) { __stcg(&cand_val[par * G + cta], best); __stcg(&cand_idx[par * G + cta], bi); }
+        if (best >= 0.0 && tid < 64) __stcg(&cand_row[((size_t)(par * G + cta)) * 64 + tid], P[(bi - row0) * GJ_PLD + tid]);
+        if (kk >= row0 && kk < row0 + R && tid >= 64 && tid < 128)
+            __stcg(&krow[par * 64 + tid - 64], P[(kk - row0) * GJ_PLD + tid - 64]);
+        grid.sync();
+        // (3) every CTA picks the same winner (L1 is bypassed: the slots are rewritten every other step)
+        if (warp == 0) {
+            double bv = -1.0; int bx = 0x7fffffff, bc = 0;
+            for (int c = lane; c < G; c += 32) {
+                const double v = __ldcg(&cand_val[par * G + c]);
+                const int ix = __ldcg(&cand_idx[par * G + c]);
+                if (gj_better(v, ix, bv, bx)) { bv = v; bx = ix; bc = c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bx, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (gj_better(ov, oi, bv, bx)) { bv = ov; bx = oi; bc = oc; }
+            }
+            if (lane == 0) {
+                if (bx == 0x7fffffff) {             // no comparable candidate at all (NaN in the data): report, keep indices sane
+                    bx = kk;
+                    if (cta == 0 && *flag == 0) *flag = 1 + kk;
+                }
+                s_win[0] = bc; s_win[1] = bx;
+            }
+        }
+        __syncthreads();
+        const int wc = s_win[0], p = s_win[1];
+        if (tid < 64) {
+            prow[tid] = __ldcg(&cand_row[((size_t)(par * G + wc)) * 64 + tid]);
+            kr[tid] = __ldcg(&krow[par * 64 + tid]);
+        }
+        __syncthreads();
+        const double d0 = prow[j];
+        double d = d0;
+        if (!(fabs(d) > 0.0)) d = 1.0;
+        const double inv = 1.0 / d;
+        if (cta == 0 && tid == 0) {
+            piv[kk] = p;
+            if (!(fabs(d0) > ptol) && *flag == 0) *flag = 1 + kk;
+        }
+        if (tid < 64) rv[tid] = (tid == j) ? inv : prow[tid] * inv;
+        // (4) swap rows kk <-> p inside the panel
+        if (p != kk) {
+            if (p >= row0 && p < row0 + R && tid < 64) P[(p - row0) * GJ_PLD + tid] = kr[tid];
+            if (kk >= row0 && kk < row0 + R && tid >= 64 && tid < 128) P[(kk - row0) * GJ_PLD + tid - 64] = prow[tid - 64];
+        }
+        __syncthreads();
+        for (int r = tid; r < R; r += 256) colv[r] = P[r * GJ_PLD + j];
+        __syncthreads();
+        // (5) the scalar step on this CTA's rows: row kk becomes the scaled pivot row, column j the negated multipliers
+        for (int e = tid; e < R * 64; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            double v;
+            if (row0 + r == kk) v = rv[c];
+            else {
+                const double cv = colv[r];
+                v = (c == j) ? -(cv * inv) : P[r * GJ_PLD + c] - cv * rv[c];
+            }
+            P[r * GJ_PLD + c] = v;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < R * 64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        A[(size_t)(row0 + r) * ld + k0 + c] = P[r * GJ_PLD + c];
+    }
+}
+
+// one thread per column outside the panel: the 64 row swaps in order, then the K rows of that column to Tbuf
+__global__ void __launch_bounds__(256) gj_swap_copy_kernel(double* __restrict__ A, int ld, int n_pad, int k0,
+                                                            const int* __restrict__ piv, double* __restrict__ Tbuf) {
+    __shared__ int sp[64];
+    if (threadIdx.x < 64) sp[threadIdx.x] = piv[k0 + threadIdx.x];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_pad || (c >= k0 && c < k0 + 64)) return;
+    for (int j = 0; j < 64; ++j) {
+        const int p = sp[j], kk = k0 + j;
+        if (p != kk) {
+            const double t = A[(size_t)kk * ld + c];
+            A[(size_t)kk * ld + c] = A[(size_t)p * ld + c];
+            A[(size_t)p * ld + c] = t;
+        }
+    }
+    for (int j = 0; j < 64; ++j) Tbuf[(size_t)j * n_pad + c] = A[(size_t)(k0 + j) * ld + c];
+}
+
+__global__ void __launch_bounds__(128) gj_gemm_kernel(double* C, int ld, int n_pad, int kb, const double* __restrict__ Tbuf) {
+    __shared__ GemmSmem sm;
+    const int J = blockIdx.x, I = blockIdx.y;
+    if (J == kb) return;
+    const double* A = C + (size_t)I * 64 * ld + (size_t)kb * 64;     // this row block of the panel
+    const double* B = Tbuf + (size_t)J * 64;                         // T[0..64)[J columns], row stride n_pad
+    double acc[4][4][2] = {};
+    gemm_tile_64<false>(acc, sm, A, ld, B, n_pad, 0, 64);
+    gemm_tile_store(acc, C + (size_t)I * 64 * ld + (size_t)J * 64, ld, 1.0, I == kb ? 0.0 : 1.0);
+}
+
+// grid of the panel kernel: rows per CTA and CTA count, 0 if the device cannot co-schedule it
+static int gj_plan(int n_pad, int* rpc_out) {
+    int dev = 0, sms = 0, coop = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || sms <= 0) return 0;
+    int max_ctas = sms < GJ_MAX_CTAS ? sms : GJ_MAX_CTAS;
+    int rpc = (n_pad + max_ctas - 1) / max_ctas;
+    if (rpc < 32) rpc = 32;
+    const size_t smem = gj_panel_smem(rpc);
+    if (smem > 227 * 1024) return 0;
+    if (cudaFuncSetAttribute(gj_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gj_panel_kernel, 256, smem) != cudaSuccess || per_sm < 1) return 0;
+    *rpc_out = rpc;
+    return (n_pad + rpc - 1) / rpc;
+}
+
+cudaError_t kbk_general_inverse(double* C, int ld, int n, int n_pad, void* work, int* flag, double ptol,
+                                cudaStream_t st, int* launches, int force_scalar) {
+    // C holds the assembled lower triangle (+ diagonal, identity in the padding); build the full matrix, then invert
+    GjWork w = gj_carve(work, n_pad);
     symmetrize_kernel<<<dim3((n_pad + 255) / 256, n_pad), 256, 0, st>>>(C, ld, n_pad);
     ++*launches;
+    int rpc = 0;
+    const int G = force_scalar ? 0 : gj_plan(n_pad, &rpc);
+    if (G > 0) {
+        const int nbk = n_pad / 64;
+        const size_t smem = gj_panel_smem(rpc);
+        for (int kb = 0; kb < nbk; ++kb) {
+            int k0 = kb * 64;
+            void* args[] = {&C, &ld, &n_pad, &k0, &rpc, &w.cand_row, &w.krow, &w.cand_val, &w.cand_idx, &w.piv, &flag, &ptol};
+            cudaError_t e = cudaLaunchCooperativeKernel((const void*)gj_panel_kernel, dim3(G), dim3(256), args, smem, st);
+            if (e != cudaSuccess) return e;
+            ++*launches;
+            if (nbk > 1) {
+                gj_swap_copy_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(C, ld, n_pad, k0, w.piv, w.Tbuf);
+                gj_gemm_kernel<<<dim3(nbk, nbk), 128, 0, st>>>(C, ld, n_pad, kb, w.Tbuf);
+                *launches += 2;
+            }
+        }
+        gj_colswap_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(C, ld, n_pad, w.piv);
+        ++*launches;
+        return cudaGetLastError();
+    }
     dim3 ug((n + 255) / 256, (n + 15) / 16);
     for (int k = 0; k < n; ++k) {
-        gj_pivot_kernel<<<1, 1024, 0, st>>>(C, ld, n, k, rowbuf, colbuf, piv, flag, ptol);
-        gj_update_kernel<<<ug, 256, 0, st>>>(C, ld, n, k, rowbuf, colbuf);
+        gj_pivot_kernel<<<1, 1024, 0, st>>>(C, ld, n, k, w.rowbuf, w.colbuf, w.piv, flag, ptol);
+        gj_update_kernel<<<ug, 256, 0, st>>>(C, ld, n, k, w.rowbuf, w.colbuf);
     }
-    gj_colswap_kernel<<<(n + 127) / 128, 128, 0, st>>>(C, ld, n, piv);
+    gj_colswap_kernel<<<(n + 127) / 128, 128, 0, st>>>(C, ld, n, w.piv);
     *launches += 2 * n + 1;
     return cudaGetLastError();
 }

@@ -164,8 +164,11 @@ cudaError_t kbk_dual(const double* W, int ld, int n, int n_pad, int n_rl, int n_
 cudaError_t kbk_pack(int dtype, const double* W, int ld, int n, int n_pad, int na, const double* Uz,
                      const PackMap& pm, void* out, cudaStream_t st);
 
-cudaError_t kbk_general_inverse(double* C, int ld, int n, int n_pad, double* rowbuf, double* colbuf, int* piv,
-                                int* flag, double ptol, cudaStream_t st, int* launches);
+// in-place inverse of the (symmetric, possibly indefinite) matrix whose lower triangle is in C: blocked Gauss-Jordan with
+// partial pivoting (cooperative panel kernel + DMMA rank-64 updates); force_scalar = 1 selects the column-at-a-time form
+size_t      kbk_general_inverse_workspace_bytes(int n_pad);
+cudaError_t kbk_general_inverse(double* C, int ld, int n, int n_pad, void* work, int* flag, double ptol,
+                                cudaStream_t st, int* launches, int force_scalar);
 cudaError_t kbk_dual_gform(const double* G, int ld, int n, int n_pad, int n_rl, int n_hd,
                            const double* ax, const double* ay, const double* az, const DriftScale& ds,
                            const double* hd, const double* values,

@@ -14,26 +14,10 @@ class OrdinaryKriging(Krige2DMixin, KrigeBase):
     """Two-dimensional ordinary kriging; see the reference docstring (ok.py:42-175) for the
     meaning of every argument. Only ``execute(..., backend='cuda')`` differs."""
 
-    def __init__(
-        self,
-        x,
-        y,
-        z,
-        variogram_model="linear",
-        variogram_parameters=None,
-        variogram_function=None,
-        nlags=6,
-        weight=False,
-        anisotropy_scaling=1.0,
-        anisotropy_angle=0.0,
-        verbose=False,
-        enable_plotting=False,
-        enable_statistics=False,
-        coordinates_type="euclidean",
-        exact_values=True,
-        pseudo_inv=False,
-        pseudo_inv_type="pinv",
-    ):
+    def __init__(self, x, y, z, variogram_model="linear", variogram_parameters=None, variogram_function=None, nlags=6,
+                 weight=False, anisotropy_scaling=1.0, anisotropy_angle=0.0, verbose=False, enable_plotting=False,
+                 enable_statistics=False, coordinates_type="euclidean", exact_values=True, pseudo_inv=False,
+                 pseudo_inv_type="pinv"):
         self._init_common_2d(x, y, z, variogram_model, variogram_parameters, variogram_function, nlags, weight,
                              anisotropy_scaling, anisotropy_angle, verbose, enable_plotting, exact_values, pseudo_inv,
                              pseudo_inv_type, coordinates_type=coordinates_type,

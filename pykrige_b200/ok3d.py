@@ -142,28 +142,10 @@ class _Krige3DMixin:
 class OrdinaryKriging3D(_Krige3DMixin, KrigeBase):
     """Three-dimensional ordinary kriging; arguments as in the reference docstring (ok3d.py:37-196)."""
 
-    def __init__(
-        self,
-        x,
-        y,
-        z,
-        val,
-        variogram_model="linear",
-        variogram_parameters=None,
-        variogram_function=None,
-        nlags=6,
-        weight=False,
-        anisotropy_scaling_y=1.0,
-        anisotropy_scaling_z=1.0,
-        anisotropy_angle_x=0.0,
-        anisotropy_angle_y=0.0,
-        anisotropy_angle_z=0.0,
-        verbose=False,
-        enable_plotting=False,
-        exact_values=True,
-        pseudo_inv=False,
-        pseudo_inv_type="pinv",
-    ):
+    def __init__(self, x, y, z, val, variogram_model="linear", variogram_parameters=None, variogram_function=None,
+                 nlags=6, weight=False, anisotropy_scaling_y=1.0, anisotropy_scaling_z=1.0, anisotropy_angle_x=0.0,
+                 anisotropy_angle_y=0.0, anisotropy_angle_z=0.0, verbose=False, enable_plotting=False,
+                 exact_values=True, pseudo_inv=False, pseudo_inv_type="pinv"):
         self._init_common_3d(x, y, z, val, variogram_model, variogram_parameters, variogram_function, nlags,
                              weight, anisotropy_scaling_y, anisotropy_scaling_z, anisotropy_angle_x,
                              anisotropy_angle_y, anisotropy_angle_z, verbose, enable_plotting, exact_values,

@@ -30,31 +30,11 @@ class UniversalKriging(Krige2DMixin, KrigeBase):
 
     UNBIAS = True  # the unbiasedness row is always present on the device path (uk.py:208)
 
-    def __init__(
-        self,
-        x,
-        y,
-        z,
-        variogram_model="linear",
-        variogram_parameters=None,
-        variogram_function=None,
-        nlags=6,
-        weight=False,
-        anisotropy_scaling=1.0,
-        anisotropy_angle=0.0,
-        drift_terms=None,
-        point_drift=None,
-        external_drift=None,
-        external_drift_x=None,
-        external_drift_y=None,
-        specified_drift=None,
-        functional_drift=None,
-        verbose=False,
-        enable_plotting=False,
-        exact_values=True,
-        pseudo_inv=False,
-        pseudo_inv_type="pinv",
-    ):
+    def __init__(self, x, y, z, variogram_model="linear", variogram_parameters=None, variogram_function=None, nlags=6,
+                 weight=False, anisotropy_scaling=1.0, anisotropy_angle=0.0, drift_terms=None, point_drift=None,
+                 external_drift=None, external_drift_x=None, external_drift_y=None, specified_drift=None,
+                 functional_drift=None, verbose=False, enable_plotting=False, exact_values=True, pseudo_inv=False,
+                 pseudo_inv_type="pinv"):
         if drift_terms is None:
             drift_terms = []
         if specified_drift is None:

@@ -16,31 +16,11 @@ class UniversalKriging3D(_Krige3DMixin, KrigeBase):
 
     UNBIAS = True  # uk3d.py:200
 
-    def __init__(
-        self,
-        x,
-        y,
-        z,
-        val,
-        variogram_model="linear",
-        variogram_parameters=None,
-        variogram_function=None,
-        nlags=6,
-        weight=False,
-        anisotropy_scaling_y=1.0,
-        anisotropy_scaling_z=1.0,
-        anisotropy_angle_x=0.0,
-        anisotropy_angle_y=0.0,
-        anisotropy_angle_z=0.0,
-        drift_terms=None,
-        specified_drift=None,
-        functional_drift=None,
-        verbose=False,
-        enable_plotting=False,
-        exact_values=True,
-        pseudo_inv=False,
-        pseudo_inv_type="pinv",
-    ):
+    def __init__(self, x, y, z, val, variogram_model="linear", variogram_parameters=None, variogram_function=None,
+                 nlags=6, weight=False, anisotropy_scaling_y=1.0, anisotropy_scaling_z=1.0, anisotropy_angle_x=0.0,
+                 anisotropy_angle_y=0.0, anisotropy_angle_z=0.0, drift_terms=None, specified_drift=None,
+                 functional_drift=None, verbose=False, enable_plotting=False, exact_values=True, pseudo_inv=False,
+                 pseudo_inv_type="pinv"):
         if drift_terms is None:
             drift_terms = []
         if specified_drift is None:
