@@ -25,6 +25,9 @@ struct Src {
     const double* d_drift; int64_t drift_stride, drift_first;
 };
 
+// general (indefinite) path: blocked Gauss-Jordan unless KB200_GJ=scalar
+#define KB_GJ_DEFAULT_BLOCKED 0
+
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
@@ -518,9 +521,10 @@ extern "C" int kb200_set_problem(kb200_handle h, int dim, int dtype, int64_t n,
         CU(h, cudaEventRecord(h->ev[3], st));
         CU(h, kbk_assemble(h->dim, h->vg, nn, np, ld, ax, ay, az, h->wC.as<double>(), st)); ++launches;
         CU(h, h->wVario.reserve(kbk_general_inverse_workspace_bytes(np)));
-        const char* gj_env = std::getenv("KB200_GJ_SCALAR");     // cross-check switch of the tests: column-at-a-time form
+        const char* gj_env = std::getenv("KB200_GJ");            // "blocked" | "scalar": cross-check switch of the tests
+        const bool gj_scalar = gj_env ? gj_env[0] == 's' : !KB_GJ_DEFAULT_BLOCKED;
         CU(h, kbk_general_inverse(h->wC.as<double>(), ld, nn, np, h->wVario.p, flag, 3.6e-15 * h->vg.c0, st, &launches,
-                                  gj_env && gj_env[0] == '1'));
+                                  gj_scalar));
         CU(h, cudaEventRecord(h->ev[4], st));
         CU(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));

@@ -1,5 +1,6 @@
 """One general-path (indefinite) factorisation for an ncu launch list: hole-effect, N = 1900."""
-import sys, numpy as np
+import os, sys, numpy as np
+os.environ["KB200_GJ"] = "blocked"
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import cases, pykrige_b200 as pk
 xyz, val = cases.synth_data(21, 1900, 2)

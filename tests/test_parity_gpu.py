@@ -297,7 +297,7 @@ def test_indefinite_variogram_takes_general_path(pk, ref_cases):
 def test_blocked_general_inverse_matches_scalar_form_and_oracle(pk, monkeypatch):
     """The general path's inverse is a blocked Gauss-Jordan (cooperative panel kernel + DMMA rank-64 updates). At a
     size with many panels (N = 1900 -> 30 panels, rows dealt over the whole grid) it must reproduce the oracle's
-    LU-based numbers (ok.py:663) and the column-at-a-time form of the same elimination (KB200_GJ_SCALAR=1), for OK
+    LU-based numbers (ok.py:663) and the column-at-a-time form of the same elimination (KB200_GJ=scalar), for OK
     and for UK; redundant points must still be reported as singular, not inverted into noise."""
     from oracle import krige_oracle as ko
     xyz, val = cases.synth_data(21, 1900, 2)
@@ -307,8 +307,8 @@ def test_blocked_general_inverse_matches_scalar_form_and_oracle(pk, monkeypatch)
     zo, so = ko.krige(xyz, val, "hole-effect", sp, pts)
     zu, su = ko.krige(xyz, val, "hole-effect", sp, pts, regional_linear=True)
     out, launches = {}, {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("KB200_GJ_SCALAR", mode)
+    for mode in ("blocked", "scalar"):
+        monkeypatch.setenv("KB200_GJ", mode)
         ok = pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, variogram_model="hole-effect", variogram_parameters=params)
         z, ss = ok.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
         launches[mode] = ok._kb_handle.timings()["launches"]
@@ -320,10 +320,10 @@ def test_blocked_general_inverse_matches_scalar_form_and_oracle(pk, monkeypatch)
         z, ss = uk.execute("points", pts[:, 0], pts[:, 1], backend="cuda")
         assert_parity(z, zu, R64, "blocked GJ uk z (scalar=%s)" % mode)
         assert_parity(ss, su, R64, "blocked GJ uk ss (scalar=%s)" % mode)
-    assert launches["0"] + 3000 < launches["1"]          # 3 launches per 64 columns instead of 2 per column
-    assert_parity(out["0"][0], out["1"][0], 1e-7, "blocked vs scalar z")
-    assert_parity(out["0"][1], out["1"][1], 1e-7, "blocked vs scalar ss")
-    monkeypatch.setenv("KB200_GJ_SCALAR", "0")
+    assert launches["blocked"] + 3000 < launches["scalar"]          # 3 launches per 64 columns instead of 2 per column
+    assert_parity(out["blocked"][0], out["scalar"][0], 1e-7, "blocked vs scalar z")
+    assert_parity(out["blocked"][1], out["scalar"][1], 1e-7, "blocked vs scalar ss")
+    monkeypatch.setenv("KB200_GJ", "blocked")
     dup = np.vstack([xyz[:700], xyz[:4]])
     okd = pk.OrdinaryKriging(dup[:, 0], dup[:, 1], np.concatenate([val[:700], val[:4]]), variogram_model="hole-effect",
                              variogram_parameters=[1.0, 250.0, 0.0])
