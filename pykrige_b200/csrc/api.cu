@@ -26,7 +26,7 @@ struct Src {
 };
 
 // general (indefinite) path: blocked Gauss-Jordan unless KB200_GJ=scalar
-#define KB_GJ_DEFAULT_BLOCKED 0
+#define KB_GJ_DEFAULT_BLOCKED 1
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
