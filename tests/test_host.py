@@ -301,3 +301,56 @@ def test_gstools_route_on_the_host():
         gstools_stub.uninstall()
     with pytest.raises(GSToolsException):                               # gstools absent
         pk.OrdinaryKriging(xyz[:, 0], xyz[:, 1], val, m)
+
+
+def _blocked_gauss_jordan(A, nb):
+    """The algebra csrc/factor.cu's general path runs (gj_panel_kernel / gj_swap_copy_kernel / gj_gemm_kernel), in numpy:
+    nb pivoted scalar steps restricted to the column panel, the recorded row swaps and ONE rank-nb update of all other
+    columns, column swaps in reverse at the end."""
+    A = A.copy()
+    n = A.shape[0]
+    piv = np.arange(n)
+    for k0 in range(0, n, nb):
+        P = A[:, k0:k0 + nb].copy()
+        for j in range(nb):
+            kk = k0 + j
+            p = kk + int(np.argmax(np.abs(P[kk:, j])))
+            piv[kk] = p
+            P[[kk, p]] = P[[p, kk]]
+            inv = 1.0 / P[kk, j]
+            rv = P[kk] * inv
+            rv[j] = inv
+            col = P[:, j].copy()
+            P -= np.outer(col, rv)
+            P[:, j] = -col * inv
+            P[kk] = rv
+        other = np.r_[0:k0, k0 + nb:n]
+        R = A[:, other]
+        for j in range(nb):
+            kk, p = k0 + j, piv[k0 + j]
+            R[[kk, p]] = R[[p, kk]]
+        T = R[k0:k0 + nb].copy()
+        R[k0:k0 + nb] = 0.0
+        A[:, other] = R + P @ T
+        A[:, k0:k0 + nb] = P
+    for k in range(n - 1, -1, -1):
+        A[:, [k, piv[k]]] = A[:, [piv[k], k]]
+    return A
+
+
+def test_blocked_gauss_jordan_algebra():
+    """64 scalar Gauss-Jordan steps compose into the block exchange of the pivot block against the rest, with the row
+    swaps deferred to the other columns: pins the algebra of the device's general (indefinite) path against
+    numpy.linalg.inv on a symmetric indefinite matrix padded with an identity block, as the device pads it."""
+    rng = np.random.default_rng(5)
+    n, n_pad = 150, 192
+    M = rng.standard_normal((n, n))
+    M = M + M.T
+    assert np.linalg.eigvalsh(M).min() < 0 < np.linalg.eigvalsh(M).max()
+    A = np.eye(n_pad)
+    A[:n, :n] = M
+    G = _blocked_gauss_jordan(A, 64)
+    assert_allclose(G[:n, :n], np.linalg.inv(M), rtol=0, atol=1e-10 * np.abs(np.linalg.inv(M)).max())
+    assert_allclose(G[n:, n:], np.eye(n_pad - n), atol=0)
+    assert np.all(G[:n, n:] == 0.0) and np.all(G[n:, :n] == 0.0)
+    assert_allclose(_blocked_gauss_jordan(A, 1), G, atol=1e-10 * np.abs(G).max())      # the column-at-a-time form
