@@ -1,14 +1,13 @@
 """UniversalKriging (2-D) with the B200 ``backend='cuda'`` execute() path.
 
 API mirror of the reference class (src/pykrige/uk.py:220-1328). Regional-linear drift is built
-on the device from the adjusted coordinates; point-log, external-Z, specified and functional
-drift terms are evaluated on the host (as in uk.py:884-910, 955-979) and shipped as extra
-drift columns of the same device system.
+on the device from the adjusted coordinates. The DATA-side columns of the other drift kinds
+(uk.py:884-910) are evaluated once on the host and enter the device system as extra columns;
+at the PREDICTION points point-log and external-Z (uk.py:955-971) are evaluated inside the solve
+kernels (kb200_set_device_drift), only specified / functional values (uk.py:972-979) are shipped.
 """
-import warnings
 import numpy as np
 
-from . import core
 from ._base import KrigeBase
 from ._krige2d import Krige2DMixin, P_INV_TYPES  # noqa: F401
 from .core import _adjust_for_anisotropy

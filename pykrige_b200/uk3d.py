@@ -3,7 +3,6 @@
 API mirror of the reference class (src/pykrige/uk3d.py:215-1146): regional-linear drift (three
 columns X, Y, Z built on the device), specified and functional drift (host-evaluated columns).
 """
-import warnings
 import numpy as np
 
 from ._base import KrigeBase
