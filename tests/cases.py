@@ -425,3 +425,34 @@ def scenario_model(module_ns, sc, data):
                   external_drift_x=np.arange(0.0, 5.1, 0.1), external_drift_y=np.arange(0.0, 6.0, 1.0))
     cols = [data[:, c] for c in range(data.shape[1])]
     return getattr(module_ns, cls)(*cols, **kw)
+
+
+# ---- automatic variogram fit (variogram_parameters=None) and bit patterns of the six model functions:
+#      inputs shared by tests/golden/make_golden.py (vgfit) and tests/test_host.py -> tests/golden/ref_vgfit.npz
+def vgfit_inputs(n, seed=77):
+    """Seeded scatter for the automatic-fit cases."""
+    rng = np.random.default_rng(seed + n)
+    x = rng.uniform(0.0, 1000.0, n)
+    y = rng.uniform(0.0, 1000.0, n)
+    z = 50.0 + 10.0 * np.sin(x / 150.0) * np.cos(y / 200.0) + rng.normal(size=n)
+    return x, y, z
+
+
+VGFIT_MODELS = ("linear", "power", "gaussian", "spherical", "exponential", "hole-effect")
+VGFIT_PARAMS = {"linear": [0.002, 0.1], "power": [0.05, 1.3, 0.1], "gaussian": [1.3, 420.0, 0.07],
+                "spherical": [0.9, 510.0, 0.03], "exponential": [1.1, 333.0, 0.05], "hole-effect": [0.8, 270.0, 0.02]}
+
+
+def vgfit_distances():
+    rng = np.random.default_rng(4242)
+    return np.concatenate([[0.0, 1e-12, 510.0, 509.99999999999994, 510.00000000000006], rng.uniform(0.0, 1500.0, 1019)])
+
+
+def cpu_fingerprint():
+    """numpy version + the SIMD features its ufunc loops dispatch on (exp / pow may differ in the last ulp between
+    dispatch targets, so bit-for-bit comparisons are only meaningful on the same fingerprint)."""
+    try:
+        from numpy._core._multiarray_umath import __cpu_features__ as feats
+    except ImportError:  # numpy < 2
+        from numpy.core._multiarray_umath import __cpu_features__ as feats
+    return np.__version__ + ":" + ",".join(sorted(k for k, v in feats.items() if v))

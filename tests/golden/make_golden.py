@@ -13,6 +13,8 @@ Writes
   tests/golden/ref_scenarios.npz : fitted parameters, lags, (z, sigmasq) and statistics of the reference for the
       whole-chain scenarios (no variogram parameters given) on the reference's own small fixtures.
   tests/golden/ref_custom.npz : (z, sigmasq) of the reference for variogram_model='custom' callables.
+  tests/golden/ref_vgfit.npz : gamma(d) of the six built-in variogram functions on fixed distance vectors (bit patterns)
+      and the parameters the reference's constructor fits (variogram_parameters=None) on seeded random scatter.
   tests/golden/ref_ctor.npz : lags/semivariance of core._initialize_variogram_model and delta/sigma/epsilon
       of core._find_statistics for the constructor-side cases of tests/cases.py.
 The O(N^4) constructor statistics of OK3D/UK/UK3D are patched out; nothing else of the
@@ -163,8 +165,30 @@ def ref_ctor():
     np.savez_compressed(os.path.join(HERE, "ref_ctor.npz"), **out)
 
 
+def ref_vgfit():
+    """gamma(d) of the reference's six variogram functions (exact bit patterns) and the constructor's automatic fit
+    (ok.py:326-346 -> core.py:582-651, soft-L1 TRF) for seeded scatter -> ref_vgfit.npz."""
+    from pykrige import variogram_models as rvm
+    out = {}
+    d = cases.vgfit_distances()
+    for m in cases.VGFIT_MODELS:
+        f = getattr(rvm, m.replace("-", "_") + "_variogram_model")
+        out["gamma/" + m] = np.asarray(f(cases.VGFIT_PARAMS[m], d.copy()), dtype=np.float64)
+    for n in (60, 300):
+        x, y, z = cases.vgfit_inputs(n)
+        for m in cases.VGFIT_MODELS:
+            for w in (False, True):
+                ok = pykrige.OrdinaryKriging(x, y, z, variogram_model=m, weight=w, nlags=8)
+                out["fit/%d/%s/%d" % (n, m, int(w))] = np.asarray(ok.variogram_model_parameters, dtype=np.float64)
+                print("fit N=%-4d %-12s weight=%d -> %s" % (n, m, w, out["fit/%d/%s/%d" % (n, m, int(w))]))
+    out["cpu_fingerprint"] = np.array(cases.cpu_fingerprint())
+    np.savez_compressed(os.path.join(HERE, "ref_vgfit.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios", "custom"]
+    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios", "custom", "vgfit"]
+    if "vgfit" in which:
+        ref_vgfit()
     if "goldens" in which:
         reference_goldens()
     if "cases" in which:
