@@ -130,6 +130,22 @@ class KrigeBase:
         self._cR = core.calc_cR(self._Q2, self._sigma)
         self._stats_state = "done"
 
+    def _statistics_policy(self, policy):
+        """End of the constructors / update_variogram_model. policy 'off' (OrdinaryKriging without enable_statistics:
+        every statistic is None), 'eager' (enable_statistics=True) or 'lazy' (the other three classes and every
+        update_variogram_model: the reference computes the statistics right here, ok3d.py:352, uk.py:380, uk3d.py:380,
+        ok.py:539 — an O(N^4) loop; here they are computed on first access). verbose=True prints what the
+        reference prints at this point (ok.py:358-375), which for 'lazy' means computing them now."""
+        if self.verbose:
+            print("Calculating statistics on variogram model fit...")
+        self._stats_state = "lazy" if policy == "eager" else policy
+        if policy == "eager" or (policy == "lazy" and self.verbose):
+            self._compute_statistics()
+            if self.verbose:
+                print("Q1 =", self.Q1)
+                print("Q2 =", self.Q2)
+                print("cR =", self.cR, "\n")
+
     def _stat(self, name):
         state = getattr(self, "_stats_state", "off")
         if state == "off":

@@ -13,6 +13,7 @@ GEO_ANISOTROPY_WARNING = "Anisotropy is not compatible with geographic coordinat
 
 class Krige2DMixin:
     _ndim = 2
+    _prints_coordinates_type = False
 
     # ---- pieces ---------------------------------------------------------------------------------------------------
     def _gstools_2d(self, variogram_model, variogram_function, check_latlon):
@@ -40,7 +41,7 @@ class Krige2DMixin:
             np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T, self.Z, self.variogram_model, vp,
             self.variogram_function, nlags, weight, self.coordinates_type, lazy=True)
         if self.verbose:
-            if self.coordinates_type != "euclidean":
+            if self._prints_coordinates_type:           # ok.py:333 (UniversalKriging has no coordinates_type)
                 print("Coordinates type: '%s'" % self.coordinates_type, "\n")
             self._print_variogram()
         if self.enable_plotting:
@@ -95,14 +96,7 @@ class Krige2DMixin:
             print("Initializing variogram model...")
         self._fit_variogram_2d(variogram_parameters, nlags, weight)
 
-        self._stats_state = "off" if statistics == "eager" else statistics
-        if statistics == "eager":
-            if self.verbose:
-                print("Calculating statistics on variogram model fit...")
-            self._compute_statistics()
-            if self.verbose:
-                self.print_statistics()
-                print()
+        self._statistics_policy(statistics)
 
     def _stats_inputs(self):
         return np.vstack((self.X_ADJUSTED, self.Y_ADJUSTED)).T, self.Z
@@ -126,7 +120,7 @@ class Krige2DMixin:
         if self.verbose:
             print("Updating variogram mode...")
         self._fit_variogram_2d(variogram_parameters, nlags, weight)
-        self._stats_state = "lazy"
+        self._statistics_policy("lazy")
 
     # ---- device description -------------------------------------------------------------------------------------------
     def _data_arrays(self):

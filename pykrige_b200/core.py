@@ -40,33 +40,38 @@ def anisotropy_matrix(ndim, scaling, angle):
     2-D: rot = R(-angle), stretch = diag(1, s).  3-D: rot = Rz @ Ry @ Rx (each by the
     negated angle), stretch = diag(1, s_y, s_z).  (core.py:148-189)
     """
+    rot, stretch = _rotation_and_stretch(ndim, scaling, angle)
+    return stretch @ rot
+
+
+def _rotation_and_stretch(ndim, scaling, angle):
+    """(rot, stretch) of the reference's anisotropy map, see anisotropy_matrix."""
     ang = -np.asarray(angle, dtype=float) * np.pi / 180.0
     if ndim == 2:
         c, s = np.cos(ang[0]), np.sin(ang[0])
-        rot = np.array([[c, -s], [s, c]])
-        stretch = np.diag([1.0, float(scaling[0])])
-    elif ndim == 3:
+        return np.array([[c, -s], [s, c]]), np.diag([1.0, float(scaling[0])])
+    if ndim == 3:
         cx, sx = np.cos(ang[0]), np.sin(ang[0])
         cy, sy = np.cos(ang[1]), np.sin(ang[1])
         cz, sz = np.cos(ang[2]), np.sin(ang[2])
         rx = np.array([[1.0, 0.0, 0.0], [0.0, cx, -sx], [0.0, sx, cx]])
         ry = np.array([[cy, 0.0, sy], [0.0, 1.0, 0.0], [-sy, 0.0, cy]])
         rz = np.array([[cz, -sz, 0.0], [sz, cz, 0.0], [0.0, 0.0, 1.0]])
-        rot = rz @ ry @ rx
-        stretch = np.diag([1.0, float(scaling[0]), float(scaling[1])])
-    elif ndim == 1:
+        return np.dot(rz, np.dot(ry, rx)), np.diag([1.0, float(scaling[0]), float(scaling[1])])
+    if ndim == 1:
         raise NotImplementedError("1-D anisotropy is not implemented")
-    else:
-        raise ValueError("anisotropy adjustment supports 2-D and 3-D only")
-    return stretch @ rot
+    raise ValueError("anisotropy adjustment supports 2-D and 3-D only")
 
 
 def _adjust_for_anisotropy(X, center, scaling, angle):
-    """X_adj = (X - c) @ Mt.T + c   (core.py:120-193).  X is [n, ndim]; not modified."""
+    """X_adj = stretch (rot (X - c)) + c   (core.py:120-193).  X is [n, ndim]; not modified.
+    Rotation first, stretch second, as two products — the association the reference uses, so that X_ADJUSTED (and
+    with it the experimental variogram and the automatic fit) carries the same bits; the device applies the
+    pre-multiplied matrix of anisotropy_matrix (csrc/common.cuh kb_adjust), which is inside the parity tolerance."""
     X = np.asarray(X, dtype=float)
     c = np.asarray(center, dtype=float)[None, :]
-    Mt = anisotropy_matrix(X.shape[1], scaling, angle)
-    return (X - c) @ Mt.T + c
+    rot, stretch = _rotation_and_stretch(X.shape[1], scaling, angle)
+    return np.dot(stretch, np.dot(rot, (X - c).T)).T + c
 
 
 def _make_variogram_parameter_list(variogram_model, variogram_model_parameters):
@@ -142,7 +147,7 @@ def _experimental_variogram(X, y, nlags, block=2048, coordinates_type="euclidean
     n = X.shape[0]
     if coordinates_type == "geographic" and X.shape[1] != 2:
         raise ValueError("Geographic coordinate type only supported for 2D datasets.")
-    small = n * (n - 1) // 2 <= 20_000_000 and coordinates_type == "euclidean"
+    small = n * (n - 1) // 2 <= 20_000_000
     # "auto": the pdist route below reproduces the reference's lags bit for bit (same summation order), which the
     # least-squares fit needs; it is cheap up to ~6300 points. Beyond that only the device can hold the pair pass.
     if device is True or (device == "auto" and n >= 2 and not small and _device_available()):
@@ -152,8 +157,15 @@ def _experimental_variogram(X, y, nlags, block=2048, coordinates_type="euclidean
         keep = cnt > 0
         return sd[keep] / cnt[keep], sg[keep] / cnt[keep]
     if small:
-        d = pdist(X, metric="euclidean")
-        g = 0.5 * pdist(y[:, None], metric="sqeuclidean")
+        if coordinates_type == "geographic":
+            # the reference's pair list (core.py:444-451): strictly-lower-triangle pairs (i > j) in row-major order,
+            # point j in the first argument slot of the (bitwise asymmetric) great-circle formula
+            i, j = np.tril_indices(n, -1)
+            d = great_circle_distance(X[j, 0], X[j, 1], X[i, 0], X[i, 1])
+            g = 0.5 * (y[j] - y[i]) ** 2.0
+        else:
+            d = pdist(X, metric="euclidean")
+            g = 0.5 * pdist(y[:, None], metric="sqeuclidean")
         dmax, dmin = np.amax(d), np.amin(d)
         dd = (dmax - dmin) / nlags
         edges = np.array([dmin + k * dd for k in range(nlags)] + [dmax + 0.001])
@@ -260,27 +272,35 @@ def _initialize_variogram_model(X, y, variogram_model, variogram_model_parameter
 
 def _krige(X, y, coords, variogram_function, variogram_model_parameters, coordinates_type="euclidean",
            pseudo_inv=False):
-    """One ordinary-kriging estimate at ``coords`` from data (X, y) (core.py:654-756); host numpy,
-    used by the lazy cross-validation statistics only."""
-    from scipy.spatial.distance import cdist
-    import scipy.linalg
+    """One ordinary-kriging estimate at ``coords`` from data (X, y) (core.py:654-756); host numpy, used by the
+    cross-validation statistics when there is no device route. Same numerical primitives as the reference
+    (pdist/cdist distances, numpy's gesv / gelsd drivers on an (n+1, 1) right-hand side, only the FIRST coincident
+    data point zeroed), so that delta / sigma / epsilon carry the reference's bits."""
+    from scipy.spatial.distance import cdist, squareform
 
     n = X.shape[0]
-    d = _pair_distances(X, X, coordinates_type)
+    coords = np.asarray(coords, dtype=float)
+    if coordinates_type == "geographic":
+        # d[i, j]: point j in the first argument slot of the (bitwise asymmetric) great-circle formula (core.py:689-691)
+        d = great_circle_distance(X[None, :, 0], X[None, :, 1], X[:, 0, None], X[:, 1, None])
+        bd = great_circle_distance(X[:, 0], X[:, 1], coords[0] * np.ones(n), coords[1] * np.ones(n))
+    elif coordinates_type == "euclidean":
+        d = squareform(pdist(X, metric="euclidean"))
+        bd = cdist(X, coords[None, :], metric="euclidean").ravel()
+    else:
+        raise ValueError("Specified coordinate type '%s' is not supported." % coordinates_type)
     a = np.zeros((n + 1, n + 1))
     a[:n, :n] = -variogram_function(variogram_model_parameters, d)
     np.fill_diagonal(a, 0.0)
     a[n, :n] = 1.0
     a[:n, n] = 1.0
-    bd = _pair_distances(X, np.asarray(coords, dtype=float)[None, :], coordinates_type).ravel()
-    b = np.zeros(n + 1)
-    b[:n] = -variogram_function(variogram_model_parameters, bd)
-    b[np.nonzero(np.absolute(bd) <= 1e-10)[0]] = 0.0
-    b[n] = 1.0
-    res = scipy.linalg.lstsq(a, b)[0] if pseudo_inv else scipy.linalg.solve(a, b)
-    zinterp = float(np.sum(res[:n] * y))
-    sigmasq = float(np.sum(res * -b))
-    return zinterp, sigmasq
+    b = np.zeros((n + 1, 1))
+    b[:n, 0] = -variogram_function(variogram_model_parameters, bd)
+    if np.any(np.absolute(bd) <= 1e-10):
+        b[int(np.flatnonzero(bd <= 1e-10)[0]), 0] = 0.0
+    b[n, 0] = 1.0
+    res = np.linalg.lstsq(a, b, rcond=None)[0] if pseudo_inv else np.linalg.solve(a, b)
+    return np.sum(res[:n, 0] * y), np.sum(res[:, 0] * -b[:, 0])
 
 
 def _find_statistics(X, y, variogram_function, variogram_model_parameters, coordinates_type="euclidean",
@@ -289,9 +309,7 @@ def _find_statistics(X, y, variogram_function, variogram_model_parameters, coord
     n = y.shape[0]
     delta = np.zeros(n)
     sigma = np.zeros(n)
-    for i in range(n):
-        if i == 0:
-            continue
+    for i in range(1, n):                 # the first point has nothing to be estimated from
         k, ss = _krige(X[:i, :], y[:i], X[i, :], variogram_function, variogram_model_parameters,
                        coordinates_type, pseudo_inv)
         if np.absolute(ss) < eps:

@@ -13,6 +13,7 @@ from ._krige2d import Krige2DMixin, P_INV_TYPES  # noqa: F401
 class OrdinaryKriging(Krige2DMixin, KrigeBase):
     """Two-dimensional ordinary kriging; see the reference docstring (ok.py:42-175) for the
     meaning of every argument. Only ``execute(..., backend='cuda')`` differs."""
+    _prints_coordinates_type = True
 
     def __init__(self, x, y, z, variogram_model="linear", variogram_parameters=None, variogram_function=None, nlags=6,
                  weight=False, anisotropy_scaling=1.0, anisotropy_angle=0.0, verbose=False, enable_plotting=False,

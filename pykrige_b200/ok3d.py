@@ -76,8 +76,7 @@ class _Krige3DMixin:
             self._print_variogram()
         if self.enable_plotting:
             self.display_variogram_model()
-        # statistics on first access only (the reference computes them here: ok3d.py:352, uk3d.py:380)
-        self._stats_state = "lazy"
+        self._statistics_policy("lazy")
 
     def _readjust(self):
         self.X_ADJUSTED, self.Y_ADJUSTED, self.Z_ADJUSTED = _adjust_for_anisotropy(
@@ -129,7 +128,7 @@ class _Krige3DMixin:
             self._print_variogram()
         if self.enable_plotting:
             self.display_variogram_model()
-        self._stats_state = "lazy"
+        self._statistics_policy("lazy")
 
     def _data_arrays(self):
         Mt = core.anisotropy_matrix(
