@@ -24,7 +24,6 @@ class KrigeBase:
         "hole-effect": variogram_models.hole_effect_variogram_model,
     }
     _ndim = 2
-    _backend_name = "ordinary kriging"
 
     # ---- variogram model selection (ok.py:208-253; GSTools models arrive as 'custom') ----
     def _select_variogram(self, variogram_model, variogram_function, gstools_dim_ok):

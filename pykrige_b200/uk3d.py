@@ -12,6 +12,8 @@ from .ok3d import _Krige3DMixin
 
 class UniversalKriging3D(_Krige3DMixin, KrigeBase):
     """Three-dimensional universal kriging; arguments as in the reference docstring (uk3d.py:37-213)."""
+    _POINTS_MSG = dict(KrigeBase._POINTS_MSG)
+    _POINTS_MSG[3] = KrigeBase._POINTS_MSG[2]      # uk3d.py:1019-1022 names only xpoints and ypoints
 
     UNBIAS = True  # uk3d.py:200
 
@@ -78,7 +80,7 @@ class UniversalKriging3D(_Krige3DMixin, KrigeBase):
         axes, sizes, flat_mask = self._prepare_points(style, (xpoints, ypoints, zpoints), mask)
         spec_drift_grids = self._specified_drift_grids(style, specified_drift_arrays, sizes, axes[0].size,
                                                        "UniversalKriging3D")
-        self._check_backend(backend, "3D universal kriging")
+        self._check_backend(backend, "3D Universal kriging")   # capital U as in uk3d.py:1132
 
         drift_at = None
         if self.specified_drift or self.functional_drift:

@@ -456,3 +456,229 @@ def cpu_fingerprint():
     except ImportError:  # numpy < 2
         from numpy.core._multiarray_umath import __cpu_features__ as feats
     return np.__version__ + ":" + ",".join(sorted(k for k, v in feats.items() if v))
+
+
+# ---- host-mirror API cases: constructor / update_variogram_model / execute()-argument validation of the four classes,
+#      run against the imported reference by tests/golden/make_golden.py (api) -> tests/golden/ref_api.npz and against
+#      pykrige_b200 by tests/test_host.py. Everything before the device call: attributes, stdout, warnings, exceptions.
+API_FUNCS = {
+    "f_xy": lambda x, y: x * y / 100.0,
+    "f_sin": lambda x, y: np.sin(x / 30.0),
+    "f_xyz": lambda x, y, z: x + y * z / 50.0,
+    "vg_lin": lambda m, d: m[0] * d,
+}
+
+
+def api_inputs():
+    """Named arrays the API cases refer to as '$name'."""
+    rng = np.random.default_rng(20260923)
+    n = 40
+    x, y, zc = rng.uniform(0, 100, n), rng.uniform(0, 100, n), rng.uniform(0, 30, n)
+    v = 10.0 + np.sin(x / 20.0) + 0.3 * rng.normal(size=n)
+    d = dict(x=x, y=y, zc=zc, v=v, gx=np.linspace(0, 100, 7), gy=np.linspace(0, 100, 5), gz=np.linspace(0, 30, 3),
+             dem=rng.uniform(0, 5, (12, 11)), demx=np.linspace(-5, 105, 11), demy=np.linspace(-5, 105, 12),
+             wells=np.array([[10.0, 20.0, 1.0], [70.0, 80.0, -2.0]]), sx=0.1 * x, sy=0.2 * y, szc=zc.copy(),
+             mask2=np.zeros((5, 7), bool), mask3=np.zeros((3, 5, 7), bool), z57=np.zeros((5, 7)), z75=np.zeros((7, 5)),
+             z47=np.zeros((4, 7)), z7=np.zeros(7), z5=np.zeros(5), z4=np.zeros(4), z51=np.zeros((5, 1)),
+             z357=np.zeros((3, 5, 7)), z753=np.zeros((7, 5, 3)), z3=np.zeros(3))
+    d["mask2"][1, 2] = True
+    d["wells2"] = d["wells"][:, :2]
+    d["demx_short"] = d["demx"][:-1]
+    d["sx_short"] = d["sx"][:-1]
+    d["gx5"], d["gx3"], d["gy3"], d["gy4"] = d["gx"][:5], d["gx"][:3], d["gy"][:3], d["gy"][:4]
+    d["mask2T"], d["mask2_rows3"], d["mask2_1d"] = d["mask2"].T, d["mask2"][:3], d["mask2"][0]
+    d["mask3T"], d["mask3_2"], d["mask3_2d"] = d["mask3"].T, d["mask3"][:2], d["mask3"][0]
+    d.update(API_FUNCS)
+    return d
+
+
+def _api(name, cls, kw=None, then=None):
+    return dict(name=name, cls=cls, kw=dict(kw or {}), then=then)
+
+
+_VP = {"linear": [0.01, 0.1], "power": [0.1, 1.2, 0.05]}
+API_CASES = []
+for _m in ("linear", "power", "gaussian", "spherical", "exponential", "hole-effect"):
+    _lst = _VP.get(_m, [2.0, 40.0, 0.1])
+    _dct = ({"slope": 1.0, "nugget": 0.1} if _m == "linear" else
+            {"scale": 0.1, "exponent": 1.2, "nugget": 0.05} if _m == "power" else {"sill": 2.0, "range": 40.0, "nugget": 0.1})
+    for _tag, _kw in (("fit", {}), ("fit_weight", dict(weight=True, nlags=4)),
+                      ("aniso_verbose", dict(anisotropy_scaling=2.5, anisotropy_angle=33.0, verbose=True)),
+                      ("stats_verbose", dict(enable_statistics=True, verbose=True)),
+                      ("list", dict(variogram_parameters=_lst)), ("dict", dict(variogram_parameters=_dct)),
+                      ("geographic", dict(coordinates_type="geographic", verbose=True))):
+        API_CASES.append(_api("ok_%s_%s" % (_m, _tag), "OrdinaryKriging", dict(variogram_model=_m, **_kw)))
+API_CASES += [
+    _api("ok_psill_dict", "OrdinaryKriging", dict(variogram_model="gaussian", variogram_parameters={"psill": 1.0, "range": 40.0, "nugget": 0.1})),
+    _api("ok_bad_list_len", "OrdinaryKriging", dict(variogram_model="gaussian", variogram_parameters=[1.0])),
+    _api("ok_bad_param_type", "OrdinaryKriging", dict(variogram_model="gaussian", variogram_parameters="bad")),
+    _api("ok_bad_dict_keys", "OrdinaryKriging", dict(variogram_model="power", variogram_parameters={"scale": 1.0})),
+    _api("ok_bad_model", "OrdinaryKriging", dict(variogram_model="nomodel")),
+    _api("ok_custom_no_function", "OrdinaryKriging", dict(variogram_model="custom", variogram_parameters=[1.0])),
+    _api("ok_custom_no_parameters", "OrdinaryKriging", dict(variogram_model="custom", variogram_function="$vg_lin")),
+    _api("ok_custom", "OrdinaryKriging", dict(variogram_model="custom", variogram_parameters=[0.02], variogram_function="$vg_lin", verbose=True)),
+    _api("ok_pinvh", "OrdinaryKriging", dict(exact_values=False, pseudo_inv=True, pseudo_inv_type="pinvh", enable_statistics=True)),
+    _api("ok_bad_pinv_type", "OrdinaryKriging", dict(pseudo_inv_type="zzz")),
+    _api("ok_bad_coordinates", "OrdinaryKriging", dict(coordinates_type="nonsense")),
+    _api("ok_bad_exact", "OrdinaryKriging", dict(exact_values="yes")),
+    _api("ok_geo_aniso_warns", "OrdinaryKriging", dict(coordinates_type="geographic", anisotropy_scaling=2.0)),
+]
+_UKW = dict(variogram_model="linear", variogram_parameters=[0.01, 0.1])
+_ALL5 = dict(drift_terms=["regional_linear", "point_log", "external_Z", "specified", "functional"], point_drift="$wells",
+             external_drift="$dem", external_drift_x="$demx", external_drift_y="$demy", specified_drift=["$sx"],
+             functional_drift=["$f_xy"], verbose=True, anisotropy_scaling=1.5, anisotropy_angle=20.0)
+API_CASES += [
+    _api("uk_plain_verbose", "UniversalKriging", dict(variogram_model="spherical", verbose=True)),
+    _api("uk_rl_verbose", "UniversalKriging", dict(variogram_model="spherical", drift_terms=["regional_linear"], verbose=True)),
+    _api("uk_external", "UniversalKriging", dict(drift_terms=["external_Z"], external_drift="$dem", external_drift_x="$demx", external_drift_y="$demy", verbose=True)),
+    _api("uk_external_missing", "UniversalKriging", dict(drift_terms=["external_Z"])),
+    _api("uk_external_bad_axis", "UniversalKriging", dict(drift_terms=["external_Z"], external_drift="$dem", external_drift_x="$demx_short", external_drift_y="$demy")),
+    _api("uk_point_log", "UniversalKriging", dict(drift_terms=["point_log"], point_drift="$wells", verbose=True)),
+    _api("uk_point_log_missing", "UniversalKriging", dict(drift_terms=["point_log"])),
+    _api("uk_point_log_two_columns", "UniversalKriging", dict(drift_terms=["point_log"], point_drift="$wells2")),
+    _api("uk_specified", "UniversalKriging", dict(drift_terms=["specified"], specified_drift=["$sx", "$sy"], verbose=True)),
+    _api("uk_specified_missing", "UniversalKriging", dict(drift_terms=["specified"])),
+    _api("uk_specified_not_list", "UniversalKriging", dict(drift_terms=["specified"], specified_drift="$sx")),
+    _api("uk_specified_short", "UniversalKriging", dict(drift_terms=["specified"], specified_drift=["$sx_short"])),
+    _api("uk_functional", "UniversalKriging", dict(drift_terms=["functional"], functional_drift=["$f_xy", "$f_sin"], verbose=True)),
+    _api("uk_functional_missing", "UniversalKriging", dict(drift_terms=["functional"])),
+    _api("uk_functional_not_list", "UniversalKriging", dict(drift_terms=["functional"], functional_drift="$f_xy")),
+    _api("uk_bogus_term", "UniversalKriging", dict(drift_terms=["bogus"])),
+    _api("uk_all_five", "UniversalKriging", _ALL5),
+    _api("uk_pinv", "UniversalKriging", dict(exact_values=False, pseudo_inv=True)),
+    _api("uk_bad_pinv_type", "UniversalKriging", dict(pseudo_inv_type="x")),
+    _api("uk_bad_exact", "UniversalKriging", dict(exact_values=1)),
+    _api("ok3d_fit_verbose", "OrdinaryKriging3D", dict(variogram_model="gaussian", verbose=True)),
+    _api("ok3d_aniso_verbose", "OrdinaryKriging3D", dict(anisotropy_scaling_y=2.0, anisotropy_scaling_z=0.5, anisotropy_angle_x=10.0,
+                                                         anisotropy_angle_y=20.0, anisotropy_angle_z=30.0, verbose=True)),
+    _api("ok3d_list", "OrdinaryKriging3D", dict(variogram_model="gaussian", variogram_parameters=[2.0, 40.0, 0.1])),
+    _api("ok3d_weight", "OrdinaryKriging3D", dict(nlags=3, weight=True)),
+    _api("ok3d_pinvh", "OrdinaryKriging3D", dict(exact_values=False, pseudo_inv=True, pseudo_inv_type="pinvh")),
+    _api("ok3d_bad_pinv_type", "OrdinaryKriging3D", dict(pseudo_inv_type="q")),
+    _api("ok3d_bad_exact", "OrdinaryKriging3D", dict(exact_values=None)),
+    _api("uk3d_rl_verbose", "UniversalKriging3D", dict(drift_terms=["regional_linear"], verbose=True)),
+    _api("uk3d_specified", "UniversalKriging3D", dict(drift_terms=["specified"], specified_drift=["$sx", "$szc"])),
+    _api("uk3d_specified_missing", "UniversalKriging3D", dict(drift_terms=["specified"])),
+    _api("uk3d_specified_not_list", "UniversalKriging3D", dict(drift_terms=["specified"], specified_drift="$sx")),
+    _api("uk3d_specified_short", "UniversalKriging3D", dict(drift_terms=["specified"], specified_drift=["$sx_short"])),
+    _api("uk3d_functional", "UniversalKriging3D", dict(drift_terms=["functional"], functional_drift=["$f_xyz"], verbose=True)),
+    _api("uk3d_functional_missing", "UniversalKriging3D", dict(drift_terms=["functional"])),
+    _api("uk3d_functional_not_list", "UniversalKriging3D", dict(drift_terms=["functional"], functional_drift="$f_xyz")),
+    _api("uk3d_bogus_term", "UniversalKriging3D", dict(drift_terms=["zzz"])),
+    _api("uk3d_all", "UniversalKriging3D", dict(variogram_model="gaussian", anisotropy_scaling_y=2.0, anisotropy_angle_z=30.0,
+                                                 drift_terms=["regional_linear", "specified", "functional"], specified_drift=["$sx"],
+                                                 functional_drift=["$f_xyz"], verbose=True)),
+]
+# update_variogram_model on a verbose object (ok.py:379-553, uk.py:630-790, ok3d.py:354-520, uk3d.py)
+for _cls, _base, _an in (("OrdinaryKriging", _UKW, dict(anisotropy_scaling=2.0, anisotropy_angle=10.0)),
+                         ("UniversalKriging", dict(_UKW, drift_terms=["regional_linear"]), dict(anisotropy_scaling=2.0, anisotropy_angle=10.0)),
+                         ("OrdinaryKriging3D", _UKW, dict(anisotropy_scaling_y=2.0, anisotropy_angle_z=10.0)),
+                         ("UniversalKriging3D", dict(_UKW, drift_terms=["regional_linear"]), dict(anisotropy_scaling_y=2.0, anisotropy_angle_z=10.0))):
+    _s = {"OrdinaryKriging": "ok", "UniversalKriging": "uk", "OrdinaryKriging3D": "ok3d", "UniversalKriging3D": "uk3d"}[_cls]
+    for _tag, _a, _k in (("to_spherical_fit", ("spherical",), {}), ("to_gaussian_list", ("gaussian", [2.0, 30.0, 0.1]), {}),
+                         ("new_anisotropy", ("linear",), _an), ("bad_model", ("nomodel",), {}), ("custom_missing", ("custom",), {}),
+                         ("to_power_dict", ("power", {"scale": 1.0, "exponent": 1.1, "nugget": 0.0}), dict(nlags=4, weight=True))):
+        API_CASES.append(_api("%s_update_%s" % (_s, _tag), _cls, dict(_base, verbose=True), ("update_variogram_model", _a, _k)))
+    API_CASES.append(_api("%s_get_statistics" % _s, _cls, _base, ("get_statistics", (), {})))
+    API_CASES.append(_api("%s_print_statistics" % _s, _cls, _base, ("print_statistics", (), {})))
+# execute(): argument validation that precedes the backend dispatch (ok.py:834-874, uk.py:1169-1274, ok3d.py:833-876,
+# uk3d.py:981-1098) — every case raises in the reference before any arithmetic
+_US = dict(_UKW, drift_terms=["specified"], specified_drift=["$sx"])
+for _s, _cls, _kw in (("ok", "OrdinaryKriging", _UKW), ("uk", "UniversalKriging", dict(_UKW, drift_terms=["regional_linear"]))):
+    for _tag, _a, _k in (("bad_style", ("bogus", "$gx", "$gy"), {}), ("masked_no_mask", ("masked", "$gx", "$gy"), {}),
+                         ("masked_bad_shape", ("masked", "$gx", "$gy"), dict(mask="$mask2_rows3")),
+                         ("masked_1d", ("masked", "$gx", "$gy"), dict(mask="$mask2_1d")),
+                         ("points_mismatch", ("points", "$gx", "$gy"), {})):
+        API_CASES.append(_api("%s_execute_%s" % (_s, _tag), _cls, _kw, ("execute", _a, _k)))
+API_CASES += [
+    _api("ok_execute_k1", "OrdinaryKriging", _UKW, ("execute", ("grid", "$gx", "$gy"), dict(n_closest_points=1))),
+    _api("ok_execute_k0", "OrdinaryKriging", _UKW, ("execute", ("grid", "$gx", "$gy"), dict(n_closest_points=0))),
+    _api("uk_execute_spec_missing", "UniversalKriging", _US, ("execute", ("grid", "$gx", "$gy"), {})),
+    _api("uk_execute_spec_not_list", "UniversalKriging", _US, ("execute", ("grid", "$gx", "$gy"), dict(specified_drift_arrays="$z57"))),
+    _api("uk_execute_spec_bad_shape", "UniversalKriging", _US, ("execute", ("grid", "$gx", "$gy"), dict(specified_drift_arrays=["$z47"]))),
+    _api("uk_execute_spec_1d_on_grid", "UniversalKriging", _US, ("execute", ("grid", "$gx", "$gy"), dict(specified_drift_arrays=["$z7"]))),
+    _api("uk_execute_spec_points_len", "UniversalKriging", _US, ("execute", ("points", "$gx5", "$gy"), dict(specified_drift_arrays=["$z4"]))),
+    _api("uk_execute_spec_points_2d", "UniversalKriging", _US, ("execute", ("points", "$gx5", "$gy"), dict(specified_drift_arrays=["$z51"]))),
+    _api("uk_execute_spec_count", "UniversalKriging", _US, ("execute", ("grid", "$gx", "$gy"), dict(specified_drift_arrays=["$z57", "$z57"]))),
+]
+_U3S = dict(_UKW, drift_terms=["specified"], specified_drift=["$sx"])
+for _s, _cls, _kw in (("ok3d", "OrdinaryKriging3D", _UKW), ("uk3d", "UniversalKriging3D", dict(_UKW, drift_terms=["regional_linear"]))):
+    for _tag, _a, _k in (("bad_style", ("bogus", "$gx", "$gy", "$gz"), {}), ("masked_no_mask", ("masked", "$gx", "$gy", "$gz"), {}),
+                         ("masked_bad_shape", ("masked", "$gx", "$gy", "$gz"), dict(mask="$mask3_2")),
+                         ("masked_2d", ("masked", "$gx", "$gy", "$gz"), dict(mask="$mask3_2d")),
+                         ("points_mismatch", ("points", "$gx3", "$gy4", "$gz"), {})):
+        API_CASES.append(_api("%s_execute_%s" % (_s, _tag), _cls, _kw, ("execute", _a, _k)))
+API_CASES += [
+    _api("uk3d_execute_spec_missing", "UniversalKriging3D", _U3S, ("execute", ("grid", "$gx", "$gy", "$gz"), {})),
+    _api("uk3d_execute_spec_not_list", "UniversalKriging3D", _U3S, ("execute", ("grid", "$gx", "$gy", "$gz"), dict(specified_drift_arrays="$z357"))),
+    _api("uk3d_execute_spec_bad_shape", "UniversalKriging3D", _U3S, ("execute", ("grid", "$gx", "$gy", "$gz"), dict(specified_drift_arrays=["$z57"]))),
+    _api("uk3d_execute_spec_points_len", "UniversalKriging3D", _U3S, ("execute", ("points", "$gx3", "$gy3", "$gz"), dict(specified_drift_arrays=["$z4"]))),
+    _api("uk3d_execute_spec_count", "UniversalKriging3D", _U3S, ("execute", ("grid", "$gx", "$gy", "$gz"), dict(specified_drift_arrays=["$z357", "$z357"]))),
+]
+
+API_STAT_ATTRS = ("delta", "sigma", "epsilon", "Q1", "Q2", "cR")
+
+
+def _api_resolve(v, named):
+    if isinstance(v, str) and v.startswith("$"):
+        return named[v[1:]]
+    if isinstance(v, list):
+        return [_api_resolve(q, named) for q in v]
+    if isinstance(v, tuple):
+        return tuple(_api_resolve(q, named) for q in v)
+    if isinstance(v, dict):
+        return {k: _api_resolve(q, named) for k, q in v.items()}
+    return v
+
+
+def api_run(module_ns, case, named, backend):
+    """Run one API case against `module_ns` (the imported reference or pykrige_b200). Returns a record:
+    kind 'ok' | 'exc', exception type and message, captured stdout, warning categories, and the public attributes of
+    the object (numeric ones as float arrays, strings/bools/None as they are; callables by __name__)."""
+    import contextlib
+    import io
+    import warnings
+    is3 = case["cls"].endswith("3D")
+    args = (named["x"], named["y"], named["zc"], named["v"]) if is3 else (named["x"], named["y"], named["v"])
+    kw = _api_resolve(case["kw"], named)
+    rec = dict(kind="ok", exc="", msg="", stdout="", warnings=[], attrs={}, ret=None)
+    buf = io.StringIO()
+    obj = None
+    try:
+        with contextlib.redirect_stdout(buf), warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            obj = getattr(module_ns, case["cls"])(*args, **kw)
+            if case["then"] is not None:
+                meth, a, k = case["then"]
+                k = dict(_api_resolve(k, named))
+                if meth == "execute":
+                    k["backend"] = backend
+                ret = getattr(obj, meth)(*_api_resolve(a, named), **k)
+                if meth == "get_statistics":
+                    rec["ret"] = np.asarray(ret, dtype=float)
+        rec["warnings"] = [x.category.__name__ for x in w]
+    except Exception as e:  # noqa: BLE001  (the exception IS the observation)
+        rec.update(kind="exc", exc=type(e).__name__, msg=str(e))
+    rec["stdout"] = buf.getvalue()
+    if obj is not None and rec["kind"] == "ok":
+        names = [k for k in vars(obj) if not k.startswith("_")]
+        names += [k for k in ("lags", "semivariance") + API_STAT_ATTRS if k not in names]
+        for k in names:
+            try:
+                val = getattr(obj, k)
+            except AttributeError:
+                continue
+            if k == "variogram_dict" or isinstance(val, dict):
+                continue
+            if callable(val):
+                rec["attrs"][k] = "callable:" + getattr(val, "__name__", "?")
+            elif val is None or isinstance(val, (str, bool)):
+                rec["attrs"][k] = val
+            elif isinstance(val, (list, tuple)) and any(callable(q) for q in val):
+                rec["attrs"][k] = "callables:" + ",".join(getattr(q, "__name__", "?") for q in val)
+            else:
+                try:
+                    rec["attrs"][k] = np.asarray(val, dtype=float)
+                except (TypeError, ValueError):
+                    pass
+    return rec

@@ -15,6 +15,9 @@ Writes
   tests/golden/ref_custom.npz : (z, sigmasq) of the reference for variogram_model='custom' callables.
   tests/golden/ref_vgfit.npz : gamma(d) of the six built-in variogram functions on fixed distance vectors (bit patterns)
       and the parameters the reference's constructor fits (variogram_parameters=None) on seeded random scatter.
+  tests/golden/ref_api.npz : what the reference's four classes do BEFORE any kriging arithmetic for tests/cases.py
+      API_CASES: public attributes, stdout, warnings, exception types and messages of the constructors,
+      update_variogram_model and the argument validation of execute().
   tests/golden/ref_ctor.npz : lags/semivariance of core._initialize_variogram_model and delta/sigma/epsilon
       of core._find_statistics for the constructor-side cases of tests/cases.py.
 The O(N^4) constructor statistics of OK3D/UK/UK3D are patched out; nothing else of the
@@ -185,8 +188,41 @@ def ref_vgfit():
     np.savez_compressed(os.path.join(HERE, "ref_vgfit.npz"), **out)
 
 
+def ref_api():
+    """Host-mirror API cases (tests/cases.py API_CASES) through the UNPATCHED reference -> ref_api.npz."""
+    import json
+    saved = [(mod, mod._find_statistics) for mod in (pykrige.ok3d, pykrige.uk, pykrige.uk3d)]
+    from pykrige import core as rcore
+    for mod, _ in saved:                       # N = 40: the real cross-validation loop is affordable
+        mod._find_statistics = rcore._find_statistics
+    named = cases.api_inputs()
+    meta, arrays = {}, {}
+    try:
+        for case in cases.API_CASES:
+            rec = cases.api_run(pykrige, case, named, backend="vectorized")
+            attrs = {}
+            for k, v in rec["attrs"].items():
+                if isinstance(v, np.ndarray):
+                    arrays[case["name"] + "/" + k] = v
+                    attrs[k] = "@array"
+                else:
+                    attrs[k] = v
+            if rec["ret"] is not None:
+                arrays[case["name"] + "/@ret"] = rec["ret"]
+            meta[case["name"]] = dict(kind=rec["kind"], exc=rec["exc"], msg=rec["msg"], stdout=rec["stdout"],
+                                      warnings=rec["warnings"], attrs=attrs)
+            print("%-40s %s %s" % (case["name"], rec["kind"], rec["exc"]))
+    finally:
+        for mod, f in saved:
+            mod._find_statistics = f
+    arrays["@meta"] = np.array(json.dumps(meta, sort_keys=True))
+    np.savez_compressed(os.path.join(HERE, "ref_api.npz"), **arrays)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios", "custom", "vgfit"]
+    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios", "custom", "vgfit", "api"]
+    if "api" in which:
+        ref_api()
     if "vgfit" in which:
         ref_vgfit()
     if "goldens" in which:
