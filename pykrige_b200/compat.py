@@ -48,7 +48,7 @@ krige_methods_kws = {
 
 def validate_method(method):
     if method not in krige_methods:
-        raise ValueError("Kriging method must be one of {}".format(list(krige_methods)))
+        raise ValueError("Kriging method must be one of {}".format(krige_methods.keys()))
 
 
 class Krige(RegressorMixin, BaseEstimator):
