@@ -124,6 +124,12 @@ class EmulatedHandle:
         if p["pinv"] and dtype != 0:
             raise NotImplementedError("pseudo_inv=True runs in float64 only")
         if p["geo"]:
+            self.ready = True
+            try:
+                import torch
+                self.blob_t = torch.ones(1, dtype=torch.float64)
+            except ImportError:
+                self.blob_t = None
             return
         P = self._adjust(p["X"])
         dcols = [P[:, c] for c in range(dim)] if p["n_rl"] else []
@@ -136,6 +142,34 @@ class EmulatedHandle:
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 scipy.linalg.inv(p["a"])
+        try:
+            import torch
+            self.blob_t = torch.from_numpy(p["a"].ravel().copy())
+        except ImportError:
+            self.blob_t = None
+        self.ready = True
+
+    # ---- multi-GPU factor blob: here simply the dense kriging matrix (kb200_describe_problem / kb200_blob_commit) ----
+    def describe_problem(self, dim, dtype, x, y, z, values, center, aniso, model, vparams, exact_values, eps,
+                         n_rl=0, drift_data=None):
+        """No 'device work': records the description and allocates the blob a broadcast will fill."""
+        import torch
+        self.calls.append("describe_problem")
+        self._describe(False, dim, x, y, z, values, center, aniso, model, vparams, exact_values, eps, n_rl, drift_data)
+        p = self.problem
+        nt = p["X"].shape[0] + (dim if p["n_rl"] else 0) + len(p["hd"]) + 1
+        self.blob_t = torch.zeros(1 if p["geo"] else nt * nt, dtype=torch.float64)
+        self.ready = False
+
+    def blob_commit(self):
+        self.calls.append("blob_commit")
+        p = self.problem
+        if not p["geo"]:
+            p["P"] = self._adjust(p["X"])
+            nt = int(round(self.blob_t.numel() ** 0.5))
+            p["a"] = self.blob_t.numpy().reshape(nt, nt).copy()
+            assert np.any(p["a"] != 0.0), "blob_commit before the broadcast arrived"
+        self.ready = True
 
     def set_problem_knn(self, dim, x, y, z, values, center, aniso, model, vparams, exact_values, eps):
         self.calls.append("set_problem_knn")
@@ -161,6 +195,7 @@ class EmulatedHandle:
     def _krige(self, Q_orig, drift_pts):
         p = self.problem
         assert p is not None and not p["knn"], "describe the global problem first"
+        assert getattr(self, "ready", False), "execute before kb200_set_problem / kb200_blob_commit"
         Q_orig = np.asarray(Q_orig, dtype=np.float64)
         m = Q_orig.shape[0]
         if m == 0:

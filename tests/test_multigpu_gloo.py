@@ -176,3 +176,112 @@ def test_two_rank_sharding_matches_single(tmp_path):
     assert "describe" in c1 and "commit" in c1 and "set_problem" not in c1
     assert c1.index("devdrift") < c1.index("describe") < c1.index("commit")
     assert int(parts[0]["raised"]) == 1 and int(parts[1]["raised"]) == 1
+
+
+# ---- second worker: the full-surface C-ABI emulator (tests/abi_emulator.py) instead of the minimal stub, so that the
+#      sharded path is exercised for universal kriging (device-evaluated and host-supplied drift columns: the drift_at
+#      callback receives the block's position in the caller's arrays), 3-D, the moving window and a custom variogram ----
+def _emulated_jobs():
+    import cases
+    rng = np.random.default_rng(17)
+    xyz, val = cases.synth_data(61, 90, 2)
+    x3, v3 = cases.synth_data(62, 70, 3)
+    gx, gy, gz = np.linspace(0, 1000, 11), np.linspace(0, 1000, 9), np.linspace(0, 250, 4)
+    mask = rng.uniform(size=(gy.size, gx.size)) < 0.35
+    mask3 = rng.uniform(size=(gz.size, gy.size, gx.size)) < 0.35
+    px, py, pz = rng.uniform(0, 1000, 53), rng.uniform(0, 1000, 53), rng.uniform(0, 250, 53)
+    dem = rng.uniform(0, 5, (8, 7))
+    demx, demy = np.linspace(-10, 1010, 7), np.linspace(-10, 1010, 8)
+    wells = np.array([[100.0, 200.0, 1.0], [700.0, 650.0, -2.0]])
+    vp = dict(variogram_model="exponential", variogram_parameters=[1.0, 300.0, 0.05])
+    uk_kw = dict(vp, drift_terms=["regional_linear", "point_log", "external_Z", "specified", "functional"],
+                 point_drift=wells, external_drift=dem, external_drift_x=demx, external_drift_y=demy,
+                 specified_drift=[1.0e-5 * xyz[:, 0] * xyz[:, 1]], functional_drift=[lambda x, y: np.sin(x / 300.0) * y / 1000.0],
+                 anisotropy_scaling=1.4, anisotropy_angle=25.0)
+    spec_grid = 1.0e-5 * gx[None, :] * gy[:, None]
+    spec_pts = 1.0e-5 * px * py
+    jobs = [
+        ("uk_grid", "UniversalKriging", (xyz[:, 0], xyz[:, 1], val), uk_kw, ("grid", gx, gy), dict(specified_drift_arrays=[spec_grid])),
+        ("uk_masked", "UniversalKriging", (xyz[:, 0], xyz[:, 1], val), uk_kw, ("masked", gx, gy), dict(mask=mask, specified_drift_arrays=[spec_grid])),
+        ("uk_points", "UniversalKriging", (xyz[:, 0], xyz[:, 1], val), uk_kw, ("points", px, py), dict(specified_drift_arrays=[spec_pts])),
+        ("ok3d_masked", "OrdinaryKriging3D", (x3[:, 0], x3[:, 1], x3[:, 2], v3), vp, ("masked", gx, gy, gz), dict(mask=mask3)),
+        ("uk3d_points", "UniversalKriging3D", (x3[:, 0], x3[:, 1], x3[:, 2], v3),
+         dict(vp, drift_terms=["regional_linear", "functional"], functional_drift=[lambda x, y, z: x * z / 1.0e5]), ("points", px, py, pz), {}),
+        ("ok_knn_grid", "OrdinaryKriging", (xyz[:, 0], xyz[:, 1], val), vp, ("grid", gx, gy), dict(n_closest_points=6)),
+        ("ok_custom_points", "OrdinaryKriging", (xyz[:, 0], xyz[:, 1], val),
+         dict(variogram_model="custom", variogram_parameters=[0.05, 0.1], variogram_function=lambda m, d: m[0] * np.sqrt(d) + m[1]),
+         ("points", px, py), {}),
+    ]
+    return jobs
+
+
+def _sharded_execute(model, multigpu, dist, args, kw, device):
+    """What a caller of execute() does under torchrun: the class validates and plans, execute_sharded runs the block.
+    Uses the public execute() with `_run_cuda` re-routed to the sharded executor (gather=True)."""
+    def run_cuda(style, axes, mask, n_closest_points=None, drift_at=None, dtype="float64", n_gpus=None):
+        return multigpu.execute_sharded(model, style, axes, dist, mask=mask, n_closest_points=n_closest_points,
+                                        dtype=dtype, drift_at=drift_at, gather=True, device=device)
+    model._run_cuda = run_cuda
+    return model.execute(*args, backend="cuda", **kw)
+
+
+def _worker_emulated(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import pykrige_b200 as pk
+    from pykrige_b200 import multigpu, _cabi
+    from abi_emulator import EmulatedHandle
+
+    def no_device():
+        raise _cabi.KrigeB200Error("emulated box")
+
+    _cabi.Handle = EmulatedHandle
+    _cabi.aux_handle = no_device
+    multigpu.blob_as_tensor = lambda h, device: h.blob_t
+    cpu = torch.device("cpu")
+    out = {}
+    for name, cls, cargs, ckw, eargs, ekw in _emulated_jobs():
+        m = getattr(pk, cls)(*cargs, **ckw)
+        z, ss = _sharded_execute(m, multigpu, dist, eargs, ekw, cpu)
+        out[name + "_z"], out[name + "_ss"] = np.ma.getdata(z), np.ma.getdata(ss)
+        out[name + "_calls"] = np.array(",".join(m._kb_handle.calls))
+    np.savez(os.path.join(outdir, "e%d.npz" % rank), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_of_every_problem_kind(tmp_path, monkeypatch):
+    """2 gloo ranks vs one process, both through the C-ABI emulator: universal kriging with all five drift kinds
+    (grid / masked / points — the host drift callback must be evaluated at the block's own positions), 3-D masked,
+    UK3D points, the moving window (no broadcast) and a tabulated custom variogram (every rank tabulates itself)."""
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker_emulated, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pykrige_b200 as pk
+    from pykrige_b200 import _cabi
+    from abi_emulator import EmulatedHandle
+
+    def no_device():
+        raise _cabi.KrigeB200Error("emulated box")
+
+    monkeypatch.setattr(_cabi, "Handle", EmulatedHandle)
+    monkeypatch.setattr(_cabi, "aux_handle", no_device)
+    parts = [np.load(os.path.join(str(tmp_path), "e%d.npz" % r)) for r in range(world)]
+    for name, cls, cargs, ckw, eargs, ekw in _emulated_jobs():
+        m = getattr(pk, cls)(*cargs, **ckw)
+        z1, s1 = m.execute(*eargs, backend="cuda", **ekw)
+        z1, s1 = np.ma.getdata(z1), np.ma.getdata(s1)
+        for p in parts:                                      # gather=True: every rank holds the complete result
+            assert p[name + "_z"].shape == z1.shape
+            np.testing.assert_allclose(p[name + "_z"], z1, rtol=1e-9, atol=1e-9 * np.abs(z1).max(), err_msg=name)
+            np.testing.assert_allclose(p[name + "_ss"], s1, rtol=1e-8, atol=1e-9 * np.abs(s1).max(), err_msg=name)
+        c0, c1 = str(parts[0][name + "_calls"]), str(parts[1][name + "_calls"])
+        if "knn" in name:                                    # the moving window broadcasts nothing
+            assert "set_problem_knn" in c0 and "set_problem_knn" in c1 and "describe_problem" not in c1
+        else:                                                # rank 0 factors, rank 1 describes + commits the broadcast
+            assert "set_problem" in c0.split(",") and "describe_problem" not in c0
+            assert "describe_problem" in c1 and "blob_commit" in c1 and "set_problem" not in c1.split(",")
