@@ -266,18 +266,27 @@ class EmulatedHandle:
 
 
 def _bilinear(ax, ay, Zg, x, y):
-    """Plain bilinear interpolation on the raster Zg[ny, nx] with node coordinates ax, ay (either direction);
-    on a node it returns the node value, on a grid line the linear interpolation — the reference's special cases
-    (uk.py:580-628) are those limits."""
-    def locate(a, v):
-        flip = a[0] > a[-1]
-        aa = a[::-1] if flip else a
-        i = np.clip(np.searchsorted(aa, v, side="right") - 1, 0, aa.size - 2)
-        t = (v - aa[i]) / (aa[i + 1] - aa[i])
-        if flip:
-            return aa.size - 2 - i, 1.0 - t
-        return i, t
-    ix, tx = locate(np.asarray(ax, float), np.asarray(x, float))
-    iy, ty = locate(np.asarray(ay, float), np.asarray(y, float))
-    z00, z01, z10, z11 = Zg[iy, ix], Zg[iy, ix + 1], Zg[iy + 1, ix], Zg[iy + 1, ix + 1]
-    return (z00 * (1 - tx) * (1 - ty) + z01 * tx * (1 - ty) + z10 * (1 - tx) * ty + z11 * tx * ty)
+    """The raster sampler of uk.py:512-628 restated: along each axis the bracketing nodes are i1 = the LAST index whose
+    coordinate is <= the query and i2 = the FIRST index whose coordinate is >= it (for ascending axes the enclosing cell;
+    for descending or unsorted axes whatever that rule selects — the reference does not sort, and neither does the
+    device); on a node the node value, on a grid line the linear interpolation along the other axis, else the bilinear
+    form over the two bracketing nodes per axis."""
+    ax, ay, x, y = (np.asarray(a, dtype=np.float64) for a in (ax, ay, x, y))
+
+    def bracket(a, v):
+        le = a[None, :] <= v[:, None]
+        ge = a[None, :] >= v[:, None]
+        assert np.all(le.any(axis=1)) and np.all(ge.any(axis=1)), "the raster does not cover the query"
+        i1 = a.size - 1 - np.argmax(le[:, ::-1], axis=1)
+        i2 = np.argmax(ge, axis=1)
+        return i1, i2
+    x1, x2 = bracket(ax, x)
+    y1, y2 = bracket(ay, y)
+    wx1, wx2 = ax[x2] - x, x - ax[x1]
+    wy1, wy2 = ay[y2] - y, y - ay[y1]
+    dx, dy = ax[x2] - ax[x1], ay[y2] - ay[y1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        full = (Zg[y1, x1] * wx1 * wy1 + Zg[y1, x2] * wx2 * wy1 + Zg[y2, x1] * wx1 * wy2 + Zg[y2, x2] * wx2 * wy2) / (dx * dy)
+        on_row = (Zg[y1, x1] * wx1 + Zg[y1, x2] * wx2) / dx          # y sits on a grid line
+        on_col = (Zg[y1, x1] * wy1 + Zg[y2, x1] * wy2) / dy          # x sits on a grid line
+    return np.where(y1 == y2, np.where(x1 == x2, Zg[y1, x1], on_row), np.where(x1 == x2, on_col, full))
