@@ -682,3 +682,110 @@ def api_run(module_ns, case, named, backend):
                 except (TypeError, ValueError):
                     pass
     return rec
+
+
+# ---- randomised whole-execute() configurations (tests/golden/make_golden.py fuzz -> ref_fuzz.npz; replayed through the
+#      host wrappers on the C-ABI emulator by tests/test_host_execute_emulated.py): classes x styles x drift kinds x
+#      anisotropy x exact_values x moving window, masks and specified-drift arrays also in the transposed orientation the
+#      reference tolerates (ok.py:855-859, uk.py:1232-1240), rasters with a descending axis, exact hits ----
+N_FUZZ = 240
+_FUZZ_MODELS = ("linear", "power", "gaussian", "spherical", "exponential")
+
+
+def _fuzz_f2(x, y):
+    return np.sin(x / 40.0) * y / 50.0
+
+
+def _fuzz_f3(x, y, z):
+    return np.sin(x / 40.0) * y / 50.0 + z / 30.0
+
+
+def fuzz_config(t):
+    """Deterministic configuration number t, or None when the draw is over-determined (more drift terms than data)."""
+    rng = np.random.default_rng(7_000_000 + t)
+    dim = 3 if rng.uniform() < 0.4 else 2
+    uk = rng.uniform() < 0.5
+    n = int(rng.integers(8, 60))
+    X = rng.uniform(0, 100, (n, dim))
+    if dim == 3:
+        X[:, 2] *= 0.3
+    v = 5 + np.sin(X[:, 0] / 20) + 0.02 * X[:, 1] + rng.normal(size=n) * 0.3
+    m = _FUZZ_MODELS[rng.integers(len(_FUZZ_MODELS))]
+    if m == "linear":
+        vp = [float(rng.uniform(0.001, 0.01)), float(rng.uniform(0, 0.2))]
+    elif m == "power":
+        vp = [float(rng.uniform(0.001, 0.01)), float(rng.uniform(0.5, 1.6)), float(rng.uniform(0, 0.2))]
+    else:
+        vp = [float(rng.uniform(0.8, 2.5)), float(rng.uniform(20.0, 90.0)), float(rng.uniform(0.01, 0.3))]
+    kw = dict(variogram_model=m, variogram_parameters=vp)
+    if rng.uniform() < 0.5:
+        if dim == 2:
+            kw.update(anisotropy_scaling=float(rng.uniform(0.3, 3)), anisotropy_angle=float(rng.uniform(-90, 90)))
+        else:
+            kw.update(anisotropy_scaling_y=float(rng.uniform(0.3, 3)), anisotropy_scaling_z=float(rng.uniform(0.3, 3)),
+                      anisotropy_angle_x=float(rng.uniform(-90, 90)), anisotropy_angle_y=float(rng.uniform(-90, 90)),
+                      anisotropy_angle_z=float(rng.uniform(-90, 90)))
+    if rng.uniform() < 0.25:
+        kw["exact_values"] = False
+    ekw = {}
+    nx, ny, nz = int(rng.integers(1, 7)), int(rng.integers(1, 7)), int(rng.integers(1, 5))
+    gx, gy, gz = np.sort(rng.uniform(0, 100, nx)), np.sort(rng.uniform(0, 100, ny)), np.sort(rng.uniform(0, 30, nz))
+    style = ("grid", "masked", "points")[rng.integers(3)]
+    if style == "points":
+        npnt = int(rng.integers(1, 12))
+        gx, gy, gz = rng.uniform(0, 100, npnt), rng.uniform(0, 100, npnt), rng.uniform(0, 30, npnt)
+        if npnt > 1 and rng.uniform() < 0.5:          # an exact hit on a data point (not as the only point: sigma^2 = 0)
+            gx[0], gy[0] = X[0, 0], X[0, 1]
+            if dim == 3:
+                gz[0] = X[0, 2]
+        nx = ny = nz = npnt
+    shape = (ny, nx) if dim == 2 else (nz, ny, nx)
+    distinct = len(set(shape)) == len(shape)
+    if style == "masked":
+        mask = rng.uniform(size=shape) < 0.4
+        if rng.uniform() < 0.3 and distinct:
+            mask = mask.T if dim == 2 else mask.swapaxes(0, 2)
+        ekw["mask"] = mask
+    cls = ("Universal" if uk else "Ordinary") + "Kriging" + ("3D" if dim == 3 else "")
+    terms = []
+    if uk:
+        if rng.uniform() < 0.6:
+            terms.append("regional_linear")
+        if dim == 2 and rng.uniform() < 0.4:
+            terms.append("point_log")
+            kw["point_drift"] = np.column_stack([rng.uniform(0, 100, 2), rng.uniform(0, 100, 2), rng.uniform(-2, 2, 2)])
+        if dim == 2 and rng.uniform() < 0.4:
+            terms.append("external_Z")
+            ex = np.linspace(-10, 110, int(rng.integers(3, 9)))
+            ey = np.linspace(-10, 110, int(rng.integers(3, 9)))
+            if rng.uniform() < 0.3:
+                ey = ey[::-1].copy()
+            kw.update(external_drift=rng.uniform(0, 5, (ey.size, ex.size)), external_drift_x=ex, external_drift_y=ey)
+        if rng.uniform() < 0.4:
+            terms.append("specified")
+            kw["specified_drift"] = [1e-3 * X[:, 0] * X[:, 1]]
+            if style == "points":
+                ekw["specified_drift_arrays"] = [1e-3 * gx * gy]
+            else:
+                g = 1e-3 * gx[None, :] * gy[:, None]
+                if dim == 3:
+                    g = np.broadcast_to(g, (nz, ny, nx)).copy()
+                if rng.uniform() < 0.3 and distinct:
+                    g = g.T if dim == 2 else g.swapaxes(0, 2)
+                ekw["specified_drift_arrays"] = [g]
+        if rng.uniform() < 0.4:
+            terms.append("functional")
+            kw["functional_drift"] = [_fuzz_f2] if dim == 2 else [_fuzz_f3]
+        kw["drift_terms"] = terms
+        n_terms = ((dim if "regional_linear" in terms else 0) + (2 if "point_log" in terms else 0)
+                   + sum(q in terms for q in ("external_Z", "specified", "functional")))
+        if n < n_terms + 3:
+            return None
+    knn = None
+    if not uk and rng.uniform() < 0.3:
+        knn = int(rng.integers(2, min(n, 9)))
+        ekw["n_closest_points"] = knn
+    data = (X[:, 0], X[:, 1], v) if dim == 2 else (X[:, 0], X[:, 1], X[:, 2], v)
+    pts = (gx, gy) if dim == 2 else (gx, gy, gz)
+    return dict(t=t, cls=cls, data=data, kw=kw, style=style, pts=pts, ekw=ekw, knn=knn,
+                text="%s n=%d %s %s %s terms=%s knn=%s" % (cls, n, m, style, shape, terms, knn))

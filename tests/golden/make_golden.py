@@ -18,6 +18,8 @@ Writes
   tests/golden/ref_api.npz : what the reference's four classes do BEFORE any kriging arithmetic for tests/cases.py
       API_CASES: public attributes, stdout, warnings, exception types and messages of the constructors,
       update_variogram_model and the argument validation of execute().
+  tests/golden/ref_fuzz.npz : (z, sigmasq) or the exception type of the reference for the randomised whole-execute()
+      configurations of tests/cases.py fuzz_config (backend='vectorized'; 'loop' for the moving window).
   tests/golden/ref_ctor.npz : lags/semivariance of core._initialize_variogram_model and delta/sigma/epsilon
       of core._find_statistics for the constructor-side cases of tests/cases.py.
 The O(N^4) constructor statistics of OK3D/UK/UK3D are patched out; nothing else of the
@@ -219,8 +221,45 @@ def ref_api():
     np.savez_compressed(os.path.join(HERE, "ref_api.npz"), **arrays)
 
 
+def ref_fuzz():
+    import warnings
+    out = {}
+    n_ok = n_exc = 0
+    for t in range(cases.N_FUZZ):
+        c = cases.fuzz_config(t)
+        if c is None:
+            continue
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                model = getattr(pykrige, c["cls"])(*c["data"], **c["kw"])
+                z, ss = model.execute(c["style"], *c["pts"], backend="loop" if c["knn"] else "vectorized", **c["ekw"])
+            out["%d/z" % t] = np.ma.getdata(z)
+            out["%d/ss" % t] = np.ma.getdata(ss)
+            out["%d/mask" % t] = np.ma.getmaskarray(z) if np.ma.isMaskedArray(z) else np.zeros(0, bool)
+            # 2-norm condition number of the reference's own kriging matrix (ok.py:626-648 / uk.py:861-920): how many
+            # digits the reference's scipy.linalg.inv itself can be trusted to
+            try:
+                a = model._get_kriging_matrix(len(c["data"][0]))
+            except TypeError:                      # uk.py / uk3d.py: _get_kriging_matrix(n, n_withdrifts)
+                n_rows = len(c["data"][0])
+                drift = c["kw"].get("drift_terms", [])
+                nd = ((2 if c["cls"].endswith("Kriging") else 3) * ("regional_linear" in drift) + 2 * ("point_log" in drift)
+                      + sum(q in drift for q in ("external_Z", "specified", "functional")))
+                a = model._get_kriging_matrix(n_rows, n_rows + nd)
+            out["%d/cond" % t] = np.array(np.linalg.cond(a))
+            n_ok += 1
+        except Exception as e:  # noqa: BLE001
+            out["%d/exc" % t] = np.array(type(e).__name__)
+            n_exc += 1
+    print("fuzz: %d results, %d exceptions" % (n_ok, n_exc))
+    np.savez_compressed(os.path.join(HERE, "ref_fuzz.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios", "custom", "vgfit", "api"]
+    which = sys.argv[1:] or ["goldens", "cases", "ctor", "pinv", "scenarios", "custom", "vgfit", "api", "fuzz"]
+    if "fuzz" in which:
+        ref_fuzz()
     if "api" in which:
         ref_api()
     if "vgfit" in which:

@@ -166,3 +166,38 @@ def test_sklearn_wrapper_through_the_host_wrappers(pk):
     uni.fit(xyz, val)
     zo, _ = ko.krige(xyz, val, "exponential", ko.stored_parameters("exponential", [1.0, 300.0, 0.05]), pts, regional_linear=True)
     assert_parity(uni.predict(pts), zo, R64, "Krige(universal).predict")
+
+
+@pytest.fixture(scope="module")
+def ref_fuzz():
+    import os
+    from conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "ref_fuzz.npz"))
+
+
+@pytest.mark.parametrize("t", range(cases.N_FUZZ))
+def test_randomised_configurations_through_the_host_wrappers(pk, t, ref_fuzz):
+    """tests/cases.py fuzz_config(t): classes x styles x drift kinds x anisotropy x exact_values x moving window, masks and
+    specified-drift arrays also transposed, rasters with a descending axis — against the imported reference
+    (tests/golden/ref_fuzz.npz)."""
+    import warnings
+    c = cases.fuzz_config(t)
+    if c is None:
+        pytest.skip("over-determined draw")
+    if "%d/exc" % t in ref_fuzz.files:
+        with pytest.raises(Exception) as ei:
+            getattr(pk, c["cls"])(*c["data"], **c["kw"]).execute(c["style"], *c["pts"], backend="cuda", **c["ekw"])
+        assert type(ei.value).__name__ == str(ref_fuzz["%d/exc" % t]), c["text"]
+        return
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        z, ss = getattr(pk, c["cls"])(*c["data"], **c["kw"]).execute(c["style"], *c["pts"], backend="cuda", **c["ekw"])
+    zr, sr, mr = ref_fuzz["%d/z" % t], ref_fuzz["%d/ss" % t], ref_fuzz["%d/mask" % t]
+    assert z.shape == zr.shape and ss.shape == sr.shape, c["text"]
+    if c["style"] == "masked":
+        assert np.array_equal(np.ma.getmaskarray(z), mr) and np.array_equal(np.ma.getmaskarray(ss), mr), c["text"]
+        keep = ~mr
+        z, ss, zr, sr = np.ma.getdata(z)[keep], np.ma.getdata(ss)[keep], zr[keep], sr[keep]
+    if zr.size:
+        assert_parity(np.ravel(z), np.ravel(zr), 1e-6, c["text"] + " z")
+        assert_parity(np.ravel(ss), np.ravel(sr), 1e-6, c["text"] + " ss")
