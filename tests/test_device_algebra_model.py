@@ -1,0 +1,141 @@
+"""CPU model of the algebra the CUDA global path runs, in numpy — a white-box pin of the formulation,
+not of the kernels: covariance form C = c0 11^T - Gamma with the covariance shift c0 chosen as csrc/api.cu does
+(sill for bounded models, gamma(bounding-box diagonal) doubled until the Cholesky succeeds for linear / power),
+Cholesky C = L L^T, W = L^-1, dual vectors U = C^-1 F, zeta = C^-1 Z on affinely rescaled drift columns (shift / scale
+as api.cu: describe), and per prediction point
+
+    q = ||W c||^2,  g = U^T c,  zc = zeta . c,  r = g - f,  mu = S^-1 r,  sigma^2 = c0 - q + r . mu,  z = zc - mu . phi.
+
+Checked against the outputs of the unmodified imported reference (inverse x RHS on the gamma-form matrix) for the
+randomised draws of tests/cases.py fuzz_config (tests/golden/ref_fuzz.npz): the two formulations must agree far inside
+the 1e-5 parity tolerance, for every class, drift kind and anisotropy — if they did not for some draw, the device could
+not either."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+import cases
+from conftest import GOLDEN
+from oracle import krige_oracle as ko
+
+
+def covariance_form_krige(P, values, model, m, Q, dcols, pcols, exact_values=True):
+    """P [n, dim], Q [npt, dim] ADJUSTED coordinates; dcols / pcols: drift columns at the data / prediction points
+    (without the unbiasedness column). Returns (z, sigma^2, attempts of the c0 search)."""
+    n = P.shape[0]
+    d = ko.cdist(P, P)
+    gam = ko.variogram(model, m, d)
+    np.fill_diagonal(gam, 0.0)                                  # ok.py:644: the nugget never sits on the diagonal
+    if model in ("linear", "power"):
+        lo, hi = P.min(axis=0), P.max(axis=0)
+        c0 = float(ko.variogram(model, m, np.sqrt(np.sum((hi - lo) ** 2))))
+        tries = 5
+    else:
+        c0, tries = float(m[0]) + float(m[2]), 1                # psill + nugget
+    L = None
+    for attempt in range(tries):
+        try:
+            L = np.linalg.cholesky(c0 - gam)
+            break
+        except np.linalg.LinAlgError:
+            c0 *= 2.0
+    if L is None:
+        pytest.skip("covariance form not positive definite: the device takes the general path (DESIGN.md 3b)")
+    # drift basis: columns shifted / scaled, then the constant (api.cu: describe; the span is unchanged)
+    F = np.ones((n, len(dcols) + 1))
+    Fq = np.ones((Q.shape[0], len(dcols) + 1))
+    for c, (dc, pc) in enumerate(zip(dcols, pcols)):
+        shift = 0.5 * (dc.max() + dc.min())
+        half = 0.5 * (dc.max() - dc.min())
+        scale = 1.0 / half if half > 0 else 1.0
+        F[:, c] = (dc - shift) * scale
+        Fq[:, c] = (pc - shift) * scale
+    W = scipy.linalg.solve_triangular(L, np.eye(n), lower=True)
+    U = W.T @ (W @ F)
+    zeta = W.T @ (W @ values)
+    S = F.T @ U
+    phi = F.T @ zeta
+    bd = ko.cdist(Q, P)
+    b = -ko.variogram(model, m, bd)
+    if exact_values:
+        b[np.abs(bd) <= ko.EPS] = 0.0
+    C = c0 + b                                                  # c_j = c0 1 + b_j[:n]
+    q = np.sum((C @ W.T) ** 2, axis=1)
+    r = C @ U - Fq
+    mu = np.linalg.solve(S, r.T).T
+    return C @ zeta - mu @ phi, c0 - q + np.sum(r * mu, axis=1), attempt + 1
+
+
+def _adjusted(c, X):
+    kw = c["kw"]
+    dim = X.shape[1]
+    data = np.column_stack(c["data"][:dim])
+    center = (data.max(axis=0) + data.min(axis=0)) / 2.0
+    if dim == 2:
+        return ko.adjust_for_anisotropy(X, center, [kw.get("anisotropy_scaling", 1.0)], [kw.get("anisotropy_angle", 0.0)])
+    return ko.adjust_for_anisotropy(X, center, [kw.get("anisotropy_scaling_y", 1.0), kw.get("anisotropy_scaling_z", 1.0)],
+                                    [kw.get("anisotropy_angle_x", 0.0), kw.get("anisotropy_angle_y", 0.0),
+                                     kw.get("anisotropy_angle_z", 0.0)])
+
+
+@pytest.fixture(scope="module")
+def ref_fuzz():
+    return np.load(os.path.join(GOLDEN, "ref_fuzz.npz"))
+
+
+GLOBAL_DRAWS = [t for t in range(cases.N_FUZZ) if (cases.fuzz_config(t) or {}).get("knn", 1) is None]
+
+
+@pytest.mark.parametrize("t", GLOBAL_DRAWS)
+def test_covariance_form_reproduces_the_reference(t, ref_fuzz):
+    c = cases.fuzz_config(t)
+    kw, dim = c["kw"], len(c["data"]) - 1
+    data = np.column_stack(c["data"][:dim])
+    values = np.asarray(c["data"][dim], dtype=float)
+    pts = [np.asarray(p, dtype=float) for p in c["pts"]]
+    Qo = np.column_stack(pts) if c["style"] == "points" else ko.grid_points(pts)
+    P, Q = _adjusted(c, data), _adjusted(c, Qo)
+    terms = kw.get("drift_terms", [])
+    dcols, pcols = [], []
+    if "regional_linear" in terms:
+        dcols += [P[:, k] for k in range(dim)]
+        pcols += [Q[:, k] for k in range(dim)]
+    if "point_log" in terms:                                    # wells live in the adjusted frame (uk.py:458-467)
+        wells = np.asarray(kw["point_drift"], dtype=float)
+        wa = _adjusted(c, wells[:, :2])
+        for (wx, wy), s in zip(wa, wells[:, 2]):
+            for X, out in ((P, dcols), (Q, pcols)):
+                with np.errstate(divide="ignore"):
+                    ld = np.log(np.sqrt((X[:, 0] - wx) ** 2 + (X[:, 1] - wy) ** 2))
+                ld[np.isinf(ld)] = -100.0
+                out.append(-s * ld)
+    if "external_Z" in terms:                                   # sampled at the ORIGINAL coordinates
+        from abi_emulator import _bilinear
+        ax, ay, Zg = kw["external_drift_x"], kw["external_drift_y"], kw["external_drift"]
+        dcols.append(_bilinear(ax, ay, Zg, data[:, 0], data[:, 1]))
+        pcols.append(_bilinear(ax, ay, Zg, Qo[:, 0], Qo[:, 1]))
+    if "specified" in terms:
+        dcols.append(1e-3 * data[:, 0] * data[:, 1])
+        pcols.append(1e-3 * Qo[:, 0] * Qo[:, 1])
+    if "functional" in terms:                                   # callables see the adjusted coordinates (uk.py:906-910)
+        f = kw["functional_drift"][0]
+        dcols.append(np.asarray(f(*[P[:, k] for k in range(dim)]), dtype=float))
+        pcols.append(np.asarray(f(*[Q[:, k] for k in range(dim)]), dtype=float))
+    model = kw["variogram_model"]
+    m = ko.stored_parameters(model, kw["variogram_parameters"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        z, ss, attempts = covariance_form_krige(P, values, model, m, Q, dcols, pcols, kw.get("exact_values", True))
+    zr, sr = np.ravel(ref_fuzz["%d/z" % t]), np.ravel(ref_fuzz["%d/ss" % t])
+    keep = np.ones(zr.size, bool)
+    if c["style"] == "masked":
+        keep = ~np.ravel(ref_fuzz["%d/mask" % t])
+    if not keep.any():
+        return
+    tol = 1e-8       # three orders inside the parity tolerance; the draws have cond(A) <= 1.3e5
+    np.testing.assert_allclose(z[keep], zr[keep], rtol=tol, atol=tol * np.abs(zr[keep]).max(), err_msg=c["text"])
+    np.testing.assert_allclose(ss[keep], sr[keep], rtol=tol, atol=tol * max(np.abs(sr[keep]).max(), 1e-300), err_msg=c["text"])
+    assert attempts <= 5
