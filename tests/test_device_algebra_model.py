@@ -139,3 +139,51 @@ def test_covariance_form_reproduces_the_reference(t, ref_fuzz):
     np.testing.assert_allclose(z[keep], zr[keep], rtol=tol, atol=tol * np.abs(zr[keep]).max(), err_msg=c["text"])
     np.testing.assert_allclose(ss[keep], sr[keep], rtol=tol, atol=tol * max(np.abs(sr[keep]).max(), 1e-300), err_msg=c["text"])
     assert attempts <= 5
+
+
+# ---- moving window: local covariance block C = c0 - gamma (c0 = sill, or gamma(2 d_k) for linear / power),
+#      augmented Cholesky with the rows [c ; 1 ; Z] -> y_c, y_1, y_Z and NO back substitution:
+#      mu = (y_1.y_c - 1) / (y_1.y_1),  z = y_c.y_Z - mu y_1.y_Z,  sigma^2 = c0 - (y_c.y_c - mu y_1.y_c) - mu
+def moving_window_model(P, values, model, m, Q, k, exact_values=True):
+    from scipy.spatial import cKDTree
+    dist, idx = cKDTree(P).query(Q, k=k, eps=0.0)
+    z = np.empty(Q.shape[0])
+    ss = np.empty(Q.shape[0])
+    for j in range(Q.shape[0]):
+        S = P[idx[j]]
+        gam = ko.variogram(model, m, ko.cdist(S, S))
+        np.fill_diagonal(gam, 0.0)
+        c0 = (float(ko.variogram(model, m, 2.0 * dist[j].max())) if model in ("linear", "power")
+              else float(m[0]) + float(m[2]))
+        L = np.linalg.cholesky(c0 - gam)
+        b = -ko.variogram(model, m, dist[j])
+        if exact_values:
+            b[np.abs(dist[j]) <= ko.EPS] = 0.0
+        y_c, y_1, y_z = (scipy.linalg.solve_triangular(L, v, lower=True) for v in (c0 + b, np.ones(k), values[idx[j]]))
+        mu = (y_1 @ y_c - 1.0) / (y_1 @ y_1)
+        z[j] = y_c @ y_z - mu * (y_1 @ y_z)
+        ss[j] = c0 - (y_c @ y_c - mu * (y_1 @ y_c)) - mu
+    return z, ss
+
+
+KNN_DRAWS = [t for t in range(cases.N_FUZZ) if (cases.fuzz_config(t) or {}).get("knn") is not None]
+
+
+@pytest.mark.parametrize("t", KNN_DRAWS)
+def test_moving_window_model_reproduces_the_reference(t, ref_fuzz):
+    c = cases.fuzz_config(t)
+    kw, dim = c["kw"], len(c["data"]) - 1
+    data = np.column_stack(c["data"][:dim])
+    values = np.asarray(c["data"][dim], dtype=float)
+    pts = [np.asarray(p, dtype=float) for p in c["pts"]]
+    Qo = np.column_stack(pts) if c["style"] == "points" else ko.grid_points(pts)
+    model = kw["variogram_model"]
+    m = ko.stored_parameters(model, kw["variogram_parameters"])
+    z, ss = moving_window_model(_adjusted(c, data), values, model, m, _adjusted(c, Qo), c["knn"], kw.get("exact_values", True))
+    zr, sr = np.ravel(ref_fuzz["%d/z" % t]), np.ravel(ref_fuzz["%d/ss" % t])
+    keep = ~np.ravel(ref_fuzz["%d/mask" % t]) if c["style"] == "masked" else np.ones(zr.size, bool)
+    if not keep.any():
+        return
+    tol = 1e-8
+    np.testing.assert_allclose(z[keep], zr[keep], rtol=tol, atol=tol * np.abs(zr[keep]).max(), err_msg=c["text"])
+    np.testing.assert_allclose(ss[keep], sr[keep], rtol=tol, atol=tol * max(np.abs(sr[keep]).max(), 1e-300), err_msg=c["text"])
