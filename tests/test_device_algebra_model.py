@@ -187,3 +187,62 @@ def test_moving_window_model_reproduces_the_reference(t, ref_fuzz):
     tol = 1e-8
     np.testing.assert_allclose(z[keep], zr[keep], rtol=tol, atol=tol * np.abs(zr[keep]).max(), err_msg=c["text"])
     np.testing.assert_allclose(ss[keep], sr[keep], rtol=tol, atol=tol * max(np.abs(sr[keep]).max(), 1e-300), err_msg=c["text"])
+
+
+# ---- dtype='float64x' / 'float64x5' / 'float64x4' (csrc/solve_i8.cu): error-free slicing of W rows and RHS columns into
+#      S signed base-128 digits (6 + 7 (S-1) bits), all digit products with d = s + t < S summed exactly in S int32
+#      accumulators, exact int64 recombination, one conversion to fp64 ------------------------------------------------
+def i8_slices(x, e, S):
+    """Balanced digits of round(x * 2^(6 + 7 (S-1) - e)): x = 2^e sum_s out[s] 2^(-6-7s) + O(2^(e-7S)), out[s] in [-64, 64]
+    (solve_i8.cu: i8_slice)."""
+    v = np.rint(np.ldexp(np.asarray(x, dtype=np.float64), 6 + 7 * (S - 1) - e)).astype(np.int64)
+    out = np.zeros((S,) + v.shape, dtype=np.int64)
+    for s in range(S - 1, 0, -1):
+        d = ((v + 64) & 127) - 64
+        out[s] = d
+        v = (v - d) >> 7
+    out[0] = v
+    return out
+
+
+def i8_matvec_rows(W, c, S):
+    """(W c)_r through the slice scheme: per-row exponents for W, one exponent for the column c."""
+    ew = np.floor(np.log2(np.max(np.abs(W), axis=1))).astype(int) + 1          # |row| * 2^-ew < 1
+    ec = int(np.floor(np.log2(np.max(np.abs(c))))) + 1
+    ws = np.stack([i8_slices(W[r], int(ew[r]), S) for r in range(W.shape[0])], axis=1)     # [S, rows, n]
+    cs = i8_slices(c, ec, S)                                                               # [S, n]
+    assert np.abs(ws).max() <= 64 and np.abs(cs).max() <= 64
+    V = np.zeros(W.shape[0], dtype=np.int64)
+    for d in range(S):
+        acc = np.zeros(W.shape[0], dtype=np.int64)
+        for s in range(d + 1):
+            acc += ws[s] @ cs[d - s]
+        assert np.abs(acc).max() < 2 ** 31, "int32 TMEM accumulator would overflow"
+        V = V * 128 + acc                                                                  # exact in int64
+    return np.ldexp(V.astype(np.float64), ew + ec - 12 - 7 * (S - 1))
+
+
+@pytest.mark.parametrize("S,bits,bound", [(6, 41, 1e-10), (5, 34, 1e-8), (4, 27, 1e-6)])
+def test_int8_slice_scheme_is_error_free_and_fp64_class(S, bits, bound):
+    rng = np.random.default_rng(99)
+    x = rng.normal(size=2000) * np.exp(rng.uniform(-20, 20, 2000))
+    e = int(np.floor(np.log2(np.abs(x).max()))) + 1
+    sl = i8_slices(x, e, S)
+    back = sum(np.ldexp(sl[s].astype(np.float64), e - 6 - 7 * s) for s in range(S))
+    assert np.array_equal(back, np.ldexp(np.rint(np.ldexp(x, bits - e)), e - bits))        # the digits carry exactly `bits` bits
+    # q = ||W c||^2 of a kriging problem (N = 600, exponential): W = chol(C)^-1, c = c0 + b for a few prediction points
+    xyz, val = cases.synth_data(5, 600, 2)
+    m = ko.stored_parameters("exponential", [1.0, 300.0, 0.05])
+    gam = ko.variogram("exponential", m, ko.cdist(xyz, xyz))
+    np.fill_diagonal(gam, 0.0)
+    c0 = m[0] + m[2]
+    W = scipy.linalg.solve_triangular(np.linalg.cholesky(c0 - gam), np.eye(600), lower=True)
+    worst = 0.0
+    for q in cases.synth_points(5, 6, 2, xyz, n_hits=1):
+        c = c0 - ko.variogram("exponential", m, np.sqrt(np.sum((xyz - q) ** 2, axis=1)))
+        exact = W @ c
+        got = i8_matvec_rows(W, c, S)
+        worst = max(worst, abs(np.sum(got ** 2) - np.sum(exact ** 2)) / np.sum(exact ** 2))
+    # relative error of q here: 1.8e-11 / 1.9e-9 / 1.9e-7; sigma^2 = c0 - q + ... loses another ~20x to cancellation (measured on the B200 at N=5000:
+    # 4e-10 / 1.3e-7 / 4e-6 on sigma^2 for S = 6 / 5 / 4)
+    assert worst < bound, worst
