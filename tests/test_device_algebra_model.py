@@ -246,3 +246,40 @@ def test_int8_slice_scheme_is_error_free_and_fp64_class(S, bits, bound):
     # relative error of q here: 1.8e-11 / 1.9e-9 / 1.9e-7; sigma^2 = c0 - q + ... loses another ~20x to cancellation (measured on the B200 at N=5000:
     # 4e-10 / 1.3e-7 / 4e-6 on sigma^2 for S = 6 / 5 / 4)
     assert worst < bound, worst
+
+
+# ---- dtype='float32' (csrc/solve_tf32.cu): 3xTF32 split W = Wh + Wl, c = ch + cl (each part representable in TF32:
+#      10 explicit mantissa bits, cvt.rna), W c ~= Wh ch + Wh cl + Wl ch accumulated in fp32 ---------------------------
+def tf32_round(x):
+    """cvt.rna.tf32.f32: round a float32 to 10 mantissa bits, ties away from zero."""
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x1000) & 0xFFFFE000).astype(np.uint32)
+    return u.view(np.float32)
+
+
+def tf32x3_matvec(W, c):
+    Wh = tf32_round(W.astype(np.float32))
+    Wl = tf32_round((W - Wh.astype(np.float64)).astype(np.float32))
+    cf = c.astype(np.float32)
+    ch = tf32_round(cf)
+    cl = tf32_round(cf - ch)
+    # products of TF32 operands are exact in fp32's 24 bits x 2 = the tensor core keeps them exact and accumulates in fp32
+    return (Wh @ ch + Wh @ cl + Wl @ ch).astype(np.float64), (Wh @ ch).astype(np.float64)
+
+
+def test_three_tf32_products_recover_fp32_accuracy():
+    xyz, val = cases.synth_data(5, 600, 2)
+    m = ko.stored_parameters("exponential", [1.0, 300.0, 0.05])
+    gam = ko.variogram("exponential", m, ko.cdist(xyz, xyz))
+    np.fill_diagonal(gam, 0.0)
+    c0 = m[0] + m[2]
+    W = scipy.linalg.solve_triangular(np.linalg.cholesky(c0 - gam), np.eye(600), lower=True)
+    err3 = err1 = 0.0
+    for q in cases.synth_points(5, 6, 2, xyz, n_hits=1):
+        c = c0 - ko.variogram("exponential", m, np.sqrt(np.sum((xyz - q) ** 2, axis=1)))
+        exact = np.sum((W @ c) ** 2)
+        y3, y1 = tf32x3_matvec(W, c)
+        err3 = max(err3, abs(np.sum(y3 ** 2) - exact) / exact)
+        err1 = max(err1, abs(np.sum(y1 ** 2) - exact) / exact)
+    assert err3 < 2e-6, err3            # fp32 class: inside the 1e-2 tolerance of the fp32 arm by four orders
+    assert err1 > 20 * err3             # a single TF32 product would not be (the reason for the split)
