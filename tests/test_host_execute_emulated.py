@@ -201,3 +201,18 @@ def test_randomised_configurations_through_the_host_wrappers(pk, t, ref_fuzz):
     if zr.size:
         assert_parity(np.ravel(z), np.ravel(zr), 1e-6, c["text"] + " z")
         assert_parity(np.ravel(ss), np.ravel(sr), 1e-6, c["text"] + " ss")
+
+
+def test_emulator_keeps_the_signatures_of_the_real_handle():
+    """The emulator stands in for _cabi.Handle: every method it offers exists on the real class with the same parameter
+    names in the same order (so a change of the C-ABI binding cannot silently leave the emulated tests behind)."""
+    import inspect
+    from pykrige_b200 import _cabi
+    for name, fn in inspect.getmembers(EmulatedHandle, predicate=inspect.isfunction):
+        if name.startswith("_"):
+            continue
+        real = getattr(_cabi.Handle, name, None)
+        assert real is not None, "Handle has no method %s" % name
+        mine = list(inspect.signature(fn).parameters)
+        theirs = list(inspect.signature(real).parameters)
+        assert [p.replace("stream", "cuda_stream") if name == "set_stream" else p for p in mine] == theirs, (name, mine, theirs)
