@@ -40,6 +40,10 @@ class UniversalKriging(Krige2DMixin, KrigeBase):
             specified_drift = []
         if functional_drift is None:
             functional_drift = []
+        # no drift term exists yet: the statistics the common body may compute (verbose=True) are those of the
+        # ordinary-kriging system, as in the reference, where they precede the drift initialisation (uk.py:380-394)
+        self.regional_linear_drift = self.external_Z_drift = self.point_log_drift = False
+        self.specified_drift = self.functional_drift = False
         self._init_common_2d(x, y, z, variogram_model, variogram_parameters, variogram_function, nlags, weight,
                              anisotropy_scaling, anisotropy_angle, verbose, enable_plotting, exact_values, pseudo_inv,
                              pseudo_inv_type, coordinates_type="euclidean", statistics="lazy")

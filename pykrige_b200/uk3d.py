@@ -28,6 +28,8 @@ class UniversalKriging3D(_Krige3DMixin, KrigeBase):
             specified_drift = []
         if functional_drift is None:
             functional_drift = []
+        # no drift term exists yet (see uk.py): constructor-time statistics describe the ordinary-kriging system
+        self.regional_linear_drift = self.specified_drift = self.functional_drift = False
         self._init_common_3d(x, y, z, val, variogram_model, variogram_parameters, variogram_function, nlags,
                              weight, anisotropy_scaling_y, anisotropy_scaling_z, anisotropy_angle_x,
                              anisotropy_angle_y, anisotropy_angle_z, verbose, enable_plotting, exact_values,

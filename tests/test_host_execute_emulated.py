@@ -216,3 +216,60 @@ def test_emulator_keeps_the_signatures_of_the_real_handle():
         mine = list(inspect.signature(fn).parameters)
         theirs = list(inspect.signature(real).parameters)
         assert [p.replace("stream", "cuda_stream") if name == "set_stream" else p for p in mine] == theirs, (name, mine, theirs)
+
+
+def test_verbose_constructors_with_a_device_present(monkeypatch, capsys):
+    """verbose=True makes the UK / 3-D constructors compute the cross-validation statistics where the reference does
+    (uk.py:380-394: BEFORE the drift terms are initialised). With a device present that goes through _ensure_problem,
+    which must then describe the ordinary-kriging system — not trip over drift attributes that do not exist yet
+    (seen on the B200 box: AttributeError 'point_log_drift')."""
+    import pykrige_b200 as pk
+    from pykrige_b200 import _cabi
+    monkeypatch.setattr(_cabi, "Handle", EmulatedHandle)
+    monkeypatch.setattr(_cabi, "aux_handle", lambda: EmulatedHandle())      # device_available() -> True
+    named = cases.api_inputs()
+    x, y, zc, v = named["x"], named["y"], named["zc"], named["v"]
+    uk = pk.UniversalKriging(x, y, v, variogram_model="linear", variogram_parameters=[0.01, 0.1], verbose=True,
+                             drift_terms=["regional_linear", "point_log", "external_Z", "specified", "functional"],
+                             point_drift=named["wells"], external_drift=named["dem"], external_drift_x=named["demx"],
+                             external_drift_y=named["demy"], specified_drift=[named["sx"] * named["sy"]], functional_drift=[named["f_sin"]])
+    out = capsys.readouterr().out
+    assert out.index("Calculating statistics") < out.index("Q1 =") < out.index("Initializing drift terms...")
+    assert uk.point_log_drift and uk.external_Z_drift and uk.specified_drift and uk.functional_drift
+    assert "set_problem" in uk._kb_handle.calls and uk._kb_handle.problem["n_rl"] == 0 and not uk._kb_handle.problem["hd"]
+    z, ss = uk.execute("points", named["gx5"], named["gy"], backend="cuda", specified_drift_arrays=[named["z5"]])
+    assert uk._kb_handle.problem["n_rl"] == 2 and len(uk._kb_handle.problem["hd"]) == 5      # described again, with the drift
+    u3 = pk.UniversalKriging3D(x, y, zc, v, variogram_model="linear", variogram_parameters=[0.01, 0.1], verbose=True,
+                               drift_terms=["regional_linear", "specified", "functional"], specified_drift=[named["sx"] * named["sy"]],
+                               functional_drift=[named["f_xyz"]])
+    assert u3.specified_drift and u3.functional_drift and u3.Q1 is not None
+    u3.update_variogram_model("gaussian", [2.0, 30.0, 0.1])
+    k3 = pk.OrdinaryKriging3D(x, y, zc, v, variogram_model="linear", variogram_parameters=[0.01, 0.1], verbose=True)
+    assert k3.Q1 is not None
+
+
+@pytest.mark.parametrize("case", cases.API_CASES, ids=[c["name"] for c in cases.API_CASES])
+def test_host_api_cases_with_a_device_present(case, monkeypatch):
+    """The API cases of tests/test_host.py once more with a (emulated) device visible to the constructors: every place
+    that may touch the device before the object is complete (constructor-time statistics under verbose=True,
+    update_variogram_model) must behave as on a CPU-only box — same outcome, same exception, same stdout apart from the
+    last digits of the statistics."""
+    import json
+    import os
+    from conftest import GOLDEN
+    import pykrige_b200 as pk
+    from pykrige_b200 import _cabi
+    monkeypatch.setattr(_cabi, "Handle", EmulatedHandle)
+    monkeypatch.setattr(_cabi, "aux_handle", lambda: EmulatedHandle())
+    d = np.load(os.path.join(GOLDEN, "ref_api.npz"))
+    want = json.loads(str(d["@meta"]))[case["name"]]
+    got = cases.api_run(pk, case, cases.api_inputs(), backend="cuda")
+    if case["name"].endswith("_execute_masked_1d"):          # tests/test_host.py: API_KNOWN_DIFFERENCES
+        assert got["exc"] == "ValueError"
+        return
+    assert (got["kind"], got["exc"], got["msg"]) == (want["kind"], want["exc"], want["msg"])
+
+    def strip_stats(text):
+        return "\n".join(ln for ln in text.split("\n") if not ln.startswith(("Q1 =", "Q2 =", "cR =")))
+    assert strip_stats(got["stdout"]) == strip_stats(want["stdout"])
+    assert got["warnings"] == want["warnings"]
