@@ -789,3 +789,59 @@ def fuzz_config(t):
     pts = (gx, gy) if dim == 2 else (gx, gy, gz)
     return dict(t=t, cls=cls, data=data, kw=kw, style=style, pts=pts, ekw=ekw, knn=knn,
                 text="%s n=%d %s %s %s terms=%s knn=%s" % (cls, n, m, style, shape, terms, knn))
+
+
+# ---- stateful sequences: execute / update_variogram_model (also with a new anisotropy) / execute on ONE object
+#      (tests/golden/make_golden.py fuzz -> ref_fuzz.npz keys 'seq<t>/<step>/z|ss'): the problem cache must follow the
+#      variogram and the re-adjusted data, functional drift sees the new frame, point_log wells keep the frame they were
+#      adjusted in at construction (the reference does not re-adjust them, uk.py:630-790) ----
+N_SEQ = 60
+
+
+def seq_config(t):
+    rng = np.random.default_rng(8_000_000 + t)
+    dim = 3 if rng.uniform() < 0.4 else 2
+    uk = rng.uniform() < 0.6
+    n = int(rng.integers(12, 40))
+    X = rng.uniform(0, 100, (n, dim))
+    v = 5 + np.sin(X[:, 0] / 20) + rng.normal(size=n) * 0.3
+    cls = ("Universal" if uk else "Ordinary") + "Kriging" + ("3D" if dim == 3 else "")
+    kw = dict(variogram_model="exponential", variogram_parameters=[1.5, 40.0, 0.1])
+    if uk:
+        terms = ["regional_linear"] if rng.uniform() < 0.5 else []
+        if dim == 2 and rng.uniform() < 0.5:
+            terms.append("point_log")
+            kw["point_drift"] = np.array([[30.0, 40.0, 1.0], [70.0, 20.0, -1.5]])
+        if rng.uniform() < 0.5:
+            terms.append("functional")
+            kw["functional_drift"] = [_fuzz_f2 if dim == 2 else _fuzz_f3]
+        kw["drift_terms"] = terms
+    data = (X[:, 0], X[:, 1], v) if dim == 2 else (X[:, 0], X[:, 1], X[:, 2], v)
+    pts = (np.sort(rng.uniform(0, 100, 4)), np.sort(rng.uniform(0, 100, 3)), np.sort(rng.uniform(0, 100, 2)))[:dim]
+    steps = []
+    for _ in range(int(rng.integers(2, 5))):
+        if rng.uniform() < 0.45:
+            steps.append(("exec",))
+            continue
+        m = ("linear", "gaussian", "spherical", "power")[rng.integers(4)]
+        p = {"linear": [0.01, 0.1], "power": [0.01, 1.2, 0.1]}.get(m) or [float(rng.uniform(1, 2)), float(rng.uniform(20, 80)), 0.1]
+        an = {}
+        if rng.uniform() < 0.6:
+            an = (dict(anisotropy_scaling=float(rng.uniform(0.5, 2)), anisotropy_angle=float(rng.uniform(-60, 60))) if dim == 2
+                  else dict(anisotropy_scaling_y=float(rng.uniform(0.5, 2)), anisotropy_angle_z=float(rng.uniform(-60, 60))))
+        steps.append(("upd", m, p, an))
+    steps.append(("exec",))
+    return dict(cls=cls, data=data, kw=kw, pts=pts, steps=steps, text="%s %s %s" % (cls, kw.get("drift_terms"), steps))
+
+
+def seq_run(module_ns, c, backend):
+    """Replay the sequence; returns the (z, ss) of every 'exec' step."""
+    obj = getattr(module_ns, c["cls"])(*c["data"], **c["kw"])
+    outs = []
+    for st in c["steps"]:
+        if st[0] == "upd":
+            obj.update_variogram_model(st[1], st[2], **st[3])
+        else:
+            z, ss = obj.execute("grid", *c["pts"], backend=backend)
+            outs.append((np.asarray(z), np.asarray(ss)))
+    return outs

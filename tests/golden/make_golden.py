@@ -253,6 +253,13 @@ def ref_fuzz():
             out["%d/exc" % t] = np.array(type(e).__name__)
             n_exc += 1
     print("fuzz: %d results, %d exceptions" % (n_ok, n_exc))
+    for t in range(cases.N_SEQ):                    # stateful sequences on one object
+        c = cases.seq_config(t)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for k, (z, ss) in enumerate(cases.seq_run(pykrige, c, "vectorized")):
+                out["seq%d/%d/z" % (t, k)] = z
+                out["seq%d/%d/ss" % (t, k)] = ss
     np.savez_compressed(os.path.join(HERE, "ref_fuzz.npz"), **out)
 
 

@@ -273,3 +273,19 @@ def test_host_api_cases_with_a_device_present(case, monkeypatch):
         return "\n".join(ln for ln in text.split("\n") if not ln.startswith(("Q1 =", "Q2 =", "cR =")))
     assert strip_stats(got["stdout"]) == strip_stats(want["stdout"])
     assert got["warnings"] == want["warnings"]
+
+
+@pytest.mark.parametrize("t", range(cases.N_SEQ))
+def test_stateful_sequences_through_the_host_wrappers(pk, t, ref_fuzz):
+    """execute / update_variogram_model (also with a new anisotropy) / execute on one object (tests/cases.py seq_config):
+    the cached device problem follows the variogram and the re-adjusted data; point_log wells keep their original
+    frame, functional drift sees the new one — as the imported reference (ref_fuzz.npz 'seq*')."""
+    import warnings
+    c = cases.seq_config(t)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        outs = cases.seq_run(pk, c, "cuda")
+    assert outs
+    for k, (z, ss) in enumerate(outs):
+        assert_parity(np.ravel(z), np.ravel(ref_fuzz["seq%d/%d/z" % (t, k)]), 1e-6, c["text"] + " z step %d" % k)
+        assert_parity(np.ravel(ss), np.ravel(ref_fuzz["seq%d/%d/ss" % (t, k)]), 1e-6, c["text"] + " ss step %d" % k)
