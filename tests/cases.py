@@ -845,3 +845,64 @@ def seq_run(module_ns, c, backend):
             z, ss = obj.execute("grid", *c["pts"], backend=backend)
             outs.append((np.asarray(z), np.asarray(ss)))
     return outs
+
+
+# ---- more randomised draws, CPU replay only (the device side of these kinds is covered by the seeded GPU cases):
+#      geographic coordinates, pseudo_inv with redundant points, exact duplicates WITHOUT pseudo_inv (the reference's
+#      scipy.linalg.inv raises LinAlgError), custom variogram callables incl. UK and anisotropy, all with and without the
+#      moving window -> ref_fuzz.npz keys 'kind<t>/...' ----
+N_KIND = 160
+_KIND_CUSTOMS = ((lambda m, d: m[0] * np.log10(d + m[1]) + m[2], [1.0, 1.0, 1.0]), (lambda m, d: m[0] * np.sqrt(d) + m[1], [0.05, 0.1]))
+
+
+def kind_config(t):
+    rng = np.random.default_rng(9_000_000 + t)
+    kind = ("geo", "pinv", "custom", "dups")[t % 4]
+    n = int(rng.integers(10, 50))
+    dim = 2
+    if kind == "geo":
+        X = np.column_stack([rng.uniform(-170, 170, n), rng.uniform(-80, 80, n)])
+    else:
+        dim = 3 if rng.uniform() < 0.3 else 2
+        X = rng.uniform(0, 100, (n, dim))
+    v = 5 + np.sin(X[:, 0] / 20) + rng.normal(size=n) * 0.3
+    kw = dict(variogram_model="exponential", variogram_parameters=[1.5, 40.0, 0.1])
+    cls = "OrdinaryKriging" + ("3D" if dim == 3 else "")
+    if kind == "geo":
+        kw["coordinates_type"] = "geographic"
+    if kind in ("pinv", "dups"):
+        X = np.vstack([X, X[:3]])
+        v = np.concatenate([v, v[:3] + (0.0 if rng.uniform() < 0.5 else 0.1)])
+        n += 3
+    if kind == "pinv":
+        kw.update(pseudo_inv=True, pseudo_inv_type=("pinv", "pinvh")[(t // 4) % 2])
+    if kind == "custom":
+        f, p = _KIND_CUSTOMS[rng.integers(2)]
+        kw = dict(variogram_model="custom", variogram_function=f, variogram_parameters=list(p))
+        if rng.uniform() < 0.5 and dim == 2:
+            kw.update(anisotropy_scaling=2.0, anisotropy_angle=30.0)
+        if rng.uniform() < 0.4:
+            cls = "UniversalKriging" + ("3D" if dim == 3 else "")
+            kw["drift_terms"] = ["regional_linear"]
+    ekw = {}
+    style = ("grid", "points", "masked")[rng.integers(3)]
+    lo, hi = X.min(0), X.max(0)
+    nx, ny, nz = int(rng.integers(1, 6)), int(rng.integers(1, 6)), int(rng.integers(1, 4))
+    gx = np.sort(rng.uniform(lo[0] - 5, hi[0] + 5, nx))
+    gy = np.sort(rng.uniform(-85, 85, ny) if kind == "geo" else rng.uniform(lo[1] - 5, hi[1] + 5, ny))
+    gz = np.sort(rng.uniform(0, 100, nz))
+    if style == "points":
+        m = int(rng.integers(1, 9))
+        gx, gy, gz = rng.uniform(lo[0], hi[0], m), rng.uniform(lo[1], hi[1], m), rng.uniform(0, 100, m)
+        nx = ny = nz = m
+    shape = (ny, nx) if dim == 2 else (nz, ny, nx)
+    if style == "masked":
+        ekw["mask"] = rng.uniform(size=shape) < 0.4
+    knn = None
+    if cls.startswith("Ordinary") and rng.uniform() < 0.35 and kind != "dups":
+        knn = int(rng.integers(2, 8))
+        ekw["n_closest_points"] = knn
+    data = (X[:, 0], X[:, 1], v) if dim == 2 else (X[:, 0], X[:, 1], X[:, 2], v)
+    pts = (gx, gy) if dim == 2 else (gx, gy, gz)
+    return dict(t=t, kind=kind, cls=cls, data=data, kw=kw, style=style, pts=pts, ekw=ekw, knn=knn,
+                text="%s %s n=%d %s %s knn=%s" % (kind, cls, n, style, shape, knn))

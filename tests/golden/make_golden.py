@@ -253,6 +253,21 @@ def ref_fuzz():
             out["%d/exc" % t] = np.array(type(e).__name__)
             n_exc += 1
     print("fuzz: %d results, %d exceptions" % (n_ok, n_exc))
+    n_ok = n_exc = 0
+    for t in range(cases.N_KIND):                   # geographic / pseudo_inv / duplicates / custom callables
+        c = cases.kind_config(t)
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                model = getattr(pykrige, c["cls"])(*c["data"], **c["kw"])
+                z, ss = model.execute(c["style"], *c["pts"], backend="loop" if c["knn"] else "vectorized", **c["ekw"])
+            out["kind%d/z" % t] = np.ma.getdata(z)
+            out["kind%d/ss" % t] = np.ma.getdata(ss)
+            n_ok += 1
+        except Exception as e:  # noqa: BLE001
+            out["kind%d/exc" % t] = np.array(type(e).__name__)
+            n_exc += 1
+    print("kinds: %d results, %d exceptions" % (n_ok, n_exc))
     for t in range(cases.N_SEQ):                    # stateful sequences on one object
         c = cases.seq_config(t)
         with warnings.catch_warnings():

@@ -289,3 +289,30 @@ def test_stateful_sequences_through_the_host_wrappers(pk, t, ref_fuzz):
     for k, (z, ss) in enumerate(outs):
         assert_parity(np.ravel(z), np.ravel(ref_fuzz["seq%d/%d/z" % (t, k)]), 1e-6, c["text"] + " z step %d" % k)
         assert_parity(np.ravel(ss), np.ravel(ref_fuzz["seq%d/%d/ss" % (t, k)]), 1e-6, c["text"] + " ss step %d" % k)
+
+
+@pytest.mark.parametrize("t", range(cases.N_KIND))
+def test_randomised_special_kinds_through_the_host_wrappers(pk, t, ref_fuzz):
+    """tests/cases.py kind_config(t): geographic coordinates, pseudo_inv with redundant points, exact duplicates without
+    it (LinAlgError, as scipy.linalg.inv in the reference), custom variogram callables (also UK / anisotropy), each with
+    and without the moving window — against the imported reference (ref_fuzz.npz 'kind*')."""
+    import warnings
+    c = cases.kind_config(t)
+
+    def run():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return getattr(pk, c["cls"])(*c["data"], **c["kw"]).execute(c["style"], *c["pts"], backend="cuda", **c["ekw"])
+    if "kind%d/exc" % t in ref_fuzz.files:
+        with pytest.raises(Exception) as ei:
+            run()
+        assert type(ei.value).__name__ == str(ref_fuzz["kind%d/exc" % t]), c["text"]
+        return
+    z, ss = run()
+    zr, sr = ref_fuzz["kind%d/z" % t], ref_fuzz["kind%d/ss" % t]
+    assert z.shape == zr.shape, c["text"]
+    keep = ~np.ma.getmaskarray(z) if c["style"] == "masked" else np.ones(zr.shape, bool)
+    if keep.any():
+        R = 2e-5 if c["kind"] == "pinv" else 1e-6          # scipy's pinv / pinvh differ from each other at 1e-6 on these
+        assert_parity(np.ma.getdata(z)[keep], zr[keep], R, c["text"] + " z")
+        assert_parity(np.ma.getdata(ss)[keep], sr[keep], R, c["text"] + " ss")
